@@ -1,0 +1,139 @@
+// gfs_device.cuh — device-side building blocks shared by the SGD, stress and debug kernels.
+//
+// Everything numerical here is written with explicit round-to-nearest intrinsics (__dmul_rn,
+// __dadd_rn, ...) so that nvcc cannot contract a*b+c into an FMA: the reference is Rust, which
+// never fuses, and the parity tests compare these functions bit-for-bit with the CPU oracle.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace gfs {
+
+// One step of a path as the kernels read it: a single 16-byte, 16-byte-aligned record, so a random
+// step costs exactly one 32-byte sector.  Replaces the reference's four parallel 8-byte arrays
+// (src/sgd.rs:14-24); path id and rank are recovered from the P+1 first_step table instead.
+struct __align__(16) StepRec {
+    uint32_t node_rev;   // (dense node idx << 1) | is_reverse        (Handle, src/graph.rs:9-19)
+    uint32_t node_len;   // sequence length of that node             (needed by the nD kernel, sgd.rs:1051-1058)
+    uint64_t pos;        // nucleotide offset of the step in its path (step_to_position, sgd.rs:18)
+};
+static_assert(sizeof(StepRec) == 16, "StepRec must be one 16-byte record");
+
+enum : uint32_t { STREAM_SGD = 1, STREAM_STRESS = 2 };
+
+// ---- Philox4x32-10 (Salmon et al. SC'11) -------------------------------------------------------
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+        c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+        k.x += 0x9E3779B9u;
+        k.y += 0xBB67AE85u;
+    }
+    return c;
+}
+
+// ---- fast_precise_pow (src/sgd.rs:155-182) -----------------------------------------------------
+// __double2int_rz saturates and maps NaN to 0 exactly like Rust's `as i32`.
+__device__ __forceinline__ double fast_precise_pow(double a, double b) {
+    const int e = __double2int_rz(b);
+    const int hi = __double2hiint(a);
+    const int diff = (int)((unsigned)hi - 1072632447u);
+    const int nh = __double2int_rz(__dadd_rn(__dmul_rn(__dsub_rn(b, (double)e), (double)diff), 1072632447.0));
+    const double frac = __hiloint2double(nh, 0);
+    double base = a, r = 1.0;
+    int ex = e;
+    while (ex != 0) {
+        if (ex & 1) r = __dmul_rn(r, base);
+        base = __dmul_rn(base, base);
+        ex >>= 1;
+    }
+    return __dmul_rn(r, frac);
+}
+
+// Per-epoch constants of the Zipf sampler: pure functions of the current theta, computed once on
+// the host with the same formulas (src/sgd.rs:132, 143, 471).
+struct ZipfConsts {
+    double theta;
+    double one_minus_theta;   // 1.0 - theta
+    double alpha;             // 1.0 / (1.0 - theta)
+    double z2;                // 1.0 + fast_precise_pow(0.5, theta)
+};
+
+// ---- DirtyZipfian::sample with min = 1, max = jump_space (src/sgd.rs:122-151) -------------------
+// __double2ull_rz saturates / maps negatives and NaN to 0 like Rust's `as u64`.
+__device__ __forceinline__ uint32_t dirty_zipf(uint32_t jump_space, const ZipfConsts& zc, double zeta, double u) {
+    const double uz = __dmul_rn(u, zeta);
+    if (uz < 1.0) return 1u;
+    if (uz < zc.z2) return 2u;
+    const double n = (double)jump_space;
+    const double eta = __ddiv_rn(__dsub_rn(1.0, fast_precise_pow(__ddiv_rn(2.0, n), zc.one_minus_theta)),
+                                 __dsub_rn(1.0, __ddiv_rn(zc.z2, zeta)));
+    const double base = __dadd_rn(__dsub_rn(__dmul_rn(eta, u), eta), 1.0);
+    const double result = __dadd_rn(1.0, __dmul_rn(n, fast_precise_pow(base, zc.alpha)));
+    const unsigned long long z = __double2ull_rz(result);
+    return z > (unsigned long long)jump_space ? jump_space : (uint32_t)z;
+}
+
+// ---- memory access helpers ---------------------------------------------------------------------
+// Step records are read-only and streamed once each: non-coherent path, no L1 allocation.
+__device__ __forceinline__ StepRec load_rec(const StepRec* p) {
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    StepRec r;
+    r.node_rev = v.x; r.node_len = v.y; r.pos = ((uint64_t)v.w << 32) | v.z;
+    return r;
+}
+__device__ __forceinline__ uint64_t make_evict_first_policy() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ uint64_t make_evict_last_policy() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ StepRec load_rec_hint(const StepRec* p, uint64_t pol) {
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p), "l"(pol));
+    StepRec r;
+    r.node_rev = v.x; r.node_len = v.y; r.pos = ((uint64_t)v.w << 32) | v.z;
+    return r;
+}
+
+// largest p in [0, P) with first_step[p] <= s   (first_step has P+1 entries, first_step[P] = S > s)
+__device__ __forceinline__ uint32_t find_path(const uint64_t* __restrict__ fs, uint32_t P, uint64_t s) {
+    uint32_t lo = 0, hi = P;   // invariant: fs[lo] <= s < fs[hi]
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (fs[mid] <= s) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+// Sum over the lanes named in `peers` (the valid lanes sharing this lane's key); every lane of
+// `active` calls, lanes outside every group pass a peers mask that does not contain themselves.
+// Returns the group sum in the group's leader (lowest lane); other lanes get an undefined value.
+template <typename T>
+__device__ __forceinline__ T group_sum(unsigned active, unsigned peers, T v, int lane, bool& is_leader) {
+    is_leader = (__ffs(peers) - 1) == lane;   // false for lanes not in their own mask
+    // fast path: no lane of the warp shares a key
+    const bool dup = __popc(peers) > 1;
+    if (!__any_sync(active, dup)) return v;
+    T acc = v;
+    unsigned rest = peers & ~(1u << lane);
+    // rounds: in round r each lane fetches the r-th other member of its group
+    const int rounds = __reduce_max_sync(active, (unsigned)__popc(rest));
+    for (int r = 0; r < rounds; ++r) {
+        const int src = rest ? (__ffs(rest) - 1) : lane;
+        const T o = __shfl_sync(active, v, src);
+        if (rest) { acc += o; rest &= rest - 1; }
+    }
+    return acc;
+}
+
+}  // namespace gfs

@@ -1,0 +1,1388 @@
+// gfs_lib.cu — libgfasort_cuda.so: kernels + C ABI (include/gfasort_cuda.h) for the path-guided SGD
+// hot path of pangenome/gfasort on B200 (sm_100a).
+//
+// Kernels
+//   K1  k1_tile_sums / k1_scan_tiles / k1_path_base / k1_write_recs
+//         path index: gather node lengths, scan them, emit one 16-byte StepRec per step.
+//         Replaces PathIndex::from_graph (reference src/sgd.rs:34-71).
+//   K2  sgd_kernel<ONE_D>   persistent 1D `Y` term loop, f64 positions.  Replaces the worker loop
+//         src/sgd.rs:442-584 and the checker thread :366-407.
+//   K3  sgd_kernel<ND>      persistent nD `L` term loop on [node][end][dim] coordinates (float or
+//         double).  Replaces src/sgd.rs:988-1156 and :925-955.
+//   K4  stress_kernel       sampled path stress.  Replaces calculate_layout_stress (:1196-1283).
+//
+// There is no CPU implementation of any of these in this library: if CUDA is unavailable every
+// entry point returns an error.
+#include <cuda_runtime.h>
+#include <cooperative_groups.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/gfasort_cuda.h"
+#include "gfs_device.cuh"
+
+namespace gfs {
+
+static thread_local std::string g_last_error;
+void set_error(const std::string& s) { g_last_error = s; }
+
+#define GFS_CUDA(call)                                                                              \
+    do {                                                                                            \
+        cudaError_t e__ = (call);                                                                   \
+        if (e__ != cudaSuccess) {                                                                   \
+            set_error(std::string(#call) + " failed: " + cudaGetErrorString(e__) + " (" __FILE__ ":" + \
+                      std::to_string(__LINE__) + ")");                                              \
+            return GFS_ERR_CUDA;                                                                    \
+        }                                                                                           \
+    } while (0)
+
+static double now_s() {
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+static long env_long(const char* name, long dflt) {
+    const char* v = std::getenv(name);
+    if (!v || !*v) return dflt;
+    return std::strtol(v, nullptr, 10);
+}
+
+// =============================================================================================
+// Host twins of the reference's scalar helpers (schedule / zeta table / per-epoch constants).
+// Compiled with -ffp-contract=off; x86-64 baseline has no FMA, so nothing is fused.
+// =============================================================================================
+static inline int32_t h_f64_as_i32(double v) {
+    if (std::isnan(v)) return 0;
+    if (v >= 2147483647.0) return INT32_MAX;
+    if (v <= -2147483648.0) return INT32_MIN;
+    return (int32_t)v;
+}
+static double h_fast_precise_pow(double a, double b) {      // src/sgd.rs:155-182
+    int32_t e = h_f64_as_i32(b);
+    uint64_t bits; std::memcpy(&bits, &a, 8);
+    int32_t diff = (int32_t)((uint32_t)(bits >> 32) - 1072632447u);
+    int32_t nh = h_f64_as_i32((b - (double)e) * (double)diff + 1072632447.0);
+    uint64_t fb = ((uint64_t)(int64_t)nh) << 32;
+    double frac; std::memcpy(&frac, &fb, 8);
+    double base = a, r = 1.0;
+    for (int32_t ex = e; ex != 0; ex >>= 1) { if (ex & 1) r *= base; base *= base; }
+    return r * frac;
+}
+static void h_schedule(const gfs_sgd_params& p, std::vector<double>& etas) {   // src/sgd.rs:617-638
+    const double w_min = 1.0 / p.eta_max, w_max = 1.0;
+    const double eta_max = 1.0 / w_min, eta_min = p.eps / w_max;
+    const double lambda = std::log(eta_max / eta_min) / ((double)p.iter_max - 1.0);
+    etas.resize(p.iter_max + 1);
+    for (uint64_t t = 0; t <= p.iter_max; ++t) {
+        int64_t dt = (int64_t)t - (int64_t)p.iter_with_max_learning_rate;
+        if (dt < 0) dt = -dt;
+        etas[t] = eta_max * std::exp(-lambda * (double)dt);
+    }
+}
+// src/sgd.rs:311-331.  The serial summation order is kept (it defines the values); the loop stops
+// at the largest jump_space any path can produce (max_path_steps), since entries beyond it are
+// unreachable (jump_space = min(space, rank) <= max_path_steps - 1, src/sgd.rs:462,477).
+static void h_zetas(const gfs_sgd_params& p, uint64_t max_path_steps, std::vector<double>& z) {
+    const uint64_t sm = p.space_max, q = p.space_quantization_step ? p.space_quantization_step : 1;
+    const uint64_t full = ((p.space <= sm) ? p.space : sm + (p.space - sm) / q + 1) + 1;
+    const uint64_t reach = std::min(p.space, max_path_steps);
+    const uint64_t reach_idx = reach > sm ? sm + (reach - sm) / q + 1 : reach;
+    const uint64_t n = std::min(full, reach_idx + 2);
+    z.assign(n, 0.0);
+    double acc = 0.0;
+    for (uint64_t i = 1; i <= reach; ++i) {
+        acc += h_fast_precise_pow(1.0 / (double)i, p.theta);
+        if (i <= sm) { if (i < n) z[i] = acc; }
+        if (i >= sm && (i - sm) % q == 0) {
+            uint64_t idx = sm + 1 + (i - sm) / q;
+            if (idx < n) z[idx] = acc;
+        }
+    }
+}
+
+// One epoch of the schedule as the kernels see it.
+struct EpochDesc {
+    double eta;
+    ZipfConsts zc;
+    uint64_t updates;     // min_term_updates
+    uint32_t cooling;
+    uint32_t pad;
+};
+
+static void h_epochs(const gfs_sgd_params& p, std::vector<EpochDesc>& out) {
+    std::vector<double> etas;
+    h_schedule(p, etas);
+    const uint64_t first_cooling = (uint64_t)std::floor(p.cooling_start * (double)p.iter_max);   // sgd.rs:297
+    out.resize(p.iter_max + 1);
+    for (uint64_t e = 0; e <= p.iter_max; ++e) {
+        EpochDesc d{};
+        d.eta = etas[e];
+        d.cooling = e > first_cooling ? 1u : 0u;                    // strict (sgd.rs:393)
+        const double theta = d.cooling ? 0.001 : p.theta;           // sgd.rs:394
+        d.zc.theta = theta;
+        d.zc.one_minus_theta = 1.0 - theta;
+        d.zc.alpha = 1.0 / (1.0 - theta);
+        d.zc.z2 = 1.0 + h_fast_precise_pow(0.5, theta);
+        d.updates = p.min_term_updates;
+        out[e] = d;
+    }
+}
+
+// =============================================================================================
+// K1 — path index
+// =============================================================================================
+constexpr int K1_THREADS = 256;
+constexpr int K1_ITEMS = 8;
+constexpr int K1_TILE = K1_THREADS * K1_ITEMS;
+
+__device__ __forceinline__ uint32_t gathered_len(uint64_t h, const uint32_t* __restrict__ node_len, uint64_t N) {
+    const uint64_t node = h >> 1;
+    return node < N ? __ldg(node_len + node) : 0u;    // missing node => +0 (src/sgd.rs:52-54)
+}
+
+__device__ __forceinline__ uint64_t block_sum_u64(uint64_t v, uint64_t* warp_buf) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) warp_buf[w] = v;
+    __syncthreads();
+    uint64_t t = 0;
+    if (threadIdx.x < 32) {
+        t = threadIdx.x < (blockDim.x >> 5) ? warp_buf[threadIdx.x] : 0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        if (threadIdx.x == 0) warp_buf[0] = t;
+    }
+    __syncthreads();
+    t = warp_buf[0];
+    __syncthreads();
+    return t;
+}
+
+// tile_sum[t] = sum of node lengths of the steps of tile t
+__global__ void __launch_bounds__(K1_THREADS)
+k1_tile_sums(const uint64_t* __restrict__ handles, const uint32_t* __restrict__ node_len, uint64_t S, uint64_t N,
+             uint64_t* __restrict__ tile_sum) {
+    __shared__ uint64_t wb[32];
+    const uint64_t base = (uint64_t)blockIdx.x * K1_TILE;
+    uint64_t s = 0;
+#pragma unroll
+    for (int k = 0; k < K1_ITEMS; ++k) {
+        const uint64_t i = base + (uint64_t)k * K1_THREADS + threadIdx.x;
+        if (i < S) s += gathered_len(handles[i], node_len, N);
+    }
+    s = block_sum_u64(s, wb);
+    if (threadIdx.x == 0) tile_sum[blockIdx.x] = s;
+}
+
+// exclusive scan of tile sums, seeded with *carry; leaves the running total in *carry. One block.
+__global__ void __launch_bounds__(1024)
+k1_scan_tiles(uint64_t* __restrict__ tile_sum, uint64_t n_tiles, uint64_t* __restrict__ carry) {
+    __shared__ uint64_t wsum[32];
+    __shared__ uint64_t running;
+    if (threadIdx.x == 0) running = *carry;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (uint64_t base = 0; base < n_tiles; base += 1024) {
+        const uint64_t i = base + threadIdx.x;
+        const uint64_t v = i < n_tiles ? tile_sum[i] : 0;
+        uint64_t inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint64_t t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        if (lane == 31) wsum[w] = inc;
+        __syncthreads();
+        if (w == 0) {
+            uint64_t ws = wsum[lane], wi = ws;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint64_t t = __shfl_up_sync(0xffffffffu, wi, o);
+                if (lane >= o) wi += t;
+            }
+            wsum[lane] = wi - ws;   // exclusive warp offsets
+        }
+        __syncthreads();
+        const uint64_t excl = running + wsum[w] + (inc - v);
+        if (i < n_tiles) tile_sum[i] = excl;
+        __syncthreads();
+        if (threadIdx.x == 1023) running = excl + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *carry = running;
+}
+
+// path_base[p] = global exclusive prefix at the first step of path p, for the paths that start
+// inside [chunk_begin, chunk_end).  One block per path of the chunk's path range.
+__global__ void __launch_bounds__(K1_THREADS)
+k1_path_base(const uint64_t* __restrict__ handles /*chunk-local*/, const uint32_t* __restrict__ node_len,
+             uint64_t N, const uint64_t* __restrict__ first_step, uint32_t p_begin, uint32_t p_end,
+             uint64_t chunk_begin, uint64_t chunk_end, const uint64_t* __restrict__ tile_prefix /*chunk-local*/,
+             uint64_t* __restrict__ path_base) {
+    __shared__ uint64_t wb[32];
+    const uint32_t p = p_begin + blockIdx.x;
+    if (p >= p_end) return;
+    const uint64_t s0 = first_step[p];
+    if (s0 < chunk_begin || s0 >= chunk_end) return;   // block-uniform
+    const uint64_t local = s0 - chunk_begin;
+    const uint64_t tile = local / K1_TILE;
+    const uint64_t tbase = tile * K1_TILE;
+    uint64_t s = 0;
+    for (uint64_t i = tbase + threadIdx.x; i < local; i += K1_THREADS) s += gathered_len(handles[i], node_len, N);
+    s = block_sum_u64(s, wb);
+    if (threadIdx.x == 0) path_base[p] = tile_prefix[tile] + s;
+}
+
+// Emit the records of one tile: pos = global prefix - path_base[path(step)].
+__global__ void __launch_bounds__(K1_THREADS)
+k1_write_recs(const uint64_t* __restrict__ handles /*chunk-local*/, const uint32_t* __restrict__ node_len,
+              uint64_t N, const uint64_t* __restrict__ first_step, uint32_t P, uint64_t chunk_begin,
+              uint64_t chunk_len, const uint64_t* __restrict__ tile_prefix, const uint64_t* __restrict__ path_base,
+              StepRec* __restrict__ recs /*global index*/) {
+    __shared__ uint32_t s_len[K1_TILE];
+    __shared__ uint32_t s_nr[K1_TILE];
+    __shared__ uint64_t s_pos[K1_TILE];
+    __shared__ uint64_t wsum[K1_THREADS / 32];
+    const uint64_t tbase = (uint64_t)blockIdx.x * K1_TILE;
+#pragma unroll
+    for (int k = 0; k < K1_ITEMS; ++k) {
+        const int j = k * K1_THREADS + threadIdx.x;
+        const uint64_t i = tbase + j;
+        uint32_t len = 0, nr = 0;
+        if (i < chunk_len) {
+            const uint64_t h = handles[i];
+            len = gathered_len(h, node_len, N);
+            const uint64_t node = h >> 1;
+            nr = (uint32_t)(((node < N ? node : N) << 1) | (h & 1));
+        }
+        s_len[j] = len; s_nr[j] = nr;
+    }
+    __syncthreads();
+    // thread t owns items [t*8, t*8+8)
+    uint64_t loc[K1_ITEMS];
+    uint64_t tsum = 0;
+#pragma unroll
+    for (int k = 0; k < K1_ITEMS; ++k) { loc[k] = tsum; tsum += s_len[threadIdx.x * K1_ITEMS + k]; }
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    uint64_t inc = tsum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint64_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) wsum[w] = inc;
+    __syncthreads();
+    uint64_t woff = 0;
+#pragma unroll
+    for (int k = 0; k < K1_THREADS / 32; ++k) woff += (k < w) ? wsum[k] : 0;
+    const uint64_t texcl = tile_prefix[blockIdx.x] + woff + (inc - tsum);
+#pragma unroll
+    for (int k = 0; k < K1_ITEMS; ++k) s_pos[threadIdx.x * K1_ITEMS + k] = texcl + loc[k];
+    __syncthreads();
+    // path of the tile's first and last step; most tiles lie inside one path
+    const uint64_t g_first = chunk_begin + tbase;
+    const uint64_t last_local = (tbase + K1_TILE <= chunk_len ? tbase + K1_TILE : chunk_len) - 1;
+    const uint32_t p_first = find_path(first_step, P, g_first);
+    const uint32_t p_last = find_path(first_step, P, chunk_begin + last_local);
+    const uint64_t base_first = path_base[p_first];
+#pragma unroll
+    for (int k = 0; k < K1_ITEMS; ++k) {
+        const int j = k * K1_THREADS + threadIdx.x;
+        const uint64_t i = tbase + j;
+        if (i < chunk_len) {
+            const uint64_t gi = chunk_begin + i;
+            uint64_t pb = base_first;
+            if (p_first != p_last) pb = path_base[find_path(first_step, P, gi)];
+            StepRec r;
+            r.node_rev = s_nr[j]; r.node_len = s_len[j]; r.pos = s_pos[j] - pb;
+            recs[gi] = r;
+        }
+    }
+}
+
+__global__ void k1_path_len(const uint64_t* __restrict__ path_base, uint32_t P, uint64_t* __restrict__ path_len) {
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < P) path_len[p] = path_base[p + 1] - path_base[p];
+}
+__global__ void k1_set_u64(uint64_t* p, uint64_t idx, const uint64_t* src) { p[idx] = *src; }
+
+__global__ void k1_export_pos(const StepRec* __restrict__ recs, uint64_t S, uint64_t* __restrict__ pos) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < S) pos[i] = recs[i].pos;
+}
+__global__ void k1_export_hl(const StepRec* __restrict__ recs, uint64_t S, uint64_t* __restrict__ h,
+                             uint32_t* __restrict__ l) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < S) { h[i] = recs[i].node_rev; l[i] = recs[i].node_len; }
+}
+
+// =============================================================================================
+// term sampling (shared by K2, K3, trace) — SURVEY.md Appendix A steps 1-5'
+// =============================================================================================
+struct KernelGraph {
+    const StepRec* recs;
+    const uint64_t* first_step;   // P+1 (global memory copy)
+    const double* zetas;          // zlen entries (global)
+    uint64_t S;
+    uint32_t P;
+    uint32_t N;
+    uint32_t zlen;
+    uint32_t space;               // min(params.space, 2^32-1): compared with ranks < 2^32
+    uint32_t space_max;
+    uint32_t q;
+};
+
+struct SampledTerm {
+    StepRec a, b;
+    uint64_t step_a, step_b;   // step indices (only the trace kernel reads them)
+    bool other_a, other_b;
+    bool valid;
+};
+
+// Draw slots of one Philox block r (see oracle/gfs_oracle.cpp PhiloxDraw):
+//   step = mulhi64(r.y:r.x, S); u = ((r.w:r.z) >> 11) * 2^-53; uniform rank = mulhi64(r.w:r.z, n);
+//   coins = bits 0..3 of r.z (zipf, back, end_a, end_b).
+template <bool ND>
+__device__ __forceinline__ void sample_term(const KernelGraph& g, const uint64_t* fs, const double* s_zetas,
+                                            uint32_t s_zlen, const EpochDesc& ep, uint4 r, SampledTerm& t) {
+    const uint64_t r01 = ((uint64_t)r.y << 32) | r.x;
+    const uint64_t r23 = ((uint64_t)r.w << 32) | r.z;
+    const uint64_t s = __umul64hi(r01, g.S);
+    const uint32_t p = find_path(fs, g.P, s);
+    const uint64_t f = fs[p];
+    const uint32_t n = (uint32_t)(fs[p + 1] - f);
+    const uint32_t ra = (uint32_t)(s - f);
+    t.a = load_rec(g.recs + s);                      // independent of everything below: issue early
+    t.valid = n > 1;                                 // path_step_count == 1 => continue (sgd.rs:448)
+    uint32_t rb = ra;
+    if (ep.cooling || (r.z & 1u)) {                  // sgd.rs:456
+        const bool back = ra > 0 && (((r.z >> 1) & 1u) || ra == n - 1);   // sgd.rs:460
+        const bool fwd = !back && ra < n - 1;                              // sgd.rs:475
+        if (back || fwd) {
+            const uint32_t span = back ? ra : n - ra - 1;
+            const uint32_t J = span < g.space ? span : g.space;
+            uint32_t k = J > g.space_max ? g.space_max + (J - g.space_max) / g.q + 1 : J;   // sgd.rs:463-467
+            k = k < g.zlen - 1 ? k : g.zlen - 1;                                           // sgd.rs:469
+            const double zeta = k < s_zlen ? s_zetas[k] : __ldg(g.zetas + k);
+            const double u = (double)(r23 >> 11) * (1.0 / 9007199254740992.0);
+            const uint32_t z = dirty_zipf(J, ep.zc, zeta, u);
+            if (back) rb = ra >= z ? ra - z : 0u;                                          // saturating_sub
+            else { const uint64_t x = (uint64_t)ra + z; rb = x < n - 1 ? (uint32_t)x : n - 1; }
+        }
+    } else {
+        rb = (uint32_t)__umul64hi(r23, (uint64_t)n);                                       // sgd.rs:493-494
+    }
+    t.valid = t.valid && (ra != rb);                                                      // sgd.rs:497
+    t.step_a = s;
+    t.step_b = t.valid ? f + rb : s;
+    t.b = load_rec(g.recs + t.step_b);
+    t.other_a = t.other_b = false;
+    if (ND) {                                                                              // sgd.rs:1060-1077
+        const bool rev_a = t.a.node_rev & 1u, rev_b = t.b.node_rev & 1u;
+        bool ua = (r.z >> 2) & 1u;
+        if (ua) { t.a.pos += t.a.node_len; ua = !rev_a; } else { ua = rev_a; }
+        bool ub = (r.z >> 3) & 1u;
+        if (ub) { t.b.pos += t.b.node_len; ub = !rev_b; } else { ub = rev_b; }
+        t.other_a = ua; t.other_b = ub;
+    }
+}
+
+__device__ __forceinline__ double term_distance(const SampledTerm& t) {
+    return fabs(__dsub_rn((double)t.a.pos, (double)t.b.pos));                              // sgd.rs:509-513
+}
+
+// =============================================================================================
+// coordinate access for K3
+// =============================================================================================
+template <typename CT> struct Arith;
+template <> struct Arith<double> {
+    static __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
+    static __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
+    static __device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
+    static __device__ __forceinline__ double div(double a, double b) { return __ddiv_rn(a, b); }
+    static __device__ __forceinline__ double sqrt(double a) { return __dsqrt_rn(a); }
+};
+template <> struct Arith<float> {
+    static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
+    static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
+    static __device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
+    static __device__ __forceinline__ float div(float a, float b) { return __fdiv_rn(a, b); }
+    static __device__ __forceinline__ float sqrt(float a) { return __fsqrt_rn(a); }
+};
+
+// positions are written by atomics at L2 and read here: bypass the (incoherent) L1 with ld.cg
+__device__ __forceinline__ double ld_pos(const double* p) {
+    double v;
+    asm volatile("ld.global.cg.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
+template <typename CT, int DS> __device__ __forceinline__ void ld_coords(const CT* p, CT (&c)[DS]);
+template <> __device__ __forceinline__ void ld_coords<float, 1>(const float* p, float (&c)[1]) {
+    asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(c[0]) : "l"(p));
+}
+template <> __device__ __forceinline__ void ld_coords<float, 2>(const float* p, float (&c)[2]) {
+    asm volatile("ld.global.cg.v2.f32 {%0,%1}, [%2];" : "=f"(c[0]), "=f"(c[1]) : "l"(p));
+}
+template <> __device__ __forceinline__ void ld_coords<float, 4>(const float* p, float (&c)[4]) {
+    asm volatile("ld.global.cg.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(c[0]), "=f"(c[1]), "=f"(c[2]), "=f"(c[3]) : "l"(p));
+}
+template <> __device__ __forceinline__ void ld_coords<float, 8>(const float* p, float (&c)[8]) {
+    asm volatile("ld.global.cg.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(c[0]), "=f"(c[1]), "=f"(c[2]), "=f"(c[3]) : "l"(p));
+    asm volatile("ld.global.cg.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(c[4]), "=f"(c[5]), "=f"(c[6]), "=f"(c[7]) : "l"(p + 4));
+}
+template <> __device__ __forceinline__ void ld_coords<double, 1>(const double* p, double (&c)[1]) { c[0] = ld_pos(p); }
+template <> __device__ __forceinline__ void ld_coords<double, 2>(const double* p, double (&c)[2]) {
+    asm volatile("ld.global.cg.v2.f64 {%0,%1}, [%2];" : "=d"(c[0]), "=d"(c[1]) : "l"(p));
+}
+template <> __device__ __forceinline__ void ld_coords<double, 4>(const double* p, double (&c)[4]) {
+    asm volatile("ld.global.cg.v2.f64 {%0,%1}, [%2];" : "=d"(c[0]), "=d"(c[1]) : "l"(p));
+    asm volatile("ld.global.cg.v2.f64 {%0,%1}, [%2];" : "=d"(c[2]), "=d"(c[3]) : "l"(p + 2));
+}
+template <> __device__ __forceinline__ void ld_coords<double, 8>(const double* p, double (&c)[8]) {
+#pragma unroll
+    for (int k = 0; k < 8; k += 2)
+        asm volatile("ld.global.cg.v2.f64 {%0,%1}, [%2];" : "=d"(c[k]), "=d"(c[k + 1]) : "l"(p + k));
+}
+
+template <typename CT, int DS> __device__ __forceinline__ void red_coords(CT* p, const CT (&d)[DS]);
+template <> __device__ __forceinline__ void red_coords<float, 1>(float* p, const float (&d)[1]) { atomicAdd(p, d[0]); }
+template <> __device__ __forceinline__ void red_coords<float, 2>(float* p, const float (&d)[2]) {
+    atomicAdd(reinterpret_cast<float2*>(p), make_float2(d[0], d[1]));          // red.global.add.v2.f32
+}
+template <> __device__ __forceinline__ void red_coords<float, 4>(float* p, const float (&d)[4]) {
+    atomicAdd(reinterpret_cast<float4*>(p), make_float4(d[0], d[1], d[2], d[3]));   // red.global.add.v4.f32
+}
+template <> __device__ __forceinline__ void red_coords<float, 8>(float* p, const float (&d)[8]) {
+    atomicAdd(reinterpret_cast<float4*>(p), make_float4(d[0], d[1], d[2], d[3]));
+    atomicAdd(reinterpret_cast<float4*>(p + 4), make_float4(d[4], d[5], d[6], d[7]));
+}
+template <> __device__ __forceinline__ void red_coords<double, 1>(double* p, const double (&d)[1]) { atomicAdd(p, d[0]); }
+template <> __device__ __forceinline__ void red_coords<double, 2>(double* p, const double (&d)[2]) {
+    atomicAdd(p, d[0]); atomicAdd(p + 1, d[1]);
+}
+template <> __device__ __forceinline__ void red_coords<double, 4>(double* p, const double (&d)[4]) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) atomicAdd(p + k, d[k]);
+}
+template <> __device__ __forceinline__ void red_coords<double, 8>(double* p, const double (&d)[8]) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) atomicAdd(p + k, d[k]);
+}
+
+// =============================================================================================
+// K2 / K3 — persistent SGD term kernel
+// =============================================================================================
+constexpr int SGD_BLOCK = 256;
+constexpr uint32_t SMEM_ZETAS_MAX = 4096;      // doubles staged per block (32 KB)
+constexpr uint32_t SMEM_FS_MAX = 2048;         // first_step entries staged per block (16 KB)
+
+struct SgdArgs {
+    KernelGraph g;
+    const EpochDesc* epochs;     // device array, iter_max+1 entries
+    uint32_t epoch_begin, epoch_end;
+    uint32_t slice, n_slices;    // run slice `slice` of n_slices equal parts of every epoch's updates
+    uint64_t* attempt_ctr;       // per-thread Philox attempt counters (persist across launches)
+    unsigned long long* counters;   // [0] applied, [1] attempts
+    uint32_t seed_lo, seed_hi;
+    uint32_t tid_base;
+    void* positions;             // 1D: double[N]; nD: CT[N*2*DS]
+};
+
+// 1D update of one warp's terms (sgd.rs:512-576), optionally merging lanes that hit the same node.
+template <bool AGG>
+__device__ __forceinline__ void apply_1d(double* X, unsigned warp_mask, int lane, bool valid, uint32_t i,
+                                         uint32_t j, double d, double eta) {
+    double r_x = 0.0;
+    if (valid) {
+        const double mu = fmin(__dmul_rn(eta, __ddiv_rn(1.0, d)), 1.0);     // sgd.rs:518-520
+        const double xi = ld_pos(X + i), xj = ld_pos(X + j);
+        double dx = __dsub_rn(xi, xj);
+        if (dx == 0.0) dx = 1e-9;                                            // sgd.rs:546-548
+        const double mag = fabs(dx);
+        const double delta = __dmul_rn(__dmul_rn(mu, __dsub_rn(mag, d)), 0.5);   // sgd.rs:552
+        const double r = __ddiv_rn(delta, mag);
+        r_x = __dmul_rn(r, dx);
+    }
+    if (AGG) {
+        bool lead;
+        const unsigned vmask = __ballot_sync(warp_mask, valid);
+        const unsigned mi = __match_any_sync(warp_mask, i) & vmask; const unsigned pi = valid ? mi : 0u;
+        const double si = group_sum(warp_mask, pi, -r_x, lane, lead);
+        if (valid && lead) atomicAdd(X + i, si);
+        const unsigned mj = __match_any_sync(warp_mask, j) & vmask; const unsigned pj = valid ? mj : 0u;
+        const double sj = group_sum(warp_mask, pj, r_x, lane, lead);
+        if (valid && lead) atomicAdd(X + j, sj);
+    } else if (valid) {
+        atomicAdd(X + i, -r_x);                                              // sgd.rs:575
+        atomicAdd(X + j, r_x);                                               // sgd.rs:576
+    }
+}
+
+// nD update (sgd.rs:1079-1149) on coordinates laid out [node][end][DS] (DS >= D, padded with zeros).
+template <typename CT, int D, int DS, bool AGG>
+__device__ __forceinline__ void apply_nd(CT* C, unsigned warp_mask, int lane, bool valid, uint32_t idx_i,
+                                         uint32_t idx_j, double d, double eta) {
+    using A = Arith<CT>;
+    CT di[DS], dj[DS];
+#pragma unroll
+    for (int k = 0; k < DS; ++k) { di[k] = CT(0); dj[k] = CT(0); }
+    if (valid) {
+        const CT mu = (CT)fmin(__dmul_rn(eta, __ddiv_rn(1.0, d)), 1.0);      // sgd.rs:1085-1086
+        CT ci[DS], cj[DS], dl[DS];
+        ld_coords<CT, DS>(C + (size_t)idx_i * DS, ci);
+        ld_coords<CT, DS>(C + (size_t)idx_j * DS, cj);
+        CT mag_sq = CT(0);
+#pragma unroll
+        for (int k = 0; k < D; ++k) { dl[k] = A::sub(ci[k], cj[k]); mag_sq = A::add(mag_sq, A::mul(dl[k], dl[k])); }
+        if (mag_sq == CT(0)) { dl[0] = (CT)1e-9; mag_sq = (CT)1e-18; }       // sgd.rs:1116-1119
+        const CT mag = A::sqrt(mag_sq);
+        const CT delta = A::mul(A::mul(mu, A::sub(mag, (CT)d)), CT(0.5));    // sgd.rs:1125
+        const CT r = A::div(delta, mag);
+#pragma unroll
+        for (int k = 0; k < D; ++k) { const CT rd = A::mul(r, dl[k]); di[k] = -rd; dj[k] = rd; }
+    }
+    if (AGG) {
+        bool lead_i, lead_j;
+        const unsigned vmask = __ballot_sync(warp_mask, valid);
+        const unsigned mi = __match_any_sync(warp_mask, idx_i) & vmask; const unsigned pi = valid ? mi : 0u;
+#pragma unroll
+        for (int k = 0; k < D; ++k) di[k] = group_sum(warp_mask, pi, di[k], lane, lead_i);
+        if (valid && lead_i) red_coords<CT, DS>(C + (size_t)idx_i * DS, di);
+        const unsigned mj = __match_any_sync(warp_mask, idx_j) & vmask; const unsigned pj = valid ? mj : 0u;
+#pragma unroll
+        for (int k = 0; k < D; ++k) dj[k] = group_sum(warp_mask, pj, dj[k], lane, lead_j);
+        if (valid && lead_j) red_coords<CT, DS>(C + (size_t)idx_j * DS, dj);
+    } else if (valid) {
+        red_coords<CT, DS>(C + (size_t)idx_i * DS, di);
+        red_coords<CT, DS>(C + (size_t)idx_j * DS, dj);
+    }
+}
+
+// D == 0: 1D `Y` (CT must be double).  D >= 1: nD `L`.
+template <typename CT, int D, int DS, bool AGG>
+__global__ void __launch_bounds__(SGD_BLOCK, 4)
+sgd_kernel(const SgdArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint64_t* s_fs = reinterpret_cast<uint64_t*>(smem_raw);
+    const bool fs_in_smem = a.g.P + 1 <= SMEM_FS_MAX;
+    const uint32_t n_fs = fs_in_smem ? a.g.P + 1 : 0;
+    double* s_zetas = reinterpret_cast<double*>(smem_raw + (size_t)n_fs * 8);
+    const uint32_t s_zlen = a.g.zlen < SMEM_ZETAS_MAX ? a.g.zlen : SMEM_ZETAS_MAX;
+    for (uint32_t k = threadIdx.x; k < n_fs; k += blockDim.x) s_fs[k] = a.g.first_step[k];
+    for (uint32_t k = threadIdx.x; k < s_zlen; k += blockDim.x) s_zetas[k] = a.g.zetas[k];
+    __syncthreads();
+    const uint64_t* fs = fs_in_smem ? s_fs : a.g.first_step;
+
+    const unsigned warp_mask = __activemask();
+    const int lane = threadIdx.x & 31;
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t T = gridDim.x * blockDim.x;
+    uint64_t attempt = a.attempt_ctr[tid];
+    uint64_t applied = 0, attempts0 = attempt;
+    const uint2 key = make_uint2(a.seed_lo, a.seed_hi);
+
+    for (uint32_t e = a.epoch_begin; e < a.epoch_end; ++e) {
+        const EpochDesc ep = a.epochs[e];
+        // this launch's share of the epoch, then this thread's share of that
+        const uint64_t m = ep.updates / a.n_slices + (a.slice < ep.updates % a.n_slices ? 1 : 0);
+        const uint64_t quota = m / T + (tid < m % T ? 1 : 0);
+        uint64_t done = 0;
+        for (;;) {
+            const bool active = done < quota;
+            if (!__any_sync(warp_mask, active)) break;
+            SampledTerm t;
+            t.valid = false;
+            double d = 0.0;
+            if (active) {
+                const uint4 r = philox4x32_10(make_uint4((uint32_t)attempt, (uint32_t)(attempt >> 32),
+                                                         a.tid_base + tid, STREAM_SGD), key);
+                ++attempt;
+                sample_term<(D > 0)>(a.g, fs, s_zetas, s_zlen, ep, r, t);
+                d = term_distance(t);
+                const uint32_t na = t.a.node_rev >> 1, nb = t.b.node_rev >> 1;
+                t.valid = t.valid && d != 0.0 && na < a.g.N && nb < a.g.N;     // sgd.rs:514, 525-538
+            }
+            if constexpr (D == 0) {
+                apply_1d<AGG>(reinterpret_cast<double*>(a.positions), warp_mask, lane, t.valid,
+                              t.a.node_rev >> 1, t.b.node_rev >> 1, d, ep.eta);
+            } else {
+                const uint32_t idx_i = (t.a.node_rev >> 1) * 2 + (t.other_a ? 1u : 0u);   // sgd.rs:1099-1103
+                const uint32_t idx_j = (t.b.node_rev >> 1) * 2 + (t.other_b ? 1u : 0u);
+                apply_nd<CT, (D > 0 ? D : 1), DS, AGG>(reinterpret_cast<CT*>(a.positions), warp_mask, lane, t.valid,
+                                                       idx_i, idx_j, d, ep.eta);
+            }
+            if (t.valid) { ++done; ++applied; }                                 // sgd.rs:579
+        }
+    }
+    a.attempt_ctr[tid] = attempt;
+    // counters: one atomic pair per full warp (partial warps: one pair per thread)
+    uint64_t att = attempt - attempts0;
+    if (warp_mask == 0xffffffffu) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            applied += __shfl_xor_sync(0xffffffffu, applied, o);
+            att += __shfl_xor_sync(0xffffffffu, att, o);
+        }
+        if (lane != 0) return;
+    }
+    atomicAdd(a.counters + 0, (unsigned long long)applied);
+    atomicAdd(a.counters + 1, (unsigned long long)att);
+}
+
+// =============================================================================================
+// K4 — sampled stress (sgd.rs:1196-1283)
+// =============================================================================================
+constexpr int STRESS_BLOCK = 256;
+// coords: stride_node doubles per node, the + end's `dims` coordinates first.
+__global__ void __launch_bounds__(STRESS_BLOCK)
+stress_kernel(KernelGraph g, const double* __restrict__ coords, uint32_t dims, uint32_t stride_node,
+              uint64_t samples, uint32_t seed_lo, uint32_t seed_hi, double* __restrict__ partial /*3 per block*/) {
+    __shared__ double red[3][STRESS_BLOCK / 32];
+    double sum = 0.0, sum_abs = 0.0, cnt = 0.0;
+    const uint2 key = make_uint2(seed_lo, seed_hi);
+    for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < samples; k += (uint64_t)gridDim.x * blockDim.x) {
+        const uint4 r = philox4x32_10(make_uint4((uint32_t)k, (uint32_t)(k >> 32), 0u, STREAM_STRESS), key);
+        const uint64_t s = __umul64hi(((uint64_t)r.y << 32) | r.x, g.S);
+        const uint32_t p = find_path(g.first_step, g.P, s);
+        const uint64_t f = g.first_step[p];
+        const uint32_t n = (uint32_t)(g.first_step[p + 1] - f);
+        if (n < 2) continue;
+        const uint32_t ra = (uint32_t)(s - f);
+        const uint32_t rb = (uint32_t)__umul64hi(((uint64_t)r.w << 32) | r.z, (uint64_t)n);
+        if (ra == rb) continue;
+        const StepRec A = load_rec(g.recs + s), B = load_rec(g.recs + f + rb);
+        const double dp = fabs(__dsub_rn((double)A.pos, (double)B.pos));
+        if (dp == 0.0) continue;
+        const uint32_t ia = A.node_rev >> 1, ib = B.node_rev >> 1;
+        if (ia >= g.N || ib >= g.N) continue;
+        double sq = 0.0;
+        for (uint32_t d = 0; d < dims; ++d) {
+            const double dl = __dsub_rn(coords[(size_t)ia * stride_node + d], coords[(size_t)ib * stride_node + d]);
+            sq = __dadd_rn(sq, __dmul_rn(dl, dl));
+        }
+        const double err = __dsub_rn(__dsqrt_rn(sq), dp);
+        sum += __ddiv_rn(__dmul_rn(err, err), __dmul_rn(dp, dp));
+        sum_abs += __ddiv_rn(fabs(err), dp);
+        cnt += 1.0;
+    }
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        sum_abs += __shfl_xor_sync(0xffffffffu, sum_abs, o);
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    }
+    if (lane == 0) { red[0][w] = sum; red[1][w] = sum_abs; red[2][w] = cnt; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a0 = 0, a1 = 0, a2 = 0;
+        for (int k = 0; k < STRESS_BLOCK / 32; ++k) { a0 += red[0][k]; a1 += red[1][k]; a2 += red[2][k]; }
+        partial[blockIdx.x * 3 + 0] = a0; partial[blockIdx.x * 3 + 1] = a1; partial[blockIdx.x * 3 + 2] = a2;
+    }
+}
+
+// =============================================================================================
+// conversion kernels (host Layout order f64 <-> device [node][end][DS] CT)
+// =============================================================================================
+template <typename CT>
+__global__ void layout_to_device(const double* __restrict__ src, CT* __restrict__ dst, uint64_t n_ends, uint32_t D, uint32_t DS) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_ends * DS) return;
+    const uint64_t e = i / DS; const uint32_t k = (uint32_t)(i % DS);
+    dst[i] = k < D ? (CT)src[e * D + k] : CT(0);
+}
+template <typename CT>
+__global__ void layout_from_device(const CT* __restrict__ src, double* __restrict__ dst, uint64_t n_ends, uint32_t D, uint32_t DS) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_ends * D) return;
+    const uint64_t e = i / D; const uint32_t k = (uint32_t)(i % D);
+    dst[i] = (double)src[e * DS + k];
+}
+
+// =============================================================================================
+// debug kernels
+// =============================================================================================
+__global__ void dbg_fpp(const double* a, const double* b, double* out, uint64_t n) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = fast_precise_pow(a[i], b[i]);
+}
+__global__ void dbg_zipf(const uint64_t* zmax, const double* theta, const double* zeta, const double* u, uint64_t* out, uint64_t n) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    ZipfConsts zc;
+    zc.theta = theta[i];
+    zc.one_minus_theta = __dsub_rn(1.0, theta[i]);
+    zc.alpha = __ddiv_rn(1.0, __dsub_rn(1.0, theta[i]));
+    zc.z2 = __dadd_rn(1.0, fast_precise_pow(0.5, theta[i]));
+    out[i] = dirty_zipf((uint32_t)zmax[i], zc, zeta[i], u[i]);
+}
+__global__ void dbg_philox(const uint32_t* ctr, const uint32_t* key, uint32_t* out, uint64_t n) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint4 r = philox4x32_10(make_uint4(ctr[4 * i], ctr[4 * i + 1], ctr[4 * i + 2], ctr[4 * i + 3]),
+                                  make_uint2(key[2 * i], key[2 * i + 1]));
+    out[4 * i] = r.x; out[4 * i + 1] = r.y; out[4 * i + 2] = r.z; out[4 * i + 3] = r.w;
+}
+template <bool ND>
+__global__ void dbg_trace(KernelGraph g, const EpochDesc* epochs, uint32_t epoch, uint32_t seed_lo, uint32_t seed_hi,
+                          uint32_t tid, uint64_t attempt0, uint64_t count, uint8_t* valid, uint64_t* step_a,
+                          uint64_t* step_b, uint8_t* flags, double* dist) {
+    const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= count) return;
+    const EpochDesc ep = epochs[epoch];
+    const uint64_t attempt = attempt0 + k;
+    const uint4 r = philox4x32_10(make_uint4((uint32_t)attempt, (uint32_t)(attempt >> 32), tid, STREAM_SGD),
+                                  make_uint2(seed_lo, seed_hi));
+    SampledTerm t;
+    sample_term<ND>(g, g.first_step, g.zetas, 0u, ep, r, t);
+    const double d = term_distance(t);
+    const bool ok = t.valid && d != 0.0;
+    valid[k] = ok;
+    step_a[k] = ok ? t.step_a : 0;
+    step_b[k] = ok ? t.step_b : 0;
+    flags[k] = ok ? (uint8_t)((t.other_a ? 1 : 0) | (t.other_b ? 2 : 0)) : 0;
+    dist[k] = ok ? d : 0.0;
+}
+
+}  // namespace gfs
+
+// =============================================================================================
+// Host-side objects
+// =============================================================================================
+using namespace gfs;
+
+struct gfs_index {
+    int device = 0;
+    uint64_t S = 0, P = 0, N = 0;
+    uint64_t max_path_steps = 0;
+    bool any_multi_step = false;
+    StepRec* d_recs = nullptr;
+    uint64_t* d_first_step = nullptr;   // P+1
+    uint64_t* d_path_len = nullptr;     // P
+    std::vector<uint64_t> h_first_step;
+    double build_seconds = 0, h2d_seconds = 0;
+};
+
+struct gfs_sgd_session {
+    const gfs_index* ix = nullptr;
+    gfs_sgd_params params{};
+    uint32_t dims = 0;          // 0 = 1D
+    uint32_t DS = 1;            // coordinate stride per node end
+    bool f64 = true;
+    bool aggregate = true;
+    int device = 0;
+    uint32_t grid = 0, block = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    void* d_pos = nullptr;
+    bool own_pos = false;
+    uint64_t n_elems = 0;       // elements in d_pos
+    double* d_zetas = nullptr; uint32_t zlen = 0;
+    EpochDesc* d_epochs = nullptr; uint32_t n_epochs = 0;
+    uint64_t* d_attempts = nullptr;
+    unsigned long long* d_counters = nullptr;
+    double* d_stage = nullptr;  // f64 staging for nD conversions
+    size_t smem_bytes = 0;
+    uint64_t rng_thread_base = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    double kernel_ms = 0.0;
+    uint64_t launches = 0;
+    double h2d_s = 0, d2h_s = 0;
+    bool ev_pending = false;
+};
+
+static int select_device(int dev) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        set_error(std::string("no CUDA device available: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count 0") +
+                  " — libgfasort_cuda has no CPU fallback");
+        return GFS_ERR_NO_DEVICE;
+    }
+    if (dev < 0) {
+        long envd = env_long("GFASORT_DEVICE", -1);
+        if (envd >= 0) dev = (int)envd;
+        else { GFS_CUDA(cudaGetDevice(&dev)); }
+    }
+    if (dev >= n) { set_error("device ordinal out of range"); return GFS_ERR_INVALID; }
+    GFS_CUDA(cudaSetDevice(dev));
+    return GFS_OK;
+}
+
+extern "C" const char* gfs_last_error(void) { return g_last_error.c_str(); }
+
+extern "C" const char* gfs_device_info(void) {
+    static thread_local std::string info;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) { info = "{\"devices\": 0}"; return info.c_str(); }
+    int dev = 0; cudaGetDevice(&dev);
+    cudaDeviceProp p; cudaGetDeviceProperties(&p, dev);
+    char buf[512];
+    std::snprintf(buf, sizeof buf,
+                  "{\"devices\": %d, \"device\": %d, \"name\": \"%s\", \"cc\": \"%d.%d\", \"sms\": %d, \"l2_bytes\": %d, "
+                  "\"global_mem\": %zu, \"persisting_l2_max\": %d}",
+                  n, dev, p.name, p.major, p.minor, p.multiProcessorCount, p.l2CacheSize, (size_t)p.totalGlobalMem,
+                  p.persistingL2CacheMaxSize);
+    info = buf;
+    return info.c_str();
+}
+
+// ---------------------------------------------------------------------------------------------
+// index build
+// ---------------------------------------------------------------------------------------------
+
+extern "C" int gfs_index_build_shard(const uint64_t* step_handles, const uint64_t* path_first_step,
+                                     const uint32_t* node_len, uint64_t S, uint64_t P, uint64_t N,
+                                     uint64_t path_begin, uint64_t path_end, int32_t device, gfs_index** out) {
+    if (!out) { set_error("gfs_index_build: out is null"); return GFS_ERR_INVALID; }
+    *out = nullptr;
+    if (!path_first_step || (S && !step_handles) || (N && !node_len)) { set_error("gfs_index_build: null input array"); return GFS_ERR_INVALID; }
+    if (path_begin > path_end || path_end > P) { set_error("gfs_index_build: bad path range"); return GFS_ERR_INVALID; }
+    if (N >= (1ull << 31)) { set_error("gfs_index_build: N must be < 2^31"); return GFS_ERR_INVALID; }
+    if (path_first_step[0] != 0 || path_first_step[P] != S) { set_error("gfs_index_build: path_first_step must start at 0 and end at S"); return GFS_ERR_INVALID; }
+    for (uint64_t p = 0; p < P; ++p) {
+        if (path_first_step[p + 1] < path_first_step[p]) { set_error("gfs_index_build: path_first_step not monotone"); return GFS_ERR_INVALID; }
+        if (path_first_step[p + 1] - path_first_step[p] >= (1ull << 32)) { set_error("gfs_index_build: a path has >= 2^32 steps"); return GFS_ERR_INVALID; }
+    }
+    if (path_end - path_begin >= (1ull << 31)) { set_error("gfs_index_build: too many paths"); return GFS_ERR_INVALID; }
+    int rc = select_device(device);
+    if (rc) return rc;
+
+    const double t_begin = now_s();
+    gfs_index* ix = new gfs_index();
+    cudaGetDevice(&ix->device);
+    const uint64_t s_begin = path_first_step[path_begin], s_end = path_first_step[path_end];
+    ix->S = s_end - s_begin; ix->P = path_end - path_begin; ix->N = N;
+    ix->h_first_step.resize(ix->P + 1);
+    for (uint64_t p = 0; p <= ix->P; ++p) ix->h_first_step[p] = path_first_step[path_begin + p] - s_begin;
+    for (uint64_t p = 0; p < ix->P; ++p) {
+        const uint64_t c = ix->h_first_step[p + 1] - ix->h_first_step[p];
+        ix->max_path_steps = std::max(ix->max_path_steps, c);
+        if (c > 1) ix->any_multi_step = true;
+    }
+    auto fail = [&](int code) { gfs_index_free(ix); return code; };
+#define IX_CUDA(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { set_error(std::string(#call) + " failed: " + cudaGetErrorString(e__)); return fail(GFS_ERR_CUDA); } } while (0)
+
+    cudaStream_t st;
+    IX_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    uint64_t* d_path_base = nullptr; uint64_t* d_carry = nullptr; uint32_t* d_node_len = nullptr;
+    uint64_t* d_handles = nullptr; uint64_t* d_tiles = nullptr;
+    IX_CUDA(cudaMalloc(&ix->d_first_step, (ix->P + 1) * 8));
+    IX_CUDA(cudaMalloc(&ix->d_path_len, std::max<uint64_t>(ix->P, 1) * 8));
+    IX_CUDA(cudaMalloc(&ix->d_recs, std::max<uint64_t>(ix->S, 1) * sizeof(StepRec)));
+    IX_CUDA(cudaMalloc(&d_path_base, (ix->P + 1) * 8));
+    IX_CUDA(cudaMalloc(&d_carry, 8));
+    IX_CUDA(cudaMalloc(&d_node_len, std::max<uint64_t>(N, 1) * 4));
+    IX_CUDA(cudaMemsetAsync(d_carry, 0, 8, st));
+    IX_CUDA(cudaMemsetAsync(d_path_base, 0, (ix->P + 1) * 8, st));
+    const double t_h2d0 = now_s();
+    IX_CUDA(cudaMemcpyAsync(ix->d_first_step, ix->h_first_step.data(), (ix->P + 1) * 8, cudaMemcpyHostToDevice, st));
+    if (N) IX_CUDA(cudaMemcpyAsync(d_node_len, node_len, N * 4, cudaMemcpyHostToDevice, st));
+    double h2d = now_s() - t_h2d0;
+
+    // chunks of at most CH steps (multiple of the tile) so that the transient handle buffer stays small
+    uint64_t CH = (uint64_t)env_long("GFASORT_INDEX_CHUNK", 1l << 28);
+    CH = std::max<uint64_t>(K1_TILE, (CH / K1_TILE) * K1_TILE);
+    const uint64_t chunk_cap = std::min<uint64_t>(CH, std::max<uint64_t>(ix->S, 1));
+    const uint64_t tiles_cap = (chunk_cap + K1_TILE - 1) / K1_TILE;
+    IX_CUDA(cudaMalloc(&d_handles, chunk_cap * 8));
+    IX_CUDA(cudaMalloc(&d_tiles, (tiles_cap + 1) * 8));
+    uint32_t p_lo = 0;
+    for (uint64_t c0 = 0; c0 < ix->S; c0 += CH) {
+        const uint64_t clen = std::min(CH, ix->S - c0);
+        const uint64_t n_tiles = (clen + K1_TILE - 1) / K1_TILE;
+        const double t0 = now_s();
+        IX_CUDA(cudaMemcpyAsync(d_handles, step_handles + s_begin + c0, clen * 8, cudaMemcpyHostToDevice, st));
+        IX_CUDA(cudaStreamSynchronize(st));
+        h2d += now_s() - t0;
+        k1_tile_sums<<<(unsigned)n_tiles, K1_THREADS, 0, st>>>(d_handles, d_node_len, clen, N, d_tiles);
+        k1_scan_tiles<<<1, 1024, 0, st>>>(d_tiles, n_tiles, d_carry);
+        // paths whose first step lies in this chunk: [p_lo, p_hi)
+        uint32_t p_hi = p_lo;
+        while (p_hi < ix->P && ix->h_first_step[p_hi] < c0 + clen) ++p_hi;
+        if (p_hi > p_lo)
+            k1_path_base<<<p_hi - p_lo, K1_THREADS, 0, st>>>(d_handles, d_node_len, N, ix->d_first_step, p_lo, p_hi, c0,
+                                                            c0 + clen, d_tiles, d_path_base);
+        k1_write_recs<<<(unsigned)n_tiles, K1_THREADS, 0, st>>>(d_handles, d_node_len, N, ix->d_first_step, (uint32_t)ix->P,
+                                                               c0, clen, d_tiles, d_path_base, ix->d_recs);
+        IX_CUDA(cudaGetLastError());
+        p_lo = p_hi;
+    }
+    // paths that start at S (empty tail paths) and the sentinel base[P] = total
+    if (ix->P) {
+        // every empty path at the very end has first_step == S: base = total
+        for (uint32_t p = p_lo; p <= ix->P; ++p) k1_set_u64<<<1, 1, 0, st>>>(d_path_base, p, d_carry);
+        k1_path_len<<<(unsigned)((ix->P + 255) / 256), 256, 0, st>>>(d_path_base, (uint32_t)ix->P, ix->d_path_len);
+    }
+    IX_CUDA(cudaStreamSynchronize(st));
+    IX_CUDA(cudaGetLastError());
+    cudaFree(d_handles); cudaFree(d_tiles); cudaFree(d_path_base); cudaFree(d_carry); cudaFree(d_node_len);
+    cudaStreamDestroy(st);
+    ix->h2d_seconds = h2d;
+    ix->build_seconds = now_s() - t_begin;
+    *out = ix;
+    return GFS_OK;
+#undef IX_CUDA
+}
+
+extern "C" int gfs_index_build(const uint64_t* step_handles, const uint64_t* path_first_step, const uint32_t* node_len,
+                               uint64_t S, uint64_t P, uint64_t N, gfs_index** out) {
+    return gfs_index_build_shard(step_handles, path_first_step, node_len, S, P, N, 0, P, -1, out);
+}
+
+extern "C" void gfs_index_free(gfs_index* ix) {
+    if (!ix) return;
+    cudaSetDevice(ix->device);
+    cudaFree(ix->d_recs); cudaFree(ix->d_first_step); cudaFree(ix->d_path_len);
+    delete ix;
+}
+
+extern "C" int gfs_index_dims(const gfs_index* ix, uint64_t* S, uint64_t* P, uint64_t* N, uint64_t* max_path_steps) {
+    if (!ix) { set_error("gfs_index_dims: null index"); return GFS_ERR_INVALID; }
+    if (S) *S = ix->S;
+    if (P) *P = ix->P;
+    if (N) *N = ix->N;
+    if (max_path_steps) *max_path_steps = ix->max_path_steps;
+    return GFS_OK;
+}
+
+extern "C" int gfs_index_export(const gfs_index* ix, uint64_t* step_pos, uint64_t* path_len) {
+    if (!ix) { set_error("gfs_index_export: null index"); return GFS_ERR_INVALID; }
+    GFS_CUDA(cudaSetDevice(ix->device));
+    if (step_pos && ix->S) {
+        uint64_t* d = nullptr;
+        const uint64_t CH = 1ull << 26;
+        GFS_CUDA(cudaMalloc(&d, std::min(CH, ix->S) * 8));
+        for (uint64_t c0 = 0; c0 < ix->S; c0 += CH) {
+            const uint64_t n = std::min(CH, ix->S - c0);
+            k1_export_pos<<<(unsigned)((n + 255) / 256), 256>>>(ix->d_recs + c0, n, d);
+            cudaError_t e = cudaMemcpy(step_pos + c0, d, n * 8, cudaMemcpyDeviceToHost);
+            if (e != cudaSuccess) { cudaFree(d); set_error(std::string("export copy failed: ") + cudaGetErrorString(e)); return GFS_ERR_CUDA; }
+        }
+        cudaFree(d);
+    }
+    if (path_len && ix->P) GFS_CUDA(cudaMemcpy(path_len, ix->d_path_len, ix->P * 8, cudaMemcpyDeviceToHost));
+    return GFS_OK;
+}
+
+extern "C" int gfs_index_export_records(const gfs_index* ix, uint64_t* step_handle, uint32_t* step_node_len) {
+    if (!ix || !step_handle || !step_node_len) { set_error("gfs_index_export_records: null argument"); return GFS_ERR_INVALID; }
+    GFS_CUDA(cudaSetDevice(ix->device));
+    if (!ix->S) return GFS_OK;
+    uint64_t* dh = nullptr; uint32_t* dl = nullptr;
+    const uint64_t CH = 1ull << 26;
+    const uint64_t cap = std::min(CH, ix->S);
+    GFS_CUDA(cudaMalloc(&dh, cap * 8));
+    GFS_CUDA(cudaMalloc(&dl, cap * 4));
+    for (uint64_t c0 = 0; c0 < ix->S; c0 += CH) {
+        const uint64_t n = std::min(CH, ix->S - c0);
+        k1_export_hl<<<(unsigned)((n + 255) / 256), 256>>>(ix->d_recs + c0, n, dh, dl);
+        cudaError_t e1 = cudaMemcpy(step_handle + c0, dh, n * 8, cudaMemcpyDeviceToHost);
+        cudaError_t e2 = cudaMemcpy(step_node_len + c0, dl, n * 4, cudaMemcpyDeviceToHost);
+        if (e1 != cudaSuccess || e2 != cudaSuccess) { cudaFree(dh); cudaFree(dl); set_error("export copy failed"); return GFS_ERR_CUDA; }
+    }
+    cudaFree(dh); cudaFree(dl);
+    return GFS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// SGD sessions
+// ---------------------------------------------------------------------------------------------
+typedef void (*sgd_kernel_fn)(const SgdArgs);
+
+template <typename CT, bool AGG>
+static sgd_kernel_fn pick_nd(uint32_t dims, uint32_t& DS) {
+    switch (dims) {
+        case 1: DS = 1; return sgd_kernel<CT, 1, 1, AGG>;
+        case 2: DS = 2; return sgd_kernel<CT, 2, 2, AGG>;
+        case 3: DS = 4; return sgd_kernel<CT, 3, 4, AGG>;
+        case 4: DS = 4; return sgd_kernel<CT, 4, 4, AGG>;
+        case 5: DS = 8; return sgd_kernel<CT, 5, 8, AGG>;
+        case 6: DS = 8; return sgd_kernel<CT, 6, 8, AGG>;
+        case 7: DS = 8; return sgd_kernel<CT, 7, 8, AGG>;
+        case 8: DS = 8; return sgd_kernel<CT, 8, 8, AGG>;
+        default: return nullptr;
+    }
+}
+static sgd_kernel_fn pick_kernel(uint32_t dims, bool f64, bool agg, uint32_t& DS) {
+    if (dims == 0) { DS = 1; return agg ? sgd_kernel<double, 0, 1, true> : sgd_kernel<double, 0, 1, false>; }
+    if (f64) return agg ? pick_nd<double, true>(dims, DS) : pick_nd<double, false>(dims, DS);
+    return agg ? pick_nd<float, true>(dims, DS) : pick_nd<float, false>(dims, DS);
+}
+
+static KernelGraph make_kgraph(const gfs_index* ix, const gfs_sgd_params& p, const double* d_zetas, uint32_t zlen) {
+    KernelGraph g{};
+    g.recs = ix->d_recs; g.first_step = ix->d_first_step; g.zetas = d_zetas;
+    g.S = ix->S; g.P = (uint32_t)ix->P; g.N = (uint32_t)ix->N; g.zlen = zlen;
+    g.space = (uint32_t)std::min<uint64_t>(p.space, 0xffffffffull);
+    g.space_max = (uint32_t)std::min<uint64_t>(p.space_max, 0xffffffffull);
+    g.q = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(p.space_quantization_step, 1), 0xffffffffull);
+    return g;
+}
+
+static int validate_params(const gfs_sgd_params* p) {
+    if (!p) { set_error("params is null"); return GFS_ERR_INVALID; }
+    if (p->iter_max >= (1ull << 31)) { set_error("iter_max too large"); return GFS_ERR_INVALID; }
+    if (!(p->theta < 1.0)) { set_error("theta must be < 1"); return GFS_ERR_INVALID; }
+    return GFS_OK;
+}
+
+extern "C" void gfs_sgd_session_destroy(gfs_sgd_session* s) {
+    if (!s) return;
+    cudaSetDevice(s->device);
+    if (s->own_pos) cudaFree(s->d_pos);
+    cudaFree(s->d_zetas); cudaFree(s->d_epochs); cudaFree(s->d_attempts); cudaFree(s->d_counters); cudaFree(s->d_stage);
+    if (s->ev0) cudaEventDestroy(s->ev0);
+    if (s->ev1) cudaEventDestroy(s->ev1);
+    if (s->own_stream && s->stream) cudaStreamDestroy(s->stream);
+    delete s;
+}
+
+extern "C" int gfs_sgd_session_create(const gfs_index* ix, const gfs_sgd_params* params, uint32_t dims,
+                                      const gfs_launch_cfg* cfg, gfs_sgd_session** out) {
+    if (!out) { set_error("gfs_sgd_session_create: out is null"); return GFS_ERR_INVALID; }
+    *out = nullptr;
+    if (!ix) { set_error("gfs_sgd_session_create: null index"); return GFS_ERR_INVALID; }
+    int rc = validate_params(params);
+    if (rc) return rc;
+    if (dims > 8) { set_error("gfs_sgd_session_create: dims must be <= 8"); return GFS_ERR_INVALID; }
+    if (!ix->any_multi_step) { set_error("no paths with multiple steps found"); return GFS_ERR_NO_VALID_PATH; }
+    if (ix->N == 0) { set_error("graph has no nodes"); return GFS_ERR_INVALID; }
+    GFS_CUDA(cudaSetDevice(ix->device));
+
+    gfs_sgd_session* s = new gfs_sgd_session();
+    s->ix = ix; s->params = *params; s->dims = dims; s->device = ix->device;
+    int agg = cfg && cfg->aggregate >= 0 ? cfg->aggregate : (int)env_long("GFASORT_AGGREGATE", 1);
+    int f64 = cfg && cfg->layout_f64 >= 0 ? cfg->layout_f64 : (int)env_long("GFASORT_LAYOUT_F64", 0);
+    s->aggregate = agg != 0;
+    s->f64 = dims == 0 ? true : (f64 != 0);
+    s->rng_thread_base = cfg ? cfg->rng_thread_base : 0;
+    auto fail = [&](int code) { gfs_sgd_session_destroy(s); return code; };
+#define SS_CUDA(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { set_error(std::string(#call) + " failed: " + cudaGetErrorString(e__)); return fail(GFS_ERR_CUDA); } } while (0)
+
+    if (cfg && cfg->stream) { s->stream = (cudaStream_t)cfg->stream; s->own_stream = false; }
+    else { SS_CUDA(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking)); s->own_stream = true; }
+    SS_CUDA(cudaEventCreate(&s->ev0));
+    SS_CUDA(cudaEventCreate(&s->ev1));
+
+    sgd_kernel_fn fn = pick_kernel(dims, s->f64, s->aggregate, s->DS);
+    if (!fn) return fail(GFS_ERR_INVALID);
+
+    // schedule, zeta table
+    std::vector<EpochDesc> epochs; h_epochs(*params, epochs);
+    std::vector<double> zetas; h_zetas(*params, ix->max_path_steps, zetas);
+    s->n_epochs = (uint32_t)epochs.size(); s->zlen = (uint32_t)zetas.size();
+    SS_CUDA(cudaMalloc(&s->d_epochs, epochs.size() * sizeof(EpochDesc)));
+    SS_CUDA(cudaMalloc(&s->d_zetas, std::max<size_t>(zetas.size(), 1) * 8));
+    SS_CUDA(cudaMemcpyAsync(s->d_epochs, epochs.data(), epochs.size() * sizeof(EpochDesc), cudaMemcpyHostToDevice, s->stream));
+    SS_CUDA(cudaMemcpyAsync(s->d_zetas, zetas.data(), zetas.size() * 8, cudaMemcpyHostToDevice, s->stream));
+    SS_CUDA(cudaStreamSynchronize(s->stream));   // host vectors go out of scope
+
+    // launch shape: persistent, every block co-resident
+    const uint32_t n_fs = (ix->P + 1 <= SMEM_FS_MAX) ? (uint32_t)ix->P + 1 : 0;
+    s->smem_bytes = (size_t)n_fs * 8 + (size_t)std::min<uint32_t>(s->zlen, SMEM_ZETAS_MAX) * 8;
+    SS_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_bytes));
+    int per_sm = 0, sms = 0;
+    SS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, SGD_BLOCK, s->smem_bytes));
+    SS_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device));
+    if (per_sm < 1) { set_error("SGD kernel does not fit on an SM"); return fail(GFS_ERR_CUDA); }
+    const uint64_t max_threads = (uint64_t)per_sm * sms * SGD_BLOCK;
+    uint64_t want = cfg && cfg->total_threads ? cfg->total_threads : (uint64_t)env_long("GFASORT_THREADS", 0);
+    if (want == 0) {
+        // auto: full occupancy, but never more threads than there is work for (>= 8 updates per
+        // thread per epoch) and never more concurrent terms than a quarter of the nodes
+        const uint64_t by_work = std::max<uint64_t>(params->min_term_updates / 8, 32);
+        const uint64_t by_nodes = std::max<uint64_t>(ix->N / 4, 32);
+        want = std::min(max_threads, std::min(by_work, by_nodes));
+    }
+    want = std::min(want, max_threads);
+    if (want >= SGD_BLOCK) { s->block = SGD_BLOCK; s->grid = (uint32_t)(want / SGD_BLOCK); }
+    else { s->block = (uint32_t)std::max<uint64_t>(want, 1); s->grid = 1; }
+    const uint64_t T = (uint64_t)s->grid * s->block;
+
+    s->n_elems = dims == 0 ? ix->N : ix->N * 2 * s->DS;
+    const size_t esz = s->f64 ? 8 : 4;
+    if (cfg && cfg->device_positions) { s->d_pos = cfg->device_positions; s->own_pos = false; }
+    else { SS_CUDA(cudaMalloc(&s->d_pos, s->n_elems * esz)); s->own_pos = true; }
+    SS_CUDA(cudaMalloc(&s->d_attempts, T * 8));
+    SS_CUDA(cudaMemsetAsync(s->d_attempts, 0, T * 8, s->stream));
+    SS_CUDA(cudaMalloc(&s->d_counters, 16));
+    SS_CUDA(cudaMemsetAsync(s->d_counters, 0, 16, s->stream));
+    *out = s;
+    return GFS_OK;
+#undef SS_CUDA
+}
+
+extern "C" int gfs_sgd_session_upload(gfs_sgd_session* s, const double* positions) {
+    if (!s || !positions) { set_error("gfs_sgd_session_upload: null argument"); return GFS_ERR_INVALID; }
+    GFS_CUDA(cudaSetDevice(s->device));
+    const double t0 = now_s();
+    if (s->dims == 0) {
+        GFS_CUDA(cudaMemcpyAsync(s->d_pos, positions, s->ix->N * 8, cudaMemcpyHostToDevice, s->stream));
+    } else if (s->f64 && s->DS == s->dims) {
+        GFS_CUDA(cudaMemcpyAsync(s->d_pos, positions, s->ix->N * 2 * s->dims * 8, cudaMemcpyHostToDevice, s->stream));
+    } else {
+        const uint64_t n_ends = s->ix->N * 2;
+        if (!s->d_stage) GFS_CUDA(cudaMalloc(&s->d_stage, n_ends * s->dims * 8));
+        GFS_CUDA(cudaMemcpyAsync(s->d_stage, positions, n_ends * s->dims * 8, cudaMemcpyHostToDevice, s->stream));
+        const uint64_t n = n_ends * s->DS;
+        if (s->f64) layout_to_device<double><<<(unsigned)((n + 255) / 256), 256, 0, s->stream>>>(s->d_stage, (double*)s->d_pos, n_ends, s->dims, s->DS);
+        else layout_to_device<float><<<(unsigned)((n + 255) / 256), 256, 0, s->stream>>>(s->d_stage, (float*)s->d_pos, n_ends, s->dims, s->DS);
+        GFS_CUDA(cudaGetLastError());
+    }
+    GFS_CUDA(cudaStreamSynchronize(s->stream));
+    s->h2d_s += now_s() - t0;
+    return GFS_OK;
+}
+
+static int session_flush_events(gfs_sgd_session* s) {
+    if (s->ev_pending) {
+        GFS_CUDA(cudaEventSynchronize(s->ev1));
+        float ms = 0;
+        GFS_CUDA(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
+        s->kernel_ms += ms;
+        s->ev_pending = false;
+    }
+    return GFS_OK;
+}
+
+extern "C" int gfs_sgd_session_download(gfs_sgd_session* s, double* positions) {
+    if (!s || !positions) { set_error("gfs_sgd_session_download: null argument"); return GFS_ERR_INVALID; }
+    GFS_CUDA(cudaSetDevice(s->device));
+    int rc = session_flush_events(s);
+    if (rc) return rc;
+    const double t0 = now_s();
+    if (s->dims == 0) {
+        GFS_CUDA(cudaMemcpyAsync(positions, s->d_pos, s->ix->N * 8, cudaMemcpyDeviceToHost, s->stream));
+    } else if (s->f64 && s->DS == s->dims) {
+        GFS_CUDA(cudaMemcpyAsync(positions, s->d_pos, s->ix->N * 2 * s->dims * 8, cudaMemcpyDeviceToHost, s->stream));
+    } else {
+        const uint64_t n_ends = s->ix->N * 2;
+        if (!s->d_stage) GFS_CUDA(cudaMalloc(&s->d_stage, n_ends * s->dims * 8));
+        const uint64_t n = n_ends * s->dims;
+        if (s->f64) layout_from_device<double><<<(unsigned)((n + 255) / 256), 256, 0, s->stream>>>((const double*)s->d_pos, s->d_stage, n_ends, s->dims, s->DS);
+        else layout_from_device<float><<<(unsigned)((n + 255) / 256), 256, 0, s->stream>>>((const float*)s->d_pos, s->d_stage, n_ends, s->dims, s->DS);
+        GFS_CUDA(cudaGetLastError());
+        GFS_CUDA(cudaMemcpyAsync(positions, s->d_stage, n * 8, cudaMemcpyDeviceToHost, s->stream));
+    }
+    GFS_CUDA(cudaStreamSynchronize(s->stream));
+    s->d2h_s += now_s() - t0;
+    return GFS_OK;
+}
+
+extern "C" int gfs_sgd_session_run(gfs_sgd_session* s, uint64_t epoch_begin, uint64_t epoch_end, uint32_t slice,
+                                   uint32_t n_slices) {
+    if (!s) { set_error("gfs_sgd_session_run: null session"); return GFS_ERR_INVALID; }
+    if (epoch_begin > epoch_end || epoch_end > s->n_epochs || n_slices == 0 || slice >= n_slices) {
+        set_error("gfs_sgd_session_run: bad epoch range or slice"); return GFS_ERR_INVALID;
+    }
+    if (epoch_begin == epoch_end) return GFS_OK;
+    GFS_CUDA(cudaSetDevice(s->device));
+    int rc = session_flush_events(s);
+    if (rc) return rc;
+    uint32_t DS;
+    sgd_kernel_fn fn = pick_kernel(s->dims, s->f64, s->aggregate, DS);
+    SgdArgs a{};
+    a.g = make_kgraph(s->ix, s->params, s->d_zetas, s->zlen);
+    a.epochs = s->d_epochs;
+    a.epoch_begin = (uint32_t)epoch_begin; a.epoch_end = (uint32_t)epoch_end;
+    a.slice = slice; a.n_slices = n_slices;
+    a.attempt_ctr = s->d_attempts; a.counters = s->d_counters;
+    a.seed_lo = (uint32_t)s->params.seed; a.seed_hi = (uint32_t)(s->params.seed >> 32);
+    a.tid_base = (uint32_t)s->rng_thread_base;
+    a.positions = s->d_pos;
+    void* kargs[] = {(void*)&a};
+    GFS_CUDA(cudaEventRecord(s->ev0, s->stream));
+    GFS_CUDA(cudaLaunchCooperativeKernel((const void*)fn, dim3(s->grid), dim3(s->block), kargs, s->smem_bytes, s->stream));
+    GFS_CUDA(cudaEventRecord(s->ev1, s->stream));
+    s->ev_pending = true;
+    s->launches += 1;
+    return GFS_OK;
+}
+
+extern "C" int gfs_sgd_session_sync(gfs_sgd_session* s) {
+    if (!s) { set_error("gfs_sgd_session_sync: null session"); return GFS_ERR_INVALID; }
+    GFS_CUDA(cudaSetDevice(s->device));
+    GFS_CUDA(cudaStreamSynchronize(s->stream));
+    return session_flush_events(s);
+}
+
+extern "C" int gfs_sgd_session_positions(gfs_sgd_session* s, void** dev_ptr, uint64_t* n_elems, uint32_t* elem_bytes) {
+    if (!s) { set_error("gfs_sgd_session_positions: null session"); return GFS_ERR_INVALID; }
+    if (dev_ptr) *dev_ptr = s->d_pos;
+    if (n_elems) *n_elems = s->n_elems;
+    if (elem_bytes) *elem_bytes = s->f64 ? 8 : 4;
+    return GFS_OK;
+}
+
+extern "C" int gfs_sgd_session_stats(gfs_sgd_session* s, gfs_stats* st) {
+    if (!s || !st) { set_error("gfs_sgd_session_stats: null argument"); return GFS_ERR_INVALID; }
+    int rc = gfs_sgd_session_sync(s);
+    if (rc) return rc;
+    unsigned long long c[2] = {0, 0};
+    GFS_CUDA(cudaMemcpy(c, s->d_counters, 16, cudaMemcpyDeviceToHost));
+    std::memset(st, 0, sizeof *st);
+    st->applied_updates = c[0]; st->attempts = c[1];
+    st->epochs = s->n_epochs; st->launches = s->launches;
+    st->kernel_seconds = s->kernel_ms * 1e-3;
+    st->h2d_seconds = s->h2d_s; st->d2h_seconds = s->d2h_s;
+    st->grid = s->grid; st->block = s->block; st->coord_bytes = s->f64 ? 8 : 4;
+    return GFS_OK;
+}
+
+static int run_whole(const gfs_index* ix, const gfs_sgd_params* params, const gfs_launch_cfg* cfg, uint32_t dims,
+                     double* pos_inout, gfs_stats* stats) {
+    if (!pos_inout) { set_error("positions buffer is null"); return GFS_ERR_INVALID; }
+    const double t0 = now_s();
+    gfs_sgd_session* s = nullptr;
+    int rc = gfs_sgd_session_create(ix, params, dims, cfg, &s);
+    if (rc) return rc;   // GFS_ERR_NO_VALID_PATH: positions untouched (sgd.rs:258-261)
+    rc = gfs_sgd_session_upload(s, pos_inout);
+    if (!rc) rc = gfs_sgd_session_run(s, 0, s->n_epochs, 0, 1);
+    if (!rc) rc = gfs_sgd_session_sync(s);
+    if (!rc) rc = gfs_sgd_session_download(s, pos_inout);
+    gfs_stats st{};
+    if (!rc) rc = gfs_sgd_session_stats(s, &st);
+    st.total_seconds = now_s() - t0;
+    if (stats && !rc) *stats = st;
+    gfs_sgd_session_destroy(s);
+    return rc;
+}
+
+extern "C" int gfs_sgd_1d_cfg(const gfs_index* ix, const gfs_sgd_params* params, const gfs_launch_cfg* cfg,
+                              double* x_inout, gfs_stats* stats) {
+    return run_whole(ix, params, cfg, 0, x_inout, stats);
+}
+extern "C" int gfs_sgd_1d(const gfs_index* ix, const gfs_sgd_params* params, double* x_inout, gfs_stats* stats) {
+    return run_whole(ix, params, nullptr, 0, x_inout, stats);
+}
+extern "C" int gfs_sgd_nd_cfg(const gfs_index* ix, const gfs_sgd_params* params, const gfs_launch_cfg* cfg,
+                              uint32_t dims, double* coords_inout, gfs_stats* stats) {
+    if (dims < 1 || dims > 8) { set_error("gfs_sgd_nd: dims must be in 1..8"); return GFS_ERR_INVALID; }
+    return run_whole(ix, params, cfg, dims, coords_inout, stats);
+}
+extern "C" int gfs_sgd_nd(const gfs_index* ix, const gfs_sgd_params* params, uint32_t dims, double* coords_inout,
+                          gfs_stats* stats) {
+    return gfs_sgd_nd_cfg(ix, params, nullptr, dims, coords_inout, stats);
+}
+
+// ---------------------------------------------------------------------------------------------
+// stress
+// ---------------------------------------------------------------------------------------------
+extern "C" int gfs_stress(const gfs_index* ix, uint32_t dims, int32_t layout_order, const double* coords,
+                          uint64_t samples, uint64_t seed, double* rms_rel, double* mean_abs_rel, uint64_t* counted) {
+    if (!ix || !coords || dims < 1) { set_error("gfs_stress: bad argument"); return GFS_ERR_INVALID; }
+    GFS_CUDA(cudaSetDevice(ix->device));
+    if (rms_rel) *rms_rel = 0;
+    if (mean_abs_rel) *mean_abs_rel = 0;
+    if (counted) *counted = 0;
+    if (ix->S < 2 || samples == 0) return GFS_OK;            // sgd.rs:1220-1222
+    const uint32_t stride = layout_order ? 2 * dims : dims;
+    double* d_coords = nullptr; double* d_partial = nullptr;
+    const size_t bytes = (size_t)ix->N * stride * 8;
+    GFS_CUDA(cudaMalloc(&d_coords, bytes));
+    cudaError_t e = cudaMemcpy(d_coords, coords, bytes, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { cudaFree(d_coords); set_error(std::string("gfs_stress copy: ") + cudaGetErrorString(e)); return GFS_ERR_CUDA; }
+    const unsigned grid = (unsigned)std::min<uint64_t>((samples + STRESS_BLOCK - 1) / STRESS_BLOCK, 148 * 8);
+    e = cudaMalloc(&d_partial, (size_t)grid * 3 * 8);
+    if (e != cudaSuccess) { cudaFree(d_coords); set_error("gfs_stress alloc"); return GFS_ERR_CUDA; }
+    gfs_sgd_params dummy{};
+    KernelGraph g = make_kgraph(ix, dummy, nullptr, 0);
+    stress_kernel<<<grid, STRESS_BLOCK>>>(g, d_coords, dims, stride, samples, (uint32_t)seed, (uint32_t)(seed >> 32), d_partial);
+    std::vector<double> part((size_t)grid * 3);
+    e = cudaMemcpy(part.data(), d_partial, part.size() * 8, cudaMemcpyDeviceToHost);
+    cudaFree(d_coords); cudaFree(d_partial);
+    if (e != cudaSuccess) { set_error(std::string("gfs_stress kernel: ") + cudaGetErrorString(e)); return GFS_ERR_CUDA; }
+    double s0 = 0, s1 = 0, c = 0;
+    for (unsigned b = 0; b < grid; ++b) { s0 += part[b * 3]; s1 += part[b * 3 + 1]; c += part[b * 3 + 2]; }
+    if (c > 0) {
+        if (rms_rel) *rms_rel = std::sqrt(s0 / c);
+        if (mean_abs_rel) *mean_abs_rel = s1 / c;
+    }
+    if (counted) *counted = (uint64_t)c;
+    return GFS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// debug / parity hooks
+// ---------------------------------------------------------------------------------------------
+template <typename T> struct DevBuf {
+    T* p = nullptr;
+    ~DevBuf() { cudaFree(p); }
+    cudaError_t alloc(size_t n) { return cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T)); }
+    cudaError_t up(const T* h, size_t n) { return cudaMemcpy(p, h, n * sizeof(T), cudaMemcpyHostToDevice); }
+    cudaError_t down(T* h, size_t n) { return cudaMemcpy(h, p, n * sizeof(T), cudaMemcpyDeviceToHost); }
+};
+
+extern "C" int gfs_debug_fast_precise_pow(const double* a, const double* b, double* out, uint64_t n) {
+    int rc = select_device(-1); if (rc) return rc;
+    DevBuf<double> da, db, dout;
+    GFS_CUDA(da.alloc(n)); GFS_CUDA(db.alloc(n)); GFS_CUDA(dout.alloc(n));
+    GFS_CUDA(da.up(a, n)); GFS_CUDA(db.up(b, n));
+    dbg_fpp<<<(unsigned)((n + 255) / 256), 256>>>(da.p, db.p, dout.p, n);
+    GFS_CUDA(cudaGetLastError());
+    GFS_CUDA(dout.down(out, n));
+    return GFS_OK;
+}
+extern "C" int gfs_debug_dirty_zipf(const uint64_t* zmax, const double* theta, const double* zeta, const double* u,
+                                    uint64_t* out, uint64_t n) {
+    int rc = select_device(-1); if (rc) return rc;
+    DevBuf<uint64_t> dz, dout; DevBuf<double> dt, dze, du;
+    GFS_CUDA(dz.alloc(n)); GFS_CUDA(dout.alloc(n)); GFS_CUDA(dt.alloc(n)); GFS_CUDA(dze.alloc(n)); GFS_CUDA(du.alloc(n));
+    GFS_CUDA(dz.up(zmax, n)); GFS_CUDA(dt.up(theta, n)); GFS_CUDA(dze.up(zeta, n)); GFS_CUDA(du.up(u, n));
+    dbg_zipf<<<(unsigned)((n + 255) / 256), 256>>>(dz.p, dt.p, dze.p, du.p, dout.p, n);
+    GFS_CUDA(cudaGetLastError());
+    GFS_CUDA(dout.down(out, n));
+    return GFS_OK;
+}
+extern "C" int gfs_debug_philox(const uint32_t* ctr4, const uint32_t* key2, uint32_t* out4, uint64_t n) {
+    int rc = select_device(-1); if (rc) return rc;
+    DevBuf<uint32_t> dc, dk, dout;
+    GFS_CUDA(dc.alloc(4 * n)); GFS_CUDA(dk.alloc(2 * n)); GFS_CUDA(dout.alloc(4 * n));
+    GFS_CUDA(dc.up(ctr4, 4 * n)); GFS_CUDA(dk.up(key2, 2 * n));
+    dbg_philox<<<(unsigned)((n + 255) / 256), 256>>>(dc.p, dk.p, dout.p, n);
+    GFS_CUDA(cudaGetLastError());
+    GFS_CUDA(dout.down(out4, 4 * n));
+    return GFS_OK;
+}
+extern "C" int gfs_debug_schedule(const gfs_sgd_params* params, double* etas) {
+    int rc = validate_params(params); if (rc) return rc;
+    std::vector<double> e; h_schedule(*params, e);
+    std::memcpy(etas, e.data(), e.size() * 8);
+    return GFS_OK;
+}
+extern "C" int gfs_debug_zetas(const gfs_index* ix, const gfs_sgd_params* params, double* zetas, uint64_t cap, uint64_t* n) {
+    int rc = validate_params(params); if (rc) return rc;
+    if (!ix) { set_error("gfs_debug_zetas: null index"); return GFS_ERR_INVALID; }
+    std::vector<double> z; h_zetas(*params, ix->max_path_steps, z);
+    if (n) *n = z.size();
+    if (zetas) std::memcpy(zetas, z.data(), std::min<uint64_t>(cap, z.size()) * 8);
+    return GFS_OK;
+}
+extern "C" int gfs_debug_trace_terms(const gfs_index* ix, const gfs_sgd_params* params, int32_t nd, uint64_t epoch,
+                                     uint32_t tid, uint64_t attempt0, uint64_t count, uint8_t* valid, uint64_t* step_a,
+                                     uint64_t* step_b, uint8_t* flags, double* dist) {
+    int rc = validate_params(params); if (rc) return rc;
+    if (!ix || epoch > params->iter_max) { set_error("gfs_debug_trace_terms: bad argument"); return GFS_ERR_INVALID; }
+    GFS_CUDA(cudaSetDevice(ix->device));
+    std::vector<EpochDesc> epochs; h_epochs(*params, epochs);
+    std::vector<double> zetas; h_zetas(*params, ix->max_path_steps, zetas);
+    DevBuf<EpochDesc> de; DevBuf<double> dz, dd; DevBuf<uint8_t> dv, df; DevBuf<uint64_t> da, db;
+    GFS_CUDA(de.alloc(epochs.size())); GFS_CUDA(dz.alloc(zetas.size()));
+    GFS_CUDA(de.up(epochs.data(), epochs.size())); GFS_CUDA(dz.up(zetas.data(), zetas.size()));
+    GFS_CUDA(dv.alloc(count)); GFS_CUDA(df.alloc(count)); GFS_CUDA(da.alloc(count)); GFS_CUDA(db.alloc(count)); GFS_CUDA(dd.alloc(count));
+    KernelGraph g = make_kgraph(ix, *params, dz.p, (uint32_t)zetas.size());
+    const unsigned grid = (unsigned)((count + 255) / 256);
+    if (nd) dbg_trace<true><<<grid, 256>>>(g, de.p, (uint32_t)epoch, (uint32_t)params->seed, (uint32_t)(params->seed >> 32), tid, attempt0, count, dv.p, da.p, db.p, df.p, dd.p);
+    else dbg_trace<false><<<grid, 256>>>(g, de.p, (uint32_t)epoch, (uint32_t)params->seed, (uint32_t)(params->seed >> 32), tid, attempt0, count, dv.p, da.p, db.p, df.p, dd.p);
+    GFS_CUDA(cudaGetLastError());
+    GFS_CUDA(dv.down(valid, count)); GFS_CUDA(da.down(step_a, count)); GFS_CUDA(db.down(step_b, count));
+    GFS_CUDA(df.down(flags, count)); GFS_CUDA(dd.down(dist, count));
+    return GFS_OK;
+}

@@ -1,0 +1,185 @@
+"""The slice of the reference's graph model that the SGD hot path reads and that `Y` writes back.
+
+Mirrors (by name and meaning) `Handle` (reference src/graph.rs:9-19) and the three fields of
+`BidirectedGraph` the path touches: `nodes[*].sequence.len()`, `paths[*].steps`, `node_order`
+(src/graph_ops.rs:10-16; read at src/sgd.rs:41-55, 276-294).  Everything else in the reference's
+graph container (edges, grooming, topological sorts, unchop) is out of scope here; edges are only
+carried along so `apply_ordering` can renumber them the way the reference does.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+
+import numpy as np
+
+
+def handle_forward(node_id):
+    return np.uint64(node_id) << np.uint64(1)
+
+
+def handle_node_id(h):
+    return h >> np.uint64(1)
+
+
+def handle_is_reverse(h):
+    return (h & np.uint64(1)) == 1
+
+
+@dataclass
+class BidirectedGraph:
+    """nodes as parallel arrays indexed by node id; paths as one concatenated handle array."""
+    present: np.ndarray                      # uint8[max_id+1], 1 <=> nodes[id].is_some()
+    seq_len: np.ndarray                      # uint64[max_id+1]
+    node_order: np.ndarray                   # uint64[], insertion order of add_node (graph_ops.rs:613-623)
+    steps: np.ndarray                        # uint64[S] Handle = id<<1 | is_rev, all paths concatenated
+    path_first: np.ndarray                   # uint64[P+1]
+    path_names: list = field(default_factory=list)
+    edges: np.ndarray = field(default_factory=lambda: np.zeros((0, 2), dtype=np.uint64))   # (from, to) handles
+    sequences: dict = field(default_factory=dict)   # id -> bytes, only when loaded from GFA text
+
+    def __post_init__(self):
+        self.present = np.ascontiguousarray(self.present, dtype=np.uint8)
+        self.seq_len = np.ascontiguousarray(self.seq_len, dtype=np.uint64)
+        self.node_order = np.ascontiguousarray(self.node_order, dtype=np.uint64)
+        self.steps = np.ascontiguousarray(self.steps, dtype=np.uint64)
+        self.path_first = np.ascontiguousarray(self.path_first, dtype=np.uint64)
+
+    # ---- reference-named queries ----
+    def node_count(self) -> int:
+        return int(self.present.sum())
+
+    @property
+    def num_paths(self) -> int:
+        return len(self.path_first) - 1
+
+    def path_steps(self, p: int) -> np.ndarray:
+        return self.steps[int(self.path_first[p]):int(self.path_first[p + 1])]
+
+    def node_ids(self) -> np.ndarray:
+        """`node_order` if non-empty, else sorted live ids (src/sgd.rs:276-284)."""
+        if len(self.node_order):
+            return self.node_order
+        return np.nonzero(self.present)[0].astype(np.uint64)
+
+    # ---- what the host does before crossing the C ABI (SURVEY.md §8b "Rust side of the call") ----
+    def live_node_ids(self) -> np.ndarray:
+        ids = self.node_ids()
+        if len(ids) == 0:
+            return ids
+        inb = ids < np.uint64(len(self.present))
+        keep = np.zeros(len(ids), dtype=bool)
+        keep[inb] = self.present[ids[inb].astype(np.int64)] != 0
+        return ids[keep]
+
+    def dense(self):
+        """(step_handles, path_first_step, node_len) in dense-idx space (src/sgd.rs:286-293).
+
+        Steps on ids without a dense idx get idx == N, the library's missing-node sentinel."""
+        live = self.live_node_ids()
+        n = len(live)
+        id2idx = np.full(len(self.present) + 1, n, dtype=np.uint64)
+        id2idx[live.astype(np.int64)] = np.arange(n, dtype=np.uint64)
+        nid = np.minimum((self.steps >> np.uint64(1)).astype(np.int64), len(self.present))
+        handles = (id2idx[nid] << np.uint64(1)) | (self.steps & np.uint64(1))
+        node_len = self.seq_len[live.astype(np.int64)].astype(np.uint32)
+        return np.ascontiguousarray(handles, dtype=np.uint64), self.path_first.copy(), node_len
+
+    @staticmethod
+    def from_dense(step_handles, path_first, node_len) -> "BidirectedGraph":
+        """Synthetic graphs: node id = dense idx + 1, ids 1..N in file order."""
+        n = len(node_len)
+        present = np.zeros(n + 1, dtype=np.uint8)
+        present[1:] = 1
+        seq_len = np.zeros(n + 1, dtype=np.uint64)
+        seq_len[1:] = node_len
+        steps = np.asarray(step_handles, dtype=np.uint64) + np.uint64(2)
+        return BidirectedGraph(present, seq_len, np.arange(1, n + 1, dtype=np.uint64), steps,
+                               np.asarray(path_first, dtype=np.uint64))
+
+    def apply_ordering(self, ordering: np.ndarray) -> None:
+        """Renumber nodes 1..N in `ordering` (handles); rewrite edges and path steps.
+
+        Follows src/graph_ops.rs:1939-2025: new id = rank + 1, orientations are kept, steps/edges on
+        ids not in the ordering are left/dropped as the reference does, and `node_order` is NOT
+        updated (SURVEY.md §8 quirk 7 — harmless for contiguous ids)."""
+        ordering = np.asarray(ordering, dtype=np.uint64)
+        if len(ordering) == 0:
+            return
+        old_ids = (ordering >> np.uint64(1)).astype(np.int64)
+        new_ids = np.arange(1, len(ordering) + 1, dtype=np.uint64)
+        size = max(len(self.present), int(old_ids.max()) + 1)
+        old_to_new = np.zeros(size, dtype=np.uint64)          # 0 = not remapped
+        old_to_new[old_ids] = new_ids
+        max_new = len(ordering)
+        present = np.zeros(max_new + 1, dtype=np.uint8)
+        seq_len = np.zeros(max_new + 1, dtype=np.uint64)
+        in_range = old_ids < len(self.present)
+        live = np.zeros(len(old_ids), dtype=bool)
+        live[in_range] = self.present[old_ids[in_range]] != 0
+        present[new_ids[live].astype(np.int64)] = 1
+        seq_len[new_ids[live].astype(np.int64)] = self.seq_len[old_ids[live]]
+        if self.sequences:
+            self.sequences = {int(n): self.sequences[int(o)] for o, n in zip(old_ids[live], new_ids[live])
+                              if int(o) in self.sequences}
+        self.present, self.seq_len = present, seq_len
+        sid = (self.steps >> np.uint64(1)).astype(np.int64)
+        mapped = np.zeros(len(sid), dtype=np.uint64)
+        ok = sid < size
+        mapped[ok] = old_to_new[sid[ok]]
+        keep_old = mapped == 0
+        self.steps = np.where(keep_old, self.steps, (mapped << np.uint64(1)) | (self.steps & np.uint64(1)))
+        if len(self.edges):
+            f = (self.edges[:, 0] >> np.uint64(1)).astype(np.int64)
+            t = (self.edges[:, 1] >> np.uint64(1)).astype(np.int64)
+            okf = (f < size) & (t < size)
+            nf = np.zeros(len(f), dtype=np.uint64)
+            nt = np.zeros(len(t), dtype=np.uint64)
+            nf[okf] = old_to_new[f[okf]]
+            nt[okf] = old_to_new[t[okf]]
+            keep = (nf != 0) & (nt != 0)
+            e = np.stack([(nf << np.uint64(1)) | (self.edges[:, 0] & np.uint64(1)),
+                          (nt << np.uint64(1)) | (self.edges[:, 1] & np.uint64(1))], axis=1)[keep]
+            self.edges = np.unique(e, axis=0) if len(e) else e
+
+
+def load_gfa(path: str) -> BidirectedGraph:
+    """The CLI's `parse_gfa` (src/bin/gfasort.rs:88-167): numeric ids; S, then L, then P lines."""
+    with open(path) as f:
+        lines = f.read().split("\n")
+    order, seqs = [], {}
+    for line in lines:
+        if line.startswith("S"):
+            parts = line.split("\t")
+            if len(parts) >= 3:
+                nid = int(parts[1])
+                if nid not in seqs:
+                    order.append(nid)
+                seqs[nid] = parts[2].encode()
+    nodes_len = (max(seqs) + 1) if seqs else 0
+    present = np.zeros(nodes_len, dtype=np.uint8)
+    seq_len = np.zeros(nodes_len, dtype=np.uint64)
+    for nid, s in seqs.items():
+        present[nid] = 1
+        seq_len[nid] = len(s)
+    edges = []
+    for line in lines:
+        if line.startswith("L"):
+            parts = line.split("\t")
+            if len(parts) >= 5:
+                fh = (int(parts[1]) << 1) | (0 if parts[2] == "+" else 1)
+                th = (int(parts[3]) << 1) | (0 if parts[4] == "+" else 1)
+                edges.append((fh, th))
+    steps, first, names = [], [0], []
+    for line in lines:
+        if line.startswith("P"):
+            parts = line.split("\t")
+            if len(parts) >= 3:
+                names.append(parts[1])
+                for s in parts[2].split(","):
+                    s = s.strip()
+                    if s:
+                        steps.append((int(s[:-1]) << 1) | (0 if s[-1] == "+" else 1))
+                first.append(len(steps))
+    return BidirectedGraph(present, seq_len, np.array(order, dtype=np.uint64), np.array(steps, dtype=np.uint64),
+                           np.array(first, dtype=np.uint64), names,
+                           np.array(edges, dtype=np.uint64).reshape(-1, 2), seqs)

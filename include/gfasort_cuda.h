@@ -1,0 +1,204 @@
+/* gfasort_cuda.h — C ABI of libgfasort_cuda.so: the B200 (sm_100a) implementation of gfasort's
+ * path-guided SGD hot path.  This header is the drop-in boundary: the (otherwise unchanged) Rust
+ * host binds exactly these symbols (see INTEGRATION.md for the `extern "C"` block and build.rs).
+ *
+ * The reference (pangenome/gfasort v0.1.0) has no FFI; the path is three Rust functions whose
+ * bodies delegate here.  Each entry point cites the reference code it replaces
+ * (paths relative to the reference repository root).
+ *
+ * Conventions
+ *   - every function is blocking unless it says "asynchronous"; returns 0 on success, non-zero on
+ *     error; gfs_last_error() returns a thread-local message for the last failure.
+ *   - the caller owns every host buffer; the library keeps no host pointer after a call returns.
+ *   - the library owns device memory behind opaque handles.
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails loudly.
+ *
+ * Node numbering: the host passes dense node indices 0..N-1 in the order of
+ * `graph.node_order` restricted to live nodes (src/sgd.rs:276-294).  A step handle is
+ * (dense_idx << 1) | is_reverse, mirroring Handle (src/graph.rs:9-19).  dense_idx >= N marks a
+ * step on a node missing from the graph: it contributes length 0 to the path offsets
+ * (src/sgd.rs:52-54) and terms touching it are skipped (src/sgd.rs:525-538).
+ */
+#ifndef GFASORT_CUDA_H
+#define GFASORT_CUDA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GFS_OK 0
+#define GFS_ERR_INVALID 1      /* bad argument */
+#define GFS_ERR_CUDA 2         /* CUDA runtime / launch failure (message has the CUDA error string) */
+#define GFS_ERR_NO_DEVICE 3    /* no usable sm_100 device */
+#define GFS_ERR_NO_VALID_PATH 4 /* no path with more than one step (src/sgd.rs:250-261, 786-798):
+                                   positions are returned unchanged */
+
+/* Opaque device-resident path index.  Replaces `PathIndex` (src/sgd.rs:14-31). */
+typedef struct gfs_index gfs_index;
+/* Opaque device-resident SGD run (positions + schedule + RNG counters). */
+typedef struct gfs_sgd_session gfs_sgd_session;
+
+/* Mirrors PathSGDParams (src/sgd.rs:196-212) and LayoutSGDParams (src/sgd.rs:676-707) field for
+ * field (LayoutSGDParams.dimensions travels as the separate `dims` argument).  `nthreads`,
+ * `delta` and `progress` are accepted and inert: the GPU picks its own thread count, `delta` is
+ * never read by the reference either (src/sgd.rs:554-567 maintains delta_max, nothing consumes it),
+ * and progress lines are the host's business.  `seed` keys the Philox4x32-10 stream the way
+ * `seed + tid` keys xoshiro256+ in the reference (src/sgd.rs:431-432). */
+typedef struct gfs_sgd_params {
+    uint64_t iter_max;
+    uint64_t iter_with_max_learning_rate;
+    uint64_t min_term_updates;
+    double delta;
+    double eps;
+    double eta_max;
+    double theta;
+    uint64_t space;
+    uint64_t space_max;
+    uint64_t space_quantization_step;
+    double cooling_start;
+    uint64_t nthreads;
+    uint64_t progress;
+    uint64_t seed;
+} gfs_sgd_params;
+
+/* Optional launch configuration (NULL = defaults / environment).  Environment variables, because
+ * the reference CLI is frozen: GFASORT_DEVICE, GFASORT_THREADS (total GPU threads, 0 = auto),
+ * GFASORT_AGGREGATE (0/1 warp-level duplicate-node aggregation, default 1),
+ * GFASORT_LAYOUT_F64 (0/1, nD coordinates in double instead of float, default 0). */
+typedef struct gfs_launch_cfg {
+    int32_t device;            /* CUDA device ordinal; -1 = current */
+    uint32_t total_threads;    /* 0 = auto (full occupancy, capped by the work available) */
+    int32_t aggregate;         /* -1 = default */
+    int32_t layout_f64;        /* -1 = default */
+    uint64_t rng_thread_base;  /* added to the thread id in the Philox counter: rank r of a
+                                  multi-GPU run passes r * 2^24 so streams never overlap */
+    void* stream;              /* cudaStream_t to launch on (NULL = library-owned stream) */
+    void* device_positions;    /* optional caller-owned device buffer for the positions (1D: N doubles;
+                                  nD: N*2*dims_stride coordinates); NULL = library-allocated */
+} gfs_launch_cfg;
+
+/* Per-run statistics (replaces the reference's stderr progress lines, src/sgd.rs:377-385, 609-611). */
+typedef struct gfs_stats {
+    uint64_t applied_updates;  /* terms applied (only these count toward min_term_updates, sgd.rs:579) */
+    uint64_t attempts;         /* terms sampled (applied + skipped) */
+    uint64_t epochs;           /* iter_max + 1 */
+    uint64_t launches;         /* kernels launched by the call */
+    double kernel_seconds;     /* CUDA-event time of the SGD kernel(s) */
+    double h2d_seconds;        /* host->device copies */
+    double d2h_seconds;        /* device->host copies */
+    double total_seconds;      /* wall time of the call */
+    uint32_t grid, block;      /* launch shape used */
+    uint32_t coord_bytes;      /* 8 = f64 positions, 4 = f32 */
+    uint32_t reserved;
+} gfs_stats;
+
+const char* gfs_last_error(void);
+/* Library / device facts as a JSON string (static storage). */
+const char* gfs_device_info(void);
+
+/* ---- path index -----------------------------------------------------------------------------
+ * Replaces PathIndex::from_graph (src/sgd.rs:34-71).  step_handles[S]: all paths' steps
+ * concatenated; path_first_step[P+1]: first step of each path, last entry = S; node_len[N]:
+ * sequence length by dense idx.  Builds on the GPU, with a segmented exclusive scan, one 16-byte
+ * record per step {node<<1|rev, node_len, offset}.  Each path must have < 2^32 steps. */
+int gfs_index_build(const uint64_t* step_handles, const uint64_t* path_first_step, const uint32_t* node_len,
+                    uint64_t S, uint64_t P, uint64_t N, gfs_index** out);
+/* As above, on `device` and on a sub-range of paths [path_begin, path_end): the shard one GPU of a
+ * multi-GPU run owns.  step_handles/path_first_step still describe the whole graph. */
+int gfs_index_build_shard(const uint64_t* step_handles, const uint64_t* path_first_step, const uint32_t* node_len,
+                          uint64_t S, uint64_t P, uint64_t N, uint64_t path_begin, uint64_t path_end,
+                          int32_t device, gfs_index** out);
+/* Copies back what PathIndex holds: step_to_position (src/sgd.rs:18) and PathInfo.length (:29).
+ * Either pointer may be NULL.  step_to_path / step_to_rank / first_step / step_count are functions
+ * of path_first_step alone and stay on the host. */
+int gfs_index_export(const gfs_index* ix, uint64_t* step_pos /*S*/, uint64_t* path_len /*P*/);
+/* Device-side accessors, for tests: handle (dense_idx<<1|rev) and node length stored per step. */
+int gfs_index_export_records(const gfs_index* ix, uint64_t* step_handle /*S*/, uint32_t* step_node_len /*S*/);
+int gfs_index_dims(const gfs_index* ix, uint64_t* S, uint64_t* P, uint64_t* N, uint64_t* max_path_steps);
+void gfs_index_free(gfs_index* ix);
+
+/* ---- one-call SGD ---------------------------------------------------------------------------
+ * gfs_sgd_1d replaces the body of path_linear_sgd after the X init (src/sgd.rs:296-601):
+ * x_inout[N] holds the initial positions on entry (src/sgd.rs:286-293) and the final ones on exit.
+ * Runs iter_max+1 epochs of exactly min_term_updates applied updates each with etas[0..=iter_max]
+ * (src/sgd.rs:617-638), cooling when epoch > floor(cooling_start*iter_max) (src/sgd.rs:393-396). */
+int gfs_sgd_1d(const gfs_index* ix, const gfs_sgd_params* params, double* x_inout, gfs_stats* stats);
+/* gfs_sgd_nd replaces the body of path_linear_sgd_layout after the coordinate init
+ * (src/sgd.rs:856-1172).  coords_inout is in Layout order coords[node*2*dims + end*dims + dim]
+ * (src/layout.rs:14-24, 52-61), N*2*dims doubles.  1 <= dims <= 8. */
+int gfs_sgd_nd(const gfs_index* ix, const gfs_sgd_params* params, uint32_t dims, double* coords_inout,
+               gfs_stats* stats);
+/* Same with an explicit launch configuration. */
+int gfs_sgd_1d_cfg(const gfs_index* ix, const gfs_sgd_params* params, const gfs_launch_cfg* cfg,
+                   double* x_inout, gfs_stats* stats);
+int gfs_sgd_nd_cfg(const gfs_index* ix, const gfs_sgd_params* params, const gfs_launch_cfg* cfg, uint32_t dims,
+                   double* coords_inout, gfs_stats* stats);
+
+/* ---- sampled stress -------------------------------------------------------------------------
+ * Replaces calculate_layout_stress (src/sgd.rs:1196-1283) on a fixed Philox(seed) sample:
+ * sample k draws step_a uniformly, a uniform partner rank on the same path, skips equal ranks and
+ * zero path distance, measures the Euclidean distance between the + ends.
+ * rms_rel = sqrt(mean((dl-dp)^2/dp^2)) (the reference's value); mean_abs_rel = mean(|dl-dp|/dp)
+ * (BASELINE.json's form).  dims == 1 with coords = x (N doubles, one per node) measures a 1D sort;
+ * dims >= 1 with layout_order != 0 takes a Layout-order array (N*2*dims). */
+int gfs_stress(const gfs_index* ix, uint32_t dims, int32_t layout_order, const double* coords, uint64_t samples,
+               uint64_t seed, double* rms_rel, double* mean_abs_rel, uint64_t* counted);
+
+/* ---- session API (device-resident runs, multi-GPU) -------------------------------------------
+ * A session holds the positions on the device between calls so that the host can run the schedule
+ * in slices and reconcile replicas between slices (NCCL all-reduce on gfs_sgd_session_positions). */
+int gfs_sgd_session_create(const gfs_index* ix, const gfs_sgd_params* params, uint32_t dims /*0 = 1D Y*/,
+                           const gfs_launch_cfg* cfg, gfs_sgd_session** out);
+int gfs_sgd_session_upload(gfs_sgd_session* s, const double* positions);     /* host -> device (converts for f32) */
+int gfs_sgd_session_download(gfs_sgd_session* s, double* positions);         /* device -> host */
+/* Asynchronous: enqueue epochs [epoch_begin, epoch_end) on the session's stream; within each epoch
+ * run only slice `slice` of `n_slices` equal parts of min_term_updates (n_slices = 1: whole epochs). */
+int gfs_sgd_session_run(gfs_sgd_session* s, uint64_t epoch_begin, uint64_t epoch_end, uint32_t slice,
+                        uint32_t n_slices);
+int gfs_sgd_session_sync(gfs_sgd_session* s);
+/* Device pointer + element count + element size (8 or 4) of the position buffer. */
+int gfs_sgd_session_positions(gfs_sgd_session* s, void** dev_ptr, uint64_t* n_elems, uint32_t* elem_bytes);
+int gfs_sgd_session_stats(gfs_sgd_session* s, gfs_stats* stats);             /* synchronises first */
+void gfs_sgd_session_destroy(gfs_sgd_session* s);
+
+/* ---- synthetic pangenome graphs (bench / tests input) -------------------------
+ * Seeded bubble-chain generator writing the C-ABI's own flat inputs.  Two calls: sizes, then fill. */
+typedef struct gfs_synth_spec {
+    uint64_t num_nodes;   /* N (exact) */
+    uint64_t num_paths;   /* P */
+    uint64_t seed;
+    uint32_t permute_ids; /* 1 = randomly permute node ids (scrambled initial order) */
+    uint32_t reserved;
+} gfs_synth_spec;
+typedef struct gfs_synth_graph gfs_synth_graph;
+int gfs_synth_create(const gfs_synth_spec* spec, gfs_synth_graph** out);
+/* Only paths [path_begin, path_end) are materialised (a rank's shard); node_len covers all N nodes. */
+int gfs_synth_create_range(const gfs_synth_spec* spec, uint64_t path_begin, uint64_t path_end,
+                           gfs_synth_graph** out);
+int gfs_synth_dims(const gfs_synth_graph* g, uint64_t* S, uint64_t* P, uint64_t* N);
+/* Pointers into the generator's own storage (valid until gfs_synth_free). */
+int gfs_synth_arrays(const gfs_synth_graph* g, const uint64_t** step_handles, const uint64_t** path_first_step,
+                     const uint32_t** node_len);
+void gfs_synth_free(gfs_synth_graph* g);
+
+/* ---- debug / parity hooks (used by tests/ only) ----------------------------------------------
+ * Device evaluation of the reference's scalar helpers, for bit-exact checks against the oracle. */
+int gfs_debug_fast_precise_pow(const double* a, const double* b, double* out, uint64_t n);
+int gfs_debug_dirty_zipf(const uint64_t* zmax, const double* theta, const double* zeta, const double* u,
+                         uint64_t* out, uint64_t n);    /* min = 1, zeta2theta = 1 + fpp(0.5, theta) */
+int gfs_debug_philox(const uint32_t* ctr4, const uint32_t* key2, uint32_t* out4, uint64_t n);
+/* Sampled terms of thread `tid`, attempts [attempt0, attempt0+count): valid flag, step_a, step_b,
+ * flags (bit0 other_end_a, bit1 other_end_b), term distance.  `epoch` selects eta/theta/cooling. */
+int gfs_debug_trace_terms(const gfs_index* ix, const gfs_sgd_params* params, int32_t nd, uint64_t epoch,
+                          uint32_t tid, uint64_t attempt0, uint64_t count, uint8_t* valid, uint64_t* step_a,
+                          uint64_t* step_b, uint8_t* flags, double* dist);
+/* Host-computed schedule and zeta table the kernels use (etas: iter_max+1; zetas: *n entries). */
+int gfs_debug_schedule(const gfs_sgd_params* params, double* etas);
+int gfs_debug_zetas(const gfs_index* ix, const gfs_sgd_params* params, double* zetas, uint64_t cap, uint64_t* n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GFASORT_CUDA_H */

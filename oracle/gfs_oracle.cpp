@@ -431,7 +431,7 @@ inline bool apply_1d(const Term& t, double eta, const HandleMap& h2i, std::atomi
     if (term_dist == 0.0) return false;
     double term_weight = 1.0 / term_dist;
     double mu = eta * term_weight;
-    mu = std::min(mu, 1.0);
+    mu = std::fmin(mu, 1.0);                                              // Rust f64::min: NaN -> other operand
     uint64_t i, j;
     if (!h2i.get((t.handle_a >> 1) << 1, i)) return false;
     if (!h2i.get((t.handle_b >> 1) << 1, j)) return false;
@@ -460,7 +460,7 @@ inline bool apply_nd(const Term& t, double eta, const HandleMap& h2i, uint64_t d
     double term_dist = std::fabs(t.pos_a - t.pos_b);
     if (term_dist == 0.0) return false;
     double term_weight = 1.0 / term_dist;
-    double mu = std::min(eta * term_weight, 1.0);
+    double mu = std::fmin(eta * term_weight, 1.0);
     uint64_t i, j;
     if (!h2i.get((t.handle_a >> 1) << 1, i)) return false;
     if (!h2i.get((t.handle_b >> 1) << 1, j)) return false;

@@ -1,0 +1,444 @@
+"""GPU parity tests (-m gpu): the CUDA path, called through the C ABI, against the CPU oracle.
+
+Bars: bit-exact for the integer / index work (path index), for the reference's scalar helpers
+(fast_precise_pow, DirtyZipfian, Philox), for term sampling, and for whole single-thread SGD runs
+(f64); sampled path stress within 2 % (relative, median over seeds) for the stochastic
+multi-thread runs (tolerance stated by BASELINE.json's north_star).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from conftest import DATA
+
+pytestmark = pytest.mark.gpu
+
+FIXTURES = ["simple", "lil", "DRB1-3123"]
+
+
+def _p(a, t):
+    return a.ctypes.data_as(t)
+
+
+def _cparams(op, G):
+    """oracle params -> gfs_sgd_params (same field order)."""
+    from gfasort_b200._cabi import SgdParams
+    return SgdParams(*[getattr(op, n) for n, _ in op._fields_])
+
+
+def _pyparams(op, G, layout=False, dims=2):
+    kw = {n: getattr(op, n) for n, _ in op._fields_}
+    kw["progress"] = bool(kw["progress"])
+    return G.LayoutSGDParams(dimensions=dims, **kw) if layout else G.PathSGDParams(**kw)
+
+
+# ------------------------------------------------------------------------------------------------
+# K1 path index: bit-exact
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", FIXTURES)
+def test_path_index_fixtures_bit_exact(name, gfs, oracle):
+    path = os.path.join(DATA, f"{name}.gfa")
+    ix = gfs.PathIndex.from_graph(gfs.load_gfa(path))
+    ref = oracle.path_index(oracle.parse_gfa(path))
+    assert np.array_equal(ix.step_positions(), ref["step_to_position"])
+    assert np.array_equal(ix.path_lengths(), ref["length"])
+    assert np.array_equal(ix.path_step_counts(), ref["step_count"])
+    assert ix.get_total_steps() == len(ref["step_to_handle"])
+    # accessors
+    for s in (0, ix.get_total_steps() // 2, ix.get_total_steps() - 1):
+        assert ix.get_path_of_step(s) == ref["step_to_path"][s]
+        assert ix.get_rank_of_step(s) == ref["step_to_rank"][s]
+        assert ix.get_handle_of_step(s) == ref["step_to_handle"][s]
+        assert ix.get_position_of_step(s) == ref["step_to_position"][s]
+    ix.close()
+
+
+@pytest.mark.parametrize("n_nodes,n_paths,chunk", [(2000, 4, None), (50_000, 8, None), (300_000, 6, 4096), (1_000_000, 32, None)])
+def test_path_index_synthetic_bit_exact(n_nodes, n_paths, chunk, gfs, oracle, monkeypatch):
+    if chunk:
+        monkeypatch.setenv("GFASORT_INDEX_CHUNK", str(chunk))     # force the multi-chunk carry path
+    s = gfs.SynthGraph(n_nodes, n_paths, seed=7)
+    ix = gfs.PathIndex.from_arrays(s.step_handles, s.path_first, s.node_len)
+    ref = oracle.path_index(oracle.Graph.from_dense(s.step_handles, s.path_first, s.node_len))
+    assert np.array_equal(ix.step_positions(), ref["step_to_position"])
+    assert np.array_equal(ix.path_lengths(), ref["length"])
+    # the records keep handle and node length
+    from gfasort_b200._cabi import lib, check, u64p, u32p
+    h = np.zeros(s.S, dtype=np.uint64)
+    l = np.zeros(s.S, dtype=np.uint32)
+    check(lib().gfs_index_export_records(ix.handle, _p(h, u64p), _p(l, u32p)))
+    assert np.array_equal(h, s.step_handles)
+    assert np.array_equal(l, s.node_len[(s.step_handles >> np.uint64(1)).astype(np.int64)])
+    ix.close()
+
+
+def test_path_index_edge_cases(gfs, oracle):
+    """empty paths, single-step paths, a missing node (length 0, sgd.rs:52-54), reverse steps."""
+    node_len = np.array([3, 5, 7, 11], dtype=np.uint32)
+    # paths: [], [0+,1-,9+(missing),2+], [3+], [], [2-,2-,0+]
+    steps = np.array([0, 3, 18, 4, 6, 5, 5, 0], dtype=np.uint64)
+    first = np.array([0, 0, 4, 5, 5, 8], dtype=np.uint64)
+    ix = gfs.PathIndex.from_arrays(steps, first, node_len)
+    assert ix.step_positions().tolist() == [0, 3, 8, 8, 0, 0, 7, 14]
+    assert ix.path_lengths().tolist() == [0, 15, 11, 0, 17]
+    assert ix.path_step_counts().tolist() == [0, 4, 1, 0, 3]
+    ix.close()
+    # same through the oracle (node id = idx+1; id 10 does not exist)
+    og = oracle.Graph.from_dense(steps, first, node_len)
+    ref = oracle.path_index(og)
+    assert ref["step_to_position"].tolist() == [0, 3, 8, 8, 0, 0, 7, 14]
+    assert ref["length"].tolist() == [0, 15, 11, 0, 17]
+
+
+def test_index_shard_matches_whole(gfs):
+    s = gfs.SynthGraph(20_000, 6, seed=3)
+    whole = gfs.PathIndex.from_arrays(s.step_handles, s.path_first, s.node_len)
+    pos = whole.step_positions()
+    for pb, pe in ((0, 2), (2, 5), (5, 6)):
+        sh = gfs.PathIndex.from_arrays(s.step_handles, s.path_first, s.node_len, path_begin=pb, path_end=pe)
+        a, b = int(s.path_first[pb]), int(s.path_first[pe])
+        assert np.array_equal(sh.step_positions(), pos[a:b])
+        assert np.array_equal(sh.path_lengths(), whole.path_lengths()[pb:pe])
+        sh.close()
+    whole.close()
+
+
+# ------------------------------------------------------------------------------------------------
+# scalar helpers: bit-exact against the oracle
+# ------------------------------------------------------------------------------------------------
+def test_fast_precise_pow_bit_exact(gfs, oracle):
+    from gfasort_b200._cabi import lib, check, f64p
+    rng = np.random.default_rng(1)
+    a = np.concatenate([rng.random(4000), 1.0 / np.arange(1, 2001), rng.random(1000) * 1e6, [1.0, 0.5, 2.0, 1e-300, 0.0]])
+    b = np.concatenate([np.full(4000, 0.99), np.full(2000, 0.99), rng.random(1000) * 3,
+                        [0.99, 0.001, 100.00000000000009, 0.01, 0.999]])
+    # the sampler's own call sites: alpha exponents
+    a = np.concatenate([a, rng.random(3000)]);  b = np.concatenate([b, np.full(1500, 1.0 / (1.0 - 0.99)), np.full(1500, 1.0 / (1.0 - 0.001))])
+    out = np.zeros_like(a)
+    check(lib().gfs_debug_fast_precise_pow(_p(a, f64p), _p(b, f64p), _p(out, f64p), len(a)))
+    ref = np.array([oracle.fast_precise_pow(x, y) for x, y in zip(a, b)])
+    assert np.array_equal(out.view(np.uint64), ref.view(np.uint64))
+
+
+def test_dirty_zipf_bit_exact(gfs, oracle):
+    from gfasort_b200._cabi import lib, check, f64p, u64p
+    rng = np.random.default_rng(2)
+    n = 20000
+    zmax = rng.integers(1, 5_000_000, n).astype(np.uint64)
+    zmax[:2000] = rng.integers(1, 200, 2000)
+    theta = np.where(rng.random(n) < 0.5, 0.99, 0.001)
+    zt = oracle.zetas(5_000_000, 100, 100, 0.99)
+    idx = np.where(zmax > 100, 100 + (zmax - 100) // 100 + 1, zmax).astype(np.int64)
+    zeta = zt[idx]
+    u = rng.random(n)
+    out = np.zeros(n, dtype=np.uint64)
+    check(lib().gfs_debug_dirty_zipf(_p(zmax, u64p), _p(theta, f64p), _p(zeta, f64p), _p(u, f64p), _p(out, u64p), n))
+    ref = np.array([oracle.dirty_zipf(1, int(m), t, z, 1.0 + oracle.fast_precise_pow(0.5, t), x)
+                    for m, t, z, x in zip(zmax, theta, zeta, u)], dtype=np.uint64)
+    assert np.array_equal(out, ref)
+
+
+def test_philox_bit_exact(gfs, oracle):
+    from gfasort_b200._cabi import lib, check, u32p
+    rng = np.random.default_rng(3)
+    n = 1000
+    ctr = rng.integers(0, 2**32, (n, 4), dtype=np.uint64).astype(np.uint32)
+    key = rng.integers(0, 2**32, (n, 2), dtype=np.uint64).astype(np.uint32)
+    ctr[0] = 0; key[0] = 0
+    out = np.zeros((n, 4), dtype=np.uint32)
+    check(lib().gfs_debug_philox(_p(ctr, u32p), _p(key, u32p), _p(out, u32p), n))
+    assert out[0].tolist() == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]      # Random123 KAT
+    ref = np.array([oracle.philox(c, k) for c, k in zip(ctr, key)], dtype=np.uint32)
+    assert np.array_equal(out, ref)
+
+
+def test_schedule_and_zetas_match_oracle(gfs, oracle):
+    from gfasort_b200._cabi import lib, check, f64p, u64p
+    path = os.path.join(DATA, "DRB1-3123.gfa")
+    og = oracle.parse_gfa(path)
+    ix = gfs.PathIndex.from_graph(gfs.load_gfa(path))
+    for layout in (False, True):
+        op = oracle.params_from_graph(og, layout)
+        cp = _cparams(op, gfs)
+        etas = np.zeros(op.iter_max + 1)
+        check(lib().gfs_debug_schedule(C.byref(cp), _p(etas, f64p)))
+        ref = oracle.schedule(1.0 / op.eta_max, 1.0, op.iter_max, op.iter_with_max_learning_rate, op.eps)
+        assert np.array_equal(etas.view(np.uint64), ref.view(np.uint64))
+        n = C.c_uint64()
+        z = np.zeros(1 << 20)
+        check(lib().gfs_debug_zetas(ix.handle, C.byref(cp), _p(z, f64p), len(z), C.byref(n)))
+        zr = oracle.zetas(op.space, op.space_max, op.space_quantization_step, op.theta)
+        m = min(n.value, len(zr))
+        # every reachable entry identical; the library's table is only truncated, never different
+        assert m >= min(len(zr), 100)
+        assert np.array_equal(z[:m - 1].view(np.uint64), zr[:m - 1].view(np.uint64))
+    ix.close()
+
+
+# ------------------------------------------------------------------------------------------------
+# term sampling: same (seed, tid, attempt) -> same term as the oracle's restated loop
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name,nd", [("DRB1-3123", False), ("DRB1-3123", True), ("lil", False), ("synth", False), ("synth", True)])
+def test_term_sampling_bit_exact(name, nd, gfs, oracle):
+    from gfasort_b200._cabi import lib, check, f64p, u64p, u8p
+    if name == "synth":
+        s = gfs.SynthGraph(200_000, 5, seed=11)
+        og = oracle.Graph.from_dense(s.step_handles, s.path_first, s.node_len)
+        ix = gfs.PathIndex.from_arrays(s.step_handles, s.path_first, s.node_len)
+    else:
+        path = os.path.join(DATA, f"{name}.gfa")
+        og = oracle.parse_gfa(path)
+        ix = gfs.PathIndex.from_graph(gfs.load_gfa(path))
+    op = oracle.params_from_graph(og, layout=nd)
+    cp = _cparams(op, gfs)
+    count = 20000
+    first_cooling = int(np.floor(op.cooling_start * op.iter_max))
+    for epoch in (0, first_cooling + 1):
+        cooling = epoch > first_cooling
+        theta = 0.001 if cooling else op.theta
+        for tid, a0 in ((0, 0), (12345, 1 << 33)):
+            v = np.zeros(count, dtype=np.uint8); sa = np.zeros(count, dtype=np.uint64); sb = np.zeros(count, dtype=np.uint64)
+            fl = np.zeros(count, dtype=np.uint8); d = np.zeros(count)
+            check(lib().gfs_debug_trace_terms(ix.handle, C.byref(cp), int(nd), epoch, tid, a0, count, _p(v, u8p),
+                                              _p(sa, u64p), _p(sb, u64p), _p(fl, u8p), _p(d, f64p)))
+            rv, rsa, rsb, rfl, rd = oracle.trace_terms(og, op, nd, cooling, theta, tid, a0, count)
+            assert np.array_equal(v, rv)
+            assert np.array_equal(sa, rsa)
+            assert np.array_equal(sb, rsb)
+            assert np.array_equal(fl, rfl)
+            assert np.array_equal(d.view(np.uint64), rd.view(np.uint64))
+            assert v.mean() > 0.9
+    ix.close()
+
+
+# ------------------------------------------------------------------------------------------------
+# whole runs, one GPU thread: bit-exact against the oracle driven by the same Philox stream
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["simple", "lil", "DRB1-3123"])
+def test_sgd_1d_single_thread_bit_exact(name, gfs, oracle):
+    path = os.path.join(DATA, f"{name}.gfa")
+    og = oracle.parse_gfa(path)
+    graph = gfs.load_gfa(path)
+    op = oracle.params_from_graph(og, nthreads=1)
+    if name == "DRB1-3123":
+        op.iter_max = 20      # 21 epochs x 35059 terms on one GPU thread
+    xo, st, rc = oracle.path_linear_sgd(og, op, mode=oracle.MODE_EXACT, draw=oracle.DRAW_PHILOX)
+    assert rc == 0
+    cfg = gfs.LaunchCfg.default()
+    cfg.total_threads = 1
+    cfg.aggregate = 0
+    x = gfs.path_linear_sgd_array(graph, _pyparams(op, gfs), cfg=cfg)
+    assert gfs.sgd.last_stats["applied_updates"] == st.applied == (op.iter_max + 1) * op.min_term_updates
+    assert gfs.sgd.last_stats["attempts"] == st.attempts
+    assert np.array_equal(x.view(np.uint64), xo.view(np.uint64))
+
+
+@pytest.mark.parametrize("dims", [1, 2, 3])
+def test_sgd_nd_single_thread_bit_exact_f64(dims, gfs, oracle):
+    path = os.path.join(DATA, "lil.gfa")
+    og = oracle.parse_gfa(path)
+    graph = gfs.load_gfa(path)
+    op = oracle.params_from_graph(og, layout=True, nthreads=1)
+    c0 = oracle.init_layout(og, dims, op.seed)
+    co, st, rc = oracle.path_linear_sgd_layout(og, op, dims, mode=oracle.MODE_EXACT, draw=oracle.DRAW_PHILOX, coords0=c0)
+    assert rc == 0
+    cfg = gfs.LaunchCfg.default()
+    cfg.total_threads = 1
+    cfg.aggregate = 0
+    cfg.layout_f64 = 1
+    lay = gfs.path_linear_sgd_layout(graph, _pyparams(op, gfs, True, dims), cfg=cfg, coords0=c0)
+    assert gfs.sgd.last_stats["applied_updates"] == st.applied
+    assert np.array_equal(lay.coords.view(np.uint64), co.view(np.uint64))
+
+
+def test_aggregation_is_equivalent_single_warp(gfs, oracle):
+    """32 threads with and without warp aggregation: same terms, sums differ only by association."""
+    path = os.path.join(DATA, "DRB1-3123.gfa")
+    graph = gfs.load_gfa(path)
+    ix = gfs.PathIndex.from_graph(graph)
+    params = gfs.YgsParams.from_graph(graph, 0, 1, ix).path_sgd
+    params.iter_max = 10
+    out = []
+    for agg in (0, 1):
+        cfg = gfs.LaunchCfg.default()
+        cfg.total_threads = 32
+        cfg.aggregate = agg
+        x = gfs.path_linear_sgd_array(graph, params, ix, cfg)
+        out.append((x, gfs.sort_stress(graph, x, 50000, ix)[1], dict(gfs.sgd.last_stats)))
+    assert out[0][2]["attempts"] == out[1][2]["attempts"]
+    assert abs(out[0][1] - out[1][1]) < 0.05 * out[0][1] + 1e-3
+    ix.close()
+
+
+# ------------------------------------------------------------------------------------------------
+# K4 stress kernel against the oracle on the same Philox sample
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dims", [1, 2])
+def test_stress_matches_oracle(dims, gfs, oracle):
+    path = os.path.join(DATA, "DRB1-3123.gfa")
+    og = oracle.parse_gfa(path)
+    graph = gfs.load_gfa(path)
+    rng = np.random.default_rng(5)
+    if dims == 1:
+        x = oracle.init_x(og) + rng.normal(0, 50, og.node_count())
+        coords = oracle.x_as_layout(x)
+        got = gfs.sort_stress(graph, x, 100000, seed=777)
+    else:
+        coords = oracle.init_layout(og, dims, 99)
+        got = gfs.layout_stress(graph, coords, dims, 100000, seed=777)
+    ref = oracle.layout_stress(og, coords, dims, 100000, draw=oracle.DRAW_PHILOX, seed=777)
+    assert got[2] == ref[2]
+    assert got[0] == pytest.approx(ref[0], rel=1e-11)
+    assert got[1] == pytest.approx(ref[1], rel=1e-11)
+    # and it agrees statistically with the reference's own xoshiro(12345) sample
+    # (mean |err|/d: the RMS form is dominated by a few short-distance pairs on an unconverged layout)
+    ref_x = oracle.layout_stress(og, coords, dims, 100000)
+    assert got[1] == pytest.approx(ref_x[1], rel=0.05)
+
+
+# ------------------------------------------------------------------------------------------------
+# stochastic parity: sampled path stress within 2 % of the oracle at the same update budget
+# ------------------------------------------------------------------------------------------------
+def _median_stress_1d(run, seeds):
+    vals = [run(s) for s in seeds]
+    return float(np.median([v[0] for v in vals])), float(np.median([v[1] for v in vals]))
+
+
+def test_sgd_1d_stress_parity_drb1(gfs, oracle):
+    path = os.path.join(DATA, "DRB1-3123.gfa")
+    og = oracle.parse_gfa(path)
+    graph = gfs.load_gfa(path)
+    ix = gfs.PathIndex.from_graph(graph)
+    op = oracle.params_from_graph(og, nthreads=os.cpu_count() or 4)
+    seeds = [9399220 + 1000 * k for k in range(5)]
+
+    def cpu(seed):
+        p = op.copy(); p.seed = seed
+        x, _, _ = oracle.path_linear_sgd(og, p, mode=oracle.MODE_REFERENCE)
+        return gfs.sort_stress(graph, x, 200000, ix)
+
+    def gpu(seed):
+        p = _pyparams(op, gfs); p.seed = seed
+        x = gfs.path_linear_sgd_array(graph, p, ix)
+        assert gfs.sgd.last_stats["applied_updates"] == (op.iter_max + 1) * op.min_term_updates
+        return gfs.sort_stress(graph, x, 200000, ix)
+
+    c_rms, c_mar = _median_stress_1d(cpu, seeds)
+    g_rms, g_mar = _median_stress_1d(gpu, seeds)
+    print(f"DRB1 Y stress: gpu mean_abs {g_mar:.5f} rms {g_rms:.5f} | oracle mean_abs {c_mar:.5f} rms {c_rms:.5f}")
+    assert g_mar <= c_mar * 1.02, "GPU 1D stress more than 2% above the oracle"
+    assert g_rms <= c_rms * 1.02
+    ix.close()
+
+
+def test_sgd_1d_stress_parity_synth(gfs, oracle):
+    s = gfs.SynthGraph(50_000, 8, seed=42)
+    og = oracle.Graph.from_dense(s.step_handles, s.path_first, s.node_len)
+    graph = gfs.BidirectedGraph.from_dense(s.step_handles, s.path_first, s.node_len)
+    ix = gfs.PathIndex.from_arrays(s.step_handles, s.path_first, s.node_len)
+    op = oracle.params_from_graph(og, nthreads=os.cpu_count() or 4)
+    seeds = [9399220 + 1000 * k for k in range(3)]
+
+    def cpu(seed):
+        p = op.copy(); p.seed = seed
+        x, _, _ = oracle.path_linear_sgd(og, p, mode=oracle.MODE_EXACT)
+        return gfs.sort_stress(graph, x, 200000, ix)
+
+    def gpu(seed):
+        p = _pyparams(op, gfs); p.seed = seed
+        x = gfs.path_linear_sgd_array(graph, p, ix)
+        return gfs.sort_stress(graph, x, 200000, ix)
+
+    c_rms, c_mar = _median_stress_1d(cpu, seeds)
+    g_rms, g_mar = _median_stress_1d(gpu, seeds)
+    x0 = s.initial_positions()
+    print(f"synth 50k Y stress: init {gfs.sort_stress(graph, x0, 200000, ix)[1]:.4f} gpu mean_abs {g_mar:.5f} rms {g_rms:.5f} | oracle mean_abs {c_mar:.5f} rms {c_rms:.5f}")
+    assert g_mar <= c_mar * 1.02 + 1e-4
+    assert g_rms <= c_rms * 1.02 + 1e-4
+    ix.close()
+
+
+@pytest.mark.parametrize("f64", [0, 1])
+def test_sgd_2d_stress_parity_drb1(f64, gfs, oracle):
+    path = os.path.join(DATA, "DRB1-3123.gfa")
+    og = oracle.parse_gfa(path)
+    graph = gfs.load_gfa(path)
+    ix = gfs.PathIndex.from_graph(graph)
+    op = oracle.params_from_graph(og, layout=True, nthreads=os.cpu_count() or 4)
+    seeds = [9399220 + 1000 * k for k in range(3)]
+    cfg = gfs.LaunchCfg.default()
+    cfg.layout_f64 = f64
+
+    def cpu(seed):
+        p = op.copy(); p.seed = seed
+        c, _, _ = oracle.path_linear_sgd_layout(og, p, 2, mode=oracle.MODE_REFERENCE)
+        return gfs.layout_stress(graph, c, 2, 200000, ix)
+
+    def gpu(seed):
+        p = _pyparams(op, gfs, True, 2); p.seed = seed
+        lay = gfs.path_linear_sgd_layout(graph, p, ix, cfg)
+        assert np.all(np.isfinite(lay.coords))
+        return gfs.layout_stress(graph, lay.coords, 2, 200000, ix)
+
+    c_rms, c_mar = _median_stress_1d(cpu, seeds)
+    g_rms, g_mar = _median_stress_1d(gpu, seeds)
+    print(f"DRB1 L(f64={f64}) stress: gpu mean_abs {g_mar:.5f} rms {g_rms:.5f} | oracle mean_abs {c_mar:.5f} rms {c_rms:.5f}")
+    assert g_mar <= c_mar * 1.02
+    assert g_rms <= c_rms * 1.02
+    ix.close()
+
+
+# ------------------------------------------------------------------------------------------------
+# reference-style invariants (tests/integration_tests.rs): nothing lost, ordering is a permutation
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", FIXTURES)
+def test_sgd_sort_only_keeps_graph(name, gfs):
+    graph = gfs.load_gfa(os.path.join(DATA, f"{name}.gfa"))
+    n_nodes, n_edges, n_steps = graph.node_count(), len(graph.edges), len(graph.steps)
+    lens_before = np.sort(graph.seq_len[graph.present != 0])
+    params = gfs.YgsParams.from_graph(graph, 0, 2).path_sgd
+    params.iter_max = 10
+    order = gfs.path_sgd_sort(graph, params)
+    assert sorted((order >> np.uint64(1)).tolist()) == sorted(graph.live_node_ids().tolist())
+    gfs.sgd_sort_only(graph, params, 0)
+    assert graph.node_count() == n_nodes and len(graph.edges) == n_edges and len(graph.steps) == n_steps
+    assert np.array_equal(np.sort(graph.seq_len[graph.present != 0]), lens_before)
+
+
+def test_no_valid_path_and_empty_graph(gfs):
+    node_len = np.array([3, 5], dtype=np.uint32)
+    g = gfs.BidirectedGraph.from_dense(np.array([0, 2], dtype=np.uint64), np.array([0, 1, 2], dtype=np.uint64), node_len)
+    assert gfs.path_linear_sgd(g, gfs.PathSGDParams()) == {}                 # sgd.rs:258-261
+    lay = gfs.path_linear_sgd_layout(g, gfs.LayoutSGDParams())
+    assert lay.num_nodes == 2 and np.all(lay.coords == 0)                    # sgd.rs:795-798
+    empty = gfs.BidirectedGraph(np.zeros(0), np.zeros(0), np.zeros(0), np.zeros(0), np.zeros(1))
+    assert gfs.path_linear_sgd(empty, gfs.PathSGDParams()) == {}             # sgd.rs:242-244
+    assert gfs.path_linear_sgd_layout(empty, gfs.LayoutSGDParams()).num_nodes == 0
+
+
+def test_session_slices_equal_whole_epochs(gfs):
+    """Running every epoch as 4 slices applies exactly the same number of updates."""
+    from gfasort_b200._cabi import lib, check, f64p, Stats
+    graph = gfs.load_gfa(os.path.join(DATA, "DRB1-3123.gfa"))
+    ix = gfs.PathIndex.from_graph(graph)
+    params = gfs.YgsParams.from_graph(graph, 0, 1, ix).path_sgd
+    params.iter_max = 6
+    cp = params.c()
+    h = C.c_void_p()
+    check(lib().gfs_sgd_session_create(ix.handle, C.byref(cp), 0, None, C.byref(h)))
+    x = gfs.initial_positions(graph)
+    check(lib().gfs_sgd_session_upload(h, _p(x, f64p)))
+    for e in range(params.iter_max + 1):
+        for k in range(4):
+            check(lib().gfs_sgd_session_run(h, e, e + 1, k, 4))
+    st = Stats()
+    check(lib().gfs_sgd_session_stats(h, C.byref(st)))
+    assert st.applied_updates == (params.iter_max + 1) * params.min_term_updates
+    assert st.launches == 4 * (params.iter_max + 1)
+    out = np.zeros_like(x)
+    check(lib().gfs_sgd_session_download(h, _p(out, f64p)))
+    lib().gfs_sgd_session_destroy(h)
+    assert np.all(np.isfinite(out)) and not np.array_equal(out, x)
+    ix.close()
