@@ -39,11 +39,11 @@ class SgdParams(C.Structure):
 class LaunchCfg(C.Structure):
     _fields_ = [("device", C.c_int32), ("total_threads", C.c_uint32), ("aggregate", C.c_int32),
                 ("layout_f64", C.c_int32), ("rng_thread_base", C.c_uint64), ("stream", C.c_void_p),
-                ("device_positions", C.c_void_p)]
+                ("device_positions", C.c_void_p), ("sample_begin", C.c_uint64), ("sample_end", C.c_uint64)]
 
     @staticmethod
     def default() -> "LaunchCfg":
-        return LaunchCfg(-1, 0, -1, -1, 0, None, None)
+        return LaunchCfg(-1, 0, -1, -1, 0, None, None, 0, 0)
 
 
 class Stats(C.Structure):
@@ -58,7 +58,7 @@ class Stats(C.Structure):
 
 class SynthSpec(C.Structure):
     _fields_ = [("num_nodes", C.c_uint64), ("num_paths", C.c_uint64), ("seed", C.c_uint64),
-                ("permute_ids", C.c_uint32), ("reserved", C.c_uint32)]
+                ("permute_ids", C.c_uint32), ("pinned", C.c_uint32)]
 
 
 # every symbol include/gfasort_cuda.h declares: name -> (restype, argtypes)
@@ -67,7 +67,8 @@ SIGNATURES = {
     "gfs_device_info": (C.c_char_p, []),
     "gfs_index_build": (C.c_int, [u64p, u64p, u32p, C.c_uint64, C.c_uint64, C.c_uint64, C.POINTER(C.c_void_p)]),
     "gfs_index_build_shard": (C.c_int, [u64p, u64p, u32p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64,
-                                        C.c_uint64, C.c_int32, C.POINTER(C.c_void_p)]),
+                                        C.c_uint64, C.c_int32, C.c_int32, u32p, C.POINTER(C.c_void_p)]),
+    "gfs_index_export_relabel": (C.c_int, [C.c_void_p, u32p]),
     "gfs_index_export": (C.c_int, [C.c_void_p, u64p, u64p]),
     "gfs_index_export_records": (C.c_int, [C.c_void_p, u64p, u32p]),
     "gfs_index_dims": (C.c_int, [C.c_void_p, u64p, u64p, u64p, u64p]),
@@ -84,11 +85,14 @@ SIGNATURES = {
     "gfs_sgd_session_download": (C.c_int, [C.c_void_p, f64p]),
     "gfs_sgd_session_run": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32]),
     "gfs_sgd_session_sync": (C.c_int, [C.c_void_p]),
+    "gfs_sgd_session_save": (C.c_int, [C.c_void_p]),
+    "gfs_sgd_session_restore": (C.c_int, [C.c_void_p]),
     "gfs_sgd_session_positions": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), u64p, u32p]),
     "gfs_sgd_session_stats": (C.c_int, [C.c_void_p, C.POINTER(Stats)]),
     "gfs_sgd_session_destroy": (None, [C.c_void_p]),
     "gfs_synth_create": (C.c_int, [C.POINTER(SynthSpec), C.POINTER(C.c_void_p)]),
     "gfs_synth_create_range": (C.c_int, [C.POINTER(SynthSpec), C.c_uint64, C.c_uint64, C.POINTER(C.c_void_p)]),
+    "gfs_synth_path_counts": (C.c_int, [C.POINTER(SynthSpec), u64p]),
     "gfs_synth_dims": (C.c_int, [C.c_void_p, u64p, u64p, u64p]),
     "gfs_synth_arrays": (C.c_int, [C.c_void_p, C.POINTER(u64p), C.POINTER(u64p), C.POINTER(u32p)]),
     "gfs_synth_free": (None, [C.c_void_p]),

@@ -316,10 +316,97 @@ __global__ void k1_export_pos(const StepRec* __restrict__ recs, uint64_t S, uint
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < S) pos[i] = recs[i].pos;
 }
-__global__ void k1_export_hl(const StepRec* __restrict__ recs, uint64_t S, uint64_t* __restrict__ h,
-                             uint32_t* __restrict__ l) {
+__global__ void k1_export_hl(const StepRec* __restrict__ recs, uint64_t S, uint32_t N, const uint32_t* __restrict__ old_of_new,
+                             uint64_t* __restrict__ h, uint32_t* __restrict__ l) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < S) { h[i] = recs[i].node_rev; l[i] = recs[i].node_len; }
+    if (i >= S) return;
+    const uint32_t nr = recs[i].node_rev;
+    uint32_t node = nr >> 1;
+    if (old_of_new && node < N) node = old_of_new[node];
+    h[i] = ((uint64_t)node << 1) | (nr & 1u);
+    l[i] = recs[i].node_len;
+}
+
+// ---------------------------------------------------------------------------------------------
+// node relabelling: internal node index = order of first appearance along the paths, so that the
+// positions of path-adjacent nodes share cache lines (the host's dense idx order is the GFA file
+// order, which says nothing about adjacency).  Purely a storage permutation: uploads scatter through
+// new_of_old, downloads gather back; no arithmetic changes.
+// ---------------------------------------------------------------------------------------------
+__global__ void rl_first_occ(const StepRec* __restrict__ recs, uint64_t S, uint32_t N, unsigned long long* __restrict__ first_occ) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= S) return;
+    const uint32_t node = recs[i].node_rev >> 1;
+    if (node < N && first_occ[node] > i) atomicMin(first_occ + node, (unsigned long long)i);
+}
+// exclusive scan of one flag per thread-item across the block; returns the block total in *total
+__device__ __forceinline__ uint32_t block_excl_scan_u32(uint32_t v, uint32_t* wsum, uint32_t* total) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    uint32_t inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+    if (lane == 31) wsum[w] = inc;
+    __syncthreads();
+    uint32_t off = 0, tot = 0;
+    for (int k = 0; k < nw; ++k) { const uint32_t x = wsum[k]; if (k < w) off += x; tot += x; }
+    __syncthreads();
+    *total = tot;
+    return off + inc - v;
+}
+// mode 0: item i is a step, flag = "first occurrence of its node"; mode 1: item i is a node, flag = "never visited"
+template <int MODE>
+__device__ __forceinline__ bool rl_flag(const StepRec* recs, const unsigned long long* first_occ, uint32_t N, uint64_t i) {
+    if (MODE == 0) { const uint32_t node = recs[i].node_rev >> 1; return node < N && first_occ[node] == i; }
+    return first_occ[i] == ~0ull;
+}
+template <int MODE>
+__global__ void __launch_bounds__(K1_THREADS)
+rl_tile_count(const StepRec* __restrict__ recs, const unsigned long long* __restrict__ first_occ, uint32_t N, uint64_t n_items,
+              uint64_t* __restrict__ tile_cnt) {
+    __shared__ uint64_t wb[32];
+    const uint64_t base = (uint64_t)blockIdx.x * K1_TILE;
+    uint64_t c = 0;
+#pragma unroll
+    for (int k = 0; k < K1_ITEMS; ++k) {
+        const uint64_t i = base + (uint64_t)k * K1_THREADS + threadIdx.x;
+        if (i < n_items) c += rl_flag<MODE>(recs, first_occ, N, i) ? 1 : 0;
+    }
+    c = block_sum_u64(c, wb);
+    if (threadIdx.x == 0) tile_cnt[blockIdx.x] = c;
+}
+template <int MODE>
+__global__ void __launch_bounds__(K1_THREADS)
+rl_assign(const StepRec* __restrict__ recs, const unsigned long long* __restrict__ first_occ, uint32_t N, uint64_t n_items,
+          const uint64_t* __restrict__ tile_prefix, uint32_t* __restrict__ new_of_old, uint32_t* __restrict__ old_of_new) {
+    __shared__ uint32_t wsum[K1_THREADS / 32];
+    const uint64_t base = (uint64_t)blockIdx.x * K1_TILE + (uint64_t)threadIdx.x * K1_ITEMS;   // 8 consecutive items
+    bool f[K1_ITEMS];
+    uint32_t cnt = 0;
+#pragma unroll
+    for (int k = 0; k < K1_ITEMS; ++k) { f[k] = (base + k < n_items) && rl_flag<MODE>(recs, first_occ, N, base + k); cnt += f[k]; }
+    uint32_t total;
+    uint32_t off = block_excl_scan_u32(cnt, wsum, &total);
+    uint64_t rank = tile_prefix[blockIdx.x] + off;
+#pragma unroll
+    for (int k = 0; k < K1_ITEMS; ++k) {
+        if (f[k]) {
+            const uint32_t old = MODE == 0 ? (recs[base + k].node_rev >> 1) : (uint32_t)(base + k);
+            new_of_old[old] = (uint32_t)rank;
+            old_of_new[rank] = old;
+            ++rank;
+        }
+    }
+}
+__global__ void rl_rewrite(StepRec* __restrict__ recs, uint64_t S, uint32_t N, const uint32_t* __restrict__ new_of_old) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= S) return;
+    const uint32_t nr = recs[i].node_rev;
+    const uint32_t node = nr >> 1;
+    if (node < N) recs[i].node_rev = (new_of_old[node] << 1) | (nr & 1u);
+}
+__global__ void rl_invert(const uint32_t* __restrict__ new_of_old, uint32_t N, uint32_t* __restrict__ old_of_new) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < N) old_of_new[new_of_old[i]] = i;
 }
 
 // =============================================================================================
@@ -336,6 +423,8 @@ struct KernelGraph {
     uint32_t space;               // min(params.space, 2^32-1): compared with ranks < 2^32
     uint32_t space_max;
     uint32_t q;
+    uint32_t l2_hints;            // 1: records evict_first, positions evict_last (L2 cache-hint policies)
+    uint64_t samp_base, samp_len; // sampled steps are drawn from [samp_base, samp_base + samp_len) (default 0, S)
 };
 
 struct SampledTerm {
@@ -350,15 +439,20 @@ struct SampledTerm {
 //   coins = bits 0..3 of r.z (zipf, back, end_a, end_b).
 template <bool ND>
 __device__ __forceinline__ void sample_term(const KernelGraph& g, const uint64_t* fs, const double* s_zetas,
-                                            uint32_t s_zlen, const EpochDesc& ep, uint4 r, SampledTerm& t) {
+                                            uint32_t s_zlen, const EpochDesc& ep, uint4 r, uint64_t win_base,
+                                            uint64_t win_len, SampledTerm& t) {
     const uint64_t r01 = ((uint64_t)r.y << 32) | r.x;
     const uint64_t r23 = ((uint64_t)r.w << 32) | r.z;
-    const uint64_t s = __umul64hi(r01, g.S);
+    // step ~ U[win_base, win_base + win_len) on the circular sampling range; the default window
+    // (samp_base, samp_len) = (0, S) is the reference's U[0, S) (sgd.rs:444)
+    uint64_t s = win_base + __umul64hi(r01, win_len);
+    if (s >= g.samp_base + g.samp_len) s -= g.samp_len;
     const uint32_t p = find_path(fs, g.P, s);
     const uint64_t f = fs[p];
     const uint32_t n = (uint32_t)(fs[p + 1] - f);
     const uint32_t ra = (uint32_t)(s - f);
-    t.a = load_rec(g.recs + s);                      // independent of everything below: issue early
+    const uint64_t pol_stream = make_evict_first_policy();
+    t.a = g.l2_hints ? load_rec_hint(g.recs + s, pol_stream) : load_rec(g.recs + s);   // issue early
     t.valid = n > 1;                                 // path_step_count == 1 => continue (sgd.rs:448)
     uint32_t rb = ra;
     if (ep.cooling || (r.z & 1u)) {                  // sgd.rs:456
@@ -381,7 +475,7 @@ __device__ __forceinline__ void sample_term(const KernelGraph& g, const uint64_t
     t.valid = t.valid && (ra != rb);                                                      // sgd.rs:497
     t.step_a = s;
     t.step_b = t.valid ? f + rb : s;
-    t.b = load_rec(g.recs + t.step_b);
+    t.b = g.l2_hints ? load_rec_hint(g.recs + t.step_b, pol_stream) : load_rec(g.recs + t.step_b);
     t.other_a = t.other_b = false;
     if (ND) {                                                                              // sgd.rs:1060-1077
         const bool rev_a = t.a.node_rev & 1u, rev_b = t.b.node_rev & 1u;
@@ -421,6 +515,14 @@ __device__ __forceinline__ double ld_pos(const double* p) {
     double v;
     asm volatile("ld.global.cg.f64 %0, [%1];" : "=d"(v) : "l"(p));
     return v;
+}
+__device__ __forceinline__ double ld_pos_keep(const double* p, uint64_t pol) {
+    double v;
+    asm volatile("ld.global.cg.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ void red_pos_keep(double* p, double v, uint64_t pol) {
+    asm volatile("red.global.add.L2::cache_hint.f64 [%0], %1, %2;" :: "l"(p), "d"(v), "l"(pol) : "memory");
 }
 template <typename CT, int DS> __device__ __forceinline__ void ld_coords(const CT* p, CT (&c)[DS]);
 template <> __device__ __forceinline__ void ld_coords<float, 1>(const float* p, float (&c)[1]) {
@@ -492,16 +594,25 @@ struct SgdArgs {
     uint32_t seed_lo, seed_hi;
     uint32_t tid_base;
     void* positions;             // 1D: double[N]; nD: CT[N*2*DS]
+    // sweep scheduling (window_steps > 0): warps pull chunks of `chunk_updates` updates from *work_ctr;
+    // chunk c of an epoch samples its steps from one of `n_sweeps` windows of `window_steps` steps that
+    // slide once over the step array per epoch, so the records being sampled stay L2-resident.
+    uint64_t window_steps;
+    uint32_t n_sweeps;
+    uint32_t chunk_updates;
+    unsigned long long* work_ctr;
 };
 
 // 1D update of one warp's terms (sgd.rs:512-576), optionally merging lanes that hit the same node.
 template <bool AGG>
 __device__ __forceinline__ void apply_1d(double* X, unsigned warp_mask, int lane, bool valid, uint32_t i,
-                                         uint32_t j, double d, double eta) {
+                                         uint32_t j, double d, double eta, bool hints) {
     double r_x = 0.0;
+    const uint64_t pol_keep = make_evict_last_policy();
     if (valid) {
         const double mu = fmin(__dmul_rn(eta, __ddiv_rn(1.0, d)), 1.0);     // sgd.rs:518-520
-        const double xi = ld_pos(X + i), xj = ld_pos(X + j);
+        const double xi = hints ? ld_pos_keep(X + i, pol_keep) : ld_pos(X + i);
+        const double xj = hints ? ld_pos_keep(X + j, pol_keep) : ld_pos(X + j);
         double dx = __dsub_rn(xi, xj);
         if (dx == 0.0) dx = 1e-9;                                            // sgd.rs:546-548
         const double mag = fabs(dx);
@@ -514,13 +625,16 @@ __device__ __forceinline__ void apply_1d(double* X, unsigned warp_mask, int lane
         const unsigned vmask = __ballot_sync(warp_mask, valid);
         const unsigned mi = __match_any_sync(warp_mask, i) & vmask; const unsigned pi = valid ? mi : 0u;
         const double si = group_sum(warp_mask, pi, -r_x, lane, lead);
-        if (valid && lead) atomicAdd(X + i, si);
+        if (valid && lead) { if (hints) red_pos_keep(X + i, si, pol_keep); else atomicAdd(X + i, si); }
         const unsigned mj = __match_any_sync(warp_mask, j) & vmask; const unsigned pj = valid ? mj : 0u;
         const double sj = group_sum(warp_mask, pj, r_x, lane, lead);
-        if (valid && lead) atomicAdd(X + j, sj);
+        if (valid && lead) { if (hints) red_pos_keep(X + j, sj, pol_keep); else atomicAdd(X + j, sj); }
     } else if (valid) {
-        atomicAdd(X + i, -r_x);                                              // sgd.rs:575
-        atomicAdd(X + j, r_x);                                               // sgd.rs:576
+        if (hints) { red_pos_keep(X + i, -r_x, pol_keep); red_pos_keep(X + j, r_x, pol_keep); }
+        else {
+            atomicAdd(X + i, -r_x);                                          // sgd.rs:575
+            atomicAdd(X + j, r_x);                                           // sgd.rs:576
+        }
     }
 }
 
@@ -587,37 +701,80 @@ sgd_kernel(const SgdArgs a) {
     uint64_t applied = 0, attempts0 = attempt;
     const uint2 key = make_uint2(a.seed_lo, a.seed_hi);
 
-    for (uint32_t e = a.epoch_begin; e < a.epoch_end; ++e) {
-        const EpochDesc ep = a.epochs[e];
-        // this launch's share of the epoch, then this thread's share of that
-        const uint64_t m = ep.updates / a.n_slices + (a.slice < ep.updates % a.n_slices ? 1 : 0);
-        const uint64_t quota = m / T + (tid < m % T ? 1 : 0);
-        uint64_t done = 0;
+    // one sampled term for every active lane of the warp; returns whether this lane applied an update
+    auto attempt_once = [&](const EpochDesc& ep, bool active, uint64_t win_base, uint64_t win_len) -> bool {
+        SampledTerm t;
+        t.valid = false;
+        double d = 0.0;
+        if (active) {
+            const uint4 r = philox4x32_10(make_uint4((uint32_t)attempt, (uint32_t)(attempt >> 32),
+                                                     a.tid_base + tid, STREAM_SGD), key);
+            ++attempt;
+            sample_term<(D > 0)>(a.g, fs, s_zetas, s_zlen, ep, r, win_base, win_len, t);
+            d = term_distance(t);
+            const uint32_t na = t.a.node_rev >> 1, nb = t.b.node_rev >> 1;
+            t.valid = t.valid && d != 0.0 && na < a.g.N && nb < a.g.N;     // sgd.rs:514, 525-538
+        }
+        if constexpr (D == 0) {
+            apply_1d<AGG>(reinterpret_cast<double*>(a.positions), warp_mask, lane, t.valid,
+                          t.a.node_rev >> 1, t.b.node_rev >> 1, d, ep.eta, a.g.l2_hints != 0);
+        } else {
+            const uint32_t idx_i = (t.a.node_rev >> 1) * 2 + (t.other_a ? 1u : 0u);   // sgd.rs:1099-1103
+            const uint32_t idx_j = (t.b.node_rev >> 1) * 2 + (t.other_b ? 1u : 0u);
+            apply_nd<CT, (D > 0 ? D : 1), DS, AGG>(reinterpret_cast<CT*>(a.positions), warp_mask, lane, t.valid,
+                                                   idx_i, idx_j, d, ep.eta);
+        }
+        return t.valid;
+    };
+
+    if (a.window_steps == 0) {
+        // static schedule: thread t applies floor(m/T) + (t < m%T) updates per epoch, steps ~ U[0,S)
+        for (uint32_t e = a.epoch_begin; e < a.epoch_end; ++e) {
+            const EpochDesc ep = a.epochs[e];
+            const uint64_t m = ep.updates / a.n_slices + (a.slice < ep.updates % a.n_slices ? 1 : 0);
+            const uint64_t quota = m / T + (tid < m % T ? 1 : 0);
+            uint64_t done = 0;
+            for (;;) {
+                const bool active = done < quota;
+                if (!__any_sync(warp_mask, active)) break;
+                if (attempt_once(ep, active, a.g.samp_base, a.g.samp_len)) { ++done; ++applied; }   // sgd.rs:579
+            }
+        }
+    } else {
+        // sweep schedule
+        const uint32_t n_lanes = __popc(warp_mask);
+        const uint32_t lane_rank = __popc(warp_mask & ((1u << lane) - 1u));
+        const int leader = __ffs(warp_mask) - 1;
+        const uint64_t m = a.epochs[a.epoch_begin].updates / a.n_slices +
+                           (a.slice < a.epochs[a.epoch_begin].updates % a.n_slices ? 1 : 0);
+        const uint64_t cpe = (m + a.chunk_updates - 1) / a.chunk_updates;                  // chunks per epoch
+        const uint64_t total = cpe * (uint64_t)(a.epoch_end - a.epoch_begin);
+        const uint64_t K = a.n_sweeps;
+        const uint64_t per_sweep = (cpe + K - 1) / K;          // chunks one sweep handles per epoch
+        const uint64_t span = a.g.samp_len / K;                // steps one sweep travels per epoch
+        uint32_t cur_e = 0xffffffffu;
+        EpochDesc ep;
         for (;;) {
-            const bool active = done < quota;
-            if (!__any_sync(warp_mask, active)) break;
-            SampledTerm t;
-            t.valid = false;
-            double d = 0.0;
-            if (active) {
-                const uint4 r = philox4x32_10(make_uint4((uint32_t)attempt, (uint32_t)(attempt >> 32),
-                                                         a.tid_base + tid, STREAM_SGD), key);
-                ++attempt;
-                sample_term<(D > 0)>(a.g, fs, s_zetas, s_zlen, ep, r, t);
-                d = term_distance(t);
-                const uint32_t na = t.a.node_rev >> 1, nb = t.b.node_rev >> 1;
-                t.valid = t.valid && d != 0.0 && na < a.g.N && nb < a.g.N;     // sgd.rs:514, 525-538
+            unsigned long long c = 0;
+            if (lane == leader) c = atomicAdd(a.work_ctr, 1ull);
+            c = __shfl_sync(warp_mask, c, leader);
+            if (c >= total) break;
+            const uint32_t e = a.epoch_begin + (uint32_t)(c / cpe);
+            const uint64_t cc = c % cpe;
+            if (e != cur_e) { ep = a.epochs[e]; cur_e = e; }
+            const uint64_t left = m - cc * a.chunk_updates;
+            const uint32_t n_upd = left < a.chunk_updates ? (uint32_t)left : a.chunk_updates;
+            const uint32_t quota = n_upd / n_lanes + (lane_rank < n_upd % n_lanes ? 1u : 0u);
+            const uint64_t k = cc % K, j = cc / K;
+            uint64_t win_base = k * span + (uint64_t)(((unsigned __int128)j * span) / per_sweep);
+            if (win_base >= a.g.samp_len) win_base -= a.g.samp_len;
+            win_base += a.g.samp_base;
+            uint32_t done = 0;
+            for (;;) {
+                const bool active = done < quota;
+                if (!__any_sync(warp_mask, active)) break;
+                if (attempt_once(ep, active, win_base, a.window_steps)) { ++done; ++applied; }
             }
-            if constexpr (D == 0) {
-                apply_1d<AGG>(reinterpret_cast<double*>(a.positions), warp_mask, lane, t.valid,
-                              t.a.node_rev >> 1, t.b.node_rev >> 1, d, ep.eta);
-            } else {
-                const uint32_t idx_i = (t.a.node_rev >> 1) * 2 + (t.other_a ? 1u : 0u);   // sgd.rs:1099-1103
-                const uint32_t idx_j = (t.b.node_rev >> 1) * 2 + (t.other_b ? 1u : 0u);
-                apply_nd<CT, (D > 0 ? D : 1), DS, AGG>(reinterpret_cast<CT*>(a.positions), warp_mask, lane, t.valid,
-                                                       idx_i, idx_j, d, ep.eta);
-            }
-            if (t.valid) { ++done; ++applied; }                                 // sgd.rs:579
         }
     }
     a.attempt_ctr[tid] = attempt;
@@ -641,8 +798,8 @@ sgd_kernel(const SgdArgs a) {
 constexpr int STRESS_BLOCK = 256;
 // coords: stride_node doubles per node, the + end's `dims` coordinates first.
 __global__ void __launch_bounds__(STRESS_BLOCK)
-stress_kernel(KernelGraph g, const double* __restrict__ coords, uint32_t dims, uint32_t stride_node,
-              uint64_t samples, uint32_t seed_lo, uint32_t seed_hi, double* __restrict__ partial /*3 per block*/) {
+stress_kernel(KernelGraph g, const uint32_t* __restrict__ old_of_new, const double* __restrict__ coords, uint32_t dims,
+              uint32_t stride_node, uint64_t samples, uint32_t seed_lo, uint32_t seed_hi, double* __restrict__ partial /*3 per block*/) {
     __shared__ double red[3][STRESS_BLOCK / 32];
     double sum = 0.0, sum_abs = 0.0, cnt = 0.0;
     const uint2 key = make_uint2(seed_lo, seed_hi);
@@ -659,8 +816,9 @@ stress_kernel(KernelGraph g, const double* __restrict__ coords, uint32_t dims, u
         const StepRec A = load_rec(g.recs + s), B = load_rec(g.recs + f + rb);
         const double dp = fabs(__dsub_rn((double)A.pos, (double)B.pos));
         if (dp == 0.0) continue;
-        const uint32_t ia = A.node_rev >> 1, ib = B.node_rev >> 1;
+        uint32_t ia = A.node_rev >> 1, ib = B.node_rev >> 1;
         if (ia >= g.N || ib >= g.N) continue;
+        if (old_of_new) { ia = old_of_new[ia]; ib = old_of_new[ib]; }
         double sq = 0.0;
         for (uint32_t d = 0; d < dims; ++d) {
             const double dl = __dsub_rn(coords[(size_t)ia * stride_node + d], coords[(size_t)ib * stride_node + d]);
@@ -690,19 +848,29 @@ stress_kernel(KernelGraph g, const double* __restrict__ coords, uint32_t dims, u
 // =============================================================================================
 // conversion kernels (host Layout order f64 <-> device [node][end][DS] CT)
 // =============================================================================================
+// src: host order, f64, `ends` node ends of D coordinates each per node (1D: ends = 1, D = 1).
+// dst: device order (node relabelled through new_of_old when non-null), CT, stride DS per end.
 template <typename CT>
-__global__ void layout_to_device(const double* __restrict__ src, CT* __restrict__ dst, uint64_t n_ends, uint32_t D, uint32_t DS) {
+__global__ void pos_to_device(const double* __restrict__ src, CT* __restrict__ dst, uint64_t N, uint32_t ends, uint32_t D,
+                              uint32_t DS, const uint32_t* __restrict__ new_of_old) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_ends * DS) return;
-    const uint64_t e = i / DS; const uint32_t k = (uint32_t)(i % DS);
-    dst[i] = k < D ? (CT)src[e * D + k] : CT(0);
+    const uint64_t per_node = (uint64_t)ends * DS;
+    if (i >= N * per_node) return;
+    const uint64_t node = i / per_node; const uint32_t r = (uint32_t)(i % per_node);
+    const uint32_t e = r / DS, k = r % DS;
+    const uint64_t dn = new_of_old ? new_of_old[node] : node;
+    dst[dn * per_node + r] = k < D ? (CT)src[(node * ends + e) * D + k] : CT(0);
 }
 template <typename CT>
-__global__ void layout_from_device(const CT* __restrict__ src, double* __restrict__ dst, uint64_t n_ends, uint32_t D, uint32_t DS) {
+__global__ void pos_from_device(const CT* __restrict__ src, double* __restrict__ dst, uint64_t N, uint32_t ends, uint32_t D,
+                                uint32_t DS, const uint32_t* __restrict__ new_of_old) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_ends * D) return;
-    const uint64_t e = i / D; const uint32_t k = (uint32_t)(i % D);
-    dst[i] = (double)src[e * DS + k];
+    const uint64_t per_node = (uint64_t)ends * D;
+    if (i >= N * per_node) return;
+    const uint64_t node = i / per_node; const uint32_t r = (uint32_t)(i % per_node);
+    const uint32_t e = r / D, k = r % D;
+    const uint64_t dn = new_of_old ? new_of_old[node] : node;
+    dst[i] = (double)src[(dn * ends + e) * DS + k];
 }
 
 // =============================================================================================
@@ -740,7 +908,7 @@ __global__ void dbg_trace(KernelGraph g, const EpochDesc* epochs, uint32_t epoch
     const uint4 r = philox4x32_10(make_uint4((uint32_t)attempt, (uint32_t)(attempt >> 32), tid, STREAM_SGD),
                                   make_uint2(seed_lo, seed_hi));
     SampledTerm t;
-    sample_term<ND>(g, g.first_step, g.zetas, 0u, ep, r, t);
+    sample_term<ND>(g, g.first_step, g.zetas, 0u, ep, r, g.samp_base, g.samp_len, t);
     const double d = term_distance(t);
     const bool ok = t.valid && d != 0.0;
     valid[k] = ok;
@@ -765,6 +933,8 @@ struct gfs_index {
     StepRec* d_recs = nullptr;
     uint64_t* d_first_step = nullptr;   // P+1
     uint64_t* d_path_len = nullptr;     // P
+    uint32_t* d_new_of_old = nullptr;   // N, null when not relabelled
+    uint32_t* d_old_of_new = nullptr;   // N
     std::vector<uint64_t> h_first_step;
     double build_seconds = 0, h2d_seconds = 0;
 };
@@ -795,6 +965,12 @@ struct gfs_sgd_session {
     uint64_t launches = 0;
     double h2d_s = 0, d2h_s = 0;
     bool ev_pending = false;
+    int l2_policy = 0;          // 0 none, 1 per-access cache hints, 2 persisting access-policy window
+    uint64_t window_steps = 0;  // 0 = static schedule
+    uint32_t n_sweeps = 1, chunk_updates = 128;
+    unsigned long long* d_work = nullptr;
+    void* d_saved = nullptr;    // gfs_sgd_session_save snapshot of the positions
+    uint64_t samp_base = 0, samp_len = 0;
 };
 
 static int select_device(int dev) {
@@ -826,9 +1002,9 @@ extern "C" const char* gfs_device_info(void) {
     char buf[512];
     std::snprintf(buf, sizeof buf,
                   "{\"devices\": %d, \"device\": %d, \"name\": \"%s\", \"cc\": \"%d.%d\", \"sms\": %d, \"l2_bytes\": %d, "
-                  "\"global_mem\": %zu, \"persisting_l2_max\": %d}",
+                  "\"global_mem\": %zu, \"persisting_l2_max\": %d, \"access_policy_max_window\": %d}",
                   n, dev, p.name, p.major, p.minor, p.multiProcessorCount, p.l2CacheSize, (size_t)p.totalGlobalMem,
-                  p.persistingL2CacheMaxSize);
+                  p.persistingL2CacheMaxSize, p.accessPolicyMaxWindowSize);
     info = buf;
     return info.c_str();
 }
@@ -837,9 +1013,47 @@ extern "C" const char* gfs_device_info(void) {
 // index build
 // ---------------------------------------------------------------------------------------------
 
+// Relabel the nodes of a built index.  given == nullptr: order of first appearance in this index's
+// steps (never-visited nodes last); else the caller's permutation (multi-GPU: one for all ranks).
+static int index_relabel(gfs_index* ix, const uint32_t* given, cudaStream_t st) {
+    if (ix->N == 0) return GFS_OK;
+    const uint32_t N = (uint32_t)ix->N;
+    GFS_CUDA(cudaMalloc(&ix->d_new_of_old, (size_t)N * 4));
+    GFS_CUDA(cudaMalloc(&ix->d_old_of_new, (size_t)N * 4));
+    if (given) {
+        GFS_CUDA(cudaMemcpyAsync(ix->d_new_of_old, given, (size_t)N * 4, cudaMemcpyHostToDevice, st));
+        rl_invert<<<(N + 255) / 256, 256, 0, st>>>(ix->d_new_of_old, N, ix->d_old_of_new);
+    } else {
+        unsigned long long* d_first = nullptr; uint64_t* d_tiles = nullptr; uint64_t* d_carry = nullptr;
+        const uint64_t tiles_s = (ix->S + K1_TILE - 1) / K1_TILE, tiles_n = ((uint64_t)N + K1_TILE - 1) / K1_TILE;
+        GFS_CUDA(cudaMalloc(&d_first, (size_t)N * 8));
+        GFS_CUDA(cudaMalloc(&d_tiles, (std::max(tiles_s, tiles_n) + 1) * 8));
+        GFS_CUDA(cudaMalloc(&d_carry, 8));
+        GFS_CUDA(cudaMemsetAsync(d_first, 0xff, (size_t)N * 8, st));
+        GFS_CUDA(cudaMemsetAsync(d_carry, 0, 8, st));
+        if (ix->S) {
+            rl_first_occ<<<(unsigned)((ix->S + 255) / 256), 256, 0, st>>>(ix->d_recs, ix->S, N, d_first);
+            rl_tile_count<0><<<(unsigned)tiles_s, K1_THREADS, 0, st>>>(ix->d_recs, d_first, N, ix->S, d_tiles);
+            k1_scan_tiles<<<1, 1024, 0, st>>>(d_tiles, tiles_s, d_carry);
+            rl_assign<0><<<(unsigned)tiles_s, K1_THREADS, 0, st>>>(ix->d_recs, d_first, N, ix->S, d_tiles, ix->d_new_of_old, ix->d_old_of_new);
+        }
+        rl_tile_count<1><<<(unsigned)tiles_n, K1_THREADS, 0, st>>>(nullptr, d_first, N, N, d_tiles);
+        k1_scan_tiles<<<1, 1024, 0, st>>>(d_tiles, tiles_n, d_carry);      // carry continues after the visited nodes
+        rl_assign<1><<<(unsigned)tiles_n, K1_THREADS, 0, st>>>(nullptr, d_first, N, N, d_tiles, ix->d_new_of_old, ix->d_old_of_new);
+        cudaError_t e = cudaStreamSynchronize(st);
+        cudaFree(d_first); cudaFree(d_tiles); cudaFree(d_carry);
+        if (e != cudaSuccess) { set_error(std::string("relabel failed: ") + cudaGetErrorString(e)); return GFS_ERR_CUDA; }
+    }
+    if (ix->S) rl_rewrite<<<(unsigned)((ix->S + 255) / 256), 256, 0, st>>>(ix->d_recs, ix->S, N, ix->d_new_of_old);
+    GFS_CUDA(cudaStreamSynchronize(st));
+    GFS_CUDA(cudaGetLastError());
+    return GFS_OK;
+}
+
 extern "C" int gfs_index_build_shard(const uint64_t* step_handles, const uint64_t* path_first_step,
                                      const uint32_t* node_len, uint64_t S, uint64_t P, uint64_t N,
-                                     uint64_t path_begin, uint64_t path_end, int32_t device, gfs_index** out) {
+                                     uint64_t path_begin, uint64_t path_end, int32_t device, int32_t relabel_mode,
+                                     const uint32_t* new_of_old, gfs_index** out) {
     if (!out) { set_error("gfs_index_build: out is null"); return GFS_ERR_INVALID; }
     *out = nullptr;
     if (!path_first_step || (S && !step_handles) || (N && !node_len)) { set_error("gfs_index_build: null input array"); return GFS_ERR_INVALID; }
@@ -923,6 +1137,11 @@ extern "C" int gfs_index_build_shard(const uint64_t* step_handles, const uint64_
     IX_CUDA(cudaStreamSynchronize(st));
     IX_CUDA(cudaGetLastError());
     cudaFree(d_handles); cudaFree(d_tiles); cudaFree(d_path_base); cudaFree(d_carry); cudaFree(d_node_len);
+    if (relabel_mode == 2 && !new_of_old) { set_error("gfs_index_build: relabel_mode 2 needs a permutation"); return fail(GFS_ERR_INVALID); }
+    if (relabel_mode == 1 || relabel_mode == 2) {
+        rc = index_relabel(ix, relabel_mode == 2 ? new_of_old : nullptr, st);
+        if (rc) return fail(rc);
+    }
     cudaStreamDestroy(st);
     ix->h2d_seconds = h2d;
     ix->build_seconds = now_s() - t_begin;
@@ -933,13 +1152,23 @@ extern "C" int gfs_index_build_shard(const uint64_t* step_handles, const uint64_
 
 extern "C" int gfs_index_build(const uint64_t* step_handles, const uint64_t* path_first_step, const uint32_t* node_len,
                                uint64_t S, uint64_t P, uint64_t N, gfs_index** out) {
-    return gfs_index_build_shard(step_handles, path_first_step, node_len, S, P, N, 0, P, -1, out);
+    return gfs_index_build_shard(step_handles, path_first_step, node_len, S, P, N, 0, P, -1,
+                                 env_long("GFASORT_RELABEL", 1) ? 1 : 0, nullptr, out);
+}
+
+extern "C" int gfs_index_export_relabel(const gfs_index* ix, uint32_t* new_of_old) {
+    if (!ix || !new_of_old) { set_error("gfs_index_export_relabel: null argument"); return GFS_ERR_INVALID; }
+    GFS_CUDA(cudaSetDevice(ix->device));
+    if (ix->d_new_of_old) GFS_CUDA(cudaMemcpy(new_of_old, ix->d_new_of_old, ix->N * 4, cudaMemcpyDeviceToHost));
+    else for (uint64_t i = 0; i < ix->N; ++i) new_of_old[i] = (uint32_t)i;
+    return GFS_OK;
 }
 
 extern "C" void gfs_index_free(gfs_index* ix) {
     if (!ix) return;
     cudaSetDevice(ix->device);
     cudaFree(ix->d_recs); cudaFree(ix->d_first_step); cudaFree(ix->d_path_len);
+    cudaFree(ix->d_new_of_old); cudaFree(ix->d_old_of_new);
     delete ix;
 }
 
@@ -982,7 +1211,7 @@ extern "C" int gfs_index_export_records(const gfs_index* ix, uint64_t* step_hand
     GFS_CUDA(cudaMalloc(&dl, cap * 4));
     for (uint64_t c0 = 0; c0 < ix->S; c0 += CH) {
         const uint64_t n = std::min(CH, ix->S - c0);
-        k1_export_hl<<<(unsigned)((n + 255) / 256), 256>>>(ix->d_recs + c0, n, dh, dl);
+        k1_export_hl<<<(unsigned)((n + 255) / 256), 256>>>(ix->d_recs + c0, n, (uint32_t)ix->N, ix->d_old_of_new, dh, dl);
         cudaError_t e1 = cudaMemcpy(step_handle + c0, dh, n * 8, cudaMemcpyDeviceToHost);
         cudaError_t e2 = cudaMemcpy(step_node_len + c0, dl, n * 4, cudaMemcpyDeviceToHost);
         if (e1 != cudaSuccess || e2 != cudaSuccess) { cudaFree(dh); cudaFree(dl); set_error("export copy failed"); return GFS_ERR_CUDA; }
@@ -1023,6 +1252,8 @@ static KernelGraph make_kgraph(const gfs_index* ix, const gfs_sgd_params& p, con
     g.space = (uint32_t)std::min<uint64_t>(p.space, 0xffffffffull);
     g.space_max = (uint32_t)std::min<uint64_t>(p.space_max, 0xffffffffull);
     g.q = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(p.space_quantization_step, 1), 0xffffffffull);
+    g.l2_hints = 0;
+    g.samp_base = 0; g.samp_len = ix->S;
     return g;
 }
 
@@ -1038,6 +1269,7 @@ extern "C" void gfs_sgd_session_destroy(gfs_sgd_session* s) {
     cudaSetDevice(s->device);
     if (s->own_pos) cudaFree(s->d_pos);
     cudaFree(s->d_zetas); cudaFree(s->d_epochs); cudaFree(s->d_attempts); cudaFree(s->d_counters); cudaFree(s->d_stage);
+    cudaFree(s->d_work); cudaFree(s->d_saved);
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
     if (s->own_stream && s->stream) cudaStreamDestroy(s->stream);
@@ -1063,6 +1295,11 @@ extern "C" int gfs_sgd_session_create(const gfs_index* ix, const gfs_sgd_params*
     s->aggregate = agg != 0;
     s->f64 = dims == 0 ? true : (f64 != 0);
     s->rng_thread_base = cfg ? cfg->rng_thread_base : 0;
+    s->samp_base = 0; s->samp_len = ix->S;
+    if (cfg && cfg->sample_end > cfg->sample_begin) {
+        if (cfg->sample_end > ix->S) { set_error("gfs_sgd_session_create: sample range outside the index"); delete s; return GFS_ERR_INVALID; }
+        s->samp_base = cfg->sample_begin; s->samp_len = cfg->sample_end - cfg->sample_begin;
+    }
     auto fail = [&](int code) { gfs_sgd_session_destroy(s); return code; };
 #define SS_CUDA(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { set_error(std::string(#call) + " failed: " + cudaGetErrorString(e__)); return fail(GFS_ERR_CUDA); } } while (0)
 
@@ -1114,6 +1351,41 @@ extern "C" int gfs_sgd_session_create(const gfs_index* ix, const gfs_sgd_params*
     SS_CUDA(cudaMemsetAsync(s->d_attempts, 0, T * 8, s->stream));
     SS_CUDA(cudaMalloc(&s->d_counters, 16));
     SS_CUDA(cudaMemsetAsync(s->d_counters, 0, 16, s->stream));
+
+    // schedule: sweep windows when the step table is much larger than L2 (GFASORT_WINDOW: total steps
+    // resident across all sweeps, 0 = static schedule, -1 = auto)
+    {
+        SS_CUDA(cudaMalloc(&s->d_work, 8));
+        long w = cfg && cfg->total_threads == 1 ? 0 : env_long("GFASORT_WINDOW", -1);
+        long k = env_long("GFASORT_SWEEPS", 4);
+        if (w < 0) w = (ix->S * sizeof(StepRec) > (64ull << 20)) ? (1l << 20) : 0;
+        if (k < 1) k = 1;
+        if ((uint64_t)w >= s->samp_len || s->samp_len / (uint64_t)k < 1024) w = 0;
+        s->n_sweeps = (uint32_t)k;
+        s->window_steps = w > 0 ? std::max<uint64_t>((uint64_t)w / (uint64_t)k, 1024) : 0;
+        s->chunk_updates = (uint32_t)std::max<long>(32, env_long("GFASORT_CHUNK", 128));
+    }
+
+    // L2 management: the position array is the only re-used data; the step records stream through.
+    s->l2_policy = (int)env_long("GFASORT_L2_POLICY", 1);
+    const long fetch = env_long("GFASORT_L2_FETCH", 32);
+    if (fetch == 32 || fetch == 64 || fetch == 128) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)fetch);
+    if (s->l2_policy == 2) {
+        cudaDeviceProp prop;
+        SS_CUDA(cudaGetDeviceProperties(&prop, s->device));
+        const size_t bytes = s->n_elems * esz;
+        const size_t set_aside = std::min<size_t>((size_t)prop.persistingL2CacheMaxSize, bytes);
+        if (set_aside > 0) {
+            SS_CUDA(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, set_aside));
+            cudaStreamAttrValue attr{};
+            attr.accessPolicyWindow.base_ptr = s->d_pos;
+            attr.accessPolicyWindow.num_bytes = std::min<size_t>(bytes, (size_t)prop.accessPolicyMaxWindowSize);
+            attr.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)set_aside / (double)bytes);
+            attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+            attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+            SS_CUDA(cudaStreamSetAttribute(s->stream, cudaStreamAttributeAccessPolicyWindow, &attr));
+        }
+    }
     *out = s;
     return GFS_OK;
 #undef SS_CUDA
@@ -1123,17 +1395,18 @@ extern "C" int gfs_sgd_session_upload(gfs_sgd_session* s, const double* position
     if (!s || !positions) { set_error("gfs_sgd_session_upload: null argument"); return GFS_ERR_INVALID; }
     GFS_CUDA(cudaSetDevice(s->device));
     const double t0 = now_s();
-    if (s->dims == 0) {
-        GFS_CUDA(cudaMemcpyAsync(s->d_pos, positions, s->ix->N * 8, cudaMemcpyHostToDevice, s->stream));
-    } else if (s->f64 && s->DS == s->dims) {
-        GFS_CUDA(cudaMemcpyAsync(s->d_pos, positions, s->ix->N * 2 * s->dims * 8, cudaMemcpyHostToDevice, s->stream));
+    const uint64_t N = s->ix->N;
+    const uint32_t ends = s->dims == 0 ? 1 : 2, D = s->dims == 0 ? 1 : s->dims;
+    const uint32_t* perm = s->ix->d_new_of_old;
+    if (!perm && s->f64 && s->DS == D) {
+        GFS_CUDA(cudaMemcpyAsync(s->d_pos, positions, N * ends * D * 8, cudaMemcpyHostToDevice, s->stream));
     } else {
-        const uint64_t n_ends = s->ix->N * 2;
-        if (!s->d_stage) GFS_CUDA(cudaMalloc(&s->d_stage, n_ends * s->dims * 8));
-        GFS_CUDA(cudaMemcpyAsync(s->d_stage, positions, n_ends * s->dims * 8, cudaMemcpyHostToDevice, s->stream));
-        const uint64_t n = n_ends * s->DS;
-        if (s->f64) layout_to_device<double><<<(unsigned)((n + 255) / 256), 256, 0, s->stream>>>(s->d_stage, (double*)s->d_pos, n_ends, s->dims, s->DS);
-        else layout_to_device<float><<<(unsigned)((n + 255) / 256), 256, 0, s->stream>>>(s->d_stage, (float*)s->d_pos, n_ends, s->dims, s->DS);
+        if (!s->d_stage) GFS_CUDA(cudaMalloc(&s->d_stage, N * ends * D * 8));
+        GFS_CUDA(cudaMemcpyAsync(s->d_stage, positions, N * ends * D * 8, cudaMemcpyHostToDevice, s->stream));
+        const uint64_t n = N * ends * s->DS;
+        const unsigned grid = (unsigned)((n + 255) / 256);
+        if (s->f64) pos_to_device<double><<<grid, 256, 0, s->stream>>>(s->d_stage, (double*)s->d_pos, N, ends, D, s->DS, perm);
+        else pos_to_device<float><<<grid, 256, 0, s->stream>>>(s->d_stage, (float*)s->d_pos, N, ends, D, s->DS, perm);
         GFS_CUDA(cudaGetLastError());
     }
     GFS_CUDA(cudaStreamSynchronize(s->stream));
@@ -1158,16 +1431,17 @@ extern "C" int gfs_sgd_session_download(gfs_sgd_session* s, double* positions) {
     int rc = session_flush_events(s);
     if (rc) return rc;
     const double t0 = now_s();
-    if (s->dims == 0) {
-        GFS_CUDA(cudaMemcpyAsync(positions, s->d_pos, s->ix->N * 8, cudaMemcpyDeviceToHost, s->stream));
-    } else if (s->f64 && s->DS == s->dims) {
-        GFS_CUDA(cudaMemcpyAsync(positions, s->d_pos, s->ix->N * 2 * s->dims * 8, cudaMemcpyDeviceToHost, s->stream));
+    const uint64_t N = s->ix->N;
+    const uint32_t ends = s->dims == 0 ? 1 : 2, D = s->dims == 0 ? 1 : s->dims;
+    const uint32_t* perm = s->ix->d_new_of_old;
+    if (!perm && s->f64 && s->DS == D) {
+        GFS_CUDA(cudaMemcpyAsync(positions, s->d_pos, N * ends * D * 8, cudaMemcpyDeviceToHost, s->stream));
     } else {
-        const uint64_t n_ends = s->ix->N * 2;
-        if (!s->d_stage) GFS_CUDA(cudaMalloc(&s->d_stage, n_ends * s->dims * 8));
-        const uint64_t n = n_ends * s->dims;
-        if (s->f64) layout_from_device<double><<<(unsigned)((n + 255) / 256), 256, 0, s->stream>>>((const double*)s->d_pos, s->d_stage, n_ends, s->dims, s->DS);
-        else layout_from_device<float><<<(unsigned)((n + 255) / 256), 256, 0, s->stream>>>((const float*)s->d_pos, s->d_stage, n_ends, s->dims, s->DS);
+        if (!s->d_stage) GFS_CUDA(cudaMalloc(&s->d_stage, N * ends * D * 8));
+        const uint64_t n = N * ends * D;
+        const unsigned grid = (unsigned)((n + 255) / 256);
+        if (s->f64) pos_from_device<double><<<grid, 256, 0, s->stream>>>((const double*)s->d_pos, s->d_stage, N, ends, D, s->DS, perm);
+        else pos_from_device<float><<<grid, 256, 0, s->stream>>>((const float*)s->d_pos, s->d_stage, N, ends, D, s->DS, perm);
         GFS_CUDA(cudaGetLastError());
         GFS_CUDA(cudaMemcpyAsync(positions, s->d_stage, n * 8, cudaMemcpyDeviceToHost, s->stream));
     }
@@ -1190,6 +1464,8 @@ extern "C" int gfs_sgd_session_run(gfs_sgd_session* s, uint64_t epoch_begin, uin
     sgd_kernel_fn fn = pick_kernel(s->dims, s->f64, s->aggregate, DS);
     SgdArgs a{};
     a.g = make_kgraph(s->ix, s->params, s->d_zetas, s->zlen);
+    a.g.l2_hints = s->l2_policy == 1 ? 1u : 0u;
+    a.g.samp_base = s->samp_base; a.g.samp_len = s->samp_len;
     a.epochs = s->d_epochs;
     a.epoch_begin = (uint32_t)epoch_begin; a.epoch_end = (uint32_t)epoch_end;
     a.slice = slice; a.n_slices = n_slices;
@@ -1197,12 +1473,33 @@ extern "C" int gfs_sgd_session_run(gfs_sgd_session* s, uint64_t epoch_begin, uin
     a.seed_lo = (uint32_t)s->params.seed; a.seed_hi = (uint32_t)(s->params.seed >> 32);
     a.tid_base = (uint32_t)s->rng_thread_base;
     a.positions = s->d_pos;
+    a.window_steps = s->window_steps; a.n_sweeps = s->n_sweeps; a.chunk_updates = s->chunk_updates;
+    a.work_ctr = s->d_work;
+    GFS_CUDA(cudaMemsetAsync(s->d_work, 0, 8, s->stream));
     void* kargs[] = {(void*)&a};
     GFS_CUDA(cudaEventRecord(s->ev0, s->stream));
     GFS_CUDA(cudaLaunchCooperativeKernel((const void*)fn, dim3(s->grid), dim3(s->block), kargs, s->smem_bytes, s->stream));
     GFS_CUDA(cudaEventRecord(s->ev1, s->stream));
     s->ev_pending = true;
     s->launches += 1;
+    return GFS_OK;
+}
+
+// Device-side snapshot / restore of the positions (asynchronous, on the session's stream): lets a
+// caller rerun the schedule from the same start without another host->device copy.
+extern "C" int gfs_sgd_session_save(gfs_sgd_session* s) {
+    if (!s) { set_error("gfs_sgd_session_save: null session"); return GFS_ERR_INVALID; }
+    GFS_CUDA(cudaSetDevice(s->device));
+    const size_t bytes = s->n_elems * (s->f64 ? 8 : 4);
+    if (!s->d_saved) GFS_CUDA(cudaMalloc(&s->d_saved, bytes));
+    GFS_CUDA(cudaMemcpyAsync(s->d_saved, s->d_pos, bytes, cudaMemcpyDeviceToDevice, s->stream));
+    return GFS_OK;
+}
+extern "C" int gfs_sgd_session_restore(gfs_sgd_session* s) {
+    if (!s || !s->d_saved) { set_error("gfs_sgd_session_restore: nothing saved"); return GFS_ERR_INVALID; }
+    GFS_CUDA(cudaSetDevice(s->device));
+    const size_t bytes = s->n_elems * (s->f64 ? 8 : 4);
+    GFS_CUDA(cudaMemcpyAsync(s->d_pos, s->d_saved, bytes, cudaMemcpyDeviceToDevice, s->stream));
     return GFS_OK;
 }
 
@@ -1294,7 +1591,7 @@ extern "C" int gfs_stress(const gfs_index* ix, uint32_t dims, int32_t layout_ord
     if (e != cudaSuccess) { cudaFree(d_coords); set_error("gfs_stress alloc"); return GFS_ERR_CUDA; }
     gfs_sgd_params dummy{};
     KernelGraph g = make_kgraph(ix, dummy, nullptr, 0);
-    stress_kernel<<<grid, STRESS_BLOCK>>>(g, d_coords, dims, stride, samples, (uint32_t)seed, (uint32_t)(seed >> 32), d_partial);
+    stress_kernel<<<grid, STRESS_BLOCK>>>(g, ix->d_old_of_new, d_coords, dims, stride, samples, (uint32_t)seed, (uint32_t)(seed >> 32), d_partial);
     std::vector<double> part((size_t)grid * 3);
     e = cudaMemcpy(part.data(), d_partial, part.size() * 8, cudaMemcpyDeviceToHost);
     cudaFree(d_coords); cudaFree(d_partial);

@@ -19,6 +19,8 @@
 #include <thread>
 #include <vector>
 
+#include <cuda_runtime.h>
+
 #include "../../include/gfasort_cuda.h"
 
 namespace gfs { void set_error(const std::string& s); }
@@ -56,40 +58,15 @@ struct Element {
 
 }  // namespace
 
-struct gfs_synth_graph {
-    uint64_t N = 0, P = 0, S = 0;
-    uint64_t path_begin = 0, path_end = 0;
-    std::vector<uint32_t> node_len;
-    std::vector<uint64_t> path_first;   // path_end - path_begin + 1 entries, local to the generated range
-    uint64_t* steps = nullptr;          // S handles (malloc'd: avoid value-initialising tens of GB)
-    ~gfs_synth_graph() { std::free(steps); }
-};
-
-extern "C" int gfs_synth_create_range(const gfs_synth_spec* spec, uint64_t path_begin, uint64_t path_end,
-                                      gfs_synth_graph** out);
-
-extern "C" int gfs_synth_create(const gfs_synth_spec* spec, gfs_synth_graph** out) {
-    if (!spec) { gfs::set_error("gfs_synth_create: null spec"); return GFS_ERR_INVALID; }
-    return gfs_synth_create_range(spec, 0, spec->num_paths, out);
-}
-
-extern "C" int gfs_synth_create_range(const gfs_synth_spec* spec, uint64_t path_begin, uint64_t path_end,
-                                      gfs_synth_graph** out) {
-    if (!spec || !out) { gfs::set_error("gfs_synth_create: null argument"); return GFS_ERR_INVALID; }
-    const uint64_t N = spec->num_nodes, P = spec->num_paths;
-    if (N < 4 || N >= (1ull << 31) || P == 0 || path_begin > path_end || path_end > P) {
-        gfs::set_error("gfs_synth_create: need 4 <= num_nodes < 2^31, num_paths >= 1, valid path range");
-        return GFS_ERR_INVALID;
-    }
-    gfs_synth_graph* g = new (std::nothrow) gfs_synth_graph();
-    if (!g) { gfs::set_error("gfs_synth_create: out of memory"); return GFS_ERR_INVALID; }
-    g->N = N; g->P = P; g->path_begin = path_begin; g->path_end = path_end;
-
+namespace {
+// chain structure + pre-permutation node lengths (serial, cheap)
+void build_chain(uint64_t N, uint64_t seed_in, std::vector<Element>& chain, std::vector<uint32_t>& len) {
+    struct { uint64_t seed; } spec_{seed_in};
+    auto* spec = &spec_;
     // ---- chain structure (serial, cheap) ----
     SplitMix64 rng(spec->seed);
-    std::vector<Element> chain;
     chain.reserve((size_t)(N * 0.93) + 16);
-    std::vector<uint32_t> len(N);
+    len.assign(N, 0);
     auto backbone_len = [&]() -> uint32_t {   // 1 + Geometric(mean 31), capped at 1024
         double u = rng.unit();
         double v = std::floor(std::log(1.0 - u) / std::log(1.0 - 1.0 / 32.0));
@@ -130,6 +107,77 @@ extern "C" int gfs_synth_create_range(const gfs_synth_spec* spec, uint64_t path_
             if (until_site) --until_site;
         }
     }
+}
+
+uint64_t walk_path(const std::vector<Element>& chain, const std::vector<uint32_t>& perm, uint64_t seed, uint64_t p, uint64_t* dst) {
+    uint64_t n = 0;
+    const size_t ne = chain.size();
+    for (size_t ei = 0; ei < ne; ++ei) {
+        const Element& e = chain[ei];
+        if (e.kind == EL_BACKBONE) {
+            if (dst) dst[n] = (uint64_t)perm[e.first_node] << 1;
+            ++n;
+            continue;
+        }
+        const bool alt = mix3(seed, p, ei) < e.alt_threshold;
+        if (e.kind == EL_SNP) {
+            if (dst) dst[n] = (uint64_t)perm[e.first_node + (alt ? 1 : 0)] << 1;
+            ++n;
+        } else if (e.kind == EL_INDEL) {
+            if (alt) { if (dst) dst[n] = (uint64_t)perm[e.first_node] << 1; ++n; }
+        } else {
+            if (dst) {
+                if (!alt) for (uint32_t i = 0; i < e.count; ++i) dst[n + i] = (uint64_t)perm[e.first_node + i] << 1;
+                else for (uint32_t i = 0; i < e.count; ++i) dst[n + i] = ((uint64_t)perm[e.first_node + e.count - 1 - i] << 1) | 1;
+            }
+            n += e.count;
+        }
+    }
+    return n;
+}
+template <class F> void parallel_for(uint64_t n, F fn) {
+    unsigned hw = std::thread::hardware_concurrency();
+    if (hw == 0) hw = 4;
+    const unsigned nt = (unsigned)std::min<uint64_t>(hw, std::max<uint64_t>(n, 1));
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < nt; ++t) th.emplace_back([&, t] { for (uint64_t k = t; k < n; k += nt) fn(k); });
+    for (auto& x : th) x.join();
+}
+}  // namespace
+
+struct gfs_synth_graph {
+    uint64_t N = 0, P = 0, S = 0;
+    uint64_t path_begin = 0, path_end = 0;
+    std::vector<uint32_t> node_len;
+    std::vector<uint64_t> path_first;   // path_end - path_begin + 1 entries, local to the generated range
+    uint64_t* steps = nullptr;          // S handles (malloc'd: avoid value-initialising tens of GB)
+    bool pinned = false;                // steps came from cudaHostAlloc
+    ~gfs_synth_graph() { if (pinned) cudaFreeHost(steps); else std::free(steps); }
+};
+
+extern "C" int gfs_synth_create_range(const gfs_synth_spec* spec, uint64_t path_begin, uint64_t path_end,
+                                      gfs_synth_graph** out);
+
+extern "C" int gfs_synth_create(const gfs_synth_spec* spec, gfs_synth_graph** out) {
+    if (!spec) { gfs::set_error("gfs_synth_create: null spec"); return GFS_ERR_INVALID; }
+    return gfs_synth_create_range(spec, 0, spec->num_paths, out);
+}
+
+extern "C" int gfs_synth_create_range(const gfs_synth_spec* spec, uint64_t path_begin, uint64_t path_end,
+                                      gfs_synth_graph** out) {
+    if (!spec || !out) { gfs::set_error("gfs_synth_create: null argument"); return GFS_ERR_INVALID; }
+    const uint64_t N = spec->num_nodes, P = spec->num_paths;
+    if (N < 4 || N >= (1ull << 31) || P == 0 || path_begin > path_end || path_end > P) {
+        gfs::set_error("gfs_synth_create: need 4 <= num_nodes < 2^31, num_paths >= 1, valid path range");
+        return GFS_ERR_INVALID;
+    }
+    gfs_synth_graph* g = new (std::nothrow) gfs_synth_graph();
+    if (!g) { gfs::set_error("gfs_synth_create: out of memory"); return GFS_ERR_INVALID; }
+    g->N = N; g->P = P; g->path_begin = path_begin; g->path_end = path_end;
+
+    std::vector<Element> chain;
+    std::vector<uint32_t> len;
+    build_chain(N, spec->seed, chain, len);
     // ---- id permutation ----
     std::vector<uint32_t> perm(N);
     for (uint64_t i = 0; i < N; ++i) perm[i] = (uint32_t)i;
@@ -147,46 +195,19 @@ extern "C" int gfs_synth_create_range(const gfs_synth_spec* spec, uint64_t path_
     const uint64_t np = path_end - path_begin;
     std::vector<uint64_t> count(np, 0);
     const uint64_t seed = spec->seed;
-    auto walk = [&](uint64_t p, uint64_t* dst) -> uint64_t {
-        uint64_t n = 0;
-        const size_t ne = chain.size();
-        for (size_t ei = 0; ei < ne; ++ei) {
-            const Element& e = chain[ei];
-            if (e.kind == EL_BACKBONE) {
-                if (dst) dst[n] = (uint64_t)perm[e.first_node] << 1;
-                ++n;
-                continue;
-            }
-            const bool alt = mix3(seed, p, ei) < e.alt_threshold;
-            if (e.kind == EL_SNP) {
-                if (dst) dst[n] = (uint64_t)perm[e.first_node + (alt ? 1 : 0)] << 1;
-                ++n;
-            } else if (e.kind == EL_INDEL) {
-                if (alt) { if (dst) dst[n] = (uint64_t)perm[e.first_node] << 1; ++n; }
-            } else {
-                if (dst) {
-                    if (!alt) for (uint32_t i = 0; i < e.count; ++i) dst[n + i] = (uint64_t)perm[e.first_node + i] << 1;
-                    else for (uint32_t i = 0; i < e.count; ++i) dst[n + i] = ((uint64_t)perm[e.first_node + e.count - 1 - i] << 1) | 1;
-                }
-                n += e.count;
-            }
-        }
-        return n;
-    };
-    unsigned hw = std::thread::hardware_concurrency();
-    if (hw == 0) hw = 4;
-    const unsigned nt = (unsigned)std::min<uint64_t>(hw, std::max<uint64_t>(np, 1));
-    auto parallel_paths = [&](auto fn) {
-        std::vector<std::thread> th;
-        for (unsigned t = 0; t < nt; ++t)
-            th.emplace_back([&, t] { for (uint64_t k = t; k < np; k += nt) fn(k); });
-        for (auto& x : th) x.join();
-    };
+    auto walk = [&](uint64_t p, uint64_t* dst) -> uint64_t { return walk_path(chain, perm, seed, p, dst); };
+    auto parallel_paths = [&](auto fn) { parallel_for(np, fn); };
     parallel_paths([&](uint64_t k) { count[k] = walk(path_begin + k, nullptr); });
     g->path_first.assign(np + 1, 0);
     for (uint64_t k = 0; k < np; ++k) g->path_first[k + 1] = g->path_first[k] + count[k];
     g->S = g->path_first[np];
-    g->steps = (uint64_t*)std::malloc(std::max<uint64_t>(g->S, 1) * sizeof(uint64_t));
+    const size_t step_bytes = std::max<uint64_t>(g->S, 1) * sizeof(uint64_t);
+    if (spec->pinned) {
+        void* ptr = nullptr;
+        if (cudaHostAlloc(&ptr, step_bytes, cudaHostAllocDefault) == cudaSuccess) { g->steps = (uint64_t*)ptr; g->pinned = true; }
+        else cudaGetLastError();   // no device / no pinned memory: fall back to pageable
+    }
+    if (!g->steps) g->steps = (uint64_t*)std::malloc(step_bytes);
     if (!g->steps) { delete g; gfs::set_error("gfs_synth_create: out of memory for steps"); return GFS_ERR_INVALID; }
     parallel_paths([&](uint64_t k) { walk(path_begin + k, g->steps + g->path_first[k]); });
     *out = g;
@@ -211,3 +232,18 @@ extern "C" int gfs_synth_arrays(const gfs_synth_graph* g, const uint64_t** step_
 }
 
 extern "C" void gfs_synth_free(gfs_synth_graph* g) { delete g; }
+
+// Step count of every path without materialising any steps (ranks of a multi-GPU run need the
+// global path_first_step to pick their slice).
+extern "C" int gfs_synth_path_counts(const gfs_synth_spec* spec, uint64_t* counts) {
+    if (!spec || !counts) { gfs::set_error("gfs_synth_path_counts: null argument"); return GFS_ERR_INVALID; }
+    const uint64_t N = spec->num_nodes, P = spec->num_paths;
+    if (N < 4 || N >= (1ull << 31) || P == 0) { gfs::set_error("gfs_synth_path_counts: bad spec"); return GFS_ERR_INVALID; }
+    std::vector<Element> chain;
+    std::vector<uint32_t> len;
+    build_chain(N, spec->seed, chain, len);
+    std::vector<uint32_t> perm;   // unused when dst == nullptr
+    const uint64_t seed = spec->seed;
+    parallel_for(P, [&](uint64_t p) { counts[p] = walk_path(chain, perm, seed, p, nullptr); });
+    return GFS_OK;
+}

@@ -17,6 +17,7 @@ in the CUDA library — nothing here falls back to the CPU.
 from __future__ import annotations
 
 import ctypes as C
+import os
 import sys
 from dataclasses import dataclass, replace
 
@@ -58,7 +59,8 @@ class PathIndex:
 
     @staticmethod
     def from_arrays(step_handles: np.ndarray, path_first: np.ndarray, node_len: np.ndarray, graph=None,
-                    path_begin: int = 0, path_end: int | None = None, device: int = -1) -> "PathIndex":
+                    path_begin: int = 0, path_end: int | None = None, device: int = -1,
+                    relabel: int | None = None, new_of_old: np.ndarray | None = None) -> "PathIndex":
         step_handles = np.ascontiguousarray(step_handles, dtype=np.uint64)
         path_first = np.ascontiguousarray(path_first, dtype=np.uint64)
         node_len = np.ascontiguousarray(node_len, dtype=np.uint32)
@@ -66,9 +68,14 @@ class PathIndex:
         if path_end is None:
             path_end = P
         h = C.c_void_p()
+        if relabel is None:
+            relabel = 2 if new_of_old is not None else int(os.environ.get("GFASORT_RELABEL", "1") != "0")
+        perm = None
+        if new_of_old is not None:
+            perm = np.ascontiguousarray(new_of_old, dtype=np.uint32)
         check(lib().gfs_index_build_shard(_p(step_handles, u64p), _p(path_first, u64p), _p(node_len, u32p),
                                           len(step_handles), P, len(node_len), path_begin, path_end, device,
-                                          C.byref(h)))
+                                          relabel, _p(perm, u32p) if perm is not None else None, C.byref(h)))
         s0, s1 = int(path_first[path_begin]), int(path_first[path_end])
         return PathIndex(h, step_handles[s0:s1], path_first[path_begin:path_end + 1] - path_first[path_begin],
                          len(node_len), graph)
@@ -77,6 +84,12 @@ class PathIndex:
         if self._h:
             lib().gfs_index_free(self._h)
             self._h = None
+
+    def relabel_permutation(self) -> np.ndarray:
+        """new_of_old[N]: the library's internal node order (identity when relabelling is off)."""
+        out = np.zeros(self._n, dtype=np.uint32)
+        check(lib().gfs_index_export_relabel(self._h, _p(out, u32p)))
+        return out
 
     def __del__(self):
         try:

@@ -22,8 +22,8 @@ SHAPES = {
 
 class SynthGraph:
     def __init__(self, num_nodes: int, num_paths: int, seed: int = 42, permute_ids: bool = True,
-                 path_begin: int = 0, path_end: int | None = None):
-        spec = SynthSpec(num_nodes, num_paths, seed, int(permute_ids), 0)
+                 path_begin: int = 0, path_end: int | None = None, pinned: bool = False):
+        spec = SynthSpec(num_nodes, num_paths, seed, int(permute_ids), int(pinned))
         if path_end is None:
             path_end = num_paths
         self._h = C.c_void_p()
@@ -60,3 +60,11 @@ class SynthGraph:
         (reference src/ygs.rs:60-79, src/sgd.rs:736-754); `space` for `Y` needs path lengths."""
         counts = np.diff(self.path_first)
         return {"sum_path_step_count": int(counts.sum()), "max_path_step_count": int(counts.max())}
+
+
+def synth_path_counts(num_nodes: int, num_paths: int, seed: int = 42) -> np.ndarray:
+    """Steps per path of the synthetic graph, without generating the steps."""
+    spec = SynthSpec(num_nodes, num_paths, seed, 1, 0)
+    counts = np.zeros(num_paths, dtype=np.uint64)
+    check(lib().gfs_synth_path_counts(C.byref(spec), counts.ctypes.data_as(u64p)))
+    return counts

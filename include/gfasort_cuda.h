@@ -76,7 +76,10 @@ typedef struct gfs_launch_cfg {
                                   multi-GPU run passes r * 2^24 so streams never overlap */
     void* stream;              /* cudaStream_t to launch on (NULL = library-owned stream) */
     void* device_positions;    /* optional caller-owned device buffer for the positions (1D: N doubles;
-                                  nD: N*2*dims_stride coordinates); NULL = library-allocated */
+                                  nD: N*2*dims_stride coordinates), in the library's internal node
+                                  order (gfs_index_export_relabel); NULL = library-allocated */
+    uint64_t sample_begin;     /* sampled steps are drawn from [sample_begin, sample_end) of the index */
+    uint64_t sample_end;       /* (partners still range over whole paths); 0,0 = every step */
 } gfs_launch_cfg;
 
 /* Per-run statistics (replaces the reference's stderr progress lines, src/sgd.rs:377-385, 609-611). */
@@ -109,7 +112,14 @@ int gfs_index_build(const uint64_t* step_handles, const uint64_t* path_first_ste
  * multi-GPU run owns.  step_handles/path_first_step still describe the whole graph. */
 int gfs_index_build_shard(const uint64_t* step_handles, const uint64_t* path_first_step, const uint32_t* node_len,
                           uint64_t S, uint64_t P, uint64_t N, uint64_t path_begin, uint64_t path_end,
-                          int32_t device, gfs_index** out);
+                          int32_t device, int32_t relabel_mode, const uint32_t* new_of_old, gfs_index** out);
+/* Internal node numbering.  The library stores positions in the order in which nodes first appear
+ * along the paths (path-adjacent nodes then share cache lines); uploads and downloads permute, so
+ * callers never see it.  relabel_mode: 0 = keep the caller's dense order, 1 = first-appearance
+ * order of this index's own steps (gfs_index_build's default; GFASORT_RELABEL=0 disables), 2 = the
+ * permutation new_of_old[N] supplied by the caller — ranks of a multi-GPU run must share one
+ * permutation so that their position replicas can be all-reduced element-wise. */
+int gfs_index_export_relabel(const gfs_index* ix, uint32_t* new_of_old /*N*/);
 /* Copies back what PathIndex holds: step_to_position (src/sgd.rs:18) and PathInfo.length (:29).
  * Either pointer may be NULL.  step_to_path / step_to_rank / first_step / step_count are functions
  * of path_first_step alone and stay on the host. */
@@ -158,6 +168,9 @@ int gfs_sgd_session_download(gfs_sgd_session* s, double* positions);         /* 
 int gfs_sgd_session_run(gfs_sgd_session* s, uint64_t epoch_begin, uint64_t epoch_end, uint32_t slice,
                         uint32_t n_slices);
 int gfs_sgd_session_sync(gfs_sgd_session* s);
+/* Asynchronous device-side snapshot / restore of the positions (rerun a schedule from the same start). */
+int gfs_sgd_session_save(gfs_sgd_session* s);
+int gfs_sgd_session_restore(gfs_sgd_session* s);
 /* Device pointer + element count + element size (8 or 4) of the position buffer. */
 int gfs_sgd_session_positions(gfs_sgd_session* s, void** dev_ptr, uint64_t* n_elems, uint32_t* elem_bytes);
 int gfs_sgd_session_stats(gfs_sgd_session* s, gfs_stats* stats);             /* synchronises first */
@@ -170,13 +183,15 @@ typedef struct gfs_synth_spec {
     uint64_t num_paths;   /* P */
     uint64_t seed;
     uint32_t permute_ids; /* 1 = randomly permute node ids (scrambled initial order) */
-    uint32_t reserved;
+    uint32_t pinned;      /* 1 = allocate the step array in page-locked host memory (cudaHostAlloc) */
 } gfs_synth_spec;
 typedef struct gfs_synth_graph gfs_synth_graph;
 int gfs_synth_create(const gfs_synth_spec* spec, gfs_synth_graph** out);
 /* Only paths [path_begin, path_end) are materialised (a rank's shard); node_len covers all N nodes. */
 int gfs_synth_create_range(const gfs_synth_spec* spec, uint64_t path_begin, uint64_t path_end,
                            gfs_synth_graph** out);
+/* Step count of each of the P paths, without materialising steps. */
+int gfs_synth_path_counts(const gfs_synth_spec* spec, uint64_t* counts /*P*/);
 int gfs_synth_dims(const gfs_synth_graph* g, uint64_t* S, uint64_t* P, uint64_t* N);
 /* Pointers into the generator's own storage (valid until gfs_synth_free). */
 int gfs_synth_arrays(const gfs_synth_graph* g, const uint64_t** step_handles, const uint64_t** path_first_step,

@@ -757,18 +757,25 @@ void oracle_init_layout(const oracle_graph* og, uint64_t dims, uint64_t seed, do
     }
 }
 
-// path_linear_sgd (sgd.rs:237-614).  x_inout: N doubles (in: init, out: final), N = live nodes.
-// mode 0 = reference (checker thread), 1 = exact-count epochs.  draw 0 = xoshiro, 1 = philox.
-int oracle_path_linear_sgd(const oracle_graph* og, const oracle_params* op, int mode, int draw,
-                           uint32_t philox_stream, uint64_t philox_tid_base, double* x_inout,
-                           uint64_t n_x, oracle_stats* st) {
-    GraphView g = view(og); Params P = conv(op);
-    PathIndex ix = PathIndex::from_graph(g);                      // :247
+// A prebuilt PathIndex + handle map, so that bench.py's repeated baseline steps time the SGD loop
+// and not the (serial) index construction.  The reference rebuilds the index on every call
+// (sgd.rs:247); reusing it only makes this baseline faster than the reference.
+struct oracle_index { PathIndex ix; HandleMap h2i_live; };
+void* oracle_index_create(const oracle_graph* og) {
+    GraphView g = view(og);
+    oracle_index* oi = new oracle_index();
+    oi->ix = PathIndex::from_graph(g);
+    oi->h2i_live = build_h2i(g, node_ids_of(g), true);
+    return oi;
+}
+void oracle_index_free(void* p) { delete (oracle_index*)p; }
+
+static int sgd_1d_with_index(const GraphView& g, const Params& P, const PathIndex& ix, const HandleMap& h2i, int mode,
+                             int draw, uint32_t philox_stream, uint64_t philox_tid_base, double* x_inout, uint64_t n_x,
+                             oracle_stats* st) {
     bool valid = false;
     for (auto& pi : ix.paths) if (pi.step_count > 1) { valid = true; break; }   // :250-261
     if (!valid) return 1;
-    auto ids = node_ids_of(g);
-    HandleMap h2i = build_h2i(g, ids, true);
     std::vector<std::atomic<uint64_t>> X(n_x);
     for (uint64_t i = 0; i < n_x; ++i) X[i].store(f64_bits(x_inout[i]));
     oracle_stats dummy; Stats s{};
@@ -778,6 +785,24 @@ int oracle_path_linear_sgd(const oracle_graph* og, const oracle_params* op, int 
     if (!st) st = &dummy;
     st->applied = s.applied; st->attempts = s.attempts; st->seconds = s.seconds; st->epochs = s.epochs;
     return 0;
+}
+
+// path_linear_sgd (sgd.rs:237-614).  x_inout: N doubles (in: init, out: final), N = live nodes.
+// mode 0 = reference (checker thread), 1 = exact-count epochs.  draw 0 = xoshiro, 1 = philox.
+int oracle_path_linear_sgd(const oracle_graph* og, const oracle_params* op, int mode, int draw,
+                           uint32_t philox_stream, uint64_t philox_tid_base, double* x_inout,
+                           uint64_t n_x, oracle_stats* st) {
+    GraphView g = view(og); Params P = conv(op);
+    PathIndex ix = PathIndex::from_graph(g);                      // :247
+    HandleMap h2i = build_h2i(g, node_ids_of(g), true);
+    return sgd_1d_with_index(g, P, ix, h2i, mode, draw, philox_stream, philox_tid_base, x_inout, n_x, st);
+}
+int oracle_path_linear_sgd_ix(void* index, const oracle_graph* og, const oracle_params* op, int mode, int draw,
+                              uint32_t philox_stream, uint64_t philox_tid_base, double* x_inout,
+                              uint64_t n_x, oracle_stats* st) {
+    oracle_index* oi = (oracle_index*)index;
+    return sgd_1d_with_index(view(og), conv(op), oi->ix, oi->h2i_live, mode, draw, philox_stream, philox_tid_base,
+                             x_inout, n_x, st);
 }
 
 // path_linear_sgd_layout (sgd.rs:773-1188).  coords_inout in Layout order (N*2*dims doubles).

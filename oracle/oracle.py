@@ -100,6 +100,12 @@ def lib():
         L.oracle_path_linear_sgd.restype = C.c_int
         L.oracle_path_linear_sgd.argtypes = [C.POINTER(_Graph), C.POINTER(OracleParams), C.c_int, C.c_int,
                                              C.c_uint32, C.c_uint64, f64p, C.c_uint64, C.POINTER(OracleStats)]
+        L.oracle_index_create.restype = C.c_void_p
+        L.oracle_index_create.argtypes = [C.POINTER(_Graph)]
+        L.oracle_index_free.restype = None
+        L.oracle_index_free.argtypes = [C.c_void_p]
+        L.oracle_path_linear_sgd_ix.restype = C.c_int
+        L.oracle_path_linear_sgd_ix.argtypes = [C.c_void_p] + L.oracle_path_linear_sgd.argtypes
         L.oracle_path_linear_sgd_layout.restype = C.c_int
         L.oracle_path_linear_sgd_layout.argtypes = [C.POINTER(_Graph), C.POINTER(OracleParams), C.c_uint64,
                                                     C.c_int, C.c_int, C.c_uint32, C.c_uint64, f64p,
@@ -310,13 +316,37 @@ def init_layout(g: Graph, dims: int, seed: int = 9399220) -> np.ndarray:
     return coords
 
 
+class PrebuiltIndex:
+    """PathIndex + handle map built once (bench.py's baseline leg reuses it across steps)."""
+
+    def __init__(self, g: Graph):
+        self._g = g
+        cg = g.c()
+        self._h = lib().oracle_index_create(C.byref(cg))
+
+    def close(self):
+        if self._h:
+            lib().oracle_index_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def path_linear_sgd(g: Graph, p: OracleParams, mode=MODE_REFERENCE, draw=DRAW_XOSHIRO, x0=None,
-                    philox_tid_base=0):
+                    philox_tid_base=0, index: "PrebuiltIndex | None" = None):
     x = init_x(g) if x0 is None else np.array(x0, dtype=np.float64)
     st = OracleStats()
     cg = g.c()
-    rc = lib().oracle_path_linear_sgd(C.byref(cg), C.byref(p), mode, draw, STREAM_SGD, philox_tid_base,
-                                      _p(x, f64p), len(x), C.byref(st))
+    if index is not None:
+        rc = lib().oracle_path_linear_sgd_ix(index._h, C.byref(cg), C.byref(p), mode, draw, STREAM_SGD,
+                                             philox_tid_base, _p(x, f64p), len(x), C.byref(st))
+    else:
+        rc = lib().oracle_path_linear_sgd(C.byref(cg), C.byref(p), mode, draw, STREAM_SGD, philox_tid_base,
+                                          _p(x, f64p), len(x), C.byref(st))
     return x, st, rc
 
 
