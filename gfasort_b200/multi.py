@@ -30,6 +30,7 @@ class Shard:
     sample_end: int
     path_begin: int        # paths whose records this rank needs (those the slice overlaps)
     path_end: int
+    first_step_of_path_begin: int = 0   # global step index of the first step of path_begin
 
     @property
     def steps(self) -> int:
@@ -43,10 +44,10 @@ def shard_steps(path_first: np.ndarray, rank: int, world: int) -> Shard:
     b = (S * rank) // world
     e = (S * (rank + 1)) // world
     if e <= b:
-        return Shard(rank, world, b, b, 0, 0)
+        return Shard(rank, world, b, b, 0, 0, 0)
     pb = int(np.searchsorted(path_first, b, side="right") - 1)
     pe = int(np.searchsorted(path_first, e - 1, side="right"))
-    return Shard(rank, world, b, e, pb, pe)
+    return Shard(rank, world, b, e, pb, pe, int(path_first[pb]))
 
 
 def epoch_quota(min_term_updates: int, shard: Shard, total_steps: int) -> int:
@@ -61,14 +62,17 @@ def reconcile(x, x_sync, mode: str, group=None):
     "avg": x <- mean over ranks.  "delta": x <- x_sync + sum over ranks of (x - x_sync); x_sync is
     then refreshed.  Returns x."""
     import torch.distributed as dist
-    world = dist.get_world_size(group)
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
     if world == 1:
         if x_sync is not None:
             x_sync.copy_(x)
         return x
     if mode == "avg":
-        dist.all_reduce(x, op=dist.ReduceOp.SUM, group=group)
-        x.mul_(1.0 / world)
+        if x.is_cuda:
+            dist.all_reduce(x, op=dist.ReduceOp.AVG, group=group)    # NCCL averages inside the collective
+        else:
+            dist.all_reduce(x, op=dist.ReduceOp.SUM, group=group)    # gloo has no AVG
+            x.mul_(1.0 / world)
     elif mode == "delta":
         # sum_g x_g = G*x_sync + sum_g delta_g  =>  x_new = sum_g x_g - (G-1)*x_sync
         dist.all_reduce(x, op=dist.ReduceOp.SUM, group=group)
@@ -78,3 +82,124 @@ def reconcile(x, x_sync, mode: str, group=None):
     if x_sync is not None:
         x_sync.copy_(x)
     return x
+
+
+# ------------------------------------------------------------------------------------------------
+# one rank of a replicated run (GPU only: drives the C-ABI session API)
+# ------------------------------------------------------------------------------------------------
+_DS = {0: 1, 1: 1, 2: 2, 3: 4, 4: 4, 5: 8, 6: 8, 7: 8, 8: 8}     # coordinate stride per node end (gfs_lib.cu pick_nd)
+
+
+class ReplicaRun:
+    """This rank's share of a `Y` (dims = 0) or `L` (dims >= 1) run.
+
+    index: the PathIndex of paths [shard.path_begin, shard.path_end) only (build_shard_index) — a
+    rank never needs the other ranks' records.  The positions live in a torch tensor (so
+    torch.distributed can all-reduce them in place) that the library's session uses as its position
+    buffer; the session launches on `self.stream`.
+    """
+
+    def __init__(self, index, n_nodes: int, shard: Shard, total_steps: int, params, dims: int = 0,
+                 device: int = 0, syncs_per_epoch: int = 1, mode: str = "avg", group=None,
+                 layout_f64: bool = False):
+        import ctypes as C
+
+        import torch
+
+        from ._cabi import LaunchCfg, check, lib
+        self.shard, self.mode, self.group, self.syncs = shard, mode, group, max(1, int(syncs_per_epoch))
+        self.dims, self.device = dims, device
+        self.index = index
+        self.N = int(n_nodes)
+        f64 = dims == 0 or layout_f64
+        n_elems = self.N if dims == 0 else self.N * 2 * _DS[dims]
+        self.x = torch.zeros(n_elems, dtype=torch.float64 if f64 else torch.float32, device=f"cuda:{device}")
+        self.x_sync = torch.empty_like(self.x) if mode == "delta" else None
+        self.stream = torch.cuda.Stream(device=device)
+        from dataclasses import replace
+        self.params = replace(params, min_term_updates=epoch_quota(params.min_term_updates, shard, total_steps))
+        self.global_updates_per_epoch = params.min_term_updates
+        cfg = LaunchCfg.default()
+        cfg.device = device
+        cfg.layout_f64 = int(layout_f64)
+        cfg.rng_thread_base = shard.rank << 24
+        cfg.stream = self.stream.cuda_stream
+        cfg.device_positions = self.x.data_ptr()
+        cfg.sample_begin = shard.sample_begin - shard.first_step_of_path_begin    # index-local step range
+        cfg.sample_end = cfg.sample_begin + shard.steps
+        self._h = C.c_void_p()
+        cp = self.params.c()
+        check(lib().gfs_sgd_session_create(self.index.handle, C.byref(cp), dims, C.byref(cfg), C.byref(self._h)))
+        self.n_epochs = params.iter_max + 1
+
+    def upload(self, positions):
+        """Host positions (f64, the caller's node order / Layout order) -> this rank's replica."""
+        import numpy as np
+
+        from ._cabi import check, f64p, lib
+        positions = np.ascontiguousarray(positions, dtype=np.float64)
+        check(lib().gfs_sgd_session_upload(self._h, positions.ctypes.data_as(f64p)))
+        if self.x_sync is not None:
+            self.x_sync.copy_(self.x)
+
+    def download(self):
+        import numpy as np
+
+        from ._cabi import check, f64p, lib
+        ends, d = (1, 1) if self.dims == 0 else (2, self.dims)
+        out = np.zeros(self.N * ends * d, dtype=np.float64)
+        check(lib().gfs_sgd_session_download(self._h, out.ctypes.data_as(f64p)))
+        return out
+
+    def run_epoch(self, epoch: int):
+        """One epoch of the schedule: `syncs` slices of this rank's quota, replicas reconciled after each."""
+        import torch
+
+        from ._cabi import check, lib
+        with torch.cuda.stream(self.stream):
+            for k in range(self.syncs):
+                check(lib().gfs_sgd_session_run(self._h, epoch, epoch + 1, k, self.syncs))
+                reconcile(self.x, self.x_sync, self.mode, self.group)
+
+    def stats(self) -> dict:
+        import ctypes as C
+
+        from ._cabi import Stats, check, lib
+        st = Stats()
+        check(lib().gfs_sgd_session_stats(self._h, C.byref(st)))
+        return st.as_dict()
+
+    def close(self):
+        from ._cabi import lib
+        if self._h:
+            lib().gfs_sgd_session_destroy(self._h)
+            self._h = None
+
+
+def build_shard_index(shard_handles, shard_first, node_len, device: int = 0, rank: int = 0, world: int = 1, group=None):
+    """PathIndex of this rank's paths, with ONE node relabelling for all ranks: rank 0 derives the
+    first-appearance order from its own records and broadcasts it, so that the position replicas
+    line up element-wise for the all-reduce.  shard_first is local to the shard (starts at 0)."""
+    import os
+
+    import numpy as np
+
+    from .sgd import PathIndex
+    assert int(shard_first[0]) == 0, "shard_first must be local to the shard (start at 0)"
+    if world == 1:
+        return PathIndex.from_arrays(shard_handles, shard_first, node_len, device=device)
+    import torch
+    import torch.distributed as dist
+    relabel = os.environ.get("GFASORT_RELABEL", "1") != "0"
+    if not relabel:
+        return PathIndex.from_arrays(shard_handles, shard_first, node_len, device=device, relabel=0)
+    perm = torch.empty(len(node_len), dtype=torch.int32, device=f"cuda:{device}")
+    ix = None
+    if rank == 0:
+        ix = PathIndex.from_arrays(shard_handles, shard_first, node_len, device=device, relabel=1)
+        perm.copy_(torch.from_numpy(ix.relabel_permutation().view(np.int32)))
+    dist.broadcast(perm, src=0, group=group)
+    if rank != 0:
+        ix = PathIndex.from_arrays(shard_handles, shard_first, node_len, device=device,
+                                   new_of_old=perm.cpu().numpy().view(np.uint32))
+    return ix
