@@ -35,45 +35,90 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
 }
 
 // ---- fast_precise_pow (src/sgd.rs:155-182) -----------------------------------------------------
-// __double2int_rz saturates and maps NaN to 0 exactly like Rust's `as i32`.
+// a^b = a^e * "a^(b-e)", e = trunc(b): the integer part by square-and-multiply, the fractional part by
+// the high-word bit trick.  __double2int_rz saturates and maps NaN to 0 exactly like Rust's `as i32`.
+// frac_pow is the bit trick alone (it is the whole function when e == 0, since 1.0 * x == x).
+__device__ __forceinline__ double frac_pow(double a, double bfrac) {
+    const int diff = (int)((unsigned)__double2hiint(a) - 1072632447u);       // wrapping, as release Rust
+    const int nh = __double2int_rz(__dadd_rn(__dmul_rn(bfrac, (double)diff), 1072632447.0));
+    return __hiloint2double(nh, 0);
+}
+// a^e, e >= 0, with exactly the multiplication order of the reference's loop (src/sgd.rs:171-179):
+// r = 1; for each bit of e from the LSB: if set r *= base; base *= base.
+__device__ __forceinline__ double int_pow(double a, int e) {
+    double base = a, r = 1.0;
+    while (e != 0) {
+        if (e & 1) r = __dmul_rn(r, base);
+        base = __dmul_rn(base, base);
+        e >>= 1;
+    }
+    return r;
+}
+// the two exponents the sampler ever uses for alpha = 1/(1-theta): 100 (theta = 0.99) and 1 (0.001);
+// same products in the same order as int_pow, without the loop.
+__device__ __forceinline__ double int_pow_100(double a) {
+    const double b2 = __dmul_rn(a, a), b4 = __dmul_rn(b2, b2), b8 = __dmul_rn(b4, b4), b16 = __dmul_rn(b8, b8);
+    const double b32 = __dmul_rn(b16, b16), b64 = __dmul_rn(b32, b32);
+    return __dmul_rn(__dmul_rn(b4, b32), b64);          // bits of 100: 4, 32, 64 (1.0 * b4 == b4)
+}
 __device__ __forceinline__ double fast_precise_pow(double a, double b) {
     const int e = __double2int_rz(b);
-    const int hi = __double2hiint(a);
-    const int diff = (int)((unsigned)hi - 1072632447u);
-    const int nh = __double2int_rz(__dadd_rn(__dmul_rn(__dsub_rn(b, (double)e), (double)diff), 1072632447.0));
-    const double frac = __hiloint2double(nh, 0);
-    double base = a, r = 1.0;
-    int ex = e;
-    while (ex != 0) {
-        if (ex & 1) r = __dmul_rn(r, base);
-        base = __dmul_rn(base, base);
-        ex >>= 1;
-    }
-    return __dmul_rn(r, frac);
+    return __dmul_rn(int_pow(a, e), frac_pow(a, __dsub_rn(b, (double)e)));
 }
 
 // Per-epoch constants of the Zipf sampler: pure functions of the current theta, computed once on
 // the host with the same formulas (src/sgd.rs:132, 143, 471).
 struct ZipfConsts {
     double theta;
-    double one_minus_theta;   // 1.0 - theta
+    double one_minus_theta;   // 1.0 - theta            (exponent of fpp(2/n, .): integer part 0)
     double alpha;             // 1.0 / (1.0 - theta)
     double z2;                // 1.0 + fast_precise_pow(0.5, theta)
+    double alpha_frac;        // alpha - trunc(alpha)
+    int alpha_e;              // trunc(alpha) as the reference's `as i32`
+    int pad;
 };
 
 // ---- DirtyZipfian::sample with min = 1, max = jump_space (src/sgd.rs:122-151) -------------------
-// __double2ull_rz saturates / maps negatives and NaN to 0 like Rust's `as u64`.
-__device__ __forceinline__ uint32_t dirty_zipf(uint32_t jump_space, const ZipfConsts& zc, double zeta, double u) {
+// Written without branches (the two fast paths become selects) so that several terms can be in
+// flight per thread, and split in two so that everything that does not need zeta — most of the
+// work — can be scheduled while the zeta load is still in flight.
+// __double2uint_rz saturates / maps negatives and NaN to 0 like Rust's `as u64` followed by
+// .min(max) with max < 2^32.
+struct ZipfPre { double n, num; };
+__device__ __forceinline__ ZipfPre dirty_zipf_pre(uint32_t jump_space, const ZipfConsts& zc) {
+    ZipfPre p;
+    p.n = (double)jump_space;
+    // 1 - theta has integer part 0 for every theta in (0, 1): fpp(2/n, 1-theta) is the bit trick alone
+    const double t0 = __ddiv_rn(2.0, p.n);
+    const double f1 = zc.one_minus_theta < 1.0 ? frac_pow(t0, zc.one_minus_theta) : fast_precise_pow(t0, zc.one_minus_theta);
+    p.num = __dsub_rn(1.0, f1);
+    return p;
+}
+__device__ __forceinline__ uint32_t dirty_zipf_post(uint32_t jump_space, const ZipfConsts& zc, const ZipfPre& p,
+                                                    double zeta, double u) {
     const double uz = __dmul_rn(u, zeta);
-    if (uz < 1.0) return 1u;
-    if (uz < zc.z2) return 2u;
-    const double n = (double)jump_space;
-    const double eta = __ddiv_rn(__dsub_rn(1.0, fast_precise_pow(__ddiv_rn(2.0, n), zc.one_minus_theta)),
-                                 __dsub_rn(1.0, __ddiv_rn(zc.z2, zeta)));
+    const double eta = __ddiv_rn(p.num, __dsub_rn(1.0, __ddiv_rn(zc.z2, zeta)));
     const double base = __dadd_rn(__dsub_rn(__dmul_rn(eta, u), eta), 1.0);
-    const double result = __dadd_rn(1.0, __dmul_rn(n, fast_precise_pow(base, zc.alpha)));
-    const unsigned long long z = __double2ull_rz(result);
-    return z > (unsigned long long)jump_space ? jump_space : (uint32_t)z;
+    double ip;
+    if (zc.alpha_e == 100) ip = int_pow_100(base);       // warp-uniform branches (per-epoch constant)
+    else if (zc.alpha_e == 1) ip = base;                 // 1.0 * base
+    else ip = int_pow(base, zc.alpha_e);
+    const double pw = __dmul_rn(ip, frac_pow(base, zc.alpha_frac));
+    const double result = __dadd_rn(1.0, __dmul_rn(p.n, pw));
+    uint32_t z = __double2uint_rz(result);
+    z = z > jump_space ? jump_space : z;
+    z = uz < zc.z2 ? 2u : z;                             // sgd.rs:142-144 (min + 1, not clamped to max)
+    z = uz < 1.0 ? 1u : z;                               // sgd.rs:139-141
+    return z;
+}
+__device__ __forceinline__ uint32_t dirty_zipf(uint32_t jump_space, const ZipfConsts& zc, double zeta, double u) {
+    return dirty_zipf_post(jump_space, zc, dirty_zipf_pre(jump_space, zc), zeta, u);
+}
+
+// exact u64 -> f64 for v < 2^52 (step offsets; gfs_index_build rejects longer paths): one DADD
+// instead of a 64-bit I2F.
+__device__ __forceinline__ double u52_to_f64(uint64_t v) {
+    return __dsub_rn(__hiloint2double(0x43300000 | (int)(v >> 32), (int)(uint32_t)v), 4503599627370496.0);
 }
 
 // ---- memory access helpers ---------------------------------------------------------------------
@@ -86,6 +131,8 @@ __device__ __forceinline__ StepRec load_rec(const StepRec* p) {
     r.node_rev = v.x; r.node_len = v.y; r.pos = ((uint64_t)v.w << 32) | v.z;
     return r;
 }
+// L2 eviction-priority hints: far partner records are read once (evict_first) so that they do not
+// push out what is re-read — the sampling window's records and the position array (evict_last).
 __device__ __forceinline__ uint64_t make_evict_first_policy() {
     uint64_t pol;
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));

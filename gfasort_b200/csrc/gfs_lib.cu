@@ -128,6 +128,8 @@ static void h_epochs(const gfs_sgd_params& p, std::vector<EpochDesc>& out) {
         d.zc.one_minus_theta = 1.0 - theta;
         d.zc.alpha = 1.0 / (1.0 - theta);
         d.zc.z2 = 1.0 + h_fast_precise_pow(0.5, theta);
+        d.zc.alpha_e = h_f64_as_i32(d.zc.alpha);
+        d.zc.alpha_frac = d.zc.alpha - (double)d.zc.alpha_e;
         d.updates = p.min_term_updates;
         out[e] = d;
     }
@@ -423,13 +425,46 @@ struct KernelGraph {
     uint32_t space;               // min(params.space, 2^32-1): compared with ranks < 2^32
     uint32_t space_max;
     uint32_t q;
-    uint32_t l2_hints;            // 1: records evict_first, positions evict_last (L2 cache-hint policies)
+    uint32_t q_is_100;            // 1: the quantisation step is the reference's 100 (constant division)
+    uint32_t blk_shift;           // path-of-block table granularity: block = step >> blk_shift
+    uint32_t l2_hints;            // bit 0: partner records evict_first, bit 1: sampled records evict_first,
+                                  // bit 2: positions evict_last
     uint64_t samp_base, samp_len; // sampled steps are drawn from [samp_base, samp_base + samp_len) (default 0, S)
 };
 
-struct SampledTerm {
+constexpr uint32_t SMEM_FS_MAX = 2048;         // first_step entries staged per block (16 KB)
+constexpr uint32_t BLK_TABLE = 4096;           // path-of-block entries staged per block (8 KB)
+
+// step -> path.  With the tables in shared memory: one 16-bit lookup (path of the first step of the
+// step's 2^shift-block) plus a short forward scan; otherwise a binary search over first_step.
+struct PathLookup {
+    const uint64_t* fs;           // P+1 entries, shared or global
+    const uint16_t* blk;          // BLK_TABLE entries in shared memory, or nullptr
+    uint32_t shift;
+    uint32_t P;
+    __device__ __forceinline__ uint32_t path_of(uint64_t s) const {
+        if (blk) {
+            uint32_t p = blk[(uint32_t)(s >> shift)];
+            while (s >= fs[p + 1]) ++p;
+            return p;
+        }
+        return find_path(fs, P, s);
+    }
+};
+
+// One term in flight.  The stages below are straight-line (selects, predicated loads) so that a
+// thread can interleave several slots: S1 issues the record load of the sampled step and the zeta
+// load, S2 turns the draw into the partner step and issues its record load, S3/S4 (in the kernel)
+// load the positions and apply the update.
+struct Slot {
     StepRec a, b;
-    uint64_t step_a, step_b;   // step indices (only the trace kernel reads them)
+    uint64_t step_a, step_b;   // step indices
+    uint64_t f;                // first step of the path
+    uint64_t r23;              // second half of the Philox block
+    double zeta;
+    uint32_t n, ra, J;
+    uint32_t coins;            // r.z
+    bool zipf, back, live;     // live: a partner is drawn (n > 1 and the Zipf branch has room to move)
     bool other_a, other_b;
     bool valid;
 };
@@ -437,58 +472,74 @@ struct SampledTerm {
 // Draw slots of one Philox block r (see oracle/gfs_oracle.cpp PhiloxDraw):
 //   step = mulhi64(r.y:r.x, S); u = ((r.w:r.z) >> 11) * 2^-53; uniform rank = mulhi64(r.w:r.z, n);
 //   coins = bits 0..3 of r.z (zipf, back, end_a, end_b).
-template <bool ND>
-__device__ __forceinline__ void sample_term(const KernelGraph& g, const uint64_t* fs, const double* s_zetas,
-                                            uint32_t s_zlen, const EpochDesc& ep, uint4 r, uint64_t win_base,
-                                            uint64_t win_len, SampledTerm& t) {
+__device__ __forceinline__ void sample_s1(const KernelGraph& g, const PathLookup& pl, const EpochDesc& ep, uint4 r,
+                                          uint64_t win_base, uint64_t win_len, bool active, Slot& t) {
     const uint64_t r01 = ((uint64_t)r.y << 32) | r.x;
-    const uint64_t r23 = ((uint64_t)r.w << 32) | r.z;
+    t.r23 = ((uint64_t)r.w << 32) | r.z;
+    t.coins = r.z;
     // step ~ U[win_base, win_base + win_len) on the circular sampling range; the default window
     // (samp_base, samp_len) = (0, S) is the reference's U[0, S) (sgd.rs:444)
     uint64_t s = win_base + __umul64hi(r01, win_len);
     if (s >= g.samp_base + g.samp_len) s -= g.samp_len;
-    const uint32_t p = find_path(fs, g.P, s);
-    const uint64_t f = fs[p];
-    const uint32_t n = (uint32_t)(fs[p + 1] - f);
-    const uint32_t ra = (uint32_t)(s - f);
-    const uint64_t pol_stream = make_evict_first_policy();
-    t.a = g.l2_hints ? load_rec_hint(g.recs + s, pol_stream) : load_rec(g.recs + s);   // issue early
-    t.valid = n > 1;                                 // path_step_count == 1 => continue (sgd.rs:448)
-    uint32_t rb = ra;
-    if (ep.cooling || (r.z & 1u)) {                  // sgd.rs:456
-        const bool back = ra > 0 && (((r.z >> 1) & 1u) || ra == n - 1);   // sgd.rs:460
-        const bool fwd = !back && ra < n - 1;                              // sgd.rs:475
-        if (back || fwd) {
-            const uint32_t span = back ? ra : n - ra - 1;
-            const uint32_t J = span < g.space ? span : g.space;
-            uint32_t k = J > g.space_max ? g.space_max + (J - g.space_max) / g.q + 1 : J;   // sgd.rs:463-467
-            k = k < g.zlen - 1 ? k : g.zlen - 1;                                           // sgd.rs:469
-            const double zeta = k < s_zlen ? s_zetas[k] : __ldg(g.zetas + k);
-            const double u = (double)(r23 >> 11) * (1.0 / 9007199254740992.0);
-            const uint32_t z = dirty_zipf(J, ep.zc, zeta, u);
-            if (back) rb = ra >= z ? ra - z : 0u;                                          // saturating_sub
-            else { const uint64_t x = (uint64_t)ra + z; rb = x < n - 1 ? (uint32_t)x : n - 1; }
-        }
-    } else {
-        rb = (uint32_t)__umul64hi(r23, (uint64_t)n);                                       // sgd.rs:493-494
-    }
-    t.valid = t.valid && (ra != rb);                                                      // sgd.rs:497
     t.step_a = s;
-    t.step_b = t.valid ? f + rb : s;
-    t.b = g.l2_hints ? load_rec_hint(g.recs + t.step_b, pol_stream) : load_rec(g.recs + t.step_b);
-    t.other_a = t.other_b = false;
-    if (ND) {                                                                              // sgd.rs:1060-1077
-        const bool rev_a = t.a.node_rev & 1u, rev_b = t.b.node_rev & 1u;
-        bool ua = (r.z >> 2) & 1u;
-        if (ua) { t.a.pos += t.a.node_len; ua = !rev_a; } else { ua = rev_a; }
-        bool ub = (r.z >> 3) & 1u;
-        if (ub) { t.b.pos += t.b.node_len; ub = !rev_b; } else { ub = rev_b; }
-        t.other_a = ua; t.other_b = ub;
+    if (active) t.a = (g.l2_hints & 2u) ? load_rec_hint(g.recs + s, make_evict_first_policy()) : load_rec(g.recs + s);
+    else { t.a.node_rev = 0; t.a.node_len = 0; t.a.pos = 0; }
+    const uint32_t p = pl.path_of(s);
+    t.f = pl.fs[p];
+    const uint32_t n = (uint32_t)(pl.fs[p + 1] - t.f);
+    const uint32_t ra = (uint32_t)(s - t.f);
+    t.n = n; t.ra = ra;
+    t.zipf = ep.cooling || (r.z & 1u);                                                     // sgd.rs:456
+    t.back = ra > 0 && (((r.z >> 1) & 1u) || ra == n - 1);                                 // sgd.rs:460
+    const bool fwd = !t.back && ra < n - 1;                                                // sgd.rs:475
+    const bool moves = t.back || fwd;
+    const uint32_t span = t.back ? ra : n - ra - 1;
+    const uint32_t J = span < g.space ? span : g.space;
+    t.J = J;
+    uint32_t k = J;                                                                        // sgd.rs:463-467
+    if (J > g.space_max) {
+        const uint32_t over = J - g.space_max;
+        k = g.space_max + (g.q_is_100 ? over / 100u : over / g.q) + 1;
     }
+    k = k < g.zlen - 1 ? k : g.zlen - 1;                                                   // sgd.rs:469
+    t.live = active && n > 1 && (!t.zipf || moves);        // n == 1 => continue (sgd.rs:448)
+    t.zeta = 1.0;
+    if (t.live && t.zipf) t.zeta = __ldg(g.zetas + k);
 }
 
-__device__ __forceinline__ double term_distance(const SampledTerm& t) {
-    return fabs(__dsub_rn((double)t.a.pos, (double)t.b.pos));                              // sgd.rs:509-513
+template <bool ND>
+__device__ __forceinline__ void sample_s2(const KernelGraph& g, const EpochDesc& ep, Slot& t) {
+    const uint32_t n = t.n, ra = t.ra;
+    // u = (r23 >> 11) * 2^-53 (sgd.rs:136 through PhiloxDraw::unit)
+    const double u = __dmul_rn((double)(t.r23 >> 11), 1.0 / 9007199254740992.0);
+    const ZipfPre pre = dirty_zipf_pre(t.J, ep.zc);
+    const uint32_t z = dirty_zipf_post(t.J, ep.zc, pre, t.zeta, u);
+    const uint32_t room = n - 1 - ra;
+    const uint32_t rb_back = ra >= z ? ra - z : 0u;                                        // saturating_sub
+    const uint32_t rb_fwd = z < room ? ra + z : n - 1;                                     // min(ra + z, n - 1)
+    const uint32_t rb_zipf = t.back ? rb_back : rb_fwd;
+    const uint32_t rb_unif = (uint32_t)__umul64hi(t.r23, (uint64_t)n);                     // sgd.rs:493-494
+    const uint32_t rb = t.zipf ? rb_zipf : rb_unif;
+    t.valid = t.live && ra != rb;                                                          // sgd.rs:497
+    t.step_b = t.valid ? t.f + rb : t.step_a;
+    if (t.valid) t.b = (g.l2_hints & 1u) ? load_rec_hint(g.recs + t.step_b, make_evict_first_policy())
+                                         : load_rec(g.recs + t.step_b);
+    else t.b = t.a;
+    t.other_a = t.other_b = false;
+}
+
+// nD end choice (sgd.rs:1060-1077); needs both records.
+__device__ __forceinline__ void sample_ends(Slot& t) {
+    const bool rev_a = t.a.node_rev & 1u, rev_b = t.b.node_rev & 1u;
+    bool ua = (t.coins >> 2) & 1u;
+    if (ua) { t.a.pos += t.a.node_len; ua = !rev_a; } else { ua = rev_a; }
+    bool ub = (t.coins >> 3) & 1u;
+    if (ub) { t.b.pos += t.b.node_len; ub = !rev_b; } else { ub = rev_b; }
+    t.other_a = ua; t.other_b = ub;
+}
+
+__device__ __forceinline__ double term_distance(const Slot& t) {
+    return fabs(__dsub_rn(u52_to_f64(t.a.pos), u52_to_f64(t.b.pos)));                      // sgd.rs:509-513
 }
 
 // =============================================================================================
@@ -581,8 +632,6 @@ template <> __device__ __forceinline__ void red_coords<double, 8>(double* p, con
 // K2 / K3 — persistent SGD term kernel
 // =============================================================================================
 constexpr int SGD_BLOCK = 256;
-constexpr uint32_t SMEM_ZETAS_MAX = 4096;      // doubles staged per block (32 KB)
-constexpr uint32_t SMEM_FS_MAX = 2048;         // first_step entries staged per block (16 KB)
 
 struct SgdArgs {
     KernelGraph g;
@@ -594,25 +643,24 @@ struct SgdArgs {
     uint32_t seed_lo, seed_hi;
     uint32_t tid_base;
     void* positions;             // 1D: double[N]; nD: CT[N*2*DS]
-    // sweep scheduling (window_steps > 0): warps pull chunks of `chunk_updates` updates from *work_ctr;
-    // chunk c of an epoch samples its steps from one of `n_sweeps` windows of `window_steps` steps that
-    // slide once over the step array per epoch, so the records being sampled stay L2-resident.
+    // sweep scheduling (window_steps > 0): warps claim chunks of `chunk_updates` updates from *work_ctr;
+    // chunk c samples its steps from a window of `window_steps` steps that slides once over the step
+    // array per epoch, so the records being sampled stay L2-resident.
     uint64_t window_steps;
-    uint32_t n_sweeps;
     uint32_t chunk_updates;
     unsigned long long* work_ctr;
 };
 
 // 1D update of one warp's terms (sgd.rs:512-576), optionally merging lanes that hit the same node.
+// r_x is the displacement computed from positions xi, xj that were loaded earlier (stage S3).
 template <bool AGG>
 __device__ __forceinline__ void apply_1d(double* X, unsigned warp_mask, int lane, bool valid, uint32_t i,
-                                         uint32_t j, double d, double eta, bool hints) {
+                                         uint32_t j, double d, double eta, double xi, double xj, bool keep) {
     double r_x = 0.0;
-    const uint64_t pol_keep = make_evict_last_policy();
+    const uint64_t pol = make_evict_last_policy();
+    auto add = [&](double* p, double v) { if (keep) red_pos_keep(p, v, pol); else atomicAdd(p, v); };
     if (valid) {
         const double mu = fmin(__dmul_rn(eta, __ddiv_rn(1.0, d)), 1.0);     // sgd.rs:518-520
-        const double xi = hints ? ld_pos_keep(X + i, pol_keep) : ld_pos(X + i);
-        const double xj = hints ? ld_pos_keep(X + j, pol_keep) : ld_pos(X + j);
         double dx = __dsub_rn(xi, xj);
         if (dx == 0.0) dx = 1e-9;                                            // sgd.rs:546-548
         const double mag = fabs(dx);
@@ -621,36 +669,36 @@ __device__ __forceinline__ void apply_1d(double* X, unsigned warp_mask, int lane
         r_x = __dmul_rn(r, dx);
     }
     if (AGG) {
-        bool lead;
         const unsigned vmask = __ballot_sync(warp_mask, valid);
-        const unsigned mi = __match_any_sync(warp_mask, i) & vmask; const unsigned pi = valid ? mi : 0u;
-        const double si = group_sum(warp_mask, pi, -r_x, lane, lead);
-        if (valid && lead) { if (hints) red_pos_keep(X + i, si, pol_keep); else atomicAdd(X + i, si); }
-        const unsigned mj = __match_any_sync(warp_mask, j) & vmask; const unsigned pj = valid ? mj : 0u;
-        const double sj = group_sum(warp_mask, pj, r_x, lane, lead);
-        if (valid && lead) { if (hints) red_pos_keep(X + j, sj, pol_keep); else atomicAdd(X + j, sj); }
-    } else if (valid) {
-        if (hints) { red_pos_keep(X + i, -r_x, pol_keep); red_pos_keep(X + j, r_x, pol_keep); }
-        else {
-            atomicAdd(X + i, -r_x);                                          // sgd.rs:575
-            atomicAdd(X + j, r_x);                                           // sgd.rs:576
+        const unsigned mi = __match_any_sync(warp_mask, i) & vmask;
+        const unsigned mj = __match_any_sync(warp_mask, j) & vmask;
+        const bool dup = valid && (__popc(mi) > 1 || __popc(mj) > 1);
+        if (!__any_sync(warp_mask, dup)) {               // common case: 64 distinct nodes in the warp
+            if (valid) { add(X + i, -r_x); add(X + j, r_x); }
+            return;
         }
+        bool lead;
+        const double si = group_sum(warp_mask, valid ? mi : 0u, -r_x, lane, lead);
+        if (valid && lead) add(X + i, si);
+        const double sj = group_sum(warp_mask, valid ? mj : 0u, r_x, lane, lead);
+        if (valid && lead) add(X + j, sj);
+    } else if (valid) {
+        add(X + i, -r_x);                                                    // sgd.rs:575
+        add(X + j, r_x);                                                     // sgd.rs:576
     }
 }
 
 // nD update (sgd.rs:1079-1149) on coordinates laid out [node][end][DS] (DS >= D, padded with zeros).
 template <typename CT, int D, int DS, bool AGG>
 __device__ __forceinline__ void apply_nd(CT* C, unsigned warp_mask, int lane, bool valid, uint32_t idx_i,
-                                         uint32_t idx_j, double d, double eta) {
+                                         uint32_t idx_j, double d, double eta, const CT (&ci)[DS], const CT (&cj)[DS]) {
     using A = Arith<CT>;
     CT di[DS], dj[DS];
 #pragma unroll
     for (int k = 0; k < DS; ++k) { di[k] = CT(0); dj[k] = CT(0); }
     if (valid) {
         const CT mu = (CT)fmin(__dmul_rn(eta, __ddiv_rn(1.0, d)), 1.0);      // sgd.rs:1085-1086
-        CT ci[DS], cj[DS], dl[DS];
-        ld_coords<CT, DS>(C + (size_t)idx_i * DS, ci);
-        ld_coords<CT, DS>(C + (size_t)idx_j * DS, cj);
+        CT dl[DS];
         CT mag_sq = CT(0);
 #pragma unroll
         for (int k = 0; k < D; ++k) { dl[k] = A::sub(ci[k], cj[k]); mag_sq = A::add(mag_sq, A::mul(dl[k], dl[k])); }
@@ -662,15 +710,20 @@ __device__ __forceinline__ void apply_nd(CT* C, unsigned warp_mask, int lane, bo
         for (int k = 0; k < D; ++k) { const CT rd = A::mul(r, dl[k]); di[k] = -rd; dj[k] = rd; }
     }
     if (AGG) {
-        bool lead_i, lead_j;
         const unsigned vmask = __ballot_sync(warp_mask, valid);
-        const unsigned mi = __match_any_sync(warp_mask, idx_i) & vmask; const unsigned pi = valid ? mi : 0u;
+        const unsigned mi = __match_any_sync(warp_mask, idx_i) & vmask;
+        const unsigned mj = __match_any_sync(warp_mask, idx_j) & vmask;
+        const bool dup = valid && (__popc(mi) > 1 || __popc(mj) > 1);
+        if (!__any_sync(warp_mask, dup)) {
+            if (valid) { red_coords<CT, DS>(C + (size_t)idx_i * DS, di); red_coords<CT, DS>(C + (size_t)idx_j * DS, dj); }
+            return;
+        }
+        bool lead_i, lead_j;
 #pragma unroll
-        for (int k = 0; k < D; ++k) di[k] = group_sum(warp_mask, pi, di[k], lane, lead_i);
+        for (int k = 0; k < D; ++k) di[k] = group_sum(warp_mask, valid ? mi : 0u, di[k], lane, lead_i);
         if (valid && lead_i) red_coords<CT, DS>(C + (size_t)idx_i * DS, di);
-        const unsigned mj = __match_any_sync(warp_mask, idx_j) & vmask; const unsigned pj = valid ? mj : 0u;
 #pragma unroll
-        for (int k = 0; k < D; ++k) dj[k] = group_sum(warp_mask, pj, dj[k], lane, lead_j);
+        for (int k = 0; k < D; ++k) dj[k] = group_sum(warp_mask, valid ? mj : 0u, dj[k], lane, lead_j);
         if (valid && lead_j) red_coords<CT, DS>(C + (size_t)idx_j * DS, dj);
     } else if (valid) {
         red_coords<CT, DS>(C + (size_t)idx_i * DS, di);
@@ -678,20 +731,30 @@ __device__ __forceinline__ void apply_nd(CT* C, unsigned warp_mask, int lane, bo
     }
 }
 
-// D == 0: 1D `Y` (CT must be double).  D >= 1: nD `L`.
-template <typename CT, int D, int DS, bool AGG>
-__global__ void __launch_bounds__(SGD_BLOCK, 4)
+// D == 0: 1D `Y` (CT must be double).  D >= 1: nD `L`.  K: terms in flight per thread.
+template <typename CT, int D, int DS, bool AGG, int K>
+__global__ void __launch_bounds__(SGD_BLOCK, (K > 1 ? 3 : 4))
 sgd_kernel(const SgdArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    // shared: first_step (P+1 u64) + path-of-block table (BLK_TABLE u16) when the path table fits
     uint64_t* s_fs = reinterpret_cast<uint64_t*>(smem_raw);
-    const bool fs_in_smem = a.g.P + 1 <= SMEM_FS_MAX;
-    const uint32_t n_fs = fs_in_smem ? a.g.P + 1 : 0;
-    double* s_zetas = reinterpret_cast<double*>(smem_raw + (size_t)n_fs * 8);
-    const uint32_t s_zlen = a.g.zlen < SMEM_ZETAS_MAX ? a.g.zlen : SMEM_ZETAS_MAX;
+    const bool tables = a.g.P + 1 <= SMEM_FS_MAX;
+    const uint32_t n_fs = tables ? a.g.P + 1 : 0;
+    uint16_t* s_blk = reinterpret_cast<uint16_t*>(smem_raw + (size_t)n_fs * 8);
     for (uint32_t k = threadIdx.x; k < n_fs; k += blockDim.x) s_fs[k] = a.g.first_step[k];
-    for (uint32_t k = threadIdx.x; k < s_zlen; k += blockDim.x) s_zetas[k] = a.g.zetas[k];
     __syncthreads();
-    const uint64_t* fs = fs_in_smem ? s_fs : a.g.first_step;
+    if (tables) {
+        for (uint32_t k = threadIdx.x; k < BLK_TABLE; k += blockDim.x) {
+            const uint64_t s0 = (uint64_t)k << a.g.blk_shift;
+            s_blk[k] = (uint16_t)(s0 < a.g.S ? find_path(s_fs, a.g.P, s0) : a.g.P - 1);
+        }
+        __syncthreads();
+    }
+    PathLookup pl;
+    pl.fs = tables ? s_fs : a.g.first_step;
+    pl.blk = tables ? s_blk : nullptr;
+    pl.shift = a.g.blk_shift;
+    pl.P = a.g.P;
 
     const unsigned warp_mask = __activemask();
     const int lane = threadIdx.x & 31;
@@ -701,30 +764,66 @@ sgd_kernel(const SgdArgs a) {
     uint64_t applied = 0, attempts0 = attempt;
     const uint2 key = make_uint2(a.seed_lo, a.seed_hi);
 
-    // one sampled term for every active lane of the warp; returns whether this lane applied an update
-    auto attempt_once = [&](const EpochDesc& ep, bool active, uint64_t win_base, uint64_t win_len) -> bool {
-        SampledTerm t;
-        t.valid = false;
-        double d = 0.0;
-        if (active) {
+    // K terms per lane per call, their stages interleaved so that K record / position loads are in
+    // flight per thread.  Slot k is active while the lane still owes more than k updates; returns how
+    // many updates this lane applied.  K = 1 keeps the strictly sequential semantics of one reference
+    // worker thread (the single-thread parity tests run it).
+    auto attempt_batch = [&](const EpochDesc& ep, uint32_t owed, uint64_t win_base, uint64_t win_len) -> uint32_t {
+        Slot t[K];
+        double dist[K];
+        CT ci[K][DS], cj[K][DS];
+        uint32_t idx_i[K], idx_j[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const bool active = owed > (uint32_t)k;
             const uint4 r = philox4x32_10(make_uint4((uint32_t)attempt, (uint32_t)(attempt >> 32),
                                                      a.tid_base + tid, STREAM_SGD), key);
-            ++attempt;
-            sample_term<(D > 0)>(a.g, fs, s_zetas, s_zlen, ep, r, win_base, win_len, t);
-            d = term_distance(t);
-            const uint32_t na = t.a.node_rev >> 1, nb = t.b.node_rev >> 1;
-            t.valid = t.valid && d != 0.0 && na < a.g.N && nb < a.g.N;     // sgd.rs:514, 525-538
+            attempt += active ? 1 : 0;
+            sample_s1(a.g, pl, ep, r, win_base, win_len, active, t[k]);
         }
-        if constexpr (D == 0) {
-            apply_1d<AGG>(reinterpret_cast<double*>(a.positions), warp_mask, lane, t.valid,
-                          t.a.node_rev >> 1, t.b.node_rev >> 1, d, ep.eta, a.g.l2_hints != 0);
-        } else {
-            const uint32_t idx_i = (t.a.node_rev >> 1) * 2 + (t.other_a ? 1u : 0u);   // sgd.rs:1099-1103
-            const uint32_t idx_j = (t.b.node_rev >> 1) * 2 + (t.other_b ? 1u : 0u);
-            apply_nd<CT, (D > 0 ? D : 1), DS, AGG>(reinterpret_cast<CT*>(a.positions), warp_mask, lane, t.valid,
-                                                   idx_i, idx_j, d, ep.eta);
+#pragma unroll
+        for (int k = 0; k < K; ++k) sample_s2<(D > 0)>(a.g, ep, t[k]);
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            if (D > 0) sample_ends(t[k]);
+            dist[k] = term_distance(t[k]);
+            const uint32_t na = t[k].a.node_rev >> 1, nb = t[k].b.node_rev >> 1;
+            t[k].valid = t[k].valid && dist[k] != 0.0 && na < a.g.N && nb < a.g.N;         // sgd.rs:514, 525-538
+            if constexpr (D == 0) {
+                idx_i[k] = na; idx_j[k] = nb;
+                const double* X = reinterpret_cast<const double*>(a.positions);
+                ci[k][0] = cj[k][0] = 0.0;
+                if (t[k].valid) {
+                    const bool keep = (a.g.l2_hints & 4u) != 0;
+                    const uint64_t pol = make_evict_last_policy();
+                    ci[k][0] = keep ? ld_pos_keep(X + na, pol) : ld_pos(X + na);
+                    cj[k][0] = keep ? ld_pos_keep(X + nb, pol) : ld_pos(X + nb);
+                }
+            } else {
+                idx_i[k] = na * 2 + (t[k].other_a ? 1u : 0u);                              // sgd.rs:1099-1103
+                idx_j[k] = nb * 2 + (t[k].other_b ? 1u : 0u);
+                const CT* C = reinterpret_cast<const CT*>(a.positions);
+#pragma unroll
+                for (int q = 0; q < DS; ++q) { ci[k][q] = CT(0); cj[k][q] = CT(0); }
+                if (t[k].valid) {
+                    ld_coords<CT, DS>(C + (size_t)idx_i[k] * DS, ci[k]);
+                    ld_coords<CT, DS>(C + (size_t)idx_j[k] * DS, cj[k]);
+                }
+            }
         }
-        return t.valid;
+        uint32_t n_applied = 0;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            if constexpr (D == 0) {
+                apply_1d<AGG>(reinterpret_cast<double*>(a.positions), warp_mask, lane, t[k].valid, idx_i[k], idx_j[k],
+                              dist[k], ep.eta, ci[k][0], cj[k][0], (a.g.l2_hints & 4u) != 0);
+            } else {
+                apply_nd<CT, (D > 0 ? D : 1), DS, AGG>(reinterpret_cast<CT*>(a.positions), warp_mask, lane, t[k].valid,
+                                                       idx_i[k], idx_j[k], dist[k], ep.eta, ci[k], cj[k]);
+            }
+            n_applied += t[k].valid ? 1u : 0u;
+        }
+        return n_applied;
     };
 
     if (a.window_steps == 0) {
@@ -735,45 +834,54 @@ sgd_kernel(const SgdArgs a) {
             const uint64_t quota = m / T + (tid < m % T ? 1 : 0);
             uint64_t done = 0;
             for (;;) {
-                const bool active = done < quota;
-                if (!__any_sync(warp_mask, active)) break;
-                if (attempt_once(ep, active, a.g.samp_base, a.g.samp_len)) { ++done; ++applied; }   // sgd.rs:579
+                const uint64_t owed64 = quota - done;
+                const uint32_t owed = owed64 > (uint64_t)K ? (uint32_t)K : (uint32_t)owed64;
+                if (!__any_sync(warp_mask, owed != 0)) break;
+                const uint32_t got = attempt_batch(ep, owed, a.g.samp_base, a.g.samp_len);          // sgd.rs:579
+                done += got; applied += got;
             }
         }
     } else {
-        // sweep schedule
+        // sweep schedule: the launch's updates are cut into chunks of `chunk_updates`; a warp claims the next
+        // chunk c from a global counter and samples its steps from the window [base(c), base(c) + window_steps),
+        // base(c) = (c mod chunks_per_epoch) * samp_len / chunks_per_epoch.  Claiming in order keeps all warps
+        // on neighbouring chunks (a static assignment lets them drift apart by SM speed), so the windows in
+        // use at any moment cover about n_warps * chunk_updates * samp_len / m + window_steps consecutive
+        // steps, whose records — and, with the node relabelling, the positions of their nodes — stay in L2
+        // while the sweep passes over them.
         const uint32_t n_lanes = __popc(warp_mask);
         const uint32_t lane_rank = __popc(warp_mask & ((1u << lane) - 1u));
         const int leader = __ffs(warp_mask) - 1;
+        const uint32_t C = a.chunk_updates;
         const uint64_t m = a.epochs[a.epoch_begin].updates / a.n_slices +
                            (a.slice < a.epochs[a.epoch_begin].updates % a.n_slices ? 1 : 0);
-        const uint64_t cpe = (m + a.chunk_updates - 1) / a.chunk_updates;                  // chunks per epoch
+        const uint64_t cpe = (m + C - 1) / C;                                           // chunks per epoch
         const uint64_t total = cpe * (uint64_t)(a.epoch_end - a.epoch_begin);
-        const uint64_t K = a.n_sweeps;
-        const uint64_t per_sweep = (cpe + K - 1) / K;          // chunks one sweep handles per epoch
-        const uint64_t span = a.g.samp_len / K;                // steps one sweep travels per epoch
-        uint32_t cur_e = 0xffffffffu;
-        EpochDesc ep;
+        const double steps_per_chunk = (double)a.g.samp_len / (double)(cpe ? cpe : 1);
+        // chunks of the current epoch are [c_lo, c_lo + cpe)
+        uint32_t e = a.epoch_begin;
+        uint64_t c_lo = 0;
+        EpochDesc ep = a.epochs[e];
         for (;;) {
             unsigned long long c = 0;
             if (lane == leader) c = atomicAdd(a.work_ctr, 1ull);
             c = __shfl_sync(warp_mask, c, leader);
             if (c >= total) break;
-            const uint32_t e = a.epoch_begin + (uint32_t)(c / cpe);
-            const uint64_t cc = c % cpe;
-            if (e != cur_e) { ep = a.epochs[e]; cur_e = e; }
-            const uint64_t left = m - cc * a.chunk_updates;
-            const uint32_t n_upd = left < a.chunk_updates ? (uint32_t)left : a.chunk_updates;
-            const uint32_t quota = n_upd / n_lanes + (lane_rank < n_upd % n_lanes ? 1u : 0u);
-            const uint64_t k = cc % K, j = cc / K;
-            uint64_t win_base = k * span + (uint64_t)(((unsigned __int128)j * span) / per_sweep);
-            if (win_base >= a.g.samp_len) win_base -= a.g.samp_len;
-            win_base += a.g.samp_base;
+            while (c >= c_lo + cpe) { c_lo += cpe; ++e; ep = a.epochs[e]; }            // claims only move forward
+            const uint64_t cc = c - c_lo;
+            const uint64_t left = m - cc * C;
+            const uint32_t n_upd = left < C ? (uint32_t)left : C;
+            const uint32_t quota = n_lanes == 32 ? (n_upd >> 5) + (lane_rank < (n_upd & 31u) ? 1u : 0u)
+                                                 : n_upd / n_lanes + (lane_rank < n_upd % n_lanes ? 1u : 0u);
+            uint64_t off = (uint64_t)((double)cc * steps_per_chunk);
+            if (off >= a.g.samp_len) off = a.g.samp_len - 1;
+            const uint64_t win_base = a.g.samp_base + off;
             uint32_t done = 0;
             for (;;) {
-                const bool active = done < quota;
-                if (!__any_sync(warp_mask, active)) break;
-                if (attempt_once(ep, active, win_base, a.window_steps)) { ++done; ++applied; }
+                const uint32_t owed = quota - done;
+                if (!__any_sync(warp_mask, owed != 0)) break;
+                const uint32_t got = attempt_batch(ep, owed, win_base, a.window_steps);
+                done += got; applied += got;
             }
         }
     }
@@ -888,6 +996,8 @@ __global__ void dbg_zipf(const uint64_t* zmax, const double* theta, const double
     zc.one_minus_theta = __dsub_rn(1.0, theta[i]);
     zc.alpha = __ddiv_rn(1.0, __dsub_rn(1.0, theta[i]));
     zc.z2 = __dadd_rn(1.0, fast_precise_pow(0.5, theta[i]));
+    zc.alpha_e = __double2int_rz(zc.alpha);
+    zc.alpha_frac = __dsub_rn(zc.alpha, (double)zc.alpha_e);
     out[i] = dirty_zipf((uint32_t)zmax[i], zc, zeta[i], u[i]);
 }
 __global__ void dbg_philox(const uint32_t* ctr, const uint32_t* key, uint32_t* out, uint64_t n) {
@@ -907,8 +1017,12 @@ __global__ void dbg_trace(KernelGraph g, const EpochDesc* epochs, uint32_t epoch
     const uint64_t attempt = attempt0 + k;
     const uint4 r = philox4x32_10(make_uint4((uint32_t)attempt, (uint32_t)(attempt >> 32), tid, STREAM_SGD),
                                   make_uint2(seed_lo, seed_hi));
-    SampledTerm t;
-    sample_term<ND>(g, g.first_step, g.zetas, 0u, ep, r, g.samp_base, g.samp_len, t);
+    Slot t;
+    PathLookup pl;
+    pl.fs = g.first_step; pl.blk = nullptr; pl.shift = 0; pl.P = g.P;
+    sample_s1(g, pl, ep, r, g.samp_base, g.samp_len, true, t);
+    sample_s2<ND>(g, ep, t);
+    if (ND) sample_ends(t);
     const double d = term_distance(t);
     const bool ok = t.valid && d != 0.0;
     valid[k] = ok;
@@ -965,9 +1079,11 @@ struct gfs_sgd_session {
     uint64_t launches = 0;
     double h2d_s = 0, d2h_s = 0;
     bool ev_pending = false;
-    int l2_policy = 0;          // 0 none, 1 per-access cache hints, 2 persisting access-policy window
+    int l2_policy = 0;          // 0 none, 2 persisting access-policy window on the positions
+    int l2_hints = 7;           // KernelGraph::l2_hints
+    int inflight = 2;           // terms in flight per thread (kernel template parameter K)
     uint64_t window_steps = 0;  // 0 = static schedule
-    uint32_t n_sweeps = 1, chunk_updates = 128;
+    uint32_t chunk_updates = 128;
     unsigned long long* d_work = nullptr;
     void* d_saved = nullptr;    // gfs_sgd_session_save snapshot of the positions
     uint64_t samp_base = 0, samp_len = 0;
@@ -1225,24 +1341,28 @@ extern "C" int gfs_index_export_records(const gfs_index* ix, uint64_t* step_hand
 // ---------------------------------------------------------------------------------------------
 typedef void (*sgd_kernel_fn)(const SgdArgs);
 
-template <typename CT, bool AGG>
+template <typename CT, bool AGG, int K>
 static sgd_kernel_fn pick_nd(uint32_t dims, uint32_t& DS) {
     switch (dims) {
-        case 1: DS = 1; return sgd_kernel<CT, 1, 1, AGG>;
-        case 2: DS = 2; return sgd_kernel<CT, 2, 2, AGG>;
-        case 3: DS = 4; return sgd_kernel<CT, 3, 4, AGG>;
-        case 4: DS = 4; return sgd_kernel<CT, 4, 4, AGG>;
-        case 5: DS = 8; return sgd_kernel<CT, 5, 8, AGG>;
-        case 6: DS = 8; return sgd_kernel<CT, 6, 8, AGG>;
-        case 7: DS = 8; return sgd_kernel<CT, 7, 8, AGG>;
-        case 8: DS = 8; return sgd_kernel<CT, 8, 8, AGG>;
+        case 1: DS = 1; return sgd_kernel<CT, 1, 1, AGG, K>;
+        case 2: DS = 2; return sgd_kernel<CT, 2, 2, AGG, K>;
+        case 3: DS = 4; return sgd_kernel<CT, 3, 4, AGG, K>;
+        case 4: DS = 4; return sgd_kernel<CT, 4, 4, AGG, K>;
+        case 5: DS = 8; return sgd_kernel<CT, 5, 8, AGG, 1>;      // wide coordinates: one term in flight
+        case 6: DS = 8; return sgd_kernel<CT, 6, 8, AGG, 1>;
+        case 7: DS = 8; return sgd_kernel<CT, 7, 8, AGG, 1>;
+        case 8: DS = 8; return sgd_kernel<CT, 8, 8, AGG, 1>;
         default: return nullptr;
     }
 }
-static sgd_kernel_fn pick_kernel(uint32_t dims, bool f64, bool agg, uint32_t& DS) {
-    if (dims == 0) { DS = 1; return agg ? sgd_kernel<double, 0, 1, true> : sgd_kernel<double, 0, 1, false>; }
-    if (f64) return agg ? pick_nd<double, true>(dims, DS) : pick_nd<double, false>(dims, DS);
-    return agg ? pick_nd<float, true>(dims, DS) : pick_nd<float, false>(dims, DS);
+template <int K>
+static sgd_kernel_fn pick_kernel_k(uint32_t dims, bool f64, bool agg, uint32_t& DS) {
+    if (dims == 0) { DS = 1; return agg ? sgd_kernel<double, 0, 1, true, K> : sgd_kernel<double, 0, 1, false, K>; }
+    if (f64) return agg ? pick_nd<double, true, K>(dims, DS) : pick_nd<double, false, K>(dims, DS);
+    return agg ? pick_nd<float, true, K>(dims, DS) : pick_nd<float, false, K>(dims, DS);
+}
+static sgd_kernel_fn pick_kernel(uint32_t dims, bool f64, bool agg, int inflight, uint32_t& DS) {
+    return inflight >= 2 ? pick_kernel_k<2>(dims, f64, agg, DS) : pick_kernel_k<1>(dims, f64, agg, DS);
 }
 
 static KernelGraph make_kgraph(const gfs_index* ix, const gfs_sgd_params& p, const double* d_zetas, uint32_t zlen) {
@@ -1252,7 +1372,10 @@ static KernelGraph make_kgraph(const gfs_index* ix, const gfs_sgd_params& p, con
     g.space = (uint32_t)std::min<uint64_t>(p.space, 0xffffffffull);
     g.space_max = (uint32_t)std::min<uint64_t>(p.space_max, 0xffffffffull);
     g.q = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(p.space_quantization_step, 1), 0xffffffffull);
+    g.q_is_100 = g.q == 100 ? 1u : 0u;
     g.l2_hints = 0;
+    g.blk_shift = 0;
+    while (((ix->S ? ix->S - 1 : 0) >> g.blk_shift) >= BLK_TABLE) ++g.blk_shift;
     g.samp_base = 0; g.samp_len = ix->S;
     return g;
 }
@@ -1308,7 +1431,13 @@ extern "C" int gfs_sgd_session_create(const gfs_index* ix, const gfs_sgd_params*
     SS_CUDA(cudaEventCreate(&s->ev0));
     SS_CUDA(cudaEventCreate(&s->ev1));
 
-    sgd_kernel_fn fn = pick_kernel(dims, s->f64, s->aggregate, s->DS);
+    // terms in flight per thread: 2 for real runs; 1 (strictly sequential per thread, like one reference
+    // worker) when the caller asks for a handful of threads, which is what the bit-exact tests do
+    {
+        const long want_threads = cfg && cfg->total_threads ? (long)cfg->total_threads : env_long("GFASORT_THREADS", 0);
+        s->inflight = (int)env_long("GFASORT_INFLIGHT", (want_threads > 0 && want_threads <= 32) ? 1 : 2);
+    }
+    sgd_kernel_fn fn = pick_kernel(dims, s->f64, s->aggregate, s->inflight, s->DS);
     if (!fn) return fail(GFS_ERR_INVALID);
 
     // schedule, zeta table
@@ -1323,7 +1452,7 @@ extern "C" int gfs_sgd_session_create(const gfs_index* ix, const gfs_sgd_params*
 
     // launch shape: persistent, every block co-resident
     const uint32_t n_fs = (ix->P + 1 <= SMEM_FS_MAX) ? (uint32_t)ix->P + 1 : 0;
-    s->smem_bytes = (size_t)n_fs * 8 + (size_t)std::min<uint32_t>(s->zlen, SMEM_ZETAS_MAX) * 8;
+    s->smem_bytes = n_fs ? (size_t)n_fs * 8 + (size_t)BLK_TABLE * 2 : 0;
     SS_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_bytes));
     int per_sm = 0, sms = 0;
     SS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, SGD_BLOCK, s->smem_bytes));
@@ -1352,22 +1481,20 @@ extern "C" int gfs_sgd_session_create(const gfs_index* ix, const gfs_sgd_params*
     SS_CUDA(cudaMalloc(&s->d_counters, 16));
     SS_CUDA(cudaMemsetAsync(s->d_counters, 0, 16, s->stream));
 
-    // schedule: sweep windows when the step table is much larger than L2 (GFASORT_WINDOW: total steps
-    // resident across all sweeps, 0 = static schedule, -1 = auto)
+    // schedule: a sliding sampling window when the step table is much larger than L2
+    // (GFASORT_WINDOW: window length in steps, 0 = static schedule with steps ~ U[0,S), -1 = auto)
     {
-        SS_CUDA(cudaMalloc(&s->d_work, 8));
         long w = cfg && cfg->total_threads == 1 ? 0 : env_long("GFASORT_WINDOW", -1);
-        long k = env_long("GFASORT_SWEEPS", 4);
-        if (w < 0) w = (ix->S * sizeof(StepRec) > (64ull << 20)) ? (1l << 20) : 0;
-        if (k < 1) k = 1;
-        if ((uint64_t)w >= s->samp_len || s->samp_len / (uint64_t)k < 1024) w = 0;
-        s->n_sweeps = (uint32_t)k;
-        s->window_steps = w > 0 ? std::max<uint64_t>((uint64_t)w / (uint64_t)k, 1024) : 0;
-        s->chunk_updates = (uint32_t)std::max<long>(32, env_long("GFASORT_CHUNK", 128));
+        if (w < 0) w = (ix->S * sizeof(StepRec) > (64ull << 20)) ? (1l << 16) : 0;
+        if ((uint64_t)w >= s->samp_len) w = 0;
+        s->window_steps = w > 0 ? std::max<uint64_t>((uint64_t)w, 1024) : 0;
+        s->chunk_updates = (uint32_t)std::max<long>(1, env_long("GFASORT_CHUNK", 128));
+        SS_CUDA(cudaMalloc(&s->d_work, 8));
     }
 
     // L2 management: the position array is the only re-used data; the step records stream through.
-    s->l2_policy = (int)env_long("GFASORT_L2_POLICY", 1);
+    s->l2_policy = (int)env_long("GFASORT_L2_POLICY", 0);
+    s->l2_hints = (int)env_long("GFASORT_L2_HINTS", 7);
     const long fetch = env_long("GFASORT_L2_FETCH", 32);
     if (fetch == 32 || fetch == 64 || fetch == 128) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)fetch);
     if (s->l2_policy == 2) {
@@ -1461,11 +1588,11 @@ extern "C" int gfs_sgd_session_run(gfs_sgd_session* s, uint64_t epoch_begin, uin
     int rc = session_flush_events(s);
     if (rc) return rc;
     uint32_t DS;
-    sgd_kernel_fn fn = pick_kernel(s->dims, s->f64, s->aggregate, DS);
+    sgd_kernel_fn fn = pick_kernel(s->dims, s->f64, s->aggregate, s->inflight, DS);
     SgdArgs a{};
     a.g = make_kgraph(s->ix, s->params, s->d_zetas, s->zlen);
-    a.g.l2_hints = s->l2_policy == 1 ? 1u : 0u;
     a.g.samp_base = s->samp_base; a.g.samp_len = s->samp_len;
+    a.g.l2_hints = (uint32_t)s->l2_hints;
     a.epochs = s->d_epochs;
     a.epoch_begin = (uint32_t)epoch_begin; a.epoch_end = (uint32_t)epoch_end;
     a.slice = slice; a.n_slices = n_slices;
@@ -1473,7 +1600,7 @@ extern "C" int gfs_sgd_session_run(gfs_sgd_session* s, uint64_t epoch_begin, uin
     a.seed_lo = (uint32_t)s->params.seed; a.seed_hi = (uint32_t)(s->params.seed >> 32);
     a.tid_base = (uint32_t)s->rng_thread_base;
     a.positions = s->d_pos;
-    a.window_steps = s->window_steps; a.n_sweeps = s->n_sweeps; a.chunk_updates = s->chunk_updates;
+    a.window_steps = s->window_steps; a.chunk_updates = s->chunk_updates;
     a.work_ctr = s->d_work;
     GFS_CUDA(cudaMemsetAsync(s->d_work, 0, 8, s->stream));
     void* kargs[] = {(void*)&a};

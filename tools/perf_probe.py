@@ -15,6 +15,7 @@ ap.add_argument("--threads", type=int, nargs="*", default=[0])
 ap.add_argument("--agg", type=int, nargs="*", default=[1, 0])
 ap.add_argument("--f64", type=int, nargs="*", default=[0])
 ap.add_argument("--stress", action="store_true")
+ap.add_argument("--sweep", type=str, default="", help="';'-separated env settings, each 'K=V,K=V', applied in turn")
 a = ap.parse_args()
 
 print(lib().gfs_device_info().decode(), flush=True)
@@ -56,9 +57,15 @@ def run(dims, threads, agg, f64):
     print(f"dims={dims} threads={st.grid}x{st.block} agg={agg} f64={f64}: warm {res['warm']/1e9:.3f} G upd/s, cool {res['cool']/1e9:.3f} G upd/s", flush=True)
     lib().gfs_sgd_session_destroy(h)
 
-for dims in a.dims:
-    for f64 in (a.f64 if dims else [1]):
-        for threads in a.threads:
-            for agg in a.agg:
-                run(dims, threads, agg, f64)
+for setting in (a.sweep.split(";") if a.sweep else [""]):
+    for kv in filter(None, setting.split(",")):
+        k, v = kv.split("=")
+        os.environ[k] = v
+    if setting:
+        print(f"== {setting}", flush=True)
+    for dims in a.dims:
+        for f64 in (a.f64 if dims else [1]):
+            for threads in a.threads:
+                for agg in a.agg:
+                    run(dims, threads, agg, f64)
 ix.close()
