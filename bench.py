@@ -255,7 +255,7 @@ def run_ours(a, wl):
             f"= {sg.S} steps; generated in {time.time()-t0:.1f}s")
     node_len = sg.node_len
     x0 = initial_positions(node_len, dims)
-    sampler = {"window": os.environ.get("GFASORT_WINDOW", "auto"), "chunk": os.environ.get("GFASORT_CHUNK", "128"),
+    sampler = {"window": os.environ.get("GFASORT_WINDOW", "auto"), "chunk": os.environ.get("GFASORT_CHUNK", "256"), "coherent": os.environ.get("GFASORT_COHERENT", "1"),
                "relabel": os.environ.get("GFASORT_RELABEL", "1")}
 
     def build_run(iter_max=None):

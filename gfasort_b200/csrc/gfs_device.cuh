@@ -54,12 +54,19 @@ __device__ __forceinline__ double int_pow(double a, int e) {
     }
     return r;
 }
-// the two exponents the sampler ever uses for alpha = 1/(1-theta): 100 (theta = 0.99) and 1 (0.001);
-// same products in the same order as int_pow, without the loop.
-__device__ __forceinline__ double int_pow_100(double a) {
-    const double b2 = __dmul_rn(a, a), b4 = __dmul_rn(b2, b2), b8 = __dmul_rn(b4, b4), b16 = __dmul_rn(b8, b8);
-    const double b32 = __dmul_rn(b16, b16), b64 = __dmul_rn(b32, b32);
-    return __dmul_rn(__dmul_rn(b4, b32), b64);          // bits of 100: 4, 32, 64 (1.0 * b4 == b4)
+// Same products in the same order for a compile-time exponent (the loop unrolls and the untaken
+// multiplications disappear).  The sampler's alpha = 1/(1-theta) truncates to 99 for the
+// reference's theta = 0.99 (1/(1-0.99) = 99.99999999999991) and to 1 for the cooling theta = 0.001.
+template <int E>
+__device__ __forceinline__ double int_pow_fixed(double a) {
+    double base = a, r = 1.0;
+    bool first = true;
+#pragma unroll
+    for (int e = E; e != 0; e >>= 1) {
+        if (e & 1) { r = first ? base : __dmul_rn(r, base); first = false; }   // 1.0 * base == base exactly
+        if (e >> 1) base = __dmul_rn(base, base);
+    }
+    return r;
 }
 __device__ __forceinline__ double fast_precise_pow(double a, double b) {
     const int e = __double2int_rz(b);
@@ -100,7 +107,7 @@ __device__ __forceinline__ uint32_t dirty_zipf_post(uint32_t jump_space, const Z
     const double eta = __ddiv_rn(p.num, __dsub_rn(1.0, __ddiv_rn(zc.z2, zeta)));
     const double base = __dadd_rn(__dsub_rn(__dmul_rn(eta, u), eta), 1.0);
     double ip;
-    if (zc.alpha_e == 100) ip = int_pow_100(base);       // warp-uniform branches (per-epoch constant)
+    if (zc.alpha_e == 99) ip = int_pow_fixed<99>(base);  // warp-uniform branches (per-epoch constant)
     else if (zc.alpha_e == 1) ip = base;                 // 1.0 * base
     else ip = int_pow(base, zc.alpha_e);
     const double pw = __dmul_rn(ip, frac_pow(base, zc.alpha_frac));

@@ -429,6 +429,7 @@ struct KernelGraph {
     uint32_t blk_shift;           // path-of-block table granularity: block = step >> blk_shift
     uint32_t l2_hints;            // bit 0: partner records evict_first, bit 1: sampled records evict_first,
                                   // bit 2: positions evict_last
+    uint32_t coherent;            // 1: the lanes of a warp sample 32 consecutive steps (see sample_s1)
     uint64_t samp_base, samp_len; // sampled steps are drawn from [samp_base, samp_base + samp_len) (default 0, S)
 };
 
@@ -473,13 +474,21 @@ struct Slot {
 //   step = mulhi64(r.y:r.x, S); u = ((r.w:r.z) >> 11) * 2^-53; uniform rank = mulhi64(r.w:r.z, n);
 //   coins = bits 0..3 of r.z (zipf, back, end_a, end_b).
 __device__ __forceinline__ void sample_s1(const KernelGraph& g, const PathLookup& pl, const EpochDesc& ep, uint4 r,
-                                          uint64_t win_base, uint64_t win_len, bool active, Slot& t) {
+                                          uint64_t win_base, uint64_t win_len, bool active, unsigned warp_mask,
+                                          int lane, Slot& t) {
     const uint64_t r01 = ((uint64_t)r.y << 32) | r.x;
     t.r23 = ((uint64_t)r.w << 32) | r.z;
     t.coins = r.z;
     // step ~ U[win_base, win_base + win_len) on the circular sampling range; the default window
     // (samp_base, samp_len) = (0, S) is the reference's U[0, S) (sgd.rs:444)
     uint64_t s = win_base + __umul64hi(r01, win_len);
+    if (g.coherent) {
+        // warp-coherent sampling (sweep schedule only): the warp's first lane draws the step, lane l takes
+        // the l-th step after it.  Every step is still drawn with the same probability over a sweep, but
+        // the 32 sampled records — and, with the node relabelling, most of their nodes' positions — are
+        // adjacent in memory: one coalesced request instead of 32.  Partners stay independent per lane.
+        s = __shfl_sync(warp_mask, s, __ffs(warp_mask) - 1) + (uint32_t)lane;
+    }
     if (s >= g.samp_base + g.samp_len) s -= g.samp_len;
     t.step_a = s;
     if (active) t.a = (g.l2_hints & 2u) ? load_rec_hint(g.recs + s, make_evict_first_policy()) : load_rec(g.recs + s);
@@ -779,7 +788,7 @@ sgd_kernel(const SgdArgs a) {
             const uint4 r = philox4x32_10(make_uint4((uint32_t)attempt, (uint32_t)(attempt >> 32),
                                                      a.tid_base + tid, STREAM_SGD), key);
             attempt += active ? 1 : 0;
-            sample_s1(a.g, pl, ep, r, win_base, win_len, active, t[k]);
+            sample_s1(a.g, pl, ep, r, win_base, win_len, active, warp_mask, lane, t[k]);
         }
 #pragma unroll
         for (int k = 0; k < K; ++k) sample_s2<(D > 0)>(a.g, ep, t[k]);
@@ -1020,7 +1029,7 @@ __global__ void dbg_trace(KernelGraph g, const EpochDesc* epochs, uint32_t epoch
     Slot t;
     PathLookup pl;
     pl.fs = g.first_step; pl.blk = nullptr; pl.shift = 0; pl.P = g.P;
-    sample_s1(g, pl, ep, r, g.samp_base, g.samp_len, true, t);
+    sample_s1(g, pl, ep, r, g.samp_base, g.samp_len, true, 0u, 0, t);      // g.coherent == 0 here
     sample_s2<ND>(g, ep, t);
     if (ND) sample_ends(t);
     const double d = term_distance(t);
@@ -1082,6 +1091,7 @@ struct gfs_sgd_session {
     int l2_policy = 0;          // 0 none, 2 persisting access-policy window on the positions
     int l2_hints = 7;           // KernelGraph::l2_hints
     int inflight = 2;           // terms in flight per thread (kernel template parameter K)
+    bool coherent = true;       // warp-coherent step sampling in the sweep schedule
     uint64_t window_steps = 0;  // 0 = static schedule
     uint32_t chunk_updates = 128;
     unsigned long long* d_work = nullptr;
@@ -1485,10 +1495,13 @@ extern "C" int gfs_sgd_session_create(const gfs_index* ix, const gfs_sgd_params*
     // (GFASORT_WINDOW: window length in steps, 0 = static schedule with steps ~ U[0,S), -1 = auto)
     {
         long w = cfg && cfg->total_threads == 1 ? 0 : env_long("GFASORT_WINDOW", -1);
-        if (w < 0) w = (ix->S * sizeof(StepRec) > (64ull << 20)) ? (1l << 16) : 0;
+        // auto: graphs whose records fit in half of L2 need no window; otherwise 2^20 steps (16 MB of
+        // records, several times the number of terms in flight) but never more than 1/8 of the range
+        if (w < 0) w = (ix->S * sizeof(StepRec) > (64ull << 20)) ? (long)std::min<uint64_t>(1ull << 20, s->samp_len / 8) : 0;
         if ((uint64_t)w >= s->samp_len) w = 0;
         s->window_steps = w > 0 ? std::max<uint64_t>((uint64_t)w, 1024) : 0;
-        s->chunk_updates = (uint32_t)std::max<long>(1, env_long("GFASORT_CHUNK", 128));
+        s->chunk_updates = (uint32_t)std::max<long>(1, env_long("GFASORT_CHUNK", 256));
+        s->coherent = env_long("GFASORT_COHERENT", 1) != 0;
         SS_CUDA(cudaMalloc(&s->d_work, 8));
     }
 
@@ -1593,6 +1606,7 @@ extern "C" int gfs_sgd_session_run(gfs_sgd_session* s, uint64_t epoch_begin, uin
     a.g = make_kgraph(s->ix, s->params, s->d_zetas, s->zlen);
     a.g.samp_base = s->samp_base; a.g.samp_len = s->samp_len;
     a.g.l2_hints = (uint32_t)s->l2_hints;
+    a.g.coherent = (s->window_steps > 0 && s->coherent) ? 1u : 0u;
     a.epochs = s->d_epochs;
     a.epoch_begin = (uint32_t)epoch_begin; a.epoch_end = (uint32_t)epoch_end;
     a.slice = slice; a.n_slices = n_slices;
