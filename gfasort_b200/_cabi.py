@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgfasort_cuda.so")
+LIB_PATH = os.environ.get("GFASORT_LIB_PATH") or os.path.join(_HERE, "libgfasort_cuda.so")   # override: experiments only
 
 u64p = C.POINTER(C.c_uint64)
 u32p = C.POINTER(C.c_uint32)

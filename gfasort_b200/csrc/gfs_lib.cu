@@ -430,6 +430,7 @@ struct KernelGraph {
     uint32_t l2_hints;            // bit 0: partner records evict_first, bit 1: sampled records evict_first,
                                   // bit 2: positions evict_last
     uint32_t coherent;            // 1: the lanes of a warp sample 32 consecutive steps (see sample_s1)
+    uint32_t partner_group;       // coherent only: 2^k adjacent lanes share one partner draw (1 = independent)
     uint64_t samp_base, samp_len; // sampled steps are drawn from [samp_base, samp_base + samp_len) (default 0, S)
 };
 
@@ -453,10 +454,9 @@ struct PathLookup {
     }
 };
 
-// One term in flight.  The stages below are straight-line (selects, predicated loads) so that a
-// thread can interleave several slots: S1 issues the record load of the sampled step and the zeta
-// load, S2 turns the draw into the partner step and issues its record load, S3/S4 (in the kernel)
-// load the positions and apply the update.
+// One term being sampled.  The stages are straight-line (selects, predicated loads): S1 turns the
+// draw into the sampled step and issues the zeta load, S2 turns it into the partner step.  The
+// kernel then requests both records and applies the update two pipeline stages later.
 struct Slot {
     StepRec a, b;
     uint64_t step_a, step_b;   // step indices
@@ -465,6 +465,7 @@ struct Slot {
     double zeta;
     uint32_t n, ra, J;
     uint32_t coins;            // r.z
+    uint32_t group_off;        // lane's offset inside its partner group (0 when partners are independent)
     bool zipf, back, live;     // live: a partner is drawn (n > 1 and the Zipf branch has room to move)
     bool other_a, other_b;
     bool valid;
@@ -479,6 +480,7 @@ __device__ __forceinline__ void sample_s1(const KernelGraph& g, const PathLookup
     const uint64_t r01 = ((uint64_t)r.y << 32) | r.x;
     t.r23 = ((uint64_t)r.w << 32) | r.z;
     t.coins = r.z;
+    t.group_off = 0;
     // step ~ U[win_base, win_base + win_len) on the circular sampling range; the default window
     // (samp_base, samp_len) = (0, S) is the reference's U[0, S) (sgd.rs:444)
     uint64_t s = win_base + __umul64hi(r01, win_len);
@@ -488,18 +490,28 @@ __device__ __forceinline__ void sample_s1(const KernelGraph& g, const PathLookup
         // the 32 sampled records — and, with the node relabelling, most of their nodes' positions — are
         // adjacent in memory: one coalesced request instead of 32.  Partners stay independent per lane.
         s = __shfl_sync(warp_mask, s, __ffs(warp_mask) - 1) + (uint32_t)lane;
+        if (g.partner_group > 1) {
+            // grouped partners: the 2^k lanes of a group (consecutive sampled steps) use the draw of the
+            // group's first lane — same branch coins, same u / uniform rank — so that their partners are
+            // (nearly) consecutive steps too and share cache lines: one 128-byte DRAM line serves up to 8
+            // terms instead of 1.  Each lane still applies the draw to its own rank and path, so every
+            // (step, partner) pair keeps the reference's probability up to O(1/path length).
+            const int lead = lane & ~(int)(g.partner_group - 1);
+            const uint32_t z_lo = __shfl_sync(warp_mask, r.z, lead), z_hi = __shfl_sync(warp_mask, r.w, lead);
+            t.r23 = ((uint64_t)z_hi << 32) | z_lo;
+            t.coins = (r.z & ~3u) | (z_lo & 3u);            // end coins (nD) stay per lane
+            t.group_off = (uint32_t)(lane - lead);
+        }
     }
     if (s >= g.samp_base + g.samp_len) s -= g.samp_len;
     t.step_a = s;
-    if (active) t.a = (g.l2_hints & 2u) ? load_rec_hint(g.recs + s, make_evict_first_policy()) : load_rec(g.recs + s);
-    else { t.a.node_rev = 0; t.a.node_len = 0; t.a.pos = 0; }
     const uint32_t p = pl.path_of(s);
     t.f = pl.fs[p];
     const uint32_t n = (uint32_t)(pl.fs[p + 1] - t.f);
     const uint32_t ra = (uint32_t)(s - t.f);
     t.n = n; t.ra = ra;
-    t.zipf = ep.cooling || (r.z & 1u);                                                     // sgd.rs:456
-    t.back = ra > 0 && (((r.z >> 1) & 1u) || ra == n - 1);                                 // sgd.rs:460
+    t.zipf = ep.cooling || (t.coins & 1u);                                                 // sgd.rs:456
+    t.back = ra > 0 && (((t.coins >> 1) & 1u) || ra == n - 1);                             // sgd.rs:460
     const bool fwd = !t.back && ra < n - 1;                                                // sgd.rs:475
     const bool moves = t.back || fwd;
     const uint32_t span = t.back ? ra : n - ra - 1;
@@ -516,7 +528,6 @@ __device__ __forceinline__ void sample_s1(const KernelGraph& g, const PathLookup
     if (t.live && t.zipf) t.zeta = __ldg(g.zetas + k);
 }
 
-template <bool ND>
 __device__ __forceinline__ void sample_s2(const KernelGraph& g, const EpochDesc& ep, Slot& t) {
     const uint32_t n = t.n, ra = t.ra;
     // u = (r23 >> 11) * 2^-53 (sgd.rs:136 through PhiloxDraw::unit)
@@ -527,13 +538,11 @@ __device__ __forceinline__ void sample_s2(const KernelGraph& g, const EpochDesc&
     const uint32_t rb_back = ra >= z ? ra - z : 0u;                                        // saturating_sub
     const uint32_t rb_fwd = z < room ? ra + z : n - 1;                                     // min(ra + z, n - 1)
     const uint32_t rb_zipf = t.back ? rb_back : rb_fwd;
-    const uint32_t rb_unif = (uint32_t)__umul64hi(t.r23, (uint64_t)n);                     // sgd.rs:493-494
+    uint32_t rb_unif = (uint32_t)__umul64hi(t.r23, (uint64_t)n) + t.group_off;             // sgd.rs:493-494
+    if (rb_unif >= n) rb_unif -= n;                        // (grouped partners: consecutive ranks, circular)
     const uint32_t rb = t.zipf ? rb_zipf : rb_unif;
     t.valid = t.live && ra != rb;                                                          // sgd.rs:497
     t.step_b = t.valid ? t.f + rb : t.step_a;
-    if (t.valid) t.b = (g.l2_hints & 1u) ? load_rec_hint(g.recs + t.step_b, make_evict_first_policy())
-                                         : load_rec(g.recs + t.step_b);
-    else t.b = t.a;
     t.other_a = t.other_b = false;
 }
 
@@ -648,7 +657,7 @@ struct SgdArgs {
     uint32_t epoch_begin, epoch_end;
     uint32_t slice, n_slices;    // run slice `slice` of n_slices equal parts of every epoch's updates
     uint64_t* attempt_ctr;       // per-thread Philox attempt counters (persist across launches)
-    unsigned long long* counters;   // [0] applied, [1] attempts
+    unsigned long long* counters;   // [0] applied, [1] attempts, [2] watchdog trips
     uint32_t seed_lo, seed_hi;
     uint32_t tid_base;
     void* positions;             // 1D: double[N]; nD: CT[N*2*DS]
@@ -658,6 +667,7 @@ struct SgdArgs {
     uint64_t window_steps;
     uint32_t chunk_updates;
     unsigned long long* work_ctr;
+    uint64_t iter_cap;           // watchdog: a warp that loops more often than this sets counters[2] and stops
 };
 
 // 1D update of one warp's terms (sgd.rs:512-576), optionally merging lanes that hit the same node.
@@ -742,7 +752,10 @@ __device__ __forceinline__ void apply_nd(CT* C, unsigned warp_mask, int lane, bo
 
 // D == 0: 1D `Y` (CT must be double).  D >= 1: nD `L`.  K: terms in flight per thread.
 template <typename CT, int D, int DS, bool AGG, int K>
-__global__ void __launch_bounds__(SGD_BLOCK, (K > 1 ? 3 : 4))
+#ifndef GFS_K1_BLOCKS
+#define GFS_K1_BLOCKS 4
+#endif
+__global__ void __launch_bounds__(SGD_BLOCK, (K > 1 ? 3 : GFS_K1_BLOCKS))
 sgd_kernel(const SgdArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // shared: first_step (P+1 u64) + path-of-block table (BLK_TABLE u16) when the path table fits
@@ -773,127 +786,201 @@ sgd_kernel(const SgdArgs a) {
     uint64_t applied = 0, attempts0 = attempt;
     const uint2 key = make_uint2(a.seed_lo, a.seed_hi);
 
-    // K terms per lane per call, their stages interleaved so that K record / position loads are in
-    // flight per thread.  Slot k is active while the lane still owes more than k updates; returns how
-    // many updates this lane applied.  K = 1 keeps the strictly sequential semantics of one reference
-    // worker thread (the single-thread parity tests run it).
-    auto attempt_batch = [&](const EpochDesc& ep, uint32_t owed, uint64_t win_base, uint64_t win_len) -> uint32_t {
-        Slot t[K];
-        double dist[K];
-        CT ci[K][DS], cj[K][DS];
-        uint32_t idx_i[K], idx_j[K];
-#pragma unroll
-        for (int k = 0; k < K; ++k) {
-            const bool active = owed > (uint32_t)k;
-            const uint4 r = philox4x32_10(make_uint4((uint32_t)attempt, (uint32_t)(attempt >> 32),
-                                                     a.tid_base + tid, STREAM_SGD), key);
-            attempt += active ? 1 : 0;
-            sample_s1(a.g, pl, ep, r, win_base, win_len, active, warp_mask, lane, t[k]);
-        }
-#pragma unroll
-        for (int k = 0; k < K; ++k) sample_s2<(D > 0)>(a.g, ep, t[k]);
-#pragma unroll
-        for (int k = 0; k < K; ++k) {
-            if (D > 0) sample_ends(t[k]);
-            dist[k] = term_distance(t[k]);
-            const uint32_t na = t[k].a.node_rev >> 1, nb = t[k].b.node_rev >> 1;
-            t[k].valid = t[k].valid && dist[k] != 0.0 && na < a.g.N && nb < a.g.N;         // sgd.rs:514, 525-538
-            if constexpr (D == 0) {
-                idx_i[k] = na; idx_j[k] = nb;
-                const double* X = reinterpret_cast<const double*>(a.positions);
-                ci[k][0] = cj[k][0] = 0.0;
-                if (t[k].valid) {
-                    const bool keep = (a.g.l2_hints & 4u) != 0;
-                    const uint64_t pol = make_evict_last_policy();
-                    ci[k][0] = keep ? ld_pos_keep(X + na, pol) : ld_pos(X + na);
-                    cj[k][0] = keep ? ld_pos_keep(X + nb, pol) : ld_pos(X + nb);
-                }
-            } else {
-                idx_i[k] = na * 2 + (t[k].other_a ? 1u : 0u);                              // sgd.rs:1099-1103
-                idx_j[k] = nb * 2 + (t[k].other_b ? 1u : 0u);
-                const CT* C = reinterpret_cast<const CT*>(a.positions);
-#pragma unroll
-                for (int q = 0; q < DS; ++q) { ci[k][q] = CT(0); cj[k][q] = CT(0); }
-                if (t[k].valid) {
-                    ld_coords<CT, DS>(C + (size_t)idx_i[k] * DS, ci[k]);
-                    ld_coords<CT, DS>(C + (size_t)idx_j[k] * DS, cj[k]);
-                }
-            }
-        }
-        uint32_t n_applied = 0;
-#pragma unroll
-        for (int k = 0; k < K; ++k) {
-            if constexpr (D == 0) {
-                apply_1d<AGG>(reinterpret_cast<double*>(a.positions), warp_mask, lane, t[k].valid, idx_i[k], idx_j[k],
-                              dist[k], ep.eta, ci[k][0], cj[k][0], (a.g.l2_hints & 4u) != 0);
-            } else {
-                apply_nd<CT, (D > 0 ? D : 1), DS, AGG>(reinterpret_cast<CT*>(a.positions), warp_mask, lane, t[k].valid,
-                                                       idx_i[k], idx_j[k], dist[k], ep.eta, ci[k], cj[k]);
-            }
-            n_applied += t[k].valid ? 1u : 0u;
-        }
-        return n_applied;
+    // ---- software pipeline -------------------------------------------------------------------------
+    // Three terms per slot are in different stages at any time (K slots per thread):
+    //   stage A   sample term i+3: Philox, path lookup, zeta load, Zipf arithmetic -> the two step indices
+    //   stage L   request the two records of term i+2 (indices from the previous A)
+    //   stage B1  term i+1: its records were requested one iteration ago and have had the whole of
+    //             stage A (~350 instructions and an L2 round trip) to arrive from DRAM; term distance,
+    //             validity, request the two positions
+    //   stage B2  term i: its positions have had one iteration to arrive; compute the update, apply it (red)
+    // Loop order is B2, B1, L, A, so that every register set is reloaded only after its consumer has run
+    // and no in-flight value is ever moved.  A term's validity is final only in B1 (zero distance,
+    // missing node), so a lane's quota is tracked optimistically: owed = target - done - in flight.
+    struct InFlight {            // term whose records are being loaded (L -> B)
+        StepRec a, b;
+        double eta;
+        uint32_t coins;
+        bool valid;
     };
+    struct Sampled {             // term whose steps are known (A -> L)
+        uint64_t sa, sb;
+        double eta;
+        uint32_t coins;
+        bool valid;
+    };
+    InFlight fl[K];
+    Sampled sm[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) { fl[k].valid = false; sm[k].valid = false; }
+    uint64_t target = 0, done = 0;           // per lane: updates owed by the chunks claimed so far / applied
 
-    if (a.window_steps == 0) {
-        // static schedule: thread t applies floor(m/T) + (t < m%T) updates per epoch, steps ~ U[0,S)
-        for (uint32_t e = a.epoch_begin; e < a.epoch_end; ++e) {
-            const EpochDesc ep = a.epochs[e];
-            const uint64_t m = ep.updates / a.n_slices + (a.slice < ep.updates % a.n_slices ? 1 : 0);
-            const uint64_t quota = m / T + (tid < m % T ? 1 : 0);
-            uint64_t done = 0;
-            for (;;) {
-                const uint64_t owed64 = quota - done;
-                const uint32_t owed = owed64 > (uint64_t)K ? (uint32_t)K : (uint32_t)owed64;
-                if (!__any_sync(warp_mask, owed != 0)) break;
-                const uint32_t got = attempt_batch(ep, owed, a.g.samp_base, a.g.samp_len);          // sgd.rs:579
-                done += got; applied += got;
-            }
-        }
-    } else {
-        // sweep schedule: the launch's updates are cut into chunks of `chunk_updates`; a warp claims the next
-        // chunk c from a global counter and samples its steps from the window [base(c), base(c) + window_steps),
-        // base(c) = (c mod chunks_per_epoch) * samp_len / chunks_per_epoch.  Claiming in order keeps all warps
-        // on neighbouring chunks (a static assignment lets them drift apart by SM speed), so the windows in
-        // use at any moment cover about n_warps * chunk_updates * samp_len / m + window_steps consecutive
-        // steps, whose records — and, with the node relabelling, the positions of their nodes — stay in L2
-        // while the sweep passes over them.
-        const uint32_t n_lanes = __popc(warp_mask);
-        const uint32_t lane_rank = __popc(warp_mask & ((1u << lane) - 1u));
-        const int leader = __ffs(warp_mask) - 1;
-        const uint32_t C = a.chunk_updates;
-        const uint64_t m = a.epochs[a.epoch_begin].updates / a.n_slices +
-                           (a.slice < a.epochs[a.epoch_begin].updates % a.n_slices ? 1 : 0);
-        const uint64_t cpe = (m + C - 1) / C;                                           // chunks per epoch
-        const uint64_t total = cpe * (uint64_t)(a.epoch_end - a.epoch_begin);
-        const double steps_per_chunk = (double)a.g.samp_len / (double)(cpe ? cpe : 1);
-        // chunks of the current epoch are [c_lo, c_lo + cpe)
-        uint32_t e = a.epoch_begin;
-        uint64_t c_lo = 0;
-        EpochDesc ep = a.epochs[e];
-        for (;;) {
+    // work claiming (warp-uniform): sets ep / win_base / win_len and raises `target`
+    const bool sweep = a.window_steps != 0;
+    const uint32_t n_lanes = __popc(warp_mask);
+    const uint32_t lane_rank = __popc(warp_mask & ((1u << lane) - 1u));
+    const int leader = __ffs(warp_mask) - 1;
+    const uint32_t C = a.chunk_updates;
+    EpochDesc ep = a.epochs[a.epoch_begin];
+    uint64_t win_base = a.g.samp_base, win_len = a.g.samp_len;
+    uint32_t e_cur = a.epoch_begin;
+    // sweep schedule (see SgdArgs): chunks of C updates claimed from a global counter; chunk cc of an epoch
+    // samples from the window starting at cc * samp_len / chunks_per_epoch.  Claiming in order keeps all
+    // warps on neighbouring chunks (a static assignment lets them drift apart by SM speed), so the windows
+    // in use at any moment cover about n_warps * C * samp_len / m + window_steps consecutive steps.
+    const uint64_t m_sweep = ep.updates / a.n_slices + (a.slice < ep.updates % a.n_slices ? 1 : 0);
+    const uint64_t cpe = sweep ? (m_sweep + C - 1) / C : 1;                           // chunks per epoch
+    const uint64_t total_chunks = cpe * (uint64_t)(a.epoch_end - a.epoch_begin);
+    const double steps_per_chunk = (double)a.g.samp_len / (double)cpe;
+    uint64_t c_lo = 0;                        // first chunk of epoch e_cur
+    bool first_claim = true;
+    auto claim = [&]() -> bool {
+        if (sweep) {
             unsigned long long c = 0;
             if (lane == leader) c = atomicAdd(a.work_ctr, 1ull);
             c = __shfl_sync(warp_mask, c, leader);
-            if (c >= total) break;
-            while (c >= c_lo + cpe) { c_lo += cpe; ++e; ep = a.epochs[e]; }            // claims only move forward
+            if (c >= total_chunks) return false;
+            while (c >= c_lo + cpe) { c_lo += cpe; ++e_cur; ep = a.epochs[e_cur]; }       // claims only move forward
             const uint64_t cc = c - c_lo;
-            const uint64_t left = m - cc * C;
+            const uint64_t left = m_sweep - cc * C;
             const uint32_t n_upd = left < C ? (uint32_t)left : C;
-            const uint32_t quota = n_lanes == 32 ? (n_upd >> 5) + (lane_rank < (n_upd & 31u) ? 1u : 0u)
-                                                 : n_upd / n_lanes + (lane_rank < n_upd % n_lanes ? 1u : 0u);
+            target += n_lanes == 32 ? (n_upd >> 5) + (lane_rank < (n_upd & 31u) ? 1u : 0u)
+                                    : n_upd / n_lanes + (lane_rank < n_upd % n_lanes ? 1u : 0u);
             uint64_t off = (uint64_t)((double)cc * steps_per_chunk);
             if (off >= a.g.samp_len) off = a.g.samp_len - 1;
-            const uint64_t win_base = a.g.samp_base + off;
-            uint32_t done = 0;
-            for (;;) {
-                const uint32_t owed = quota - done;
-                if (!__any_sync(warp_mask, owed != 0)) break;
-                const uint32_t got = attempt_batch(ep, owed, win_base, a.window_steps);
-                done += got; applied += got;
+            win_base = a.g.samp_base + off;
+            win_len = a.window_steps;
+            return true;
+        }
+        // static schedule: one "chunk" per epoch; thread t applies floor(m/T) + (t < m%T) updates, steps ~ U[0,S)
+        if (!first_claim) ++e_cur;
+        first_claim = false;
+        if (e_cur >= a.epoch_end) return false;
+        ep = a.epochs[e_cur];
+        const uint64_t m = ep.updates / a.n_slices + (a.slice < ep.updates % a.n_slices ? 1 : 0);
+        target += m / T + (tid < m % T ? 1 : 0);
+        return true;
+    };
+    bool more = true;
+
+    struct Loaded {              // term whose positions are being loaded (B1 -> B2)
+        CT ci[DS], cj[DS];
+        double dist, eta;
+        uint32_t idx_i, idx_j;
+        bool ok;
+    };
+    Loaded xs[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) xs[k].ok = false;
+
+    uint64_t iters = 0;
+    for (;;) {
+        if (++iters > a.iter_cap) {          // never taken in a healthy run; turns a would-be hang into an error
+            if (lane == leader) atomicAdd(a.counters + 2, 1ull);
+            break;
+        }
+        // ---- B2: apply the terms whose positions were requested in the previous iteration
+        bool any_ok = false;
+#pragma unroll
+        for (int k = 0; k < K; ++k) any_ok = any_ok || xs[k].ok;
+#ifdef GFS_EXP_NOAPPLY
+#pragma unroll
+        for (int k = 0; k < K; ++k) { done += xs[k].ok ? 1u : 0u; if (xs[k].dist == 1.2345e-300) ((double*)a.positions)[0] = (double)xs[k].ci[0] + (double)xs[k].cj[0]; }
+        any_ok = false;
+#endif
+        if (__any_sync(warp_mask, any_ok)) {
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                if constexpr (D == 0) {
+                    apply_1d<AGG>(reinterpret_cast<double*>(a.positions), warp_mask, lane, xs[k].ok, xs[k].idx_i, xs[k].idx_j,
+                                  xs[k].dist, xs[k].eta, xs[k].ci[0], xs[k].cj[0], (a.g.l2_hints & 4u) != 0);
+                } else {
+                    apply_nd<CT, (D > 0 ? D : 1), DS, AGG>(reinterpret_cast<CT*>(a.positions), warp_mask, lane, xs[k].ok,
+                                                           xs[k].idx_i, xs[k].idx_j, xs[k].dist, xs[k].eta, xs[k].ci, xs[k].cj);
+                }
+                done += xs[k].ok ? 1u : 0u;                                                // sgd.rs:579
             }
         }
+        // ---- B1: the records requested in the previous iteration have arrived: term distance, validity,
+        //          and the requests for the two positions
+        uint32_t pending = 0;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            bool oa = false, ob = false;
+            StepRec ra = fl[k].a, rb = fl[k].b;
+            if (D > 0) {                                                                   // sgd.rs:1060-1077
+                const bool rev_a = ra.node_rev & 1u, rev_b = rb.node_rev & 1u;
+                oa = (fl[k].coins >> 2) & 1u;
+                if (oa) { ra.pos += ra.node_len; oa = !rev_a; } else { oa = rev_a; }
+                ob = (fl[k].coins >> 3) & 1u;
+                if (ob) { rb.pos += rb.node_len; ob = !rev_b; } else { ob = rev_b; }
+            }
+            xs[k].dist = fabs(__dsub_rn(u52_to_f64(ra.pos), u52_to_f64(rb.pos)));          // sgd.rs:509-513
+            xs[k].eta = fl[k].eta;
+            const uint32_t na = ra.node_rev >> 1, nb = rb.node_rev >> 1;
+            xs[k].ok = fl[k].valid && xs[k].dist != 0.0 && na < a.g.N && nb < a.g.N;       // sgd.rs:514, 525-538
+            if constexpr (D == 0) {
+                xs[k].idx_i = na; xs[k].idx_j = nb;
+                const double* X = reinterpret_cast<const double*>(a.positions);
+                xs[k].ci[0] = xs[k].cj[0] = 0.0;
+                if (xs[k].ok) {
+                    const bool keep = (a.g.l2_hints & 4u) != 0;
+                    const uint64_t pol = make_evict_last_policy();
+                    xs[k].ci[0] = keep ? ld_pos_keep(X + na, pol) : ld_pos(X + na);
+                    xs[k].cj[0] = keep ? ld_pos_keep(X + nb, pol) : ld_pos(X + nb);
+                }
+            } else {
+                xs[k].idx_i = na * 2 + (oa ? 1u : 0u);                                     // sgd.rs:1099-1103
+                xs[k].idx_j = nb * 2 + (ob ? 1u : 0u);
+                const CT* Cc = reinterpret_cast<const CT*>(a.positions);
+#pragma unroll
+                for (int q = 0; q < DS; ++q) { xs[k].ci[q] = CT(0); xs[k].cj[q] = CT(0); }
+                if (xs[k].ok) {
+                    ld_coords<CT, DS>(Cc + (size_t)xs[k].idx_i * DS, xs[k].ci);
+                    ld_coords<CT, DS>(Cc + (size_t)xs[k].idx_j * DS, xs[k].cj);
+                }
+            }
+            pending += xs[k].ok ? 1u : 0u;
+        }
+        // ---- L: request the records of the terms sampled in the previous iteration
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            fl[k].valid = sm[k].valid; fl[k].coins = sm[k].coins; fl[k].eta = sm[k].eta;
+            if (sm[k].valid) {
+                fl[k].a = (a.g.l2_hints & 2u) ? load_rec_hint(a.g.recs + sm[k].sa, make_evict_first_policy()) : load_rec(a.g.recs + sm[k].sa);
+                fl[k].b = (a.g.l2_hints & 1u) ? load_rec_hint(a.g.recs + sm[k].sb, make_evict_first_policy()) : load_rec(a.g.recs + sm[k].sb);
+                ++pending;
+            }
+            sm[k].valid = false;
+        }
+        // ---- A: sample the next terms
+        uint64_t owed = target - done - pending;
+        // a new chunk is claimed when every lane has sampled its share; the static schedule (which the
+        // bit-exact single-thread tests use) also waits until that share is confirmed applied, so that a
+        // term never runs with the next epoch's eta
+        const bool need_claim = sweep ? !__any_sync(warp_mask, owed != 0)
+                                      : !__any_sync(warp_mask, owed != 0 || pending != 0);
+        if (need_claim && more) {
+            more = claim();
+            owed = target - done - pending;
+        }
+        if (__any_sync(warp_mask, owed != 0)) {
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                const bool active = owed > (uint64_t)k;
+                const uint4 r = philox4x32_10(make_uint4((uint32_t)attempt, (uint32_t)(attempt >> 32),
+                                                         a.tid_base + tid, STREAM_SGD), key);
+                attempt += active ? 1 : 0;
+                Slot t;
+                sample_s1(a.g, pl, ep, r, win_base, win_len, active, warp_mask, lane, t);
+                sample_s2(a.g, ep, t);
+                sm[k].sa = t.step_a; sm[k].sb = t.step_b; sm[k].valid = t.valid; sm[k].coins = t.coins; sm[k].eta = ep.eta;
+            }
+        } else if (!more && !__any_sync(warp_mask, pending != 0)) {
+            break;
+        }
     }
+    applied = done;
     a.attempt_ctr[tid] = attempt;
     // counters: one atomic pair per full warp (partial warps: one pair per thread)
     uint64_t att = attempt - attempts0;
@@ -1030,7 +1117,9 @@ __global__ void dbg_trace(KernelGraph g, const EpochDesc* epochs, uint32_t epoch
     PathLookup pl;
     pl.fs = g.first_step; pl.blk = nullptr; pl.shift = 0; pl.P = g.P;
     sample_s1(g, pl, ep, r, g.samp_base, g.samp_len, true, 0u, 0, t);      // g.coherent == 0 here
-    sample_s2<ND>(g, ep, t);
+    sample_s2(g, ep, t);
+    t.a = load_rec(g.recs + t.step_a);
+    t.b = load_rec(g.recs + t.step_b);
     if (ND) sample_ends(t);
     const double d = term_distance(t);
     const bool ok = t.valid && d != 0.0;
@@ -1092,6 +1181,7 @@ struct gfs_sgd_session {
     int l2_hints = 7;           // KernelGraph::l2_hints
     int inflight = 2;           // terms in flight per thread (kernel template parameter K)
     bool coherent = true;       // warp-coherent step sampling in the sweep schedule
+    uint32_t partner_group = 1; // lanes sharing one partner draw (power of two)
     uint64_t window_steps = 0;  // 0 = static schedule
     uint32_t chunk_updates = 128;
     unsigned long long* d_work = nullptr;
@@ -1471,10 +1561,11 @@ extern "C" int gfs_sgd_session_create(const gfs_index* ix, const gfs_sgd_params*
     const uint64_t max_threads = (uint64_t)per_sm * sms * SGD_BLOCK;
     uint64_t want = cfg && cfg->total_threads ? cfg->total_threads : (uint64_t)env_long("GFASORT_THREADS", 0);
     if (want == 0) {
-        // auto: full occupancy, but never more threads than there is work for (>= 8 updates per
-        // thread per epoch) and never more concurrent terms than a quarter of the nodes
+        // auto: full occupancy, but never more threads than there is work for (>= 8 updates per thread
+        // per epoch) and never more terms in flight (3 pipeline stages x K per thread) than half the nodes:
+        // beyond that, early epochs (mu = 1) work from positions that are too stale and converge slower
         const uint64_t by_work = std::max<uint64_t>(params->min_term_updates / 8, 32);
-        const uint64_t by_nodes = std::max<uint64_t>(ix->N / 4, 32);
+        const uint64_t by_nodes = std::max<uint64_t>(ix->N / (2ull * 3ull * (uint64_t)std::max(s->inflight, 1)), 32);
         want = std::min(max_threads, std::min(by_work, by_nodes));
     }
     want = std::min(want, max_threads);
@@ -1488,8 +1579,8 @@ extern "C" int gfs_sgd_session_create(const gfs_index* ix, const gfs_sgd_params*
     else { SS_CUDA(cudaMalloc(&s->d_pos, s->n_elems * esz)); s->own_pos = true; }
     SS_CUDA(cudaMalloc(&s->d_attempts, T * 8));
     SS_CUDA(cudaMemsetAsync(s->d_attempts, 0, T * 8, s->stream));
-    SS_CUDA(cudaMalloc(&s->d_counters, 16));
-    SS_CUDA(cudaMemsetAsync(s->d_counters, 0, 16, s->stream));
+    SS_CUDA(cudaMalloc(&s->d_counters, 24));
+    SS_CUDA(cudaMemsetAsync(s->d_counters, 0, 24, s->stream));
 
     // schedule: a sliding sampling window when the step table is much larger than L2
     // (GFASORT_WINDOW: window length in steps, 0 = static schedule with steps ~ U[0,S), -1 = auto)
@@ -1502,6 +1593,9 @@ extern "C" int gfs_sgd_session_create(const gfs_index* ix, const gfs_sgd_params*
         s->window_steps = w > 0 ? std::max<uint64_t>((uint64_t)w, 1024) : 0;
         s->chunk_updates = (uint32_t)std::max<long>(1, env_long("GFASORT_CHUNK", 256));
         s->coherent = env_long("GFASORT_COHERENT", 1) != 0;
+        long pg = env_long("GFASORT_PARTNER_GROUP", 1);
+        s->partner_group = 1;
+        while (s->partner_group * 2 <= (uint32_t)std::min<long>(std::max<long>(pg, 1), 32)) s->partner_group *= 2;
         SS_CUDA(cudaMalloc(&s->d_work, 8));
     }
 
@@ -1607,6 +1701,7 @@ extern "C" int gfs_sgd_session_run(gfs_sgd_session* s, uint64_t epoch_begin, uin
     a.g.samp_base = s->samp_base; a.g.samp_len = s->samp_len;
     a.g.l2_hints = (uint32_t)s->l2_hints;
     a.g.coherent = (s->window_steps > 0 && s->coherent) ? 1u : 0u;
+    a.g.partner_group = a.g.coherent ? s->partner_group : 1u;
     a.epochs = s->d_epochs;
     a.epoch_begin = (uint32_t)epoch_begin; a.epoch_end = (uint32_t)epoch_end;
     a.slice = slice; a.n_slices = n_slices;
@@ -1616,6 +1711,12 @@ extern "C" int gfs_sgd_session_run(gfs_sgd_session* s, uint64_t epoch_begin, uin
     a.positions = s->d_pos;
     a.window_steps = s->window_steps; a.chunk_updates = s->chunk_updates;
     a.work_ctr = s->d_work;
+    {
+        // generous bound on loop iterations per warp: 64x its fair share of the launch's attempts + slack
+        const uint64_t m = s->params.min_term_updates / n_slices + 1;
+        const uint64_t T = (uint64_t)s->grid * s->block;
+        a.iter_cap = ((m / T + 1) * (epoch_end - epoch_begin)) * 64 + (1ull << 16);
+    }
     GFS_CUDA(cudaMemsetAsync(s->d_work, 0, 8, s->stream));
     void* kargs[] = {(void*)&a};
     GFS_CUDA(cudaEventRecord(s->ev0, s->stream));
@@ -1663,8 +1764,12 @@ extern "C" int gfs_sgd_session_stats(gfs_sgd_session* s, gfs_stats* st) {
     if (!s || !st) { set_error("gfs_sgd_session_stats: null argument"); return GFS_ERR_INVALID; }
     int rc = gfs_sgd_session_sync(s);
     if (rc) return rc;
-    unsigned long long c[2] = {0, 0};
-    GFS_CUDA(cudaMemcpy(c, s->d_counters, 16, cudaMemcpyDeviceToHost));
+    unsigned long long c[3] = {0, 0, 0};
+    GFS_CUDA(cudaMemcpy(c, s->d_counters, 24, cudaMemcpyDeviceToHost));
+    if (c[2] != 0) {
+        set_error("SGD kernel watchdog tripped: a warp exceeded its iteration bound (sampling cannot find valid terms?)");
+        return GFS_ERR_CUDA;
+    }
     std::memset(st, 0, sizeof *st);
     st->applied_updates = c[0]; st->attempts = c[1];
     st->epochs = s->n_epochs; st->launches = s->launches;
