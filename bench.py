@@ -354,14 +354,14 @@ def run_ours(a, wl):
         h2d = sg.S * 8 + (sg.P + 1) * 8 + nodes * 4 + x0.nbytes
         e2e_updates = (p2.iter_max + 1) * M
         stress = None
-        if world == 1 and a.stress:
-            g = None
-            stress = G.layout_stress(g, xf, max(dims, 1), 1_000_000, ix, layout_order=dims > 0)
+        if a.stress and rank == 0:      # N > 1: sampled over the paths rank 0 holds
+            stress = G.layout_stress(None, xf, max(dims, 1), 1_000_000, ix, layout_order=dims > 0)
         e2e = {"value": e2e_updates / dt, "unit": "updates/s", "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(xf.nbytes), "seconds": dt, "epochs": p2.iter_max + 1,
                "what": "gfs_index_build from pinned host arrays + upload + full schedule + download, wall clock "
                        "around synchronised calls; one e2e step = one complete Y/L call",
-               "stress_mean_abs_rel": stress[1] if stress else None, "stress_rms_rel": stress[0] if stress else None}
+               "stress_mean_abs_rel": stress[1] if stress else None, "stress_rms_rel": stress[0] if stress else None,
+               "stress_over": ("all paths" if world == 1 else f"paths [{shard.path_begin},{shard.path_end}) of rank 0") if stress else None}
         run.close(); ix.close()
     sg.close()
 

@@ -41,7 +41,7 @@ def main():
                 if a.updates:
                     try:
                         f = float(v.replace(",", ""))
-                        scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3}.get(units[i], 1.0)
+                        scale = {"Tbyte": 1e12, "Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3}.get(units[i], 1.0)
                         extra = f" {f * scale / a.updates:.2f} |" if (".sum" in k and "time" not in k) else " |"
                     except ValueError:
                         extra = " |"
