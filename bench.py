@@ -340,12 +340,19 @@ def run_ours(a, wl):
         barrier()
         t0 = time.perf_counter()
         ix, p2, run = build_run(e_iter)               # H2D: step handles, first_step, node lengths (pinned host)
+        t1 = time.perf_counter()
         run.upload(x0)                                # H2D: initial positions
+        t2 = time.perf_counter()
         for e in range(p2.iter_max + 1):
             run.run_epoch(e)
+        torch.cuda.synchronize()
+        t3 = time.perf_counter()
         xf = run.download()                           # D2H: final positions
         barrier()
         dt = time.perf_counter() - t0
+        if rank == 0:
+            log(f"[bench] e2e phases: index build + session {t1-t0:.3f}s, upload {t2-t1:.3f}s, "
+                f"{p2.iter_max+1} epochs {t3-t2:.3f}s, download {time.perf_counter()-t3:.3f}s")
         t = torch.tensor([dt], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -430,7 +430,6 @@ struct KernelGraph {
     uint32_t l2_hints;            // bit 0: partner records evict_first, bit 1: sampled records evict_first,
                                   // bit 2: positions evict_last
     uint32_t coherent;            // 1: the lanes of a warp sample 32 consecutive steps (see sample_s1)
-    uint32_t partner_group;       // coherent only: 2^k adjacent lanes share one partner draw (1 = independent)
     uint64_t samp_base, samp_len; // sampled steps are drawn from [samp_base, samp_base + samp_len) (default 0, S)
 };
 
@@ -465,7 +464,6 @@ struct Slot {
     double zeta;
     uint32_t n, ra, J;
     uint32_t coins;            // r.z
-    uint32_t group_off;        // lane's offset inside its partner group (0 when partners are independent)
     bool zipf, back, live;     // live: a partner is drawn (n > 1 and the Zipf branch has room to move)
     bool other_a, other_b;
     bool valid;
@@ -480,7 +478,6 @@ __device__ __forceinline__ void sample_s1(const KernelGraph& g, const PathLookup
     const uint64_t r01 = ((uint64_t)r.y << 32) | r.x;
     t.r23 = ((uint64_t)r.w << 32) | r.z;
     t.coins = r.z;
-    t.group_off = 0;
     // step ~ U[win_base, win_base + win_len) on the circular sampling range; the default window
     // (samp_base, samp_len) = (0, S) is the reference's U[0, S) (sgd.rs:444)
     uint64_t s = win_base + __umul64hi(r01, win_len);
@@ -490,18 +487,6 @@ __device__ __forceinline__ void sample_s1(const KernelGraph& g, const PathLookup
         // the 32 sampled records — and, with the node relabelling, most of their nodes' positions — are
         // adjacent in memory: one coalesced request instead of 32.  Partners stay independent per lane.
         s = __shfl_sync(warp_mask, s, __ffs(warp_mask) - 1) + (uint32_t)lane;
-        if (g.partner_group > 1) {
-            // grouped partners: the 2^k lanes of a group (consecutive sampled steps) use the draw of the
-            // group's first lane — same branch coins, same u / uniform rank — so that their partners are
-            // (nearly) consecutive steps too and share cache lines: one 128-byte DRAM line serves up to 8
-            // terms instead of 1.  Each lane still applies the draw to its own rank and path, so every
-            // (step, partner) pair keeps the reference's probability up to O(1/path length).
-            const int lead = lane & ~(int)(g.partner_group - 1);
-            const uint32_t z_lo = __shfl_sync(warp_mask, r.z, lead), z_hi = __shfl_sync(warp_mask, r.w, lead);
-            t.r23 = ((uint64_t)z_hi << 32) | z_lo;
-            t.coins = (r.z & ~3u) | (z_lo & 3u);            // end coins (nD) stay per lane
-            t.group_off = (uint32_t)(lane - lead);
-        }
     }
     if (s >= g.samp_base + g.samp_len) s -= g.samp_len;
     t.step_a = s;
@@ -538,8 +523,7 @@ __device__ __forceinline__ void sample_s2(const KernelGraph& g, const EpochDesc&
     const uint32_t rb_back = ra >= z ? ra - z : 0u;                                        // saturating_sub
     const uint32_t rb_fwd = z < room ? ra + z : n - 1;                                     // min(ra + z, n - 1)
     const uint32_t rb_zipf = t.back ? rb_back : rb_fwd;
-    uint32_t rb_unif = (uint32_t)__umul64hi(t.r23, (uint64_t)n) + t.group_off;             // sgd.rs:493-494
-    if (rb_unif >= n) rb_unif -= n;                        // (grouped partners: consecutive ranks, circular)
+    const uint32_t rb_unif = (uint32_t)__umul64hi(t.r23, (uint64_t)n);                     // sgd.rs:493-494
     const uint32_t rb = t.zipf ? rb_zipf : rb_unif;
     t.valid = t.live && ra != rb;                                                          // sgd.rs:497
     t.step_b = t.valid ? t.f + rb : t.step_a;
@@ -783,7 +767,7 @@ sgd_kernel(const SgdArgs a) {
     const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t T = gridDim.x * blockDim.x;
     uint64_t attempt = a.attempt_ctr[tid];
-    uint64_t applied = 0, attempts0 = attempt;
+    uint64_t applied = 0, n_attempts = 0;
     const uint2 key = make_uint2(a.seed_lo, a.seed_hi);
 
     // ---- software pipeline -------------------------------------------------------------------------
@@ -970,7 +954,11 @@ sgd_kernel(const SgdArgs a) {
                 const bool active = owed > (uint64_t)k;
                 const uint4 r = philox4x32_10(make_uint4((uint32_t)attempt, (uint32_t)(attempt >> 32),
                                                          a.tid_base + tid, STREAM_SGD), key);
-                attempt += active ? 1 : 0;
+                // the Philox counter advances with every draw this lane makes — also on draws made only on
+                // behalf of other lanes (warp-coherent steps, grouped partners): a lane that has finished
+                // its share must not keep serving the same block to its neighbours
+                attempt += (active || a.g.coherent) ? 1 : 0;
+                n_attempts += active ? 1 : 0;
                 Slot t;
                 sample_s1(a.g, pl, ep, r, win_base, win_len, active, warp_mask, lane, t);
                 sample_s2(a.g, ep, t);
@@ -983,7 +971,7 @@ sgd_kernel(const SgdArgs a) {
     applied = done;
     a.attempt_ctr[tid] = attempt;
     // counters: one atomic pair per full warp (partial warps: one pair per thread)
-    uint64_t att = attempt - attempts0;
+    uint64_t att = n_attempts;
     if (warp_mask == 0xffffffffu) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
@@ -1181,7 +1169,6 @@ struct gfs_sgd_session {
     int l2_hints = 7;           // KernelGraph::l2_hints
     int inflight = 2;           // terms in flight per thread (kernel template parameter K)
     bool coherent = true;       // warp-coherent step sampling in the sweep schedule
-    uint32_t partner_group = 1; // lanes sharing one partner draw (power of two)
     uint64_t window_steps = 0;  // 0 = static schedule
     uint32_t chunk_updates = 128;
     unsigned long long* d_work = nullptr;
@@ -1593,9 +1580,6 @@ extern "C" int gfs_sgd_session_create(const gfs_index* ix, const gfs_sgd_params*
         s->window_steps = w > 0 ? std::max<uint64_t>((uint64_t)w, 1024) : 0;
         s->chunk_updates = (uint32_t)std::max<long>(1, env_long("GFASORT_CHUNK", 256));
         s->coherent = env_long("GFASORT_COHERENT", 1) != 0;
-        long pg = env_long("GFASORT_PARTNER_GROUP", 1);
-        s->partner_group = 1;
-        while (s->partner_group * 2 <= (uint32_t)std::min<long>(std::max<long>(pg, 1), 32)) s->partner_group *= 2;
         SS_CUDA(cudaMalloc(&s->d_work, 8));
     }
 
@@ -1701,7 +1685,6 @@ extern "C" int gfs_sgd_session_run(gfs_sgd_session* s, uint64_t epoch_begin, uin
     a.g.samp_base = s->samp_base; a.g.samp_len = s->samp_len;
     a.g.l2_hints = (uint32_t)s->l2_hints;
     a.g.coherent = (s->window_steps > 0 && s->coherent) ? 1u : 0u;
-    a.g.partner_group = a.g.coherent ? s->partner_group : 1u;
     a.epochs = s->d_epochs;
     a.epoch_begin = (uint32_t)epoch_begin; a.epoch_end = (uint32_t)epoch_end;
     a.slice = slice; a.n_slices = n_slices;

@@ -102,11 +102,15 @@ class PathIndex:
         return self._h
 
     def _export(self):
+        """Step offsets (S x 8 bytes device -> host): only the accessors that need them pay for it."""
         if self._pos is None:
-            S, P = self.get_total_steps(), self.num_paths()
-            self._pos = np.zeros(S, dtype=np.uint64)
-            self._len = np.zeros(P, dtype=np.uint64)
-            check(lib().gfs_index_export(self._h, _p(self._pos, u64p), _p(self._len, u64p)))
+            self._pos = np.empty(self.get_total_steps(), dtype=np.uint64)
+            check(lib().gfs_index_export(self._h, _p(self._pos, u64p), None))
+
+    def _export_lengths(self):
+        if self._len is None:
+            self._len = np.zeros(self.num_paths(), dtype=np.uint64)
+            check(lib().gfs_index_export(self._h, None, _p(self._len, u64p)))
 
     # --- accessors, names as in the reference ---
     def get_total_steps(self) -> int:
@@ -143,7 +147,7 @@ class PathIndex:
         return len(self._first) - 1
 
     def get_path_length(self, path_idx: int) -> int:
-        self._export()
+        self._export_lengths()
         return int(self._len[path_idx])
 
     # bulk views (numpy) for tests / parameter derivation
@@ -152,7 +156,7 @@ class PathIndex:
         return self._pos
 
     def path_lengths(self) -> np.ndarray:
-        self._export()
+        self._export_lengths()
         return self._len
 
     def path_step_counts(self) -> np.ndarray:
