@@ -363,6 +363,13 @@ def run_ours(a, wl):
         stress = None
         if a.stress and rank == 0:      # N > 1: sampled over the paths rank 0 holds
             stress = G.layout_stress(None, xf, max(dims, 1), 1_000_000, ix, layout_order=dims > 0)
+        stress_k = None
+        if a.stress and rank == 0 and world == 1 and a.stress_paths:
+            k = min(a.stress_paths, paths)
+            six = G.PathIndex.from_arrays(sg.step_handles, sg.path_first, node_len, path_begin=0, path_end=k, device=local, relabel=0)
+            stress_k = G.layout_stress(None, xf, max(dims, 1), 1_000_000, six, layout_order=dims > 0)
+            six.close()
+            log(f"[bench] stress over paths [0,{k}): mean_abs {stress_k[1]:.4e} rms {stress_k[0]:.4e}")
         e2e = {"value": e2e_updates / dt, "unit": "updates/s", "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(xf.nbytes), "seconds": dt, "epochs": p2.iter_max + 1,
                "what": "gfs_index_build from pinned host arrays + upload + full schedule + download, wall clock "
@@ -409,8 +416,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=os.environ.get("GFASORT_BENCH_WORKLOAD", "y10m"), choices=sorted(WORKLOADS))
     ap.add_argument("--seed", type=int, default=42)
-    ap.add_argument("--syncs", type=int, default=int(os.environ.get("GFASORT_SYNCS", "4")), help="replica reconciles per epoch (N > 1)")
-    ap.add_argument("--reconcile", default="avg", choices=["avg", "delta"])
+    ap.add_argument("--syncs", type=int, default=int(os.environ.get("GFASORT_SYNCS", "2")), help="replica reconciles per epoch (N > 1)")
+    ap.add_argument("--reconcile", default=os.environ.get("GFASORT_RECONCILE", "tavg"), choices=["avg", "tavg", "delta"])
+    ap.add_argument("--stress-paths", type=int, default=0, help="N = 1: also report the stress over the first K paths only (to compare with rank 0 of a multi-GPU run)")
     ap.add_argument("--e2e-epochs", type=int, default=-1, help="-1 = the full schedule, 0 = skip the e2e leg")
     ap.add_argument("--stress", type=int, default=1, help="report the sampled path stress of the e2e result")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")

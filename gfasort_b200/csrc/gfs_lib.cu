@@ -1066,6 +1066,29 @@ __global__ void pos_from_device(const CT* __restrict__ src, double* __restrict__
 }
 
 // =============================================================================================
+// K5 — replica reconcile helpers (multi-GPU; the all-reduce itself is NCCL, driven by the host)
+// =============================================================================================
+// pack:  buf[i] = float(x[i] - x_sync[i]),  buf[n + i] = (x[i] != x_sync[i])      (one f32 buffer, one all-reduce)
+// apply: x[i] = x_sync[i] + buf[i] / max(buf[n + i], 1);  x_sync[i] = x[i]
+// i.e. the mean of the displacements over the replicas that moved the element since the last sync.
+template <typename CT>
+__global__ void __launch_bounds__(256) rc_pack(const CT* __restrict__ x, const CT* __restrict__ xs, uint64_t n, float* __restrict__ buf) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const CT d = x[i] - xs[i];
+        buf[i] = (float)d;
+        buf[n + i] = d != CT(0) ? 1.0f : 0.0f;
+    }
+}
+template <typename CT>
+__global__ void __launch_bounds__(256) rc_apply(CT* __restrict__ x, CT* __restrict__ xs, uint64_t n, const float* __restrict__ buf) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const float c = buf[n + i];
+        const CT v = xs[i] + (CT)buf[i] / (CT)(c > 1.0f ? c : 1.0f);
+        x[i] = v; xs[i] = v;
+    }
+}
+
+// =============================================================================================
 // debug kernels
 // =============================================================================================
 __global__ void dbg_fpp(const double* a, const double* b, double* out, uint64_t n) {
@@ -1910,5 +1933,27 @@ extern "C" int gfs_debug_trace_terms(const gfs_index* ix, const gfs_sgd_params* 
     GFS_CUDA(cudaGetLastError());
     GFS_CUDA(dv.down(valid, count)); GFS_CUDA(da.down(step_a, count)); GFS_CUDA(db.down(step_b, count));
     GFS_CUDA(df.down(flags, count)); GFS_CUDA(dd.down(dist, count));
+    return GFS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// replica reconcile helpers
+// ---------------------------------------------------------------------------------------------
+extern "C" int gfs_reconcile_pack(const void* x, const void* x_sync, uint64_t n, uint32_t elem_bytes, float* buf, void* stream) {
+    if (!x || !x_sync || !buf || (elem_bytes != 4 && elem_bytes != 8)) { set_error("gfs_reconcile_pack: bad argument"); return GFS_ERR_INVALID; }
+    if (n == 0) return GFS_OK;
+    const unsigned grid = (unsigned)std::min<uint64_t>((n + 255) / 256, 148 * 16);
+    if (elem_bytes == 8) rc_pack<double><<<grid, 256, 0, (cudaStream_t)stream>>>((const double*)x, (const double*)x_sync, n, buf);
+    else rc_pack<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)x, (const float*)x_sync, n, buf);
+    GFS_CUDA(cudaGetLastError());
+    return GFS_OK;
+}
+extern "C" int gfs_reconcile_apply(void* x, void* x_sync, uint64_t n, uint32_t elem_bytes, const float* buf, void* stream) {
+    if (!x || !x_sync || !buf || (elem_bytes != 4 && elem_bytes != 8)) { set_error("gfs_reconcile_apply: bad argument"); return GFS_ERR_INVALID; }
+    if (n == 0) return GFS_OK;
+    const unsigned grid = (unsigned)std::min<uint64_t>((n + 255) / 256, 148 * 16);
+    if (elem_bytes == 8) rc_apply<double><<<grid, 256, 0, (cudaStream_t)stream>>>((double*)x, (double*)x_sync, n, buf);
+    else rc_apply<float><<<grid, 256, 0, (cudaStream_t)stream>>>((float*)x, (float*)x_sync, n, buf);
+    GFS_CUDA(cudaGetLastError());
     return GFS_OK;
 }

@@ -9,8 +9,8 @@ lives inside one path (reference src/sgd.rs:445, 502-503) — positions do not. 
     min_term_updates * |slice| / S of every epoch, which keeps the global sampling distribution
     uniform over steps (src/sgd.rs:435, 444);
   * replicas are reconciled `syncs_per_epoch` times per epoch by an all-reduce over the position
-    array: "avg" (north star: mean of the replicas) or "delta" (sum of the replicas' displacements
-    since the last sync, i.e. Hogwild with staleness).
+    array: "avg" (north star: mean of the replicas), "tavg" (mean over the replicas that moved the
+    node since the last sync) or "delta" (sum of the replicas' displacements, i.e. Hogwild with staleness).
 
 Everything here is host logic over torch tensors; it runs unchanged on CPU tensors with the gloo
 backend, which is how tests/test_multi_gloo.py covers it without GPUs.
@@ -57,7 +57,7 @@ def epoch_quota(min_term_updates: int, shard: Shard, total_steps: int) -> int:
     return hi - lo
 
 
-def reconcile(x, x_sync, mode: str, group=None):
+def reconcile(x, x_sync, mode: str, group=None, scratch=None):
     """All-reduce the replicas in place.  x: this rank's positions (torch tensor).
     "avg": x <- mean over ranks.  "delta": x <- x_sync + sum over ranks of (x - x_sync); x_sync is
     then refreshed.  Returns x."""
@@ -77,6 +77,29 @@ def reconcile(x, x_sync, mode: str, group=None):
         # sum_g x_g = G*x_sync + sum_g delta_g  =>  x_new = sum_g x_g - (G-1)*x_sync
         dist.all_reduce(x, op=dist.ReduceOp.SUM, group=group)
         x.add_(x_sync, alpha=-(world - 1))
+    elif mode == "tavg":
+        # mean of the displacements over the replicas that MOVED the element since the last sync:
+        # x_new = x_sync + sum_g delta_g / max(1, #{g: delta_g != 0}).  Equal to "avg" where every replica
+        # touched the node; a node only one rank's paths visit keeps its full displacement instead of 1/G of it.
+        import torch
+        if x.is_cuda:
+            # the library's two fused kernels around one f32 all-reduce (displacements travel as f32: the
+            # rounding is relative to the displacement, not to the position), on the current stream
+            from ._cabi import check, lib
+            n = x.numel()
+            if scratch is None or scratch.numel() != 2 * n:
+                scratch = torch.empty(2 * n, dtype=torch.float32, device=x.device)
+            st = torch.cuda.current_stream(x.device).cuda_stream
+            check(lib().gfs_reconcile_pack(x.data_ptr(), x_sync.data_ptr(), n, x.element_size(), scratch.data_ptr(), st))
+            dist.all_reduce(scratch, op=dist.ReduceOp.SUM, group=group)
+            check(lib().gfs_reconcile_apply(x.data_ptr(), x_sync.data_ptr(), n, x.element_size(), scratch.data_ptr(), st))
+            return x                                   # apply refreshed x_sync already
+        buf = torch.empty((2,) + tuple(x.shape), dtype=x.dtype, device=x.device)
+        torch.sub(x, x_sync, out=buf[0])
+        buf[1].copy_(buf[0] != 0)
+        dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
+        buf[1].clamp_(min=1)
+        torch.addcdiv(x_sync, buf[0], buf[1], out=x)
     else:
         raise ValueError(f"unknown reconcile mode {mode!r}")
     if x_sync is not None:
@@ -114,7 +137,8 @@ class ReplicaRun:
         f64 = dims == 0 or layout_f64
         n_elems = self.N if dims == 0 else self.N * 2 * _DS[dims]
         self.x = torch.zeros(n_elems, dtype=torch.float64 if f64 else torch.float32, device=f"cuda:{device}")
-        self.x_sync = torch.empty_like(self.x) if mode == "delta" else None
+        self.x_sync = torch.empty_like(self.x) if mode in ("delta", "tavg") else None
+        self.scratch = torch.empty(2 * n_elems, dtype=torch.float32, device=self.x.device) if mode == "tavg" else None
         self.stream = torch.cuda.Stream(device=device)
         from dataclasses import replace
         self.params = replace(params, min_term_updates=epoch_quota(params.min_term_updates, shard, total_steps))
@@ -159,7 +183,7 @@ class ReplicaRun:
         with torch.cuda.stream(self.stream):
             for k in range(self.syncs):
                 check(lib().gfs_sgd_session_run(self._h, epoch, epoch + 1, k, self.syncs))
-                reconcile(self.x, self.x_sync, self.mode, self.group)
+                reconcile(self.x, self.x_sync, self.mode, self.group, self.scratch)
 
     def stats(self) -> dict:
         import ctypes as C

@@ -176,6 +176,17 @@ int gfs_sgd_session_positions(gfs_sgd_session* s, void** dev_ptr, uint64_t* n_el
 int gfs_sgd_session_stats(gfs_sgd_session* s, gfs_stats* stats);             /* synchronises first */
 void gfs_sgd_session_destroy(gfs_sgd_session* s);
 
+/* ---- replica reconcile (multi-GPU) ---------------------------------------------
+ * The exchange step of a replicated run is one all-reduce(sum) of `buf` (2n floats) that the host
+ * issues (NCCL) between these two asynchronous kernels, all on `stream`:
+ *   pack:  buf[i] = x[i] - x_sync[i];  buf[n+i] = (x[i] != x_sync[i])
+ *   apply: x[i] = x_sync[i] + buf[i] / max(buf[n+i], 1);  x_sync[i] = x[i]
+ * = the mean of the displacements over the replicas that moved the element since the last sync
+ * (equal to the plain replica mean wherever every replica moved it).  x / x_sync: device pointers to
+ * n elements of elem_bytes (8 = f64 positions, 4 = f32 coordinates). */
+int gfs_reconcile_pack(const void* x, const void* x_sync, uint64_t n, uint32_t elem_bytes, float* buf, void* stream);
+int gfs_reconcile_apply(void* x, void* x_sync, uint64_t n, uint32_t elem_bytes, const float* buf, void* stream);
+
 /* ---- synthetic pangenome graphs (bench / tests input) -------------------------
  * Seeded bubble-chain generator writing the C-ABI's own flat inputs.  Two calls: sizes, then fill. */
 typedef struct gfs_synth_spec {

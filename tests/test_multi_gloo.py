@@ -64,6 +64,16 @@ def _worker(rank, world, port, out_dir):
         want = x_sync + sum(deltas)
         assert torch.allclose(x, want, atol=1e-12), "delta"
         assert torch.equal(xs, x), "x_sync refreshed"
+        # --- tavg: mean over the replicas that moved the element; untouched elements stay put
+        xs = x_sync.clone()
+        moved = [torch.rand(1000, generator=torch.Generator().manual_seed(200 + r)) < 0.5 for r in range(world)]
+        x = xs + deltas[rank] * moved[rank]
+        reconcile(x, xs, "tavg")
+        cnt = sum(m.double() for m in moved).clamp(min=1)
+        want = x_sync + sum(d * m for d, m in zip(deltas, moved)) / cnt
+        assert torch.allclose(x, want, atol=1e-12), "tavg"
+        none = ~(moved[0] | moved[1])
+        assert torch.equal(x[none], x_sync[none])
         # replicas are identical after a reconcile (bitwise: same reduction on every rank)
         gathered = [torch.empty_like(x) for _ in range(world)]
         dist.all_gather(gathered, x)
