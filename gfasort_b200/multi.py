@@ -155,6 +155,7 @@ class ReplicaRun:
         cp = self.params.c()
         check(lib().gfs_sgd_session_create(self.index.handle, C.byref(cp), dims, C.byref(cfg), C.byref(self._h)))
         self.n_epochs = params.iter_max + 1
+        torch.cuda.synchronize(device)        # allocations / zero fills on torch's stream are done before the session's stream runs
 
     def upload(self, positions):
         """Host positions (f64, the caller's node order / Layout order) -> this rank's replica."""
@@ -162,9 +163,15 @@ class ReplicaRun:
 
         from ._cabi import check, f64p, lib
         positions = np.ascontiguousarray(positions, dtype=np.float64)
+        import torch
         check(lib().gfs_sgd_session_upload(self._h, positions.ctypes.data_as(f64p)))
         if self.x_sync is not None:
-            self.x_sync.copy_(self.x)
+            # on the session's stream: torch's default stream does not order against it (non-blocking
+            # streams), and a snapshot racing the first SGD launch would leave the ranks with different
+            # x_sync — which "tavg" / "delta" never repair
+            with torch.cuda.stream(self.stream):
+                self.x_sync.copy_(self.x)
+        torch.cuda.synchronize(self.device)
 
     def download(self):
         import numpy as np
