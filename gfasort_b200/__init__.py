@@ -10,7 +10,7 @@ from .graph import BidirectedGraph, load_gfa  # noqa: F401
 from .layout import Layout  # noqa: F401
 from .sgd import (LayoutSGDParams, PathIndex, PathSGDParams, YgsParams, calculate_layout_stress,  # noqa: F401
                   initial_layout, initial_positions, layout_stress, path_linear_sgd, path_linear_sgd_array,
-                  path_linear_sgd_layout, path_sgd_sort, sgd_sort_only, sort_stress)
+                  path_linear_sgd_layout, path_sgd_sort, sgd_sort_only, sort_positions, sort_stress)
 from .synth import SynthGraph  # noqa: F401
 
 __version__ = "0.1.0"

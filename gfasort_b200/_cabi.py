@@ -90,6 +90,9 @@ SIGNATURES = {
     "gfs_sgd_session_positions": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), u64p, u32p]),
     "gfs_sgd_session_stats": (C.c_int, [C.c_void_p, C.POINTER(Stats)]),
     "gfs_sgd_session_destroy": (None, [C.c_void_p]),
+    "gfs_sort_positions": (C.c_int, [f64p, C.c_uint64, u32p]),
+    "gfs_sgd_session_sort": (C.c_int, [C.c_void_p, u32p]),
+    "gfs_sgd_sort_1d": (C.c_int, [C.c_void_p, C.POINTER(SgdParams), f64p, u32p, C.POINTER(Stats)]),
     "gfs_reconcile_pack": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p]),
     "gfs_reconcile_apply": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p]),
     "gfs_synth_create": (C.c_int, [C.POINTER(SynthSpec), C.POINTER(C.c_void_p)]),

@@ -1066,6 +1066,109 @@ __global__ void pos_from_device(const CT* __restrict__ src, double* __restrict__
 }
 
 // =============================================================================================
+// K6 — order by position (the host side of path_sgd_sort, src/sgd.rs:659-671)
+// =============================================================================================
+// Stable LSD radix sort of (key = order-preserving image of the f64 position, value = dense idx), 8-bit
+// digits, 8 passes.  Stability + values starting as 0..n-1 gives "ties by dense idx" (the reference sorts
+// (idx, pos) pairs in HashMap iteration order with a stable sort, i.e. its tie order is unspecified).
+constexpr int RS_THREADS = 256;
+constexpr int RS_ITEMS = 16;                       // keys per thread, processed in index order
+constexpr int RS_TILE = RS_THREADS * RS_ITEMS;
+
+// f64 -> u64 whose unsigned order is the numeric order; -0.0 == +0.0 (partial_cmp: Equal); NaN last.
+__device__ __forceinline__ uint64_t f64_sort_key(double v) {
+    if (v != v) return ~0ull;
+    if (v == 0.0) v = 0.0;
+    const uint64_t b = (uint64_t)__double_as_longlong(v);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+__global__ void rs_make_keys(const double* __restrict__ x, uint64_t n, uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { keys[i] = f64_sort_key(x[i]); vals[i] = (uint32_t)i; }
+}
+// hist[d * n_blocks + b] = number of keys of tile b whose digit is d
+__global__ void __launch_bounds__(RS_THREADS)
+rs_hist(const uint64_t* __restrict__ keys, uint64_t n, int shift, uint32_t n_blocks, uint32_t* __restrict__ hist) {
+    __shared__ uint32_t h[256];
+    h[threadIdx.x] = 0;
+    __syncthreads();
+    const uint64_t base = (uint64_t)blockIdx.x * RS_TILE;
+#pragma unroll
+    for (int k = 0; k < RS_ITEMS; ++k) {
+        const uint64_t i = base + (uint64_t)k * RS_THREADS + threadIdx.x;
+        if (i < n) atomicAdd(&h[(uint32_t)(keys[i] >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    hist[(size_t)threadIdx.x * n_blocks + blockIdx.x] = h[threadIdx.x];
+}
+// exclusive scan of hist in place (digit-major), one block
+__global__ void __launch_bounds__(1024) rs_scan(uint32_t* __restrict__ hist, uint64_t m) {
+    __shared__ uint32_t wsum[32];
+    __shared__ uint32_t running;
+    if (threadIdx.x == 0) running = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (uint64_t b0 = 0; b0 < m; b0 += 1024) {
+        const uint64_t i = b0 + threadIdx.x;
+        const uint32_t v = i < m ? hist[i] : 0u;
+        uint32_t inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+        if (lane == 31) wsum[w] = inc;
+        __syncthreads();
+        if (w == 0) {
+            const uint32_t ws = wsum[lane];
+            uint32_t wi = ws;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, wi, o); if (lane >= o) wi += t; }
+            wsum[lane] = wi - ws;
+        }
+        __syncthreads();
+        const uint32_t excl = running + wsum[w] + inc - v;
+        if (i < m) hist[i] = excl;
+        __syncthreads();
+        if (threadIdx.x == 1023) running = excl + v;
+        __syncthreads();
+    }
+}
+// stable scatter: tile b writes its keys of digit d to offs[d * n_blocks + b] + (rank among the tile's digit-d keys)
+__global__ void __launch_bounds__(RS_THREADS)
+rs_scatter(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals, uint64_t n, int shift, uint32_t n_blocks,
+           const uint32_t* __restrict__ offs, uint64_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out) {
+    __shared__ uint32_t bin_off[256];                       // next free slot of each digit for this tile
+    __shared__ uint32_t warp_cnt[RS_THREADS / 32][256];
+    bin_off[threadIdx.x] = offs[(size_t)threadIdx.x * n_blocks + blockIdx.x];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const uint64_t base = (uint64_t)blockIdx.x * RS_TILE;
+    for (int k = 0; k < RS_ITEMS; ++k) {                    // 256 consecutive keys at a time, in index order
+#pragma unroll
+        for (int q = 0; q < RS_THREADS / 32; ++q) warp_cnt[q][threadIdx.x] = 0;
+        __syncthreads();
+        const uint64_t i = base + (uint64_t)k * RS_THREADS + threadIdx.x;
+        const bool ok = i < n;
+        const uint64_t key = ok ? keys[i] : 0ull;
+        const uint32_t d = ok ? ((uint32_t)(key >> shift) & 255u) : 256u;       // 256: matches only other padding lanes
+        const unsigned peers = __match_any_sync(0xffffffffu, d);
+        const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
+        if (ok && rank == 0) warp_cnt[w][d] = __popc(peers);
+        __syncthreads();
+        {   // thread t owns digit t: turn per-warp counts into per-warp offsets, advance the tile's cursor
+            uint32_t run = bin_off[threadIdx.x];
+#pragma unroll
+            for (int q = 0; q < RS_THREADS / 32; ++q) { const uint32_t c = warp_cnt[q][threadIdx.x]; warp_cnt[q][threadIdx.x] = run; run += c; }
+            bin_off[threadIdx.x] = run;
+        }
+        __syncthreads();
+        if (ok) {
+            const uint32_t dst = warp_cnt[w][d] + rank;
+            keys_out[dst] = key;
+            vals_out[dst] = vals[i];
+        }
+        __syncthreads();
+    }
+}
+
+// =============================================================================================
 // K5 — replica reconcile helpers (multi-GPU; the all-reduce itself is NCCL, driven by the host)
 // =============================================================================================
 // pack:  buf[i] = float(x[i] - x_sync[i]),  buf[n + i] = (x[i] != x_sync[i])      (one f32 buffer, one all-reduce)
@@ -1956,4 +2059,88 @@ extern "C" int gfs_reconcile_apply(void* x, void* x_sync, uint64_t n, uint32_t e
     else rc_apply<float><<<grid, 256, 0, (cudaStream_t)stream>>>((float*)x, (float*)x_sync, n, buf);
     GFS_CUDA(cudaGetLastError());
     return GFS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// order by position
+// ---------------------------------------------------------------------------------------------
+// d_x: n positions on the device, in the caller's node order.  d_order: n dense indices.  Asynchronous on st.
+static int sort_positions_device(const double* d_x, uint64_t n, uint32_t* d_order, cudaStream_t st, uint64_t* launches) {
+    if (n == 0) return GFS_OK;
+    if (n >= (1ull << 32)) { set_error("sort: n must be < 2^32"); return GFS_ERR_INVALID; }
+    const uint32_t n_blocks = (uint32_t)((n + RS_TILE - 1) / RS_TILE);
+    uint64_t *k0 = nullptr, *k1 = nullptr; uint32_t *v1 = nullptr, *hist = nullptr;
+    GFS_CUDA(cudaMalloc(&k0, n * 8)); GFS_CUDA(cudaMalloc(&k1, n * 8));
+    GFS_CUDA(cudaMalloc(&v1, n * 4)); GFS_CUDA(cudaMalloc(&hist, (size_t)256 * n_blocks * 4));
+    uint32_t* v0 = d_order;
+    rs_make_keys<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_x, n, k0, v0);
+    uint64_t nl = 1;
+    for (int pass = 0; pass < 8; ++pass) {
+        rs_hist<<<n_blocks, RS_THREADS, 0, st>>>(k0, n, pass * 8, n_blocks, hist);
+        rs_scan<<<1, 1024, 0, st>>>(hist, (uint64_t)256 * n_blocks);
+        rs_scatter<<<n_blocks, RS_THREADS, 0, st>>>(k0, v0, n, pass * 8, n_blocks, hist, k1, v1);
+        std::swap(k0, k1); std::swap(v0, v1);
+        nl += 3;
+    }
+    // 8 passes: the result is back in the buffers it started in (v0 == d_order)
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    cudaFree(k0); cudaFree(k1); cudaFree(v1 == d_order ? v0 : v1); cudaFree(hist);
+    if (e != cudaSuccess) { set_error(std::string("sort failed: ") + cudaGetErrorString(e)); return GFS_ERR_CUDA; }
+    if (launches) *launches += nl;
+    return GFS_OK;
+}
+
+extern "C" int gfs_sort_positions(const double* x, uint64_t n, uint32_t* order) {
+    if ((n && !x) || (n && !order)) { set_error("gfs_sort_positions: null argument"); return GFS_ERR_INVALID; }
+    int rc = select_device(-1); if (rc) return rc;
+    if (n == 0) return GFS_OK;
+    DevBuf<double> dx; DevBuf<uint32_t> dord;
+    GFS_CUDA(dx.alloc(n)); GFS_CUDA(dord.alloc(n));
+    GFS_CUDA(dx.up(x, n));
+    rc = sort_positions_device(dx.p, n, dord.p, nullptr, nullptr);
+    if (rc) return rc;
+    GFS_CUDA(dord.down(order, n));
+    return GFS_OK;
+}
+
+extern "C" int gfs_sgd_session_sort(gfs_sgd_session* s, uint32_t* order) {
+    if (!s || !order) { set_error("gfs_sgd_session_sort: null argument"); return GFS_ERR_INVALID; }
+    if (s->dims != 0) { set_error("gfs_sgd_session_sort: 1D sessions only"); return GFS_ERR_INVALID; }
+    GFS_CUDA(cudaSetDevice(s->device));
+    int rc = session_flush_events(s);
+    if (rc) return rc;
+    const uint64_t N = s->ix->N;
+    // positions in the caller's node order (undo the internal relabelling), then sort
+    if (!s->d_stage) GFS_CUDA(cudaMalloc(&s->d_stage, N * 8));
+    pos_from_device<double><<<(unsigned)((N + 255) / 256), 256, 0, s->stream>>>((const double*)s->d_pos, s->d_stage, N, 1, 1, 1, s->ix->d_new_of_old);
+    GFS_CUDA(cudaGetLastError());
+    DevBuf<uint32_t> dord;
+    GFS_CUDA(dord.alloc(N));
+    rc = sort_positions_device(s->d_stage, N, dord.p, s->stream, &s->launches);
+    if (rc) return rc;
+    const double t0 = now_s();
+    GFS_CUDA(dord.down(order, N));
+    s->d2h_s += now_s() - t0;
+    return GFS_OK;
+}
+
+extern "C" int gfs_sgd_sort_1d(const gfs_index* ix, const gfs_sgd_params* params, double* x_inout, uint32_t* order_out,
+                               gfs_stats* stats) {
+    if (!x_inout || !order_out) { set_error("gfs_sgd_sort_1d: null buffer"); return GFS_ERR_INVALID; }
+    const double t0 = now_s();
+    gfs_sgd_session* s = nullptr;
+    int rc = gfs_sgd_session_create(ix, params, 0, nullptr, &s);
+    if (rc) return rc;
+    rc = gfs_sgd_session_upload(s, x_inout);
+    if (!rc) rc = gfs_sgd_session_run(s, 0, s->n_epochs, 0, 1);
+    if (!rc) rc = gfs_sgd_session_sync(s);
+    if (!rc) rc = gfs_sgd_session_sort(s, order_out);
+    if (!rc) rc = gfs_sgd_session_download(s, x_inout);
+    gfs_stats st{};
+    if (!rc) rc = gfs_sgd_session_stats(s, &st);
+    st.total_seconds = now_s() - t0;
+    if (stats && !rc) *stats = st;
+    gfs_sgd_session_destroy(s);
+    return rc;
 }

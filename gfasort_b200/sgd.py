@@ -304,16 +304,41 @@ def path_linear_sgd_array(graph: BidirectedGraph, params: PathSGDParams, path_in
             ix.close()
 
 
+def sort_positions(x: np.ndarray) -> np.ndarray:
+    """Dense indices ordered by position (stable, ties by idx) — on the GPU (gfs_sort_positions)."""
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    order = np.zeros(len(x), dtype=np.uint32)
+    check(lib().gfs_sort_positions(_p(x, f64p), len(x), _p(order, u32p)))
+    return order
+
+
 def path_sgd_sort(graph: BidirectedGraph, params: PathSGDParams, path_index: PathIndex | None = None) -> np.ndarray:
     """src/sgd.rs:641-672: forward handles of all nodes, sorted by final position (stable; ties by
-    dense idx — the reference's tie order is HashMap iteration order, i.e. unspecified)."""
-    x = path_linear_sgd_array(graph, params, path_index)
-    if x is None:
+    dense idx — the reference's tie order is HashMap iteration order, i.e. unspecified).  SGD and sort
+    both run on the device (gfs_sgd_sort_1d); only the order comes back."""
+    if graph.node_count() == 0:
         return np.zeros(0, dtype=np.uint64)
-    node_ids = graph.node_ids()
-    order = np.argsort(x, kind="stable")
-    order = order[order < len(node_ids)]
-    return node_ids[order].astype(np.uint64) << np.uint64(1)
+    own = path_index is None
+    ix = PathIndex.from_graph(graph) if own else path_index
+    try:
+        x = initial_positions(graph)
+        order = np.zeros(len(x), dtype=np.uint32)
+        st = Stats()
+        cp = params.c()
+        rc = lib().gfs_sgd_sort_1d(ix.handle, C.byref(cp), _p(x, f64p), _p(order, u32p), C.byref(st))
+        if rc == _cabi.GFS_ERR_NO_VALID_PATH:
+            print("[path_sgd] No paths with multiple steps found", file=sys.stderr)
+            return np.zeros(0, dtype=np.uint64)
+        check(rc)
+        last_stats.clear()
+        last_stats.update(st.as_dict())
+        last_stats["positions"] = x
+        node_ids = graph.node_ids()
+        order = order[order < len(node_ids)]
+        return node_ids[order.astype(np.int64)].astype(np.uint64) << np.uint64(1)
+    finally:
+        if own:
+            ix.close()
 
 
 def sgd_sort_only(graph: BidirectedGraph, params: PathSGDParams, verbose: int = 0) -> None:

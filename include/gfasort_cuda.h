@@ -176,6 +176,17 @@ int gfs_sgd_session_positions(gfs_sgd_session* s, void** dev_ptr, uint64_t* n_el
 int gfs_sgd_session_stats(gfs_sgd_session* s, gfs_stats* stats);             /* synchronises first */
 void gfs_sgd_session_destroy(gfs_sgd_session* s);
 
+/* ---- order by position -----------------------------------------------------
+ * The host side of path_sgd_sort (src/sgd.rs:659-671) on the device: order[k] = dense idx of the node
+ * with the k-th smallest position; stable, ties by dense idx (the reference's stable sort starts from
+ * HashMap iteration order, so its tie order is unspecified); -0.0 == +0.0; NaN last.  n < 2^32. */
+int gfs_sort_positions(const double* x /*host, n*/, uint64_t n, uint32_t* order /*host, n*/);
+/* Same on a 1D session's current positions (no position download, no host sort). */
+int gfs_sgd_session_sort(gfs_sgd_session* s, uint32_t* order /*host, N*/);
+/* path_sgd_sort in one call: gfs_sgd_1d followed by the sort; x_inout as in gfs_sgd_1d. */
+int gfs_sgd_sort_1d(const gfs_index* ix, const gfs_sgd_params* params, double* x_inout, uint32_t* order_out /*N*/,
+                    gfs_stats* stats);
+
 /* ---- replica reconcile (multi-GPU) ---------------------------------------------
  * The exchange step of a replicated run is one all-reduce(sum) of `buf` (2n floats) that the host
  * issues (NCCL) between these two asynchronous kernels, all on `stream`:
