@@ -12,5 +12,7 @@ from .sgd import (LayoutSGDParams, PathIndex, PathSGDParams, YgsParams, calculat
                   initial_layout, initial_positions, layout_stress, path_linear_sgd, path_linear_sgd_array,
                   path_linear_sgd_layout, path_sgd_sort, sgd_sort_only, sort_positions, sort_stress)
 from .synth import SynthGraph  # noqa: F401
+from .ygs import (apply_grooming_with_reorder, count_edge_directions, exact_odgi_topological_order,  # noqa: F401
+                  find_head_nodes, groom, groom_only, topological_sort_only, ygs_sort)
 
 __version__ = "0.1.0"

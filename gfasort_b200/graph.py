@@ -142,6 +142,38 @@ class BidirectedGraph:
             self.edges = np.unique(e, axis=0) if len(e) else e
 
 
+def edges_from_paths(steps: np.ndarray, path_first: np.ndarray) -> np.ndarray:
+    """The edge set a GFA writer would emit for a graph given only by its paths: every pair of consecutive
+    steps, stored once per {edge, complement} like add_edge (graph_ops.rs:626-638).  For synthetic graphs."""
+    steps = np.asarray(steps, dtype=np.uint64)
+    first = np.asarray(path_first, dtype=np.int64)
+    if len(steps) < 2:
+        return np.zeros((0, 2), dtype=np.uint64)
+    a, b = steps[:-1], steps[1:]
+    keep = np.ones(len(a), dtype=bool)
+    keep[first[1:-1] - 1] = False                         # no edge across a path boundary
+    a, b = a[keep], b[keep]
+    # one edge per {a->b, b^1->a^1} class, kept in the form in which a path first walks it (what a GFA
+    # writer emitting L lines in path order would store)
+    ca, cb = b ^ np.uint64(1), a ^ np.uint64(1)
+    swap = (ca < a) | ((ca == a) & (cb < b))
+    idx = unique_pair_index(np.where(swap, ca, a), np.where(swap, cb, b))
+    return np.stack([a[idx], b[idx]], axis=1)
+
+
+def unique_pair_index(a: np.ndarray, b: np.ndarray) -> np.ndarray:
+    """Indices (increasing) of the first occurrence of every distinct pair (a[i], b[i])."""
+    if len(a) == 0:
+        return np.zeros(0, dtype=np.int64)
+    if int(a.max()) < (1 << 32) and int(b.max()) < (1 << 32):
+        key = (a.astype(np.uint64) << np.uint64(32)) | b.astype(np.uint64)          # one 1-D sort instead of a row sort
+        _, idx = np.unique(key, return_index=True)
+    else:
+        _, idx = np.unique(np.stack([a, b], axis=1), axis=0, return_index=True)
+    idx.sort()
+    return idx
+
+
 def load_gfa(path: str) -> BidirectedGraph:
     """The CLI's `parse_gfa` (src/bin/gfasort.rs:88-167): numeric ids; S, then L, then P lines."""
     with open(path) as f:
@@ -161,14 +193,17 @@ def load_gfa(path: str) -> BidirectedGraph:
     for nid, s in seqs.items():
         present[nid] = 1
         seq_len[nid] = len(s)
-    edges = []
+    edges, seen = [], set()
     for line in lines:
         if line.startswith("L"):
             parts = line.split("\t")
             if len(parts) >= 5:
                 fh = (int(parts[1]) << 1) | (0 if parts[2] == "+" else 1)
                 th = (int(parts[3]) << 1) | (0 if parts[4] == "+" else 1)
-                edges.append((fh, th))
+                # add_edge (graph_ops.rs:626-638): skipped when the edge or its complement is already stored
+                if (fh, th) not in seen and (th ^ 1, fh ^ 1) not in seen:
+                    seen.add((fh, th))
+                    edges.append((fh, th))
     steps, first, names = [], [0], []
     for line in lines:
         if line.startswith("P"):

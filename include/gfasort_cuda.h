@@ -187,6 +187,24 @@ int gfs_sgd_session_sort(gfs_sgd_session* s, uint32_t* order /*host, N*/);
 int gfs_sgd_sort_1d(const gfs_index* ix, const gfs_sgd_params* params, double* x_inout, uint32_t* order_out /*N*/,
                     gfs_stats* stats);
 
+/* ---- host steps downstream of `Y` (CPU code, no device needed) -----------------
+ * Linear-time versions of the reference's O(N*E) grooming and heads-first topological sort, emitting the
+ * same orders.  Graph as flat arrays: present[nodes_len] (1 = node id exists), E unique edges as
+ * (edge_from[e], edge_to[e]) handles (id << 1 | is_reverse), paths as steps[] + path_first[P+1].
+ * Outputs hold one handle per present node. */
+/* find_head_nodes (src/graph_ops.rs:1138-1183): forward handles with no incoming edge, by earliest path rank. */
+int gfs_find_head_nodes(const uint8_t* present, uint64_t nodes_len, const uint64_t* edge_from, const uint64_t* edge_to,
+                        uint64_t E, const uint64_t* steps, const uint64_t* path_first, uint64_t P,
+                        uint64_t* heads_out, uint64_t* n_heads);
+/* groom(use_bfs = true) (src/groom.rs:49-275): nodes in increasing id, as a reverse handle when flipped. */
+int gfs_groom_order(const uint8_t* present, uint64_t nodes_len, const uint64_t* edge_from, const uint64_t* edge_to,
+                    uint64_t E, const uint64_t* steps, const uint64_t* path_first, uint64_t P,
+                    uint64_t* order_out, uint64_t* n_flipped);
+/* exact_odgi_topological_order(use_heads = true, use_tails = false) (src/graph_ops.rs:1232-1485). */
+int gfs_topological_order(const uint8_t* present, uint64_t nodes_len, const uint64_t* edge_from, const uint64_t* edge_to,
+                          uint64_t E, const uint64_t* steps, const uint64_t* path_first, uint64_t P,
+                          uint64_t* order_out, uint64_t* n_out);
+
 /* ---- replica reconcile (multi-GPU) ---------------------------------------------
  * The exchange step of a replicated run is one all-reduce(sum) of `buf` (2n floats) that the host
  * issues (NCCL) between these two asynchronous kernels, all on `stream`:

@@ -31,7 +31,9 @@ f64p = C.POINTER(C.c_double)
 def build(force: bool = False) -> str:
     """Compile the oracle with oracle/Makefile (g++).  Building the checker is not using it."""
     src = os.path.join(_HERE, "gfs_oracle.cpp")
-    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < os.path.getmtime(src):
+    src2 = os.path.join(_HERE, "graph_oracle.cpp")
+    newest = max(os.path.getmtime(src), os.path.getmtime(src2))
+    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < newest:
         subprocess.run(["make", "-C", _HERE, "clean", "all"], check=True, capture_output=True)
     return _LIB_PATH
 
@@ -119,6 +121,10 @@ def lib():
                                            C.c_uint64, C.c_uint32, f64p, u64p]
         L.oracle_sort_by_position.restype = None
         L.oracle_sort_by_position.argtypes = [f64p, C.c_uint64, u64p]
+        for name in ("oracle_find_head_nodes", "oracle_groom", "oracle_topological_order"):
+            fn = getattr(L, name)
+            fn.restype = C.c_uint64
+            fn.argtypes = [u8p, C.c_uint64, u64p, u64p, C.c_uint64, u64p, u64p, C.c_uint64, u64p]
         _lib = L
     return _lib
 
@@ -396,3 +402,40 @@ def sort_by_position(x: np.ndarray) -> np.ndarray:
     order = np.zeros(len(x), dtype=np.uint64)
     lib().oracle_sort_by_position(_p(x, f64p), len(x), _p(order, u64p))
     return order
+
+
+# ------------------------------------------------------------------------------------------------
+# `g` and `s`: literal (O(N*E)) restatements of groom / find_head_nodes / exact_odgi_topological_order
+# ------------------------------------------------------------------------------------------------
+def _graph_args(present, edges, steps, path_first):
+    present = np.ascontiguousarray(present, dtype=np.uint8)
+    edges = np.ascontiguousarray(edges, dtype=np.uint64).reshape(-1, 2)
+    ef = np.ascontiguousarray(edges[:, 0]); et = np.ascontiguousarray(edges[:, 1])
+    steps = np.ascontiguousarray(steps, dtype=np.uint64)
+    path_first = np.ascontiguousarray(path_first, dtype=np.uint64)
+    keep = (present, ef, et, steps, path_first)
+    return keep, (_p(present, u8p), len(present), _p(ef, u64p), _p(et, u64p), len(ef), _p(steps, u64p),
+                  _p(path_first, u64p), len(path_first) - 1)
+
+
+def find_head_nodes(present, edges, steps, path_first) -> np.ndarray:
+    keep, args = _graph_args(present, edges, steps, path_first)
+    out = np.zeros(int(keep[0].sum()) + 1, dtype=np.uint64)
+    n = lib().oracle_find_head_nodes(*args, _p(out, u64p))
+    return out[:n]
+
+
+def groom(present, edges, steps, path_first):
+    """(handles in increasing node id, reverse when flipped; number flipped) — groom.rs:49-199, BFS mode."""
+    keep, args = _graph_args(present, edges, steps, path_first)
+    out = np.zeros(int(keep[0].sum()), dtype=np.uint64)
+    nf = lib().oracle_groom(*args, _p(out, u64p))
+    return out, nf
+
+
+def topological_order(present, edges, steps, path_first) -> np.ndarray:
+    """exact_odgi_topological_order(use_heads=true, use_tails=false) — graph_ops.rs:1232-1485."""
+    keep, args = _graph_args(present, edges, steps, path_first)
+    out = np.zeros(int(keep[0].sum()), dtype=np.uint64)
+    n = lib().oracle_topological_order(*args, _p(out, u64p))
+    return out[:n]

@@ -568,3 +568,68 @@ def test_path_sgd_sort_orders_by_position(gfs):
     idx_of = {int(nid): k for k, nid in enumerate(graph.node_ids())}
     xs = np.array([x[idx_of[int(i)]] for i in ids])
     assert np.all(np.diff(xs) >= 0)                                                 # non-decreasing positions
+
+
+# ------------------------------------------------------------------------------------------------
+# downstream validity (SURVEY.md §8c iii): `Y` on the GPU, then the host's `g` and `s`
+# ------------------------------------------------------------------------------------------------
+def _oracle_ygs(graph, og, oracle, gfs, seed):
+    """The same pipeline with the oracle's Y (exact budget) and its literal O(N*E) g / s."""
+    op = oracle.params_from_graph(og, nthreads=os.cpu_count() or 4)
+    op.seed = seed
+    x, _, _ = oracle.path_linear_sgd(og, op, mode=oracle.MODE_EXACT)
+    order = oracle.sort_by_position(x)
+    graph.apply_ordering(graph.node_ids()[order.astype(np.int64)].astype(np.uint64) << np.uint64(1))
+    groomed, _ = oracle.groom(graph.present, graph.edges, graph.steps, graph.path_first)
+    gfs.apply_grooming_with_reorder(graph, groomed, True)
+    graph.apply_ordering(oracle.topological_order(graph.present, graph.edges, graph.steps, graph.path_first))
+
+
+def test_ygs_pipeline_drb1_valid_and_as_good_as_oracle(gfs, oracle):
+    from gfasort_b200 import ygs
+    path = os.path.join(DATA, "DRB1-3123.gfa")
+    g0 = gfs.load_gfa(path)
+    n, e, s = g0.node_count(), len(g0.edges), len(g0.steps)
+    seqs = ygs.path_sequences(g0)
+    fracs = {"gpu": [], "oracle": []}
+    for seed in (9399220, 9400220, 9401220):
+        g = gfs.load_gfa(path)
+        params = gfs.YgsParams.from_graph(g, 0, 1)
+        params.path_sgd.seed = seed
+        gfs.ygs_sort(g, params)
+        assert (g.node_count(), len(g.edges), len(g.steps)) == (n, e, s)               # integration_tests.rs:147-172
+        assert sorted(g.live_node_ids().tolist()) == list(range(1, n + 1))              # a permutation, renumbered 1..N
+        assert ygs.path_sequences(g) == seqs                                            # paths spell the same sequences
+        fwd, bwd = gfs.count_edge_directions(g)
+        fracs["gpu"].append(fwd / (fwd + bwd))
+        go = gfs.load_gfa(path)
+        _oracle_ygs(go, oracle.parse_gfa(path), oracle, gfs, seed)
+        assert ygs.path_sequences(go) == seqs
+        fwd, bwd = gfs.count_edge_directions(go)
+        fracs["oracle"].append(fwd / (fwd + bwd))
+    print(f"DRB1 Ygs forward-edge fraction: gpu {np.median(fracs['gpu']):.4f} {fracs['gpu']} | oracle {np.median(fracs['oracle']):.4f}")
+    assert np.median(fracs["gpu"]) >= np.median(fracs["oracle"]) - 0.01
+
+
+def test_ygs_pipeline_config2_valid(gfs):
+    """BASELINE.json config 2: synthetic 1M-node / 32-path graph, full `Ygs` with the GPU `Y`."""
+    import time
+    from gfasort_b200.graph import edges_from_paths
+    s = gfs.SynthGraph(1_000_000, 32, seed=42)
+    g = gfs.BidirectedGraph.from_dense(s.step_handles, s.path_first, s.node_len)
+    g.edges = edges_from_paths(g.steps, g.path_first)
+    n, e = g.node_count(), len(g.edges)
+    lens_along = g.seq_len[(g.steps >> np.uint64(1)).astype(np.int64)].copy()
+    f0, b0 = gfs.count_edge_directions(g)
+    t0 = time.time()
+    params = gfs.YgsParams.from_graph(g, 0, 1)
+    gfs.ygs_sort(g, params)
+    dt = time.time() - t0
+    assert g.node_count() == n and len(g.edges) == e
+    assert sorted(g.live_node_ids().tolist()) == list(range(1, n + 1))
+    assert np.array_equal(g.seq_len[(g.steps >> np.uint64(1)).astype(np.int64)], lens_along)
+    fwd, bwd = gfs.count_edge_directions(g)
+    ids = (g.steps >> np.uint64(1)).astype(np.int64)
+    inc = float((np.diff(ids[int(g.path_first[0]):int(g.path_first[1])]) > 0).mean())
+    print(f"config 2 Ygs: {dt:.1f}s; forward edges {f0/(f0+b0):.3f} -> {fwd/(fwd+bwd):.4f}; path 0 increasing {inc:.4f}")
+    assert fwd / (fwd + bwd) > 0.97 and inc > 0.97
