@@ -11,6 +11,7 @@ from .layout import Layout  # noqa: F401
 from .sgd import (LayoutSGDParams, PathIndex, PathSGDParams, YgsParams, calculate_layout_stress,  # noqa: F401
                   initial_layout, initial_positions, layout_stress, path_linear_sgd, path_linear_sgd_array,
                   path_linear_sgd_layout, path_sgd_sort, sgd_sort_only, sort_positions, sort_stress)
+from .io import load_gfa_flat, write_gfa, write_layout_tsv  # noqa: F401
 from .synth import SynthGraph  # noqa: F401
 from .ygs import (apply_grooming_with_reorder, count_edge_directions, exact_odgi_topological_order,  # noqa: F401
                   find_head_nodes, groom, groom_only, topological_sort_only, ygs_sort)

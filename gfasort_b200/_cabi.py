@@ -96,6 +96,16 @@ SIGNATURES = {
     "gfs_find_head_nodes": (C.c_int, [u8p, C.c_uint64, u64p, u64p, C.c_uint64, u64p, u64p, C.c_uint64, u64p, u64p]),
     "gfs_groom_order": (C.c_int, [u8p, C.c_uint64, u64p, u64p, C.c_uint64, u64p, u64p, C.c_uint64, u64p, u64p]),
     "gfs_topological_order": (C.c_int, [u8p, C.c_uint64, u64p, u64p, C.c_uint64, u64p, u64p, C.c_uint64, u64p, u64p]),
+    "gfs_gfa_parse_file": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
+    "gfs_gfa_parse_text": (C.c_int, [C.c_char_p, C.c_uint64, C.POINTER(C.c_void_p)]),
+    "gfs_gfa_dims": (C.c_int, [C.c_void_p, u64p, u64p, u64p, u64p, u64p]),
+    "gfs_gfa_arrays": (C.c_int, [C.c_void_p, C.POINTER(u8p), C.POINTER(u64p), C.POINTER(u64p), C.POINTER(u64p),
+                                 C.POINTER(u64p), C.POINTER(u64p), C.POINTER(u64p)]),
+    "gfs_gfa_text": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(u64p), C.POINTER(u64p), C.POINTER(u64p)]),
+    "gfs_gfa_free": (None, [C.c_void_p]),
+    "gfs_layout_write_tsv": (C.c_int, [f64p, C.c_uint64, C.c_uint32, C.c_char_p, u64p]),
+    "gfs_gfa_write": (C.c_int, [C.c_char_p, u8p, C.c_uint64, C.c_char_p, u64p, u64p, u64p, u64p, C.c_uint64, u64p, u64p,
+                                C.c_uint64, C.c_char_p, u64p, u64p, u64p]),
     "gfs_reconcile_pack": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p]),
     "gfs_reconcile_apply": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p]),
     "gfs_synth_create": (C.c_int, [C.POINTER(SynthSpec), C.POINTER(C.c_void_p)]),

@@ -141,27 +141,6 @@ __device__ __forceinline__ StepRec load_rec(const StepRec* p) {
     r.node_rev = v.x; r.node_len = v.y; r.pos = ((uint64_t)v.w << 32) | v.z;
     return r;
 }
-// L2 eviction-priority hints: far partner records are read once (evict_first) so that they do not
-// push out what is re-read — the sampling window's records and the position array (evict_last).
-__device__ __forceinline__ uint64_t make_evict_first_policy() {
-    uint64_t pol;
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-    return pol;
-}
-__device__ __forceinline__ uint64_t make_evict_last_policy() {
-    uint64_t pol;
-    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
-    return pol;
-}
-__device__ __forceinline__ StepRec load_rec_hint(const StepRec* p, uint64_t pol) {
-    uint4 v;
-    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
-                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p), "l"(pol));
-    StepRec r;
-    r.node_rev = v.x; r.node_len = v.y; r.pos = ((uint64_t)v.w << 32) | v.z;
-    return r;
-}
-
 // largest p in [0, P) with first_step[p] <= s   (first_step has P+1 entries, first_step[P] = S > s)
 __device__ __forceinline__ uint32_t find_path(const uint64_t* __restrict__ fs, uint32_t P, uint64_t s) {
     uint32_t lo = 0, hi = P;   // invariant: fs[lo] <= s < fs[hi]

@@ -427,8 +427,6 @@ struct KernelGraph {
     uint32_t q;
     uint32_t q_is_100;            // 1: the quantisation step is the reference's 100 (constant division)
     uint32_t blk_shift;           // path-of-block table granularity: block = step >> blk_shift
-    uint32_t l2_hints;            // bit 0: partner records evict_first, bit 1: sampled records evict_first,
-                                  // bit 2: positions evict_last
     uint32_t coherent;            // 1: the lanes of a warp sample 32 consecutive steps (see sample_s1)
     uint64_t samp_base, samp_len; // sampled steps are drawn from [samp_base, samp_base + samp_len) (default 0, S)
 };
@@ -569,14 +567,6 @@ __device__ __forceinline__ double ld_pos(const double* p) {
     asm volatile("ld.global.cg.f64 %0, [%1];" : "=d"(v) : "l"(p));
     return v;
 }
-__device__ __forceinline__ double ld_pos_keep(const double* p, uint64_t pol) {
-    double v;
-    asm volatile("ld.global.cg.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol));
-    return v;
-}
-__device__ __forceinline__ void red_pos_keep(double* p, double v, uint64_t pol) {
-    asm volatile("red.global.add.L2::cache_hint.f64 [%0], %1, %2;" :: "l"(p), "d"(v), "l"(pol) : "memory");
-}
 template <typename CT, int DS> __device__ __forceinline__ void ld_coords(const CT* p, CT (&c)[DS]);
 template <> __device__ __forceinline__ void ld_coords<float, 1>(const float* p, float (&c)[1]) {
     asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(c[0]) : "l"(p));
@@ -658,10 +648,9 @@ struct SgdArgs {
 // r_x is the displacement computed from positions xi, xj that were loaded earlier (stage S3).
 template <bool AGG>
 __device__ __forceinline__ void apply_1d(double* X, unsigned warp_mask, int lane, bool valid, uint32_t i,
-                                         uint32_t j, double d, double eta, double xi, double xj, bool keep) {
+                                         uint32_t j, double d, double eta, double xi, double xj) {
     double r_x = 0.0;
-    const uint64_t pol = make_evict_last_policy();
-    auto add = [&](double* p, double v) { if (keep) red_pos_keep(p, v, pol); else atomicAdd(p, v); };
+    auto add = [&](double* p, double v) { atomicAdd(p, v); };        // red.global.add.f64 (result unused)
     if (valid) {
         const double mu = fmin(__dmul_rn(eta, __ddiv_rn(1.0, d)), 1.0);     // sgd.rs:518-520
         double dx = __dsub_rn(xi, xj);
@@ -877,7 +866,7 @@ sgd_kernel(const SgdArgs a) {
             for (int k = 0; k < K; ++k) {
                 if constexpr (D == 0) {
                     apply_1d<AGG>(reinterpret_cast<double*>(a.positions), warp_mask, lane, xs[k].ok, xs[k].idx_i, xs[k].idx_j,
-                                  xs[k].dist, xs[k].eta, xs[k].ci[0], xs[k].cj[0], (a.g.l2_hints & 4u) != 0);
+                                  xs[k].dist, xs[k].eta, xs[k].ci[0], xs[k].cj[0]);
                 } else {
                     apply_nd<CT, (D > 0 ? D : 1), DS, AGG>(reinterpret_cast<CT*>(a.positions), warp_mask, lane, xs[k].ok,
                                                            xs[k].idx_i, xs[k].idx_j, xs[k].dist, xs[k].eta, xs[k].ci, xs[k].cj);
@@ -907,12 +896,7 @@ sgd_kernel(const SgdArgs a) {
                 xs[k].idx_i = na; xs[k].idx_j = nb;
                 const double* X = reinterpret_cast<const double*>(a.positions);
                 xs[k].ci[0] = xs[k].cj[0] = 0.0;
-                if (xs[k].ok) {
-                    const bool keep = (a.g.l2_hints & 4u) != 0;
-                    const uint64_t pol = make_evict_last_policy();
-                    xs[k].ci[0] = keep ? ld_pos_keep(X + na, pol) : ld_pos(X + na);
-                    xs[k].cj[0] = keep ? ld_pos_keep(X + nb, pol) : ld_pos(X + nb);
-                }
+                if (xs[k].ok) { xs[k].ci[0] = ld_pos(X + na); xs[k].cj[0] = ld_pos(X + nb); }
             } else {
                 xs[k].idx_i = na * 2 + (oa ? 1u : 0u);                                     // sgd.rs:1099-1103
                 xs[k].idx_j = nb * 2 + (ob ? 1u : 0u);
@@ -931,8 +915,8 @@ sgd_kernel(const SgdArgs a) {
         for (int k = 0; k < K; ++k) {
             fl[k].valid = sm[k].valid; fl[k].coins = sm[k].coins; fl[k].eta = sm[k].eta;
             if (sm[k].valid) {
-                fl[k].a = (a.g.l2_hints & 2u) ? load_rec_hint(a.g.recs + sm[k].sa, make_evict_first_policy()) : load_rec(a.g.recs + sm[k].sa);
-                fl[k].b = (a.g.l2_hints & 1u) ? load_rec_hint(a.g.recs + sm[k].sb, make_evict_first_policy()) : load_rec(a.g.recs + sm[k].sb);
+                fl[k].a = load_rec(a.g.recs + sm[k].sa);
+                fl[k].b = load_rec(a.g.recs + sm[k].sb);
                 ++pending;
             }
             sm[k].valid = false;
@@ -1291,8 +1275,6 @@ struct gfs_sgd_session {
     uint64_t launches = 0;
     double h2d_s = 0, d2h_s = 0;
     bool ev_pending = false;
-    int l2_policy = 0;          // 0 none, 2 persisting access-policy window on the positions
-    int l2_hints = 7;           // KernelGraph::l2_hints
     int inflight = 2;           // terms in flight per thread (kernel template parameter K)
     bool coherent = true;       // warp-coherent step sampling in the sweep schedule
     uint64_t window_steps = 0;  // 0 = static schedule
@@ -1586,7 +1568,6 @@ static KernelGraph make_kgraph(const gfs_index* ix, const gfs_sgd_params& p, con
     g.space_max = (uint32_t)std::min<uint64_t>(p.space_max, 0xffffffffull);
     g.q = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(p.space_quantization_step, 1), 0xffffffffull);
     g.q_is_100 = g.q == 100 ? 1u : 0u;
-    g.l2_hints = 0;
     g.blk_shift = 0;
     while (((ix->S ? ix->S - 1 : 0) >> g.blk_shift) >= BLK_TABLE) ++g.blk_shift;
     g.samp_base = 0; g.samp_len = ix->S;
@@ -1709,27 +1690,6 @@ extern "C" int gfs_sgd_session_create(const gfs_index* ix, const gfs_sgd_params*
         SS_CUDA(cudaMalloc(&s->d_work, 8));
     }
 
-    // L2 management: the position array is the only re-used data; the step records stream through.
-    s->l2_policy = (int)env_long("GFASORT_L2_POLICY", 0);
-    s->l2_hints = (int)env_long("GFASORT_L2_HINTS", 7);
-    const long fetch = env_long("GFASORT_L2_FETCH", 32);
-    if (fetch == 32 || fetch == 64 || fetch == 128) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)fetch);
-    if (s->l2_policy == 2) {
-        cudaDeviceProp prop;
-        SS_CUDA(cudaGetDeviceProperties(&prop, s->device));
-        const size_t bytes = s->n_elems * esz;
-        const size_t set_aside = std::min<size_t>((size_t)prop.persistingL2CacheMaxSize, bytes);
-        if (set_aside > 0) {
-            SS_CUDA(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, set_aside));
-            cudaStreamAttrValue attr{};
-            attr.accessPolicyWindow.base_ptr = s->d_pos;
-            attr.accessPolicyWindow.num_bytes = std::min<size_t>(bytes, (size_t)prop.accessPolicyMaxWindowSize);
-            attr.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)set_aside / (double)bytes);
-            attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-            attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-            SS_CUDA(cudaStreamSetAttribute(s->stream, cudaStreamAttributeAccessPolicyWindow, &attr));
-        }
-    }
     *out = s;
     return GFS_OK;
 #undef SS_CUDA
@@ -1809,7 +1769,6 @@ extern "C" int gfs_sgd_session_run(gfs_sgd_session* s, uint64_t epoch_begin, uin
     SgdArgs a{};
     a.g = make_kgraph(s->ix, s->params, s->d_zetas, s->zlen);
     a.g.samp_base = s->samp_base; a.g.samp_len = s->samp_len;
-    a.g.l2_hints = (uint32_t)s->l2_hints;
     a.g.coherent = (s->window_steps > 0 && s->coherent) ? 1u : 0u;
     a.epochs = s->d_epochs;
     a.epoch_begin = (uint32_t)epoch_begin; a.epoch_end = (uint32_t)epoch_end;

@@ -205,6 +205,29 @@ int gfs_topological_order(const uint8_t* present, uint64_t nodes_len, const uint
                           uint64_t E, const uint64_t* steps, const uint64_t* path_first, uint64_t P,
                           uint64_t* order_out, uint64_t* n_out);
 
+/* ---- flat ingest and buffered writers (CPU code) ------------------------------
+ * gfs_gfa_parse_*: the CLI's parse_gfa (src/bin/gfasort.rs:88-167) in one pass, straight into flat arrays:
+ * present / seq_len indexed by node id, node_order (add_node order, src/graph_ops.rs:613-623), edges unique
+ * per {edge, complement} (add_edge, :626-638), concatenated path steps.  Sequences and path names are
+ * (offset, length) pairs into the kept text.  Pointers stay valid until gfs_gfa_free. */
+typedef struct gfs_gfa gfs_gfa;
+int gfs_gfa_parse_file(const char* path, gfs_gfa** out);
+int gfs_gfa_parse_text(const char* text, uint64_t len, gfs_gfa** out);
+int gfs_gfa_dims(const gfs_gfa* g, uint64_t* nodes_len, uint64_t* n_nodes, uint64_t* n_edges, uint64_t* n_steps,
+                 uint64_t* n_paths);
+int gfs_gfa_arrays(const gfs_gfa* g, const uint8_t** present, const uint64_t** seq_len, const uint64_t** node_order,
+                   const uint64_t** edge_from, const uint64_t** edge_to, const uint64_t** steps, const uint64_t** path_first);
+int gfs_gfa_text(const gfs_gfa* g, const char** text, const uint64_t** seq_off, const uint64_t** name_off,
+                 const uint64_t** name_len);
+void gfs_gfa_free(gfs_gfa* g);
+/* Layout::write_tsv (src/layout.rs:138-163), byte for byte, through one buffer. coords: Layout order. */
+int gfs_layout_write_tsv(const double* coords, uint64_t num_nodes, uint32_t dims, const char* path, uint64_t* bytes_written);
+/* BidirectedGraph::write_gfa (src/graph_ops.rs:693-738), buffered; L lines in the given edge order. */
+int gfs_gfa_write(const char* path, const uint8_t* present, uint64_t nodes_len, const char* seq_blob, const uint64_t* seq_off,
+                  const uint64_t* seq_len, const uint64_t* edge_from, const uint64_t* edge_to, uint64_t E, const uint64_t* steps,
+                  const uint64_t* path_first, uint64_t P, const char* name_blob, const uint64_t* name_off,
+                  const uint64_t* name_len, uint64_t* bytes_written);
+
 /* ---- replica reconcile (multi-GPU) ---------------------------------------------
  * The exchange step of a replicated run is one all-reduce(sum) of `buf` (2n floats) that the host
  * issues (NCCL) between these two asynchronous kernels, all on `stream`:
