@@ -388,9 +388,10 @@ def test_sgd_1d_stress_parity_synth(mode, iter_max, gfs, oracle, monkeypatch):
         assert g_mar <= c_mar * 1.02 + 1e-5
         assert g_rms <= c_rms * 1.08
     else:
-        # mid-schedule (not a reference configuration): the sweep schedule converges a little slower
-        # (measured +3..7 %, iid +2 %), and catches up by the end of the schedule
-        assert g_mar <= c_mar * 1.10
+        # mid-schedule (not a reference configuration; printed for the record): the layout is still moving,
+        # the measure varies by 10-20 % between runs on either side, and the sweep schedule trails the oracle
+        # by a few percent before catching up — so only a gross-error bound here
+        assert g_mar <= c_mar * 1.5
     ix.close()
 
 
@@ -422,8 +423,10 @@ def test_sgd_2d_stress_parity_synth(mode, gfs, oracle, monkeypatch):
     ix.close()
 
 
-@pytest.mark.parametrize("f64", [0, 1])
-def test_sgd_2d_stress_parity_drb1(f64, gfs, oracle):
+@pytest.mark.parametrize("dims,f64", [(2, 0), (2, 1), (3, 0), (4, 0), (5, 0)])
+def test_sgd_nd_stress_parity_drb1(dims, f64, gfs, oracle):
+    """`L` at the reference's budget (layout-iter 30): float2 (D = 2), float4 (D = 3 padded, D = 4) and the
+    two-vector path (D = 5) against the f64 oracle in the same number of dimensions."""
     path = os.path.join(DATA, "DRB1-3123.gfa")
     og = oracle.parse_gfa(path)
     graph = gfs.load_gfa(path)
@@ -435,18 +438,19 @@ def test_sgd_2d_stress_parity_drb1(f64, gfs, oracle):
 
     def cpu(seed):
         p = op.copy(); p.seed = seed
-        c, _, _ = oracle.path_linear_sgd_layout(og, p, 2, mode=oracle.MODE_EXACT)     # same iteration budget
-        return gfs.layout_stress(graph, c, 2, 200000, ix)
+        c, _, _ = oracle.path_linear_sgd_layout(og, p, dims, mode=oracle.MODE_EXACT)     # same iteration budget
+        return gfs.layout_stress(graph, c, dims, 200000, ix)
 
     def gpu(seed):
-        p = _pyparams(op, gfs, True, 2); p.seed = seed
+        p = _pyparams(op, gfs, True, dims); p.seed = seed
         lay = gfs.path_linear_sgd_layout(graph, p, ix, cfg)
-        assert np.all(np.isfinite(lay.coords))
-        return gfs.layout_stress(graph, lay.coords, 2, 200000, ix)
+        assert np.all(np.isfinite(lay.coords)) and lay.dimensions == dims and len(lay.coords) == graph.node_count() * 2 * dims
+        assert gfs.sgd.last_stats["applied_updates"] == (op.iter_max + 1) * op.min_term_updates
+        return gfs.layout_stress(graph, lay.coords, dims, 200000, ix)
 
     c_rms, c_mar = _median_stress_1d(cpu, seeds)
     g_rms, g_mar = _median_stress_1d(gpu, seeds)
-    print(f"DRB1 L(f64={f64}) stress: gpu mean_abs {g_mar:.5f} rms {g_rms:.5f} | oracle mean_abs {c_mar:.5f} rms {c_rms:.5f}")
+    print(f"DRB1 L(D={dims}, f64={f64}) stress: gpu mean_abs {g_mar:.5f} rms {g_rms:.5f} | oracle mean_abs {c_mar:.5f} rms {c_rms:.5f}")
     assert g_mar <= c_mar * 1.02
     assert g_rms <= c_rms * 1.02
     ix.close()
