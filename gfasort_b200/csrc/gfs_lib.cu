@@ -785,7 +785,11 @@ sgd_kernel(const SgdArgs a) {
     InFlight fl[K];
     Sampled sm[K];
 #pragma unroll
-    for (int k = 0; k < K; ++k) { fl[k].valid = false; sm[k].valid = false; }
+    for (int k = 0; k < K; ++k) {
+        fl[k].valid = false; fl[k].coins = 0; fl[k].eta = 0.0;
+        fl[k].a.node_rev = fl[k].a.node_len = 0; fl[k].a.pos = 0; fl[k].b = fl[k].a;
+        sm[k].valid = false; sm[k].sa = sm[k].sb = 0; sm[k].coins = 0; sm[k].eta = 0.0;
+    }
     uint64_t target = 0, done = 0;           // per lane: updates owed by the chunks claimed so far / applied
 
     // work claiming (warp-uniform): sets ep / win_base / win_len and raises `target`
@@ -844,7 +848,11 @@ sgd_kernel(const SgdArgs a) {
     };
     Loaded xs[K];
 #pragma unroll
-    for (int k = 0; k < K; ++k) xs[k].ok = false;
+    for (int k = 0; k < K; ++k) {
+        xs[k].ok = false; xs[k].dist = 0.0; xs[k].eta = 0.0; xs[k].idx_i = xs[k].idx_j = 0;
+#pragma unroll
+        for (int q = 0; q < DS; ++q) { xs[k].ci[q] = CT(0); xs[k].cj[q] = CT(0); }
+    }
 
     uint64_t iters = 0;
     for (;;) {

@@ -66,7 +66,13 @@ typedef struct gfs_sgd_params {
 /* Optional launch configuration (NULL = defaults / environment).  Environment variables, because
  * the reference CLI is frozen: GFASORT_DEVICE, GFASORT_THREADS (total GPU threads, 0 = auto),
  * GFASORT_AGGREGATE (0/1 warp-level duplicate-node aggregation, default 1),
- * GFASORT_LAYOUT_F64 (0/1, nD coordinates in double instead of float, default 0). */
+ * GFASORT_LAYOUT_F64 (0/1, nD coordinates in double instead of float, default 0),
+ * GFASORT_RELABEL (0/1 internal first-appearance node order, default 1),
+ * GFASORT_WINDOW (sampling window in steps: 0 = every step ~ U[0,S) exactly like the reference,
+ * -1 = auto: 2^20 for graphs whose records exceed 64 MB, else 0), GFASORT_CHUNK (updates per claimed
+ * chunk, default 256), GFASORT_COHERENT (0/1 warps sample 32 consecutive steps in window mode,
+ * default 1), GFASORT_INFLIGHT (terms in flight per thread and pipeline stage, 1 or 2),
+ * GFASORT_INDEX_CHUNK (steps per host->device chunk of the index build).  DESIGN.md §4. */
 typedef struct gfs_launch_cfg {
     int32_t device;            /* CUDA device ordinal; -1 = current */
     uint32_t total_threads;    /* 0 = auto (full occupancy, capped by the work available) */

@@ -418,8 +418,12 @@ def test_sgd_2d_stress_parity_synth(mode, gfs, oracle, monkeypatch):
     c_rms, c_mar = _median_stress_1d(cpu, seeds)
     g_rms, g_mar = _median_stress_1d(gpu, seeds)
     print(f"synth {s.N // 1000}k L [{mode}] stress: gpu(f32) mean_abs {g_mar:.5f} rms {g_rms:.5f} | oracle(f64) mean_abs {c_mar:.5f} rms {c_rms:.5f}")
-    assert g_mar <= c_mar * 1.02 + 1e-5
-    assert g_rms <= c_rms * 1.08
+    # After only 31 epochs these synthetic layouts are still settling: the ORACLE's own median over 3 seeds
+    # moves between 0.00129 and 0.00170 (20k nodes) from one run to the next (16 free-running threads), the
+    # GPU's between 0.00124 and 0.00145.  A 2 % statement is not testable here — DRB1 (stable to 0.2 %) carries
+    # it for `L` (test_sgd_nd_stress_parity_drb1); this test guards against gross regressions of either schedule.
+    assert g_mar <= c_mar * 1.25
+    assert g_rms <= c_rms * 1.25
     ix.close()
 
 
@@ -643,3 +647,27 @@ def test_ygs_pipeline_config2_valid(gfs):
     frac = fwd / (fwd + bwd)
     assert max(frac, 1 - frac) > 0.97 and max(inc, 1 - inc) > 0.95
     assert (frac > 0.5) == (inc > 0.5)
+
+
+def test_session_save_restore(gfs):
+    """gfs_sgd_session_save / _restore: rerunning from a device-side snapshot needs no host copy."""
+    from gfasort_b200._cabi import lib, check, f64p
+    graph = gfs.load_gfa(os.path.join(DATA, "DRB1-3123.gfa"))
+    ix = gfs.PathIndex.from_graph(graph)
+    params = gfs.YgsParams.from_graph(graph, 0, 1, ix).path_sgd
+    params.iter_max = 5
+    cp = params.c()
+    h = C.c_void_p()
+    check(lib().gfs_sgd_session_create(ix.handle, C.byref(cp), 0, None, C.byref(h)))
+    x0 = gfs.initial_positions(graph)
+    check(lib().gfs_sgd_session_upload(h, _p(x0, f64p)))
+    check(lib().gfs_sgd_session_save(h))
+    check(lib().gfs_sgd_session_run(h, 0, 3, 0, 1))
+    moved = np.zeros_like(x0)
+    check(lib().gfs_sgd_session_download(h, _p(moved, f64p)))
+    check(lib().gfs_sgd_session_restore(h))
+    back = np.zeros_like(x0)
+    check(lib().gfs_sgd_session_download(h, _p(back, f64p)))
+    lib().gfs_sgd_session_destroy(h)
+    ix.close()
+    assert not np.array_equal(moved, x0) and np.array_equal(back, x0)
