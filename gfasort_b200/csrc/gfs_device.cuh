@@ -172,4 +172,13 @@ __device__ __forceinline__ T group_sum(unsigned active, unsigned peers, T v, int
     return acc;
 }
 
+// One epoch of the schedule as the kernels see it.
+struct EpochDesc {
+    double eta;
+    ZipfConsts zc;
+    uint64_t updates;     // min_term_updates
+    uint32_t cooling;
+    uint32_t pad;
+};
+
 }  // namespace gfs

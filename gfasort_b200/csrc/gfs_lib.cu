@@ -1,17 +1,18 @@
 // gfs_lib.cu — libgfasort_cuda.so: kernels + C ABI (include/gfasort_cuda.h) for the path-guided SGD
 // hot path of pangenome/gfasort on B200 (sm_100a).
 //
-// Kernels
-//   K1  k1_tile_sums / k1_scan_tiles / k1_path_base / k1_write_recs
-//         path index: gather node lengths, scan them, emit one 16-byte StepRec per step.
-//         Replaces PathIndex::from_graph (reference src/sgd.rs:34-71).
-//   K2  sgd_kernel<ONE_D>   persistent 1D `Y` term loop, f64 positions.  Replaces the worker loop
-//         src/sgd.rs:442-584 and the checker thread :366-407.
-//   K3  sgd_kernel<ND>      persistent nD `L` term loop on [node][end][dim] coordinates (float or
-//         double).  Replaces src/sgd.rs:988-1156 and :925-955.
-//   K4  stress_kernel       sampled path stress.  Replaces calculate_layout_stress (:1196-1283).
+// This file: host-side objects (index, session), the schedule / zeta-table twins of the reference's
+// scalar helpers, and every `extern "C"` entry point.  The kernels live in the headers it includes:
+//   gfs_device.cuh          Philox4x32-10, fast_precise_pow, DirtyZipfian, record loads, warp group sums
+//   gfs_kernels_index.cuh   K1  path index (k1_*) and node relabelling (rl_*).   PathIndex::from_graph, sgd.rs:34-71
+//   gfs_kernels_sgd.cuh     K2/K3 sgd_kernel<CT, D, DS, AGG, K>: the persistent, software-pipelined term kernel
+//                           (1D `Y`, f64; nD `L`, f32/f64).   Worker loops sgd.rs:442-584, 988-1156; checkers :366-407, :925-955
+//   gfs_kernels_aux.cuh     K4 stress_kernel (calculate_layout_stress, :1196-1283), layout conversions,
+//                           K5 rc_pack / rc_apply (multi-GPU reconcile), K6 rs_* (order by position), debug kernels
+// Host code in other files: gfs_synth.cpp (synthetic graphs), gfs_host_graph.cpp (linear-time `g` / `s`),
+// gfs_io.cpp (flat GFA ingest, buffered writers).
 //
-// There is no CPU implementation of any of these in this library: if CUDA is unavailable every
+// There is no CPU implementation of any kernel in this library: if CUDA is unavailable every compute
 // entry point returns an error.
 #include <cuda_runtime.h>
 #include <cooperative_groups.h>
@@ -105,14 +106,6 @@ static void h_zetas(const gfs_sgd_params& p, uint64_t max_path_steps, std::vecto
     }
 }
 
-// One epoch of the schedule as the kernels see it.
-struct EpochDesc {
-    double eta;
-    ZipfConsts zc;
-    uint64_t updates;     // min_term_updates
-    uint32_t cooling;
-    uint32_t pad;
-};
 
 static void h_epochs(const gfs_sgd_params& p, std::vector<EpochDesc>& out) {
     std::vector<double> etas;
@@ -135,1108 +128,11 @@ static void h_epochs(const gfs_sgd_params& p, std::vector<EpochDesc>& out) {
     }
 }
 
-// =============================================================================================
-// K1 — path index
-// =============================================================================================
-constexpr int K1_THREADS = 256;
-constexpr int K1_ITEMS = 8;
-constexpr int K1_TILE = K1_THREADS * K1_ITEMS;
-
-__device__ __forceinline__ uint32_t gathered_len(uint64_t h, const uint32_t* __restrict__ node_len, uint64_t N) {
-    const uint64_t node = h >> 1;
-    return node < N ? __ldg(node_len + node) : 0u;    // missing node => +0 (src/sgd.rs:52-54)
-}
-
-__device__ __forceinline__ uint64_t block_sum_u64(uint64_t v, uint64_t* warp_buf) {
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if (lane == 0) warp_buf[w] = v;
-    __syncthreads();
-    uint64_t t = 0;
-    if (threadIdx.x < 32) {
-        t = threadIdx.x < (blockDim.x >> 5) ? warp_buf[threadIdx.x] : 0;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-        if (threadIdx.x == 0) warp_buf[0] = t;
-    }
-    __syncthreads();
-    t = warp_buf[0];
-    __syncthreads();
-    return t;
-}
-
-// tile_sum[t] = sum of node lengths of the steps of tile t
-__global__ void __launch_bounds__(K1_THREADS)
-k1_tile_sums(const uint64_t* __restrict__ handles, const uint32_t* __restrict__ node_len, uint64_t S, uint64_t N,
-             uint64_t* __restrict__ tile_sum) {
-    __shared__ uint64_t wb[32];
-    const uint64_t base = (uint64_t)blockIdx.x * K1_TILE;
-    uint64_t s = 0;
-#pragma unroll
-    for (int k = 0; k < K1_ITEMS; ++k) {
-        const uint64_t i = base + (uint64_t)k * K1_THREADS + threadIdx.x;
-        if (i < S) s += gathered_len(handles[i], node_len, N);
-    }
-    s = block_sum_u64(s, wb);
-    if (threadIdx.x == 0) tile_sum[blockIdx.x] = s;
-}
-
-// exclusive scan of tile sums, seeded with *carry; leaves the running total in *carry. One block.
-__global__ void __launch_bounds__(1024)
-k1_scan_tiles(uint64_t* __restrict__ tile_sum, uint64_t n_tiles, uint64_t* __restrict__ carry) {
-    __shared__ uint64_t wsum[32];
-    __shared__ uint64_t running;
-    if (threadIdx.x == 0) running = *carry;
-    __syncthreads();
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    for (uint64_t base = 0; base < n_tiles; base += 1024) {
-        const uint64_t i = base + threadIdx.x;
-        const uint64_t v = i < n_tiles ? tile_sum[i] : 0;
-        uint64_t inc = v;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint64_t t = __shfl_up_sync(0xffffffffu, inc, o);
-            if (lane >= o) inc += t;
-        }
-        if (lane == 31) wsum[w] = inc;
-        __syncthreads();
-        if (w == 0) {
-            uint64_t ws = wsum[lane], wi = ws;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint64_t t = __shfl_up_sync(0xffffffffu, wi, o);
-                if (lane >= o) wi += t;
-            }
-            wsum[lane] = wi - ws;   // exclusive warp offsets
-        }
-        __syncthreads();
-        const uint64_t excl = running + wsum[w] + (inc - v);
-        if (i < n_tiles) tile_sum[i] = excl;
-        __syncthreads();
-        if (threadIdx.x == 1023) running = excl + v;
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) *carry = running;
-}
-
-// path_base[p] = global exclusive prefix at the first step of path p, for the paths that start
-// inside [chunk_begin, chunk_end).  One block per path of the chunk's path range.
-__global__ void __launch_bounds__(K1_THREADS)
-k1_path_base(const uint64_t* __restrict__ handles /*chunk-local*/, const uint32_t* __restrict__ node_len,
-             uint64_t N, const uint64_t* __restrict__ first_step, uint32_t p_begin, uint32_t p_end,
-             uint64_t chunk_begin, uint64_t chunk_end, const uint64_t* __restrict__ tile_prefix /*chunk-local*/,
-             uint64_t* __restrict__ path_base) {
-    __shared__ uint64_t wb[32];
-    const uint32_t p = p_begin + blockIdx.x;
-    if (p >= p_end) return;
-    const uint64_t s0 = first_step[p];
-    if (s0 < chunk_begin || s0 >= chunk_end) return;   // block-uniform
-    const uint64_t local = s0 - chunk_begin;
-    const uint64_t tile = local / K1_TILE;
-    const uint64_t tbase = tile * K1_TILE;
-    uint64_t s = 0;
-    for (uint64_t i = tbase + threadIdx.x; i < local; i += K1_THREADS) s += gathered_len(handles[i], node_len, N);
-    s = block_sum_u64(s, wb);
-    if (threadIdx.x == 0) path_base[p] = tile_prefix[tile] + s;
-}
-
-// Emit the records of one tile: pos = global prefix - path_base[path(step)].
-__global__ void __launch_bounds__(K1_THREADS)
-k1_write_recs(const uint64_t* __restrict__ handles /*chunk-local*/, const uint32_t* __restrict__ node_len,
-              uint64_t N, const uint64_t* __restrict__ first_step, uint32_t P, uint64_t chunk_begin,
-              uint64_t chunk_len, const uint64_t* __restrict__ tile_prefix, const uint64_t* __restrict__ path_base,
-              StepRec* __restrict__ recs /*global index*/) {
-    __shared__ uint32_t s_len[K1_TILE];
-    __shared__ uint32_t s_nr[K1_TILE];
-    __shared__ uint64_t s_pos[K1_TILE];
-    __shared__ uint64_t wsum[K1_THREADS / 32];
-    const uint64_t tbase = (uint64_t)blockIdx.x * K1_TILE;
-#pragma unroll
-    for (int k = 0; k < K1_ITEMS; ++k) {
-        const int j = k * K1_THREADS + threadIdx.x;
-        const uint64_t i = tbase + j;
-        uint32_t len = 0, nr = 0;
-        if (i < chunk_len) {
-            const uint64_t h = handles[i];
-            len = gathered_len(h, node_len, N);
-            const uint64_t node = h >> 1;
-            nr = (uint32_t)(((node < N ? node : N) << 1) | (h & 1));
-        }
-        s_len[j] = len; s_nr[j] = nr;
-    }
-    __syncthreads();
-    // thread t owns items [t*8, t*8+8)
-    uint64_t loc[K1_ITEMS];
-    uint64_t tsum = 0;
-#pragma unroll
-    for (int k = 0; k < K1_ITEMS; ++k) { loc[k] = tsum; tsum += s_len[threadIdx.x * K1_ITEMS + k]; }
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    uint64_t inc = tsum;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const uint64_t t = __shfl_up_sync(0xffffffffu, inc, o);
-        if (lane >= o) inc += t;
-    }
-    if (lane == 31) wsum[w] = inc;
-    __syncthreads();
-    uint64_t woff = 0;
-#pragma unroll
-    for (int k = 0; k < K1_THREADS / 32; ++k) woff += (k < w) ? wsum[k] : 0;
-    const uint64_t texcl = tile_prefix[blockIdx.x] + woff + (inc - tsum);
-#pragma unroll
-    for (int k = 0; k < K1_ITEMS; ++k) s_pos[threadIdx.x * K1_ITEMS + k] = texcl + loc[k];
-    __syncthreads();
-    // path of the tile's first and last step; most tiles lie inside one path
-    const uint64_t g_first = chunk_begin + tbase;
-    const uint64_t last_local = (tbase + K1_TILE <= chunk_len ? tbase + K1_TILE : chunk_len) - 1;
-    const uint32_t p_first = find_path(first_step, P, g_first);
-    const uint32_t p_last = find_path(first_step, P, chunk_begin + last_local);
-    const uint64_t base_first = path_base[p_first];
-#pragma unroll
-    for (int k = 0; k < K1_ITEMS; ++k) {
-        const int j = k * K1_THREADS + threadIdx.x;
-        const uint64_t i = tbase + j;
-        if (i < chunk_len) {
-            const uint64_t gi = chunk_begin + i;
-            uint64_t pb = base_first;
-            if (p_first != p_last) pb = path_base[find_path(first_step, P, gi)];
-            StepRec r;
-            r.node_rev = s_nr[j]; r.node_len = s_len[j]; r.pos = s_pos[j] - pb;
-            recs[gi] = r;
-        }
-    }
-}
-
-__global__ void k1_path_len(const uint64_t* __restrict__ path_base, uint32_t P, uint64_t* __restrict__ path_len) {
-    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p < P) path_len[p] = path_base[p + 1] - path_base[p];
-}
-__global__ void k1_set_u64(uint64_t* p, uint64_t idx, const uint64_t* src) { p[idx] = *src; }
-
-__global__ void k1_export_pos(const StepRec* __restrict__ recs, uint64_t S, uint64_t* __restrict__ pos) {
-    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < S) pos[i] = recs[i].pos;
-}
-__global__ void k1_export_hl(const StepRec* __restrict__ recs, uint64_t S, uint32_t N, const uint32_t* __restrict__ old_of_new,
-                             uint64_t* __restrict__ h, uint32_t* __restrict__ l) {
-    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= S) return;
-    const uint32_t nr = recs[i].node_rev;
-    uint32_t node = nr >> 1;
-    if (old_of_new && node < N) node = old_of_new[node];
-    h[i] = ((uint64_t)node << 1) | (nr & 1u);
-    l[i] = recs[i].node_len;
-}
-
-// ---------------------------------------------------------------------------------------------
-// node relabelling: internal node index = order of first appearance along the paths, so that the
-// positions of path-adjacent nodes share cache lines (the host's dense idx order is the GFA file
-// order, which says nothing about adjacency).  Purely a storage permutation: uploads scatter through
-// new_of_old, downloads gather back; no arithmetic changes.
-// ---------------------------------------------------------------------------------------------
-__global__ void rl_first_occ(const StepRec* __restrict__ recs, uint64_t S, uint32_t N, unsigned long long* __restrict__ first_occ) {
-    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= S) return;
-    const uint32_t node = recs[i].node_rev >> 1;
-    if (node < N && first_occ[node] > i) atomicMin(first_occ + node, (unsigned long long)i);
-}
-// exclusive scan of one flag per thread-item across the block; returns the block total in *total
-__device__ __forceinline__ uint32_t block_excl_scan_u32(uint32_t v, uint32_t* wsum, uint32_t* total) {
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    uint32_t inc = v;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
-    if (lane == 31) wsum[w] = inc;
-    __syncthreads();
-    uint32_t off = 0, tot = 0;
-    for (int k = 0; k < nw; ++k) { const uint32_t x = wsum[k]; if (k < w) off += x; tot += x; }
-    __syncthreads();
-    *total = tot;
-    return off + inc - v;
-}
-// mode 0: item i is a step, flag = "first occurrence of its node"; mode 1: item i is a node, flag = "never visited"
-template <int MODE>
-__device__ __forceinline__ bool rl_flag(const StepRec* recs, const unsigned long long* first_occ, uint32_t N, uint64_t i) {
-    if (MODE == 0) { const uint32_t node = recs[i].node_rev >> 1; return node < N && first_occ[node] == i; }
-    return first_occ[i] == ~0ull;
-}
-template <int MODE>
-__global__ void __launch_bounds__(K1_THREADS)
-rl_tile_count(const StepRec* __restrict__ recs, const unsigned long long* __restrict__ first_occ, uint32_t N, uint64_t n_items,
-              uint64_t* __restrict__ tile_cnt) {
-    __shared__ uint64_t wb[32];
-    const uint64_t base = (uint64_t)blockIdx.x * K1_TILE;
-    uint64_t c = 0;
-#pragma unroll
-    for (int k = 0; k < K1_ITEMS; ++k) {
-        const uint64_t i = base + (uint64_t)k * K1_THREADS + threadIdx.x;
-        if (i < n_items) c += rl_flag<MODE>(recs, first_occ, N, i) ? 1 : 0;
-    }
-    c = block_sum_u64(c, wb);
-    if (threadIdx.x == 0) tile_cnt[blockIdx.x] = c;
-}
-template <int MODE>
-__global__ void __launch_bounds__(K1_THREADS)
-rl_assign(const StepRec* __restrict__ recs, const unsigned long long* __restrict__ first_occ, uint32_t N, uint64_t n_items,
-          const uint64_t* __restrict__ tile_prefix, uint32_t* __restrict__ new_of_old, uint32_t* __restrict__ old_of_new) {
-    __shared__ uint32_t wsum[K1_THREADS / 32];
-    const uint64_t base = (uint64_t)blockIdx.x * K1_TILE + (uint64_t)threadIdx.x * K1_ITEMS;   // 8 consecutive items
-    bool f[K1_ITEMS];
-    uint32_t cnt = 0;
-#pragma unroll
-    for (int k = 0; k < K1_ITEMS; ++k) { f[k] = (base + k < n_items) && rl_flag<MODE>(recs, first_occ, N, base + k); cnt += f[k]; }
-    uint32_t total;
-    uint32_t off = block_excl_scan_u32(cnt, wsum, &total);
-    uint64_t rank = tile_prefix[blockIdx.x] + off;
-#pragma unroll
-    for (int k = 0; k < K1_ITEMS; ++k) {
-        if (f[k]) {
-            const uint32_t old = MODE == 0 ? (recs[base + k].node_rev >> 1) : (uint32_t)(base + k);
-            new_of_old[old] = (uint32_t)rank;
-            old_of_new[rank] = old;
-            ++rank;
-        }
-    }
-}
-__global__ void rl_rewrite(StepRec* __restrict__ recs, uint64_t S, uint32_t N, const uint32_t* __restrict__ new_of_old) {
-    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= S) return;
-    const uint32_t nr = recs[i].node_rev;
-    const uint32_t node = nr >> 1;
-    if (node < N) recs[i].node_rev = (new_of_old[node] << 1) | (nr & 1u);
-}
-__global__ void rl_invert(const uint32_t* __restrict__ new_of_old, uint32_t N, uint32_t* __restrict__ old_of_new) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < N) old_of_new[new_of_old[i]] = i;
-}
-
-// =============================================================================================
-// term sampling (shared by K2, K3, trace) — SURVEY.md Appendix A steps 1-5'
-// =============================================================================================
-struct KernelGraph {
-    const StepRec* recs;
-    const uint64_t* first_step;   // P+1 (global memory copy)
-    const double* zetas;          // zlen entries (global)
-    uint64_t S;
-    uint32_t P;
-    uint32_t N;
-    uint32_t zlen;
-    uint32_t space;               // min(params.space, 2^32-1): compared with ranks < 2^32
-    uint32_t space_max;
-    uint32_t q;
-    uint32_t q_is_100;            // 1: the quantisation step is the reference's 100 (constant division)
-    uint32_t blk_shift;           // path-of-block table granularity: block = step >> blk_shift
-    uint32_t coherent;            // 1: the lanes of a warp sample 32 consecutive steps (see sample_s1)
-    uint64_t samp_base, samp_len; // sampled steps are drawn from [samp_base, samp_base + samp_len) (default 0, S)
-};
-
-constexpr uint32_t SMEM_FS_MAX = 2048;         // first_step entries staged per block (16 KB)
-constexpr uint32_t BLK_TABLE = 4096;           // path-of-block entries staged per block (8 KB)
-
-// step -> path.  With the tables in shared memory: one 16-bit lookup (path of the first step of the
-// step's 2^shift-block) plus a short forward scan; otherwise a binary search over first_step.
-struct PathLookup {
-    const uint64_t* fs;           // P+1 entries, shared or global
-    const uint16_t* blk;          // BLK_TABLE entries in shared memory, or nullptr
-    uint32_t shift;
-    uint32_t P;
-    __device__ __forceinline__ uint32_t path_of(uint64_t s) const {
-        if (blk) {
-            uint32_t p = blk[(uint32_t)(s >> shift)];
-            while (s >= fs[p + 1]) ++p;
-            return p;
-        }
-        return find_path(fs, P, s);
-    }
-};
-
-// One term being sampled.  The stages are straight-line (selects, predicated loads): S1 turns the
-// draw into the sampled step and issues the zeta load, S2 turns it into the partner step.  The
-// kernel then requests both records and applies the update two pipeline stages later.
-struct Slot {
-    StepRec a, b;
-    uint64_t step_a, step_b;   // step indices
-    uint64_t f;                // first step of the path
-    uint64_t r23;              // second half of the Philox block
-    double zeta;
-    uint32_t n, ra, J;
-    uint32_t coins;            // r.z
-    bool zipf, back, live;     // live: a partner is drawn (n > 1 and the Zipf branch has room to move)
-    bool other_a, other_b;
-    bool valid;
-};
-
-// Draw slots of one Philox block r (see oracle/gfs_oracle.cpp PhiloxDraw):
-//   step = mulhi64(r.y:r.x, S); u = ((r.w:r.z) >> 11) * 2^-53; uniform rank = mulhi64(r.w:r.z, n);
-//   coins = bits 0..3 of r.z (zipf, back, end_a, end_b).
-__device__ __forceinline__ void sample_s1(const KernelGraph& g, const PathLookup& pl, const EpochDesc& ep, uint4 r,
-                                          uint64_t win_base, uint64_t win_len, bool active, unsigned warp_mask,
-                                          int lane, Slot& t) {
-    const uint64_t r01 = ((uint64_t)r.y << 32) | r.x;
-    t.r23 = ((uint64_t)r.w << 32) | r.z;
-    t.coins = r.z;
-    // step ~ U[win_base, win_base + win_len) on the circular sampling range; the default window
-    // (samp_base, samp_len) = (0, S) is the reference's U[0, S) (sgd.rs:444)
-    uint64_t s = win_base + __umul64hi(r01, win_len);
-    if (g.coherent) {
-        // warp-coherent sampling (sweep schedule only): the warp's first lane draws the step, lane l takes
-        // the l-th step after it.  Every step is still drawn with the same probability over a sweep, but
-        // the 32 sampled records — and, with the node relabelling, most of their nodes' positions — are
-        // adjacent in memory: one coalesced request instead of 32.  Partners stay independent per lane.
-        s = __shfl_sync(warp_mask, s, __ffs(warp_mask) - 1) + (uint32_t)lane;
-    }
-    if (s >= g.samp_base + g.samp_len) s -= g.samp_len;
-    t.step_a = s;
-    const uint32_t p = pl.path_of(s);
-    t.f = pl.fs[p];
-    const uint32_t n = (uint32_t)(pl.fs[p + 1] - t.f);
-    const uint32_t ra = (uint32_t)(s - t.f);
-    t.n = n; t.ra = ra;
-    t.zipf = ep.cooling || (t.coins & 1u);                                                 // sgd.rs:456
-    t.back = ra > 0 && (((t.coins >> 1) & 1u) || ra == n - 1);                             // sgd.rs:460
-    const bool fwd = !t.back && ra < n - 1;                                                // sgd.rs:475
-    const bool moves = t.back || fwd;
-    const uint32_t span = t.back ? ra : n - ra - 1;
-    const uint32_t J = span < g.space ? span : g.space;
-    t.J = J;
-    uint32_t k = J;                                                                        // sgd.rs:463-467
-    if (J > g.space_max) {
-        const uint32_t over = J - g.space_max;
-        k = g.space_max + (g.q_is_100 ? over / 100u : over / g.q) + 1;
-    }
-    k = k < g.zlen - 1 ? k : g.zlen - 1;                                                   // sgd.rs:469
-    t.live = active && n > 1 && (!t.zipf || moves);        // n == 1 => continue (sgd.rs:448)
-    t.zeta = 1.0;
-    if (t.live && t.zipf) t.zeta = __ldg(g.zetas + k);
-}
-
-__device__ __forceinline__ void sample_s2(const KernelGraph& g, const EpochDesc& ep, Slot& t) {
-    const uint32_t n = t.n, ra = t.ra;
-    // u = (r23 >> 11) * 2^-53 (sgd.rs:136 through PhiloxDraw::unit)
-    const double u = __dmul_rn((double)(t.r23 >> 11), 1.0 / 9007199254740992.0);
-    const ZipfPre pre = dirty_zipf_pre(t.J, ep.zc);
-    const uint32_t z = dirty_zipf_post(t.J, ep.zc, pre, t.zeta, u);
-    const uint32_t room = n - 1 - ra;
-    const uint32_t rb_back = ra >= z ? ra - z : 0u;                                        // saturating_sub
-    const uint32_t rb_fwd = z < room ? ra + z : n - 1;                                     // min(ra + z, n - 1)
-    const uint32_t rb_zipf = t.back ? rb_back : rb_fwd;
-    const uint32_t rb_unif = (uint32_t)__umul64hi(t.r23, (uint64_t)n);                     // sgd.rs:493-494
-    const uint32_t rb = t.zipf ? rb_zipf : rb_unif;
-    t.valid = t.live && ra != rb;                                                          // sgd.rs:497
-    t.step_b = t.valid ? t.f + rb : t.step_a;
-    t.other_a = t.other_b = false;
-}
-
-// nD end choice (sgd.rs:1060-1077); needs both records.
-__device__ __forceinline__ void sample_ends(Slot& t) {
-    const bool rev_a = t.a.node_rev & 1u, rev_b = t.b.node_rev & 1u;
-    bool ua = (t.coins >> 2) & 1u;
-    if (ua) { t.a.pos += t.a.node_len; ua = !rev_a; } else { ua = rev_a; }
-    bool ub = (t.coins >> 3) & 1u;
-    if (ub) { t.b.pos += t.b.node_len; ub = !rev_b; } else { ub = rev_b; }
-    t.other_a = ua; t.other_b = ub;
-}
-
-__device__ __forceinline__ double term_distance(const Slot& t) {
-    return fabs(__dsub_rn(u52_to_f64(t.a.pos), u52_to_f64(t.b.pos)));                      // sgd.rs:509-513
-}
-
-// =============================================================================================
-// coordinate access for K3
-// =============================================================================================
-template <typename CT> struct Arith;
-template <> struct Arith<double> {
-    static __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
-    static __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
-    static __device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
-    static __device__ __forceinline__ double div(double a, double b) { return __ddiv_rn(a, b); }
-    static __device__ __forceinline__ double sqrt(double a) { return __dsqrt_rn(a); }
-};
-template <> struct Arith<float> {
-    static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
-    static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
-    static __device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
-    static __device__ __forceinline__ float div(float a, float b) { return __fdiv_rn(a, b); }
-    static __device__ __forceinline__ float sqrt(float a) { return __fsqrt_rn(a); }
-};
-
-// positions are written by atomics at L2 and read here: bypass the (incoherent) L1 with ld.cg
-__device__ __forceinline__ double ld_pos(const double* p) {
-    double v;
-    asm volatile("ld.global.cg.f64 %0, [%1];" : "=d"(v) : "l"(p));
-    return v;
-}
-template <typename CT, int DS> __device__ __forceinline__ void ld_coords(const CT* p, CT (&c)[DS]);
-template <> __device__ __forceinline__ void ld_coords<float, 1>(const float* p, float (&c)[1]) {
-    asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(c[0]) : "l"(p));
-}
-template <> __device__ __forceinline__ void ld_coords<float, 2>(const float* p, float (&c)[2]) {
-    asm volatile("ld.global.cg.v2.f32 {%0,%1}, [%2];" : "=f"(c[0]), "=f"(c[1]) : "l"(p));
-}
-template <> __device__ __forceinline__ void ld_coords<float, 4>(const float* p, float (&c)[4]) {
-    asm volatile("ld.global.cg.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(c[0]), "=f"(c[1]), "=f"(c[2]), "=f"(c[3]) : "l"(p));
-}
-template <> __device__ __forceinline__ void ld_coords<float, 8>(const float* p, float (&c)[8]) {
-    asm volatile("ld.global.cg.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(c[0]), "=f"(c[1]), "=f"(c[2]), "=f"(c[3]) : "l"(p));
-    asm volatile("ld.global.cg.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(c[4]), "=f"(c[5]), "=f"(c[6]), "=f"(c[7]) : "l"(p + 4));
-}
-template <> __device__ __forceinline__ void ld_coords<double, 1>(const double* p, double (&c)[1]) { c[0] = ld_pos(p); }
-template <> __device__ __forceinline__ void ld_coords<double, 2>(const double* p, double (&c)[2]) {
-    asm volatile("ld.global.cg.v2.f64 {%0,%1}, [%2];" : "=d"(c[0]), "=d"(c[1]) : "l"(p));
-}
-template <> __device__ __forceinline__ void ld_coords<double, 4>(const double* p, double (&c)[4]) {
-    asm volatile("ld.global.cg.v2.f64 {%0,%1}, [%2];" : "=d"(c[0]), "=d"(c[1]) : "l"(p));
-    asm volatile("ld.global.cg.v2.f64 {%0,%1}, [%2];" : "=d"(c[2]), "=d"(c[3]) : "l"(p + 2));
-}
-template <> __device__ __forceinline__ void ld_coords<double, 8>(const double* p, double (&c)[8]) {
-#pragma unroll
-    for (int k = 0; k < 8; k += 2)
-        asm volatile("ld.global.cg.v2.f64 {%0,%1}, [%2];" : "=d"(c[k]), "=d"(c[k + 1]) : "l"(p + k));
-}
-
-template <typename CT, int DS> __device__ __forceinline__ void red_coords(CT* p, const CT (&d)[DS]);
-template <> __device__ __forceinline__ void red_coords<float, 1>(float* p, const float (&d)[1]) { atomicAdd(p, d[0]); }
-template <> __device__ __forceinline__ void red_coords<float, 2>(float* p, const float (&d)[2]) {
-    atomicAdd(reinterpret_cast<float2*>(p), make_float2(d[0], d[1]));          // red.global.add.v2.f32
-}
-template <> __device__ __forceinline__ void red_coords<float, 4>(float* p, const float (&d)[4]) {
-    atomicAdd(reinterpret_cast<float4*>(p), make_float4(d[0], d[1], d[2], d[3]));   // red.global.add.v4.f32
-}
-template <> __device__ __forceinline__ void red_coords<float, 8>(float* p, const float (&d)[8]) {
-    atomicAdd(reinterpret_cast<float4*>(p), make_float4(d[0], d[1], d[2], d[3]));
-    atomicAdd(reinterpret_cast<float4*>(p + 4), make_float4(d[4], d[5], d[6], d[7]));
-}
-template <> __device__ __forceinline__ void red_coords<double, 1>(double* p, const double (&d)[1]) { atomicAdd(p, d[0]); }
-template <> __device__ __forceinline__ void red_coords<double, 2>(double* p, const double (&d)[2]) {
-    atomicAdd(p, d[0]); atomicAdd(p + 1, d[1]);
-}
-template <> __device__ __forceinline__ void red_coords<double, 4>(double* p, const double (&d)[4]) {
-#pragma unroll
-    for (int k = 0; k < 4; ++k) atomicAdd(p + k, d[k]);
-}
-template <> __device__ __forceinline__ void red_coords<double, 8>(double* p, const double (&d)[8]) {
-#pragma unroll
-    for (int k = 0; k < 8; ++k) atomicAdd(p + k, d[k]);
-}
-
-// =============================================================================================
-// K2 / K3 — persistent SGD term kernel
-// =============================================================================================
-constexpr int SGD_BLOCK = 256;
-
-struct SgdArgs {
-    KernelGraph g;
-    const EpochDesc* epochs;     // device array, iter_max+1 entries
-    uint32_t epoch_begin, epoch_end;
-    uint32_t slice, n_slices;    // run slice `slice` of n_slices equal parts of every epoch's updates
-    uint64_t* attempt_ctr;       // per-thread Philox attempt counters (persist across launches)
-    unsigned long long* counters;   // [0] applied, [1] attempts, [2] watchdog trips
-    uint32_t seed_lo, seed_hi;
-    uint32_t tid_base;
-    void* positions;             // 1D: double[N]; nD: CT[N*2*DS]
-    // sweep scheduling (window_steps > 0): warps claim chunks of `chunk_updates` updates from *work_ctr;
-    // chunk c samples its steps from a window of `window_steps` steps that slides once over the step
-    // array per epoch, so the records being sampled stay L2-resident.
-    uint64_t window_steps;
-    uint32_t chunk_updates;
-    unsigned long long* work_ctr;
-    uint64_t iter_cap;           // watchdog: a warp that loops more often than this sets counters[2] and stops
-};
-
-// 1D update of one warp's terms (sgd.rs:512-576), optionally merging lanes that hit the same node.
-// r_x is the displacement computed from positions xi, xj that were loaded earlier (stage S3).
-template <bool AGG>
-__device__ __forceinline__ void apply_1d(double* X, unsigned warp_mask, int lane, bool valid, uint32_t i,
-                                         uint32_t j, double d, double eta, double xi, double xj) {
-    double r_x = 0.0;
-    auto add = [&](double* p, double v) { atomicAdd(p, v); };        // red.global.add.f64 (result unused)
-    if (valid) {
-        const double mu = fmin(__dmul_rn(eta, __ddiv_rn(1.0, d)), 1.0);     // sgd.rs:518-520
-        double dx = __dsub_rn(xi, xj);
-        if (dx == 0.0) dx = 1e-9;                                            // sgd.rs:546-548
-        const double mag = fabs(dx);
-        const double delta = __dmul_rn(__dmul_rn(mu, __dsub_rn(mag, d)), 0.5);   // sgd.rs:552
-        const double r = __ddiv_rn(delta, mag);
-        r_x = __dmul_rn(r, dx);
-    }
-    if (AGG) {
-        const unsigned vmask = __ballot_sync(warp_mask, valid);
-        const unsigned mi = __match_any_sync(warp_mask, i) & vmask;
-        const unsigned mj = __match_any_sync(warp_mask, j) & vmask;
-        const bool dup = valid && (__popc(mi) > 1 || __popc(mj) > 1);
-        if (!__any_sync(warp_mask, dup)) {               // common case: 64 distinct nodes in the warp
-            if (valid) { add(X + i, -r_x); add(X + j, r_x); }
-            return;
-        }
-        bool lead;
-        const double si = group_sum(warp_mask, valid ? mi : 0u, -r_x, lane, lead);
-        if (valid && lead) add(X + i, si);
-        const double sj = group_sum(warp_mask, valid ? mj : 0u, r_x, lane, lead);
-        if (valid && lead) add(X + j, sj);
-    } else if (valid) {
-        add(X + i, -r_x);                                                    // sgd.rs:575
-        add(X + j, r_x);                                                     // sgd.rs:576
-    }
-}
-
-// nD update (sgd.rs:1079-1149) on coordinates laid out [node][end][DS] (DS >= D, padded with zeros).
-template <typename CT, int D, int DS, bool AGG>
-__device__ __forceinline__ void apply_nd(CT* C, unsigned warp_mask, int lane, bool valid, uint32_t idx_i,
-                                         uint32_t idx_j, double d, double eta, const CT (&ci)[DS], const CT (&cj)[DS]) {
-    using A = Arith<CT>;
-    CT di[DS], dj[DS];
-#pragma unroll
-    for (int k = 0; k < DS; ++k) { di[k] = CT(0); dj[k] = CT(0); }
-    if (valid) {
-        const CT mu = (CT)fmin(__dmul_rn(eta, __ddiv_rn(1.0, d)), 1.0);      // sgd.rs:1085-1086
-        CT dl[DS];
-        CT mag_sq = CT(0);
-#pragma unroll
-        for (int k = 0; k < D; ++k) { dl[k] = A::sub(ci[k], cj[k]); mag_sq = A::add(mag_sq, A::mul(dl[k], dl[k])); }
-        if (mag_sq == CT(0)) { dl[0] = (CT)1e-9; mag_sq = (CT)1e-18; }       // sgd.rs:1116-1119
-        const CT mag = A::sqrt(mag_sq);
-        const CT delta = A::mul(A::mul(mu, A::sub(mag, (CT)d)), CT(0.5));    // sgd.rs:1125
-        const CT r = A::div(delta, mag);
-#pragma unroll
-        for (int k = 0; k < D; ++k) { const CT rd = A::mul(r, dl[k]); di[k] = -rd; dj[k] = rd; }
-    }
-    if (AGG) {
-        const unsigned vmask = __ballot_sync(warp_mask, valid);
-        const unsigned mi = __match_any_sync(warp_mask, idx_i) & vmask;
-        const unsigned mj = __match_any_sync(warp_mask, idx_j) & vmask;
-        const bool dup = valid && (__popc(mi) > 1 || __popc(mj) > 1);
-        if (!__any_sync(warp_mask, dup)) {
-            if (valid) { red_coords<CT, DS>(C + (size_t)idx_i * DS, di); red_coords<CT, DS>(C + (size_t)idx_j * DS, dj); }
-            return;
-        }
-        bool lead_i, lead_j;
-#pragma unroll
-        for (int k = 0; k < D; ++k) di[k] = group_sum(warp_mask, valid ? mi : 0u, di[k], lane, lead_i);
-        if (valid && lead_i) red_coords<CT, DS>(C + (size_t)idx_i * DS, di);
-#pragma unroll
-        for (int k = 0; k < D; ++k) dj[k] = group_sum(warp_mask, valid ? mj : 0u, dj[k], lane, lead_j);
-        if (valid && lead_j) red_coords<CT, DS>(C + (size_t)idx_j * DS, dj);
-    } else if (valid) {
-        red_coords<CT, DS>(C + (size_t)idx_i * DS, di);
-        red_coords<CT, DS>(C + (size_t)idx_j * DS, dj);
-    }
-}
-
-// D == 0: 1D `Y` (CT must be double).  D >= 1: nD `L`.  K: terms in flight per thread.
-template <typename CT, int D, int DS, bool AGG, int K>
-#ifndef GFS_K1_BLOCKS
-#define GFS_K1_BLOCKS 4
-#endif
-__global__ void __launch_bounds__(SGD_BLOCK, (K > 1 ? 3 : GFS_K1_BLOCKS))
-sgd_kernel(const SgdArgs a) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    // shared: first_step (P+1 u64) + path-of-block table (BLK_TABLE u16) when the path table fits
-    uint64_t* s_fs = reinterpret_cast<uint64_t*>(smem_raw);
-    const bool tables = a.g.P + 1 <= SMEM_FS_MAX;
-    const uint32_t n_fs = tables ? a.g.P + 1 : 0;
-    uint16_t* s_blk = reinterpret_cast<uint16_t*>(smem_raw + (size_t)n_fs * 8);
-    for (uint32_t k = threadIdx.x; k < n_fs; k += blockDim.x) s_fs[k] = a.g.first_step[k];
-    __syncthreads();
-    if (tables) {
-        for (uint32_t k = threadIdx.x; k < BLK_TABLE; k += blockDim.x) {
-            const uint64_t s0 = (uint64_t)k << a.g.blk_shift;
-            s_blk[k] = (uint16_t)(s0 < a.g.S ? find_path(s_fs, a.g.P, s0) : a.g.P - 1);
-        }
-        __syncthreads();
-    }
-    PathLookup pl;
-    pl.fs = tables ? s_fs : a.g.first_step;
-    pl.blk = tables ? s_blk : nullptr;
-    pl.shift = a.g.blk_shift;
-    pl.P = a.g.P;
-
-    const unsigned warp_mask = __activemask();
-    const int lane = threadIdx.x & 31;
-    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t T = gridDim.x * blockDim.x;
-    uint64_t attempt = a.attempt_ctr[tid];
-    uint64_t applied = 0, n_attempts = 0;
-    const uint2 key = make_uint2(a.seed_lo, a.seed_hi);
-
-    // ---- software pipeline -------------------------------------------------------------------------
-    // Three terms per slot are in different stages at any time (K slots per thread):
-    //   stage A   sample term i+3: Philox, path lookup, zeta load, Zipf arithmetic -> the two step indices
-    //   stage L   request the two records of term i+2 (indices from the previous A)
-    //   stage B1  term i+1: its records were requested one iteration ago and have had the whole of
-    //             stage A (~350 instructions and an L2 round trip) to arrive from DRAM; term distance,
-    //             validity, request the two positions
-    //   stage B2  term i: its positions have had one iteration to arrive; compute the update, apply it (red)
-    // Loop order is B2, B1, L, A, so that every register set is reloaded only after its consumer has run
-    // and no in-flight value is ever moved.  A term's validity is final only in B1 (zero distance,
-    // missing node), so a lane's quota is tracked optimistically: owed = target - done - in flight.
-    struct InFlight {            // term whose records are being loaded (L -> B)
-        StepRec a, b;
-        double eta;
-        uint32_t coins;
-        bool valid;
-    };
-    struct Sampled {             // term whose steps are known (A -> L)
-        uint64_t sa, sb;
-        double eta;
-        uint32_t coins;
-        bool valid;
-    };
-    InFlight fl[K];
-    Sampled sm[K];
-#pragma unroll
-    for (int k = 0; k < K; ++k) {
-        fl[k].valid = false; fl[k].coins = 0; fl[k].eta = 0.0;
-        fl[k].a.node_rev = fl[k].a.node_len = 0; fl[k].a.pos = 0; fl[k].b = fl[k].a;
-        sm[k].valid = false; sm[k].sa = sm[k].sb = 0; sm[k].coins = 0; sm[k].eta = 0.0;
-    }
-    uint64_t target = 0, done = 0;           // per lane: updates owed by the chunks claimed so far / applied
-
-    // work claiming (warp-uniform): sets ep / win_base / win_len and raises `target`
-    const bool sweep = a.window_steps != 0;
-    const uint32_t n_lanes = __popc(warp_mask);
-    const uint32_t lane_rank = __popc(warp_mask & ((1u << lane) - 1u));
-    const int leader = __ffs(warp_mask) - 1;
-    const uint32_t C = a.chunk_updates;
-    EpochDesc ep = a.epochs[a.epoch_begin];
-    uint64_t win_base = a.g.samp_base, win_len = a.g.samp_len;
-    uint32_t e_cur = a.epoch_begin;
-    // sweep schedule (see SgdArgs): chunks of C updates claimed from a global counter; chunk cc of an epoch
-    // samples from the window starting at cc * samp_len / chunks_per_epoch.  Claiming in order keeps all
-    // warps on neighbouring chunks (a static assignment lets them drift apart by SM speed), so the windows
-    // in use at any moment cover about n_warps * C * samp_len / m + window_steps consecutive steps.
-    const uint64_t m_sweep = ep.updates / a.n_slices + (a.slice < ep.updates % a.n_slices ? 1 : 0);
-    const uint64_t cpe = sweep ? (m_sweep + C - 1) / C : 1;                           // chunks per epoch
-    const uint64_t total_chunks = cpe * (uint64_t)(a.epoch_end - a.epoch_begin);
-    const double steps_per_chunk = (double)a.g.samp_len / (double)cpe;
-    uint64_t c_lo = 0;                        // first chunk of epoch e_cur
-    bool first_claim = true;
-    auto claim = [&]() -> bool {
-        if (sweep) {
-            unsigned long long c = 0;
-            if (lane == leader) c = atomicAdd(a.work_ctr, 1ull);
-            c = __shfl_sync(warp_mask, c, leader);
-            if (c >= total_chunks) return false;
-            while (c >= c_lo + cpe) { c_lo += cpe; ++e_cur; ep = a.epochs[e_cur]; }       // claims only move forward
-            const uint64_t cc = c - c_lo;
-            const uint64_t left = m_sweep - cc * C;
-            const uint32_t n_upd = left < C ? (uint32_t)left : C;
-            target += n_lanes == 32 ? (n_upd >> 5) + (lane_rank < (n_upd & 31u) ? 1u : 0u)
-                                    : n_upd / n_lanes + (lane_rank < n_upd % n_lanes ? 1u : 0u);
-            uint64_t off = (uint64_t)((double)cc * steps_per_chunk);
-            if (off >= a.g.samp_len) off = a.g.samp_len - 1;
-            win_base = a.g.samp_base + off;
-            win_len = a.window_steps;
-            return true;
-        }
-        // static schedule: one "chunk" per epoch; thread t applies floor(m/T) + (t < m%T) updates, steps ~ U[0,S)
-        if (!first_claim) ++e_cur;
-        first_claim = false;
-        if (e_cur >= a.epoch_end) return false;
-        ep = a.epochs[e_cur];
-        const uint64_t m = ep.updates / a.n_slices + (a.slice < ep.updates % a.n_slices ? 1 : 0);
-        target += m / T + (tid < m % T ? 1 : 0);
-        return true;
-    };
-    bool more = true;
-
-    struct Loaded {              // term whose positions are being loaded (B1 -> B2)
-        CT ci[DS], cj[DS];
-        double dist, eta;
-        uint32_t idx_i, idx_j;
-        bool ok;
-    };
-    Loaded xs[K];
-#pragma unroll
-    for (int k = 0; k < K; ++k) {
-        xs[k].ok = false; xs[k].dist = 0.0; xs[k].eta = 0.0; xs[k].idx_i = xs[k].idx_j = 0;
-#pragma unroll
-        for (int q = 0; q < DS; ++q) { xs[k].ci[q] = CT(0); xs[k].cj[q] = CT(0); }
-    }
-
-    uint64_t iters = 0;
-    for (;;) {
-        if (++iters > a.iter_cap) {          // never taken in a healthy run; turns a would-be hang into an error
-            if (lane == leader) atomicAdd(a.counters + 2, 1ull);
-            break;
-        }
-        // ---- B2: apply the terms whose positions were requested in the previous iteration
-        bool any_ok = false;
-#pragma unroll
-        for (int k = 0; k < K; ++k) any_ok = any_ok || xs[k].ok;
-#ifdef GFS_EXP_NOAPPLY
-#pragma unroll
-        for (int k = 0; k < K; ++k) { done += xs[k].ok ? 1u : 0u; if (xs[k].dist == 1.2345e-300) ((double*)a.positions)[0] = (double)xs[k].ci[0] + (double)xs[k].cj[0]; }
-        any_ok = false;
-#endif
-        if (__any_sync(warp_mask, any_ok)) {
-#pragma unroll
-            for (int k = 0; k < K; ++k) {
-                if constexpr (D == 0) {
-                    apply_1d<AGG>(reinterpret_cast<double*>(a.positions), warp_mask, lane, xs[k].ok, xs[k].idx_i, xs[k].idx_j,
-                                  xs[k].dist, xs[k].eta, xs[k].ci[0], xs[k].cj[0]);
-                } else {
-                    apply_nd<CT, (D > 0 ? D : 1), DS, AGG>(reinterpret_cast<CT*>(a.positions), warp_mask, lane, xs[k].ok,
-                                                           xs[k].idx_i, xs[k].idx_j, xs[k].dist, xs[k].eta, xs[k].ci, xs[k].cj);
-                }
-                done += xs[k].ok ? 1u : 0u;                                                // sgd.rs:579
-            }
-        }
-        // ---- B1: the records requested in the previous iteration have arrived: term distance, validity,
-        //          and the requests for the two positions
-        uint32_t pending = 0;
-#pragma unroll
-        for (int k = 0; k < K; ++k) {
-            bool oa = false, ob = false;
-            StepRec ra = fl[k].a, rb = fl[k].b;
-            if (D > 0) {                                                                   // sgd.rs:1060-1077
-                const bool rev_a = ra.node_rev & 1u, rev_b = rb.node_rev & 1u;
-                oa = (fl[k].coins >> 2) & 1u;
-                if (oa) { ra.pos += ra.node_len; oa = !rev_a; } else { oa = rev_a; }
-                ob = (fl[k].coins >> 3) & 1u;
-                if (ob) { rb.pos += rb.node_len; ob = !rev_b; } else { ob = rev_b; }
-            }
-            xs[k].dist = fabs(__dsub_rn(u52_to_f64(ra.pos), u52_to_f64(rb.pos)));          // sgd.rs:509-513
-            xs[k].eta = fl[k].eta;
-            const uint32_t na = ra.node_rev >> 1, nb = rb.node_rev >> 1;
-            xs[k].ok = fl[k].valid && xs[k].dist != 0.0 && na < a.g.N && nb < a.g.N;       // sgd.rs:514, 525-538
-            if constexpr (D == 0) {
-                xs[k].idx_i = na; xs[k].idx_j = nb;
-                const double* X = reinterpret_cast<const double*>(a.positions);
-                xs[k].ci[0] = xs[k].cj[0] = 0.0;
-                if (xs[k].ok) { xs[k].ci[0] = ld_pos(X + na); xs[k].cj[0] = ld_pos(X + nb); }
-            } else {
-                xs[k].idx_i = na * 2 + (oa ? 1u : 0u);                                     // sgd.rs:1099-1103
-                xs[k].idx_j = nb * 2 + (ob ? 1u : 0u);
-                const CT* Cc = reinterpret_cast<const CT*>(a.positions);
-#pragma unroll
-                for (int q = 0; q < DS; ++q) { xs[k].ci[q] = CT(0); xs[k].cj[q] = CT(0); }
-                if (xs[k].ok) {
-                    ld_coords<CT, DS>(Cc + (size_t)xs[k].idx_i * DS, xs[k].ci);
-                    ld_coords<CT, DS>(Cc + (size_t)xs[k].idx_j * DS, xs[k].cj);
-                }
-            }
-            pending += xs[k].ok ? 1u : 0u;
-        }
-        // ---- L: request the records of the terms sampled in the previous iteration
-#pragma unroll
-        for (int k = 0; k < K; ++k) {
-            fl[k].valid = sm[k].valid; fl[k].coins = sm[k].coins; fl[k].eta = sm[k].eta;
-            if (sm[k].valid) {
-                fl[k].a = load_rec(a.g.recs + sm[k].sa);
-                fl[k].b = load_rec(a.g.recs + sm[k].sb);
-                ++pending;
-            }
-            sm[k].valid = false;
-        }
-        // ---- A: sample the next terms
-        uint64_t owed = target - done - pending;
-        // a new chunk is claimed when every lane has sampled its share; the static schedule (which the
-        // bit-exact single-thread tests use) also waits until that share is confirmed applied, so that a
-        // term never runs with the next epoch's eta
-        const bool need_claim = sweep ? !__any_sync(warp_mask, owed != 0)
-                                      : !__any_sync(warp_mask, owed != 0 || pending != 0);
-        if (need_claim && more) {
-            more = claim();
-            owed = target - done - pending;
-        }
-        if (__any_sync(warp_mask, owed != 0)) {
-#pragma unroll
-            for (int k = 0; k < K; ++k) {
-                const bool active = owed > (uint64_t)k;
-                const uint4 r = philox4x32_10(make_uint4((uint32_t)attempt, (uint32_t)(attempt >> 32),
-                                                         a.tid_base + tid, STREAM_SGD), key);
-                // the Philox counter advances with every draw this lane makes — also on draws made only on
-                // behalf of other lanes (warp-coherent steps, grouped partners): a lane that has finished
-                // its share must not keep serving the same block to its neighbours
-                attempt += (active || a.g.coherent) ? 1 : 0;
-                n_attempts += active ? 1 : 0;
-                Slot t;
-                sample_s1(a.g, pl, ep, r, win_base, win_len, active, warp_mask, lane, t);
-                sample_s2(a.g, ep, t);
-                sm[k].sa = t.step_a; sm[k].sb = t.step_b; sm[k].valid = t.valid; sm[k].coins = t.coins; sm[k].eta = ep.eta;
-            }
-        } else if (!more && !__any_sync(warp_mask, pending != 0)) {
-            break;
-        }
-    }
-    applied = done;
-    a.attempt_ctr[tid] = attempt;
-    // counters: one atomic pair per full warp (partial warps: one pair per thread)
-    uint64_t att = n_attempts;
-    if (warp_mask == 0xffffffffu) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            applied += __shfl_xor_sync(0xffffffffu, applied, o);
-            att += __shfl_xor_sync(0xffffffffu, att, o);
-        }
-        if (lane != 0) return;
-    }
-    atomicAdd(a.counters + 0, (unsigned long long)applied);
-    atomicAdd(a.counters + 1, (unsigned long long)att);
-}
-
-// =============================================================================================
-// K4 — sampled stress (sgd.rs:1196-1283)
-// =============================================================================================
-constexpr int STRESS_BLOCK = 256;
-// coords: stride_node doubles per node, the + end's `dims` coordinates first.
-__global__ void __launch_bounds__(STRESS_BLOCK)
-stress_kernel(KernelGraph g, const uint32_t* __restrict__ old_of_new, const double* __restrict__ coords, uint32_t dims,
-              uint32_t stride_node, uint64_t samples, uint32_t seed_lo, uint32_t seed_hi, double* __restrict__ partial /*3 per block*/) {
-    __shared__ double red[3][STRESS_BLOCK / 32];
-    double sum = 0.0, sum_abs = 0.0, cnt = 0.0;
-    const uint2 key = make_uint2(seed_lo, seed_hi);
-    for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < samples; k += (uint64_t)gridDim.x * blockDim.x) {
-        const uint4 r = philox4x32_10(make_uint4((uint32_t)k, (uint32_t)(k >> 32), 0u, STREAM_STRESS), key);
-        const uint64_t s = __umul64hi(((uint64_t)r.y << 32) | r.x, g.S);
-        const uint32_t p = find_path(g.first_step, g.P, s);
-        const uint64_t f = g.first_step[p];
-        const uint32_t n = (uint32_t)(g.first_step[p + 1] - f);
-        if (n < 2) continue;
-        const uint32_t ra = (uint32_t)(s - f);
-        const uint32_t rb = (uint32_t)__umul64hi(((uint64_t)r.w << 32) | r.z, (uint64_t)n);
-        if (ra == rb) continue;
-        const StepRec A = load_rec(g.recs + s), B = load_rec(g.recs + f + rb);
-        const double dp = fabs(__dsub_rn((double)A.pos, (double)B.pos));
-        if (dp == 0.0) continue;
-        uint32_t ia = A.node_rev >> 1, ib = B.node_rev >> 1;
-        if (ia >= g.N || ib >= g.N) continue;
-        if (old_of_new) { ia = old_of_new[ia]; ib = old_of_new[ib]; }
-        double sq = 0.0;
-        for (uint32_t d = 0; d < dims; ++d) {
-            const double dl = __dsub_rn(coords[(size_t)ia * stride_node + d], coords[(size_t)ib * stride_node + d]);
-            sq = __dadd_rn(sq, __dmul_rn(dl, dl));
-        }
-        const double err = __dsub_rn(__dsqrt_rn(sq), dp);
-        sum += __ddiv_rn(__dmul_rn(err, err), __dmul_rn(dp, dp));
-        sum_abs += __ddiv_rn(fabs(err), dp);
-        cnt += 1.0;
-    }
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        sum += __shfl_xor_sync(0xffffffffu, sum, o);
-        sum_abs += __shfl_xor_sync(0xffffffffu, sum_abs, o);
-        cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-    }
-    if (lane == 0) { red[0][w] = sum; red[1][w] = sum_abs; red[2][w] = cnt; }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        double a0 = 0, a1 = 0, a2 = 0;
-        for (int k = 0; k < STRESS_BLOCK / 32; ++k) { a0 += red[0][k]; a1 += red[1][k]; a2 += red[2][k]; }
-        partial[blockIdx.x * 3 + 0] = a0; partial[blockIdx.x * 3 + 1] = a1; partial[blockIdx.x * 3 + 2] = a2;
-    }
-}
-
-// =============================================================================================
-// conversion kernels (host Layout order f64 <-> device [node][end][DS] CT)
-// =============================================================================================
-// src: host order, f64, `ends` node ends of D coordinates each per node (1D: ends = 1, D = 1).
-// dst: device order (node relabelled through new_of_old when non-null), CT, stride DS per end.
-template <typename CT>
-__global__ void pos_to_device(const double* __restrict__ src, CT* __restrict__ dst, uint64_t N, uint32_t ends, uint32_t D,
-                              uint32_t DS, const uint32_t* __restrict__ new_of_old) {
-    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const uint64_t per_node = (uint64_t)ends * DS;
-    if (i >= N * per_node) return;
-    const uint64_t node = i / per_node; const uint32_t r = (uint32_t)(i % per_node);
-    const uint32_t e = r / DS, k = r % DS;
-    const uint64_t dn = new_of_old ? new_of_old[node] : node;
-    dst[dn * per_node + r] = k < D ? (CT)src[(node * ends + e) * D + k] : CT(0);
-}
-template <typename CT>
-__global__ void pos_from_device(const CT* __restrict__ src, double* __restrict__ dst, uint64_t N, uint32_t ends, uint32_t D,
-                                uint32_t DS, const uint32_t* __restrict__ new_of_old) {
-    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const uint64_t per_node = (uint64_t)ends * D;
-    if (i >= N * per_node) return;
-    const uint64_t node = i / per_node; const uint32_t r = (uint32_t)(i % per_node);
-    const uint32_t e = r / D, k = r % D;
-    const uint64_t dn = new_of_old ? new_of_old[node] : node;
-    dst[i] = (double)src[(dn * ends + e) * DS + k];
-}
-
-// =============================================================================================
-// K6 — order by position (the host side of path_sgd_sort, src/sgd.rs:659-671)
-// =============================================================================================
-// Stable LSD radix sort of (key = order-preserving image of the f64 position, value = dense idx), 8-bit
-// digits, 8 passes.  Stability + values starting as 0..n-1 gives "ties by dense idx" (the reference sorts
-// (idx, pos) pairs in HashMap iteration order with a stable sort, i.e. its tie order is unspecified).
-constexpr int RS_THREADS = 256;
-constexpr int RS_ITEMS = 16;                       // keys per thread, processed in index order
-constexpr int RS_TILE = RS_THREADS * RS_ITEMS;
-
-// f64 -> u64 whose unsigned order is the numeric order; -0.0 == +0.0 (partial_cmp: Equal); NaN last.
-__device__ __forceinline__ uint64_t f64_sort_key(double v) {
-    if (v != v) return ~0ull;
-    if (v == 0.0) v = 0.0;
-    const uint64_t b = (uint64_t)__double_as_longlong(v);
-    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
-}
-__global__ void rs_make_keys(const double* __restrict__ x, uint64_t n, uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
-    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) { keys[i] = f64_sort_key(x[i]); vals[i] = (uint32_t)i; }
-}
-// hist[d * n_blocks + b] = number of keys of tile b whose digit is d
-__global__ void __launch_bounds__(RS_THREADS)
-rs_hist(const uint64_t* __restrict__ keys, uint64_t n, int shift, uint32_t n_blocks, uint32_t* __restrict__ hist) {
-    __shared__ uint32_t h[256];
-    h[threadIdx.x] = 0;
-    __syncthreads();
-    const uint64_t base = (uint64_t)blockIdx.x * RS_TILE;
-#pragma unroll
-    for (int k = 0; k < RS_ITEMS; ++k) {
-        const uint64_t i = base + (uint64_t)k * RS_THREADS + threadIdx.x;
-        if (i < n) atomicAdd(&h[(uint32_t)(keys[i] >> shift) & 255u], 1u);
-    }
-    __syncthreads();
-    hist[(size_t)threadIdx.x * n_blocks + blockIdx.x] = h[threadIdx.x];
-}
-// exclusive scan of hist in place (digit-major), one block
-__global__ void __launch_bounds__(1024) rs_scan(uint32_t* __restrict__ hist, uint64_t m) {
-    __shared__ uint32_t wsum[32];
-    __shared__ uint32_t running;
-    if (threadIdx.x == 0) running = 0;
-    __syncthreads();
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    for (uint64_t b0 = 0; b0 < m; b0 += 1024) {
-        const uint64_t i = b0 + threadIdx.x;
-        const uint32_t v = i < m ? hist[i] : 0u;
-        uint32_t inc = v;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
-        if (lane == 31) wsum[w] = inc;
-        __syncthreads();
-        if (w == 0) {
-            const uint32_t ws = wsum[lane];
-            uint32_t wi = ws;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, wi, o); if (lane >= o) wi += t; }
-            wsum[lane] = wi - ws;
-        }
-        __syncthreads();
-        const uint32_t excl = running + wsum[w] + inc - v;
-        if (i < m) hist[i] = excl;
-        __syncthreads();
-        if (threadIdx.x == 1023) running = excl + v;
-        __syncthreads();
-    }
-}
-// stable scatter: tile b writes its keys of digit d to offs[d * n_blocks + b] + (rank among the tile's digit-d keys)
-__global__ void __launch_bounds__(RS_THREADS)
-rs_scatter(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals, uint64_t n, int shift, uint32_t n_blocks,
-           const uint32_t* __restrict__ offs, uint64_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out) {
-    __shared__ uint32_t bin_off[256];                       // next free slot of each digit for this tile
-    __shared__ uint32_t warp_cnt[RS_THREADS / 32][256];
-    bin_off[threadIdx.x] = offs[(size_t)threadIdx.x * n_blocks + blockIdx.x];
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const uint64_t base = (uint64_t)blockIdx.x * RS_TILE;
-    for (int k = 0; k < RS_ITEMS; ++k) {                    // 256 consecutive keys at a time, in index order
-#pragma unroll
-        for (int q = 0; q < RS_THREADS / 32; ++q) warp_cnt[q][threadIdx.x] = 0;
-        __syncthreads();
-        const uint64_t i = base + (uint64_t)k * RS_THREADS + threadIdx.x;
-        const bool ok = i < n;
-        const uint64_t key = ok ? keys[i] : 0ull;
-        const uint32_t d = ok ? ((uint32_t)(key >> shift) & 255u) : 256u;       // 256: matches only other padding lanes
-        const unsigned peers = __match_any_sync(0xffffffffu, d);
-        const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
-        if (ok && rank == 0) warp_cnt[w][d] = __popc(peers);
-        __syncthreads();
-        {   // thread t owns digit t: turn per-warp counts into per-warp offsets, advance the tile's cursor
-            uint32_t run = bin_off[threadIdx.x];
-#pragma unroll
-            for (int q = 0; q < RS_THREADS / 32; ++q) { const uint32_t c = warp_cnt[q][threadIdx.x]; warp_cnt[q][threadIdx.x] = run; run += c; }
-            bin_off[threadIdx.x] = run;
-        }
-        __syncthreads();
-        if (ok) {
-            const uint32_t dst = warp_cnt[w][d] + rank;
-            keys_out[dst] = key;
-            vals_out[dst] = vals[i];
-        }
-        __syncthreads();
-    }
-}
-
-// =============================================================================================
-// K5 — replica reconcile helpers (multi-GPU; the all-reduce itself is NCCL, driven by the host)
-// =============================================================================================
-// pack:  buf[i] = float(x[i] - x_sync[i]),  buf[n + i] = (x[i] != x_sync[i])      (one f32 buffer, one all-reduce)
-// apply: x[i] = x_sync[i] + buf[i] / max(buf[n + i], 1);  x_sync[i] = x[i]
-// i.e. the mean of the displacements over the replicas that moved the element since the last sync.
-template <typename CT>
-__global__ void __launch_bounds__(256) rc_pack(const CT* __restrict__ x, const CT* __restrict__ xs, uint64_t n, float* __restrict__ buf) {
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
-        const CT d = x[i] - xs[i];
-        buf[i] = (float)d;
-        buf[n + i] = d != CT(0) ? 1.0f : 0.0f;
-    }
-}
-template <typename CT>
-__global__ void __launch_bounds__(256) rc_apply(CT* __restrict__ x, CT* __restrict__ xs, uint64_t n, const float* __restrict__ buf) {
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
-        const float c = buf[n + i];
-        const CT v = xs[i] + (CT)buf[i] / (CT)(c > 1.0f ? c : 1.0f);
-        x[i] = v; xs[i] = v;
-    }
-}
-
-// =============================================================================================
-// debug kernels
-// =============================================================================================
-__global__ void dbg_fpp(const double* a, const double* b, double* out, uint64_t n) {
-    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = fast_precise_pow(a[i], b[i]);
-}
-__global__ void dbg_zipf(const uint64_t* zmax, const double* theta, const double* zeta, const double* u, uint64_t* out, uint64_t n) {
-    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    ZipfConsts zc;
-    zc.theta = theta[i];
-    zc.one_minus_theta = __dsub_rn(1.0, theta[i]);
-    zc.alpha = __ddiv_rn(1.0, __dsub_rn(1.0, theta[i]));
-    zc.z2 = __dadd_rn(1.0, fast_precise_pow(0.5, theta[i]));
-    zc.alpha_e = __double2int_rz(zc.alpha);
-    zc.alpha_frac = __dsub_rn(zc.alpha, (double)zc.alpha_e);
-    out[i] = dirty_zipf((uint32_t)zmax[i], zc, zeta[i], u[i]);
-}
-__global__ void dbg_philox(const uint32_t* ctr, const uint32_t* key, uint32_t* out, uint64_t n) {
-    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const uint4 r = philox4x32_10(make_uint4(ctr[4 * i], ctr[4 * i + 1], ctr[4 * i + 2], ctr[4 * i + 3]),
-                                  make_uint2(key[2 * i], key[2 * i + 1]));
-    out[4 * i] = r.x; out[4 * i + 1] = r.y; out[4 * i + 2] = r.z; out[4 * i + 3] = r.w;
-}
-template <bool ND>
-__global__ void dbg_trace(KernelGraph g, const EpochDesc* epochs, uint32_t epoch, uint32_t seed_lo, uint32_t seed_hi,
-                          uint32_t tid, uint64_t attempt0, uint64_t count, uint8_t* valid, uint64_t* step_a,
-                          uint64_t* step_b, uint8_t* flags, double* dist) {
-    const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= count) return;
-    const EpochDesc ep = epochs[epoch];
-    const uint64_t attempt = attempt0 + k;
-    const uint4 r = philox4x32_10(make_uint4((uint32_t)attempt, (uint32_t)(attempt >> 32), tid, STREAM_SGD),
-                                  make_uint2(seed_lo, seed_hi));
-    Slot t;
-    PathLookup pl;
-    pl.fs = g.first_step; pl.blk = nullptr; pl.shift = 0; pl.P = g.P;
-    sample_s1(g, pl, ep, r, g.samp_base, g.samp_len, true, 0u, 0, t);      // g.coherent == 0 here
-    sample_s2(g, ep, t);
-    t.a = load_rec(g.recs + t.step_a);
-    t.b = load_rec(g.recs + t.step_b);
-    if (ND) sample_ends(t);
-    const double d = term_distance(t);
-    const bool ok = t.valid && d != 0.0;
-    valid[k] = ok;
-    step_a[k] = ok ? t.step_a : 0;
-    step_b[k] = ok ? t.step_b : 0;
-    flags[k] = ok ? (uint8_t)((t.other_a ? 1 : 0) | (t.other_b ? 2 : 0)) : 0;
-    dist[k] = ok ? d : 0.0;
-}
-
 }  // namespace gfs
+
+#include "gfs_kernels_index.cuh"
+#include "gfs_kernels_sgd.cuh"
+#include "gfs_kernels_aux.cuh"
 
 // =============================================================================================
 // Host-side objects
