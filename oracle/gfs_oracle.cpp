@@ -15,10 +15,14 @@
 // arithmetic that lives in un-vendored crates (rand 0.9 `Uniform`, rand_xoshiro 0.7
 // `Xoshiro256Plus::seed_from_u64`, rand_distr 0.5 `StandardNormal`; Cargo.lock is git-ignored)
 // is restated here from the crates' published algorithms (xoshiro256+ / SplitMix64 seeding /
-// widening-multiply rejection for bounded ints / 53-bit mantissa uniform).  => "parity
-// unpinned" at the RNG boundary; everything deterministic (path index, fast_precise_pow,
-// DirtyZipfian given u, eta schedule, zeta table, X init, layout order) is pinned by the
-// hand-derived known answers in tests/golden/known_answers.json.
+// widening-multiply rejection for bounded ints / 53-bit mantissa uniform).  The generator cores
+// (SplitMix64, xoshiro256+) are pinned by their published known-answer vectors
+// (tests/test_oracle.py::test_splitmix64_published_vectors, ::test_xoshiro256plus_published_vector);
+// rand's `Uniform<usize>` rejection rule and rand_distr's ziggurat `StandardNormal` (replaced here by
+// Marsaglia polar) are restated from the crates' documentation and stay unpinned.  => "parity
+// unpinned" at the RNG boundary (whole-run parity is statistical); everything deterministic (path
+// index, fast_precise_pow, DirtyZipfian given u, eta schedule, zeta table, X init, layout order) is
+// pinned by the hand-derived known answers in tests/golden/known_answers.json.
 //
 // Two draw policies feed the SAME restated term loop:
 //   * XoshiroDraw — the reference's RNG and lazy draw order (sgd.rs:431-494, 1062-1071)
@@ -135,18 +139,26 @@ void zetas_fill(uint64_t space, uint64_t space_max, uint64_t q, double theta, do
 // RNGs
 // ---------------------------------------------------------------------------------------------
 // rand_xoshiro 0.7: Xoshiro256Plus, seed_from_u64 = 4 outputs of SplitMix64(seed).
+// SplitMix64 (Steele, Lea, Flood; Vigna's splitmix64.c): the seeding generator of rand_core's
+// `seed_from_u64` for the xoshiro family.  Pinned by published vectors in tests/test_oracle.py.
+static inline uint64_t splitmix64_next(uint64_t& x) {
+    x += 0x9e3779b97f4a7c15ULL;
+    uint64_t z = x;
+    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ULL;
+    z = (z ^ (z >> 27)) * 0x94d049bb133111ebULL;
+    return z ^ (z >> 31);
+}
 struct Xoshiro256Plus {
     uint64_t s[4];
     static Xoshiro256Plus seed_from_u64(uint64_t seed) {
         Xoshiro256Plus r;
         uint64_t x = seed;
-        for (int i = 0; i < 4; ++i) {
-            x += 0x9e3779b97f4a7c15ULL;
-            uint64_t z = x;
-            z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ULL;
-            z = (z ^ (z >> 27)) * 0x94d049bb133111ebULL;
-            r.s[i] = z ^ (z >> 31);
-        }
+        for (int i = 0; i < 4; ++i) r.s[i] = splitmix64_next(x);
+        return r;
+    }
+    static Xoshiro256Plus from_state(const uint64_t st[4]) {
+        Xoshiro256Plus r;
+        for (int i = 0; i < 4; ++i) r.s[i] = st[i];
         return r;
     }
     inline uint64_t next_u64() {
@@ -685,6 +697,18 @@ void oracle_philox4x32_10(const uint32_t* ctr, const uint32_t* key, uint32_t* ou
 void oracle_xoshiro_u64(uint64_t seed, uint64_t n, uint64_t* out) {
     auto r = Xoshiro256Plus::seed_from_u64(seed);
     for (uint64_t i = 0; i < n; ++i) out[i] = r.next_u64();
+}
+void oracle_splitmix64(uint64_t seed, uint64_t n, uint64_t* out) {
+    uint64_t x = seed;
+    for (uint64_t i = 0; i < n; ++i) out[i] = splitmix64_next(x);
+}
+void oracle_xoshiro_from_state(const uint64_t* state4, uint64_t n, uint64_t* out) {
+    auto r = Xoshiro256Plus::from_state(state4);
+    for (uint64_t i = 0; i < n; ++i) out[i] = r.next_u64();
+}
+void oracle_xoshiro_f64(uint64_t seed, uint64_t n, double* out) {
+    auto r = Xoshiro256Plus::seed_from_u64(seed);
+    for (uint64_t i = 0; i < n; ++i) out[i] = r.next_f64();
 }
 void oracle_xoshiro_below(uint64_t seed, uint64_t bound, uint64_t n, uint64_t* out) {
     auto r = Xoshiro256Plus::seed_from_u64(seed);

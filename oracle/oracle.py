@@ -91,6 +91,12 @@ def lib():
         L.oracle_xoshiro_u64.argtypes = [C.c_uint64, C.c_uint64, u64p]
         L.oracle_xoshiro_below.restype = None
         L.oracle_xoshiro_below.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, u64p]
+        L.oracle_splitmix64.restype = None
+        L.oracle_splitmix64.argtypes = [C.c_uint64, C.c_uint64, u64p]
+        L.oracle_xoshiro_from_state.restype = None
+        L.oracle_xoshiro_from_state.argtypes = [u64p, C.c_uint64, u64p]
+        L.oracle_xoshiro_f64.restype = None
+        L.oracle_xoshiro_f64.argtypes = [C.c_uint64, C.c_uint64, f64p]
         L.oracle_path_index.restype = None
         L.oracle_path_index.argtypes = [C.POINTER(_Graph)] + [u64p] * 7
         L.oracle_params_from_graph.restype = None
@@ -286,6 +292,41 @@ def philox(ctr, key) -> np.ndarray:
     o = np.zeros(4, dtype=np.uint32)
     lib().oracle_philox4x32_10(_p(c, u32p), _p(k, u32p), _p(o, u32p))
     return o
+
+
+def splitmix64(seed: int, n: int) -> np.ndarray:
+    out = np.zeros(n, dtype=np.uint64)
+    lib().oracle_splitmix64(seed, n, _p(out, u64p))
+    return out
+
+
+def xoshiro_from_state(state4, n: int) -> np.ndarray:
+    """n outputs of xoshiro256+ started from the raw state (rand_xoshiro `from_seed`, little-endian words)."""
+    st = np.asarray(state4, dtype=np.uint64)
+    out = np.zeros(n, dtype=np.uint64)
+    lib().oracle_xoshiro_from_state(_p(st, u64p), n, _p(out, u64p))
+    return out
+
+
+def xoshiro_u64(seed: int, n: int) -> np.ndarray:
+    """n outputs of Xoshiro256Plus::seed_from_u64(seed)."""
+    out = np.zeros(n, dtype=np.uint64)
+    lib().oracle_xoshiro_u64(seed, n, _p(out, u64p))
+    return out
+
+
+def xoshiro_f64(seed: int, n: int) -> np.ndarray:
+    """n draws of rng.random::<f64>() = (next_u64 >> 11) * 2^-53."""
+    out = np.zeros(n, dtype=np.float64)
+    lib().oracle_xoshiro_f64(seed, n, _p(out, f64p))
+    return out
+
+
+def xoshiro_below(seed: int, bound: int, n: int) -> np.ndarray:
+    """n draws of Uniform::new(0, bound).sample(&mut rng) for usize (rand 0.9 UniformUsize)."""
+    out = np.zeros(n, dtype=np.uint64)
+    lib().oracle_xoshiro_below(seed, bound, n, _p(out, u64p))
+    return out
 
 
 def path_index(g: Graph) -> dict:

@@ -202,3 +202,61 @@ def test_no_multi_step_path(oracle):
     p = oracle.params_from_graph(g)
     x, st, rc = oracle.path_linear_sgd(g, p, mode=oracle.MODE_EXACT)
     assert rc != 0 and st.applied == 0                                      # sgd.rs:250-261
+
+
+# ---- RNG cores of the un-vendored crates: published known-answer vectors -----------
+def test_splitmix64_published_vectors(oracle, ka):
+    for row in ka["splitmix64"]:
+        got = oracle.splitmix64(row["seed"], len(row["out"]))
+        assert [int(v) for v in got] == row["out"]
+
+
+def test_xoshiro256plus_published_vector(oracle, ka):
+    row = ka["xoshiro256plus_state_1_2_3_4"]
+    got = oracle.xoshiro_from_state(row["state"], len(row["out"]))
+    assert [int(v) for v in got] == row["out"]
+
+
+def test_xoshiro_seed_from_u64_is_splitmix_state(oracle):
+    # rand_core's seed_from_u64 for xoshiro256+: the state is four SplitMix64 outputs
+    for seed in (0, 12345, 9399220, 9399221, 2**64 - 1):
+        st = oracle.splitmix64(seed, 4)
+        assert np.array_equal(oracle.xoshiro_u64(seed, 16), oracle.xoshiro_from_state(st, 16))
+        # first output = s[0] + s[3] (mod 2^64)
+        assert int(oracle.xoshiro_u64(seed, 1)[0]) == (int(st[0]) + int(st[3])) % 2**64
+
+
+def test_xoshiro_float_and_bounded_draws(oracle):
+    seed = 9399220
+    raw = oracle.xoshiro_u64(seed, 256)
+    # random::<f64>(): 53 high bits scaled by 2^-53 (sgd.rs:136, 456, 460)
+    f = oracle.xoshiro_f64(seed, 256)
+    assert np.array_equal(f, (raw >> np.uint64(11)).astype(np.float64) * 2.0**-53)
+    assert f.min() >= 0.0 and f.max() < 1.0
+    # Uniform::new(0, n) for usize, n <= 2^32: widening multiply of the HIGH 32 bits with rejection of
+    # low products below (2^32 - n) % n  (sgd.rs:435, 444, 493)
+    for n in (2, 3, 10, 35059, 2**31 + 5):
+        got = oracle.xoshiro_below(seed, n, 32)
+        want, k = [], 0
+        thresh = (2**32 - n) % n
+        while len(want) < 32:
+            m = (int(raw[k]) >> 32) * n
+            k += 1
+            if (m & 0xFFFFFFFF) >= thresh:
+                want.append(m >> 32)
+        assert [int(v) for v in got] == want and max(want) < n
+    # n > 2^32: the 64-bit lane
+    n = 2**40 + 7
+    got = oracle.xoshiro_below(seed, n, 16)
+    thresh = (2**64 - n) % n
+    want, k = [], 0
+    while len(want) < 16:
+        m = int(raw[k]) * n
+        k += 1
+        if (m & (2**64 - 1)) >= thresh:
+            want.append(m >> 64)
+    assert [int(v) for v in got] == want
+    # uniformity (chi-square, 10 cells, 20000 draws): 99.9 % quantile of chi2(9) is 27.9
+    d = oracle.xoshiro_below(7, 10, 20000)
+    cnt = np.bincount(d.astype(np.int64), minlength=10)
+    assert ((cnt - 2000.0) ** 2 / 2000.0).sum() < 27.9
