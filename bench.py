@@ -278,7 +278,7 @@ def run_ours(a, wl):
     run.upload(x0)
     n_epochs = params.iter_max + 1
     M = params.min_term_updates
-    K, W = a.steps, a.warmup
+    K, W = a.steps, max(a.warmup, 3)      # timing rule: at least 3 untimed warm-up steps, whatever was asked for
     for k in range(W):
         run.run_epoch(epoch_of_step(k, max(W, 1), n_epochs))
     barrier()

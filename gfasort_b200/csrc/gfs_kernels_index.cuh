@@ -42,12 +42,15 @@ k1_tile_sums(const uint64_t* __restrict__ handles, const uint32_t* __restrict__ 
              uint64_t* __restrict__ tile_sum) {
     __shared__ uint64_t wb[32];
     const uint64_t base = (uint64_t)blockIdx.x * K1_TILE;
-    uint64_t s = 0;
+    uint64_t hh[K1_ITEMS];                  // all handle loads first, then all gathers: two round trips
 #pragma unroll
     for (int k = 0; k < K1_ITEMS; ++k) {
         const uint64_t i = base + (uint64_t)k * K1_THREADS + threadIdx.x;
-        if (i < S) s += gathered_len(handles[i], node_len, N);
+        hh[k] = i < S ? __ldg(handles + i) : ~0ull;              // past the end: node >= N => length 0
     }
+    uint64_t s = 0;
+#pragma unroll
+    for (int k = 0; k < K1_ITEMS; ++k) s += gathered_len(hh[k], node_len, N);
     s = block_sum_u64(s, wb);
     if (threadIdx.x == 0) tile_sum[blockIdx.x] = s;
 }
@@ -112,35 +115,43 @@ k1_path_base(const uint64_t* __restrict__ handles /*chunk-local*/, const uint32_
 }
 
 // Emit the records of one tile: pos = global prefix - path_base[path(step)].
+// Loads and stores are strided (thread t owns items k*256 + t: coalesced handle loads, one 16-byte
+// store per record), the scan is blocked (thread t sums items [8t, 8t+8)); the two views meet in
+// shared memory, padded by one word per 32 (lengths) / one entry per 16 (offsets) so that neither
+// view has bank conflicts.  All eight handle loads are issued before the first gather, so a thread
+// waits for two memory round trips, not sixteen.
+__device__ __forceinline__ int k1_pad32(int j) { return j + (j >> 5); }
+__device__ __forceinline__ int k1_pad16(int j) { return j + (j >> 4); }
+
 __global__ void __launch_bounds__(K1_THREADS)
 k1_write_recs(const uint64_t* __restrict__ handles /*chunk-local*/, const uint32_t* __restrict__ node_len,
               uint64_t N, const uint64_t* __restrict__ first_step, uint32_t P, uint64_t chunk_begin,
               uint64_t chunk_len, const uint64_t* __restrict__ tile_prefix, const uint64_t* __restrict__ path_base,
               StepRec* __restrict__ recs /*global index*/) {
-    __shared__ uint32_t s_len[K1_TILE];
-    __shared__ uint32_t s_nr[K1_TILE];
-    __shared__ uint64_t s_pos[K1_TILE];
+    __shared__ uint32_t s_len[K1_TILE + K1_TILE / 32];
+    __shared__ uint64_t s_pos[K1_TILE + K1_TILE / 16];
     __shared__ uint64_t wsum[K1_THREADS / 32];
     const uint64_t tbase = (uint64_t)blockIdx.x * K1_TILE;
+    uint64_t hh[K1_ITEMS];
 #pragma unroll
     for (int k = 0; k < K1_ITEMS; ++k) {
-        const int j = k * K1_THREADS + threadIdx.x;
-        const uint64_t i = tbase + j;
-        uint32_t len = 0, nr = 0;
-        if (i < chunk_len) {
-            const uint64_t h = handles[i];
-            len = gathered_len(h, node_len, N);
-            const uint64_t node = h >> 1;
-            nr = (uint32_t)(((node < N ? node : N) << 1) | (h & 1));
-        }
-        s_len[j] = len; s_nr[j] = nr;
+        const uint64_t i = tbase + (uint64_t)(k * K1_THREADS + threadIdx.x);
+        hh[k] = i < chunk_len ? __ldg(handles + i) : ~0ull;      // past the end: node >= N => length 0
+    }
+    uint32_t len[K1_ITEMS], nr[K1_ITEMS];
+#pragma unroll
+    for (int k = 0; k < K1_ITEMS; ++k) {
+        const uint64_t node = hh[k] >> 1;
+        len[k] = gathered_len(hh[k], node_len, N);
+        nr[k] = (uint32_t)(((node < N ? node : N) << 1) | (hh[k] & 1));
+        s_len[k1_pad32(k * K1_THREADS + threadIdx.x)] = len[k];
     }
     __syncthreads();
     // thread t owns items [t*8, t*8+8)
     uint64_t loc[K1_ITEMS];
     uint64_t tsum = 0;
 #pragma unroll
-    for (int k = 0; k < K1_ITEMS; ++k) { loc[k] = tsum; tsum += s_len[threadIdx.x * K1_ITEMS + k]; }
+    for (int k = 0; k < K1_ITEMS; ++k) { loc[k] = tsum; tsum += s_len[k1_pad32(threadIdx.x * K1_ITEMS + k)]; }
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     uint64_t inc = tsum;
 #pragma unroll
@@ -155,7 +166,7 @@ k1_write_recs(const uint64_t* __restrict__ handles /*chunk-local*/, const uint32
     for (int k = 0; k < K1_THREADS / 32; ++k) woff += (k < w) ? wsum[k] : 0;
     const uint64_t texcl = tile_prefix[blockIdx.x] + woff + (inc - tsum);
 #pragma unroll
-    for (int k = 0; k < K1_ITEMS; ++k) s_pos[threadIdx.x * K1_ITEMS + k] = texcl + loc[k];
+    for (int k = 0; k < K1_ITEMS; ++k) s_pos[k1_pad16(threadIdx.x * K1_ITEMS + k)] = texcl + loc[k];
     __syncthreads();
     // path of the tile's first and last step; most tiles lie inside one path
     const uint64_t g_first = chunk_begin + tbase;
@@ -171,9 +182,9 @@ k1_write_recs(const uint64_t* __restrict__ handles /*chunk-local*/, const uint32
             const uint64_t gi = chunk_begin + i;
             uint64_t pb = base_first;
             if (p_first != p_last) pb = path_base[find_path(first_step, P, gi)];
-            StepRec r;
-            r.node_rev = s_nr[j]; r.node_len = s_len[j]; r.pos = s_pos[j] - pb;
-            recs[gi] = r;
+            const uint64_t pos = s_pos[k1_pad16(j)] - pb;
+            // StepRec {node_rev, node_len, pos} as one 16-byte store (see load_rec)
+            *reinterpret_cast<uint4*>(recs + gi) = make_uint4(nr[k], len[k], (uint32_t)pos, (uint32_t)(pos >> 32));
         }
     }
 }

@@ -44,6 +44,27 @@ void set_error(const std::string& s) { g_last_error = s; }
         }                                                                                           \
     } while (0)
 
+// Scoped device buffer / stream: transient allocations are released on every return path.
+template <typename T> struct DevBuf {
+    T* p = nullptr;
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    ~DevBuf() { cudaFree(p); }
+    void release() { cudaFree(p); p = nullptr; }
+    cudaError_t alloc(size_t n) { return cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T)); }
+    cudaError_t up(const T* h, size_t n) { return cudaMemcpy(p, h, n * sizeof(T), cudaMemcpyHostToDevice); }
+    cudaError_t down(T* h, size_t n) { return cudaMemcpy(h, p, n * sizeof(T), cudaMemcpyDeviceToHost); }
+};
+struct ScopedStream {
+    cudaStream_t st = nullptr;
+    ScopedStream() = default;
+    ScopedStream(const ScopedStream&) = delete;
+    ScopedStream& operator=(const ScopedStream&) = delete;
+    ~ScopedStream() { if (st) cudaStreamDestroy(st); }
+    cudaError_t create() { return cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking); }
+};
+
 static double now_s() {
     return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
@@ -239,11 +260,12 @@ static int index_relabel(gfs_index* ix, const uint32_t* given, cudaStream_t st) 
         GFS_CUDA(cudaMemcpyAsync(ix->d_new_of_old, given, (size_t)N * 4, cudaMemcpyHostToDevice, st));
         rl_invert<<<(N + 255) / 256, 256, 0, st>>>(ix->d_new_of_old, N, ix->d_old_of_new);
     } else {
-        unsigned long long* d_first = nullptr; uint64_t* d_tiles = nullptr; uint64_t* d_carry = nullptr;
+        DevBuf<unsigned long long> b_first; DevBuf<uint64_t> b_tiles, b_carry;
         const uint64_t tiles_s = (ix->S + K1_TILE - 1) / K1_TILE, tiles_n = ((uint64_t)N + K1_TILE - 1) / K1_TILE;
-        GFS_CUDA(cudaMalloc(&d_first, (size_t)N * 8));
-        GFS_CUDA(cudaMalloc(&d_tiles, (std::max(tiles_s, tiles_n) + 1) * 8));
-        GFS_CUDA(cudaMalloc(&d_carry, 8));
+        GFS_CUDA(b_first.alloc(N));
+        GFS_CUDA(b_tiles.alloc(std::max(tiles_s, tiles_n) + 1));
+        GFS_CUDA(b_carry.alloc(1));
+        unsigned long long* d_first = b_first.p; uint64_t* d_tiles = b_tiles.p; uint64_t* d_carry = b_carry.p;
         GFS_CUDA(cudaMemsetAsync(d_first, 0xff, (size_t)N * 8, st));
         GFS_CUDA(cudaMemsetAsync(d_carry, 0, 8, st));
         if (ix->S) {
@@ -255,8 +277,7 @@ static int index_relabel(gfs_index* ix, const uint32_t* given, cudaStream_t st) 
         rl_tile_count<1><<<(unsigned)tiles_n, K1_THREADS, 0, st>>>(nullptr, d_first, N, N, d_tiles);
         k1_scan_tiles<<<1, 1024, 0, st>>>(d_tiles, tiles_n, d_carry);      // carry continues after the visited nodes
         rl_assign<1><<<(unsigned)tiles_n, K1_THREADS, 0, st>>>(nullptr, d_first, N, N, d_tiles, ix->d_new_of_old, ix->d_old_of_new);
-        cudaError_t e = cudaStreamSynchronize(st);
-        cudaFree(d_first); cudaFree(d_tiles); cudaFree(d_carry);
+        cudaError_t e = cudaStreamSynchronize(st);      // the scratch buffers go out of scope below
         if (e != cudaSuccess) { set_error(std::string("relabel failed: ") + cudaGetErrorString(e)); return GFS_ERR_CUDA; }
     }
     if (ix->S) rl_rewrite<<<(unsigned)((ix->S + 255) / 256), 256, 0, st>>>(ix->d_recs, ix->S, N, ix->d_new_of_old);
@@ -298,16 +319,17 @@ extern "C" int gfs_index_build_shard(const uint64_t* step_handles, const uint64_
     auto fail = [&](int code) { gfs_index_free(ix); return code; };
 #define IX_CUDA(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { set_error(std::string(#call) + " failed: " + cudaGetErrorString(e__)); return fail(GFS_ERR_CUDA); } } while (0)
 
-    cudaStream_t st;
-    IX_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-    uint64_t* d_path_base = nullptr; uint64_t* d_carry = nullptr; uint32_t* d_node_len = nullptr;
-    uint64_t* d_handles = nullptr; uint64_t* d_tiles = nullptr;
+    ScopedStream sst;
+    IX_CUDA(sst.create());
+    cudaStream_t st = sst.st;
+    DevBuf<uint64_t> b_path_base, b_carry, b_handles, b_tiles; DevBuf<uint32_t> b_node_len;
     IX_CUDA(cudaMalloc(&ix->d_first_step, (ix->P + 1) * 8));
     IX_CUDA(cudaMalloc(&ix->d_path_len, std::max<uint64_t>(ix->P, 1) * 8));
     IX_CUDA(cudaMalloc(&ix->d_recs, std::max<uint64_t>(ix->S, 1) * sizeof(StepRec)));
-    IX_CUDA(cudaMalloc(&d_path_base, (ix->P + 1) * 8));
-    IX_CUDA(cudaMalloc(&d_carry, 8));
-    IX_CUDA(cudaMalloc(&d_node_len, std::max<uint64_t>(N, 1) * 4));
+    IX_CUDA(b_path_base.alloc(ix->P + 1));
+    IX_CUDA(b_carry.alloc(1));
+    IX_CUDA(b_node_len.alloc(N));
+    uint64_t* d_path_base = b_path_base.p; uint64_t* d_carry = b_carry.p; uint32_t* d_node_len = b_node_len.p;
     IX_CUDA(cudaMemsetAsync(d_carry, 0, 8, st));
     IX_CUDA(cudaMemsetAsync(d_path_base, 0, (ix->P + 1) * 8, st));
     const double t_h2d0 = now_s();
@@ -320,8 +342,9 @@ extern "C" int gfs_index_build_shard(const uint64_t* step_handles, const uint64_
     CH = std::max<uint64_t>(K1_TILE, (CH / K1_TILE) * K1_TILE);
     const uint64_t chunk_cap = std::min<uint64_t>(CH, std::max<uint64_t>(ix->S, 1));
     const uint64_t tiles_cap = (chunk_cap + K1_TILE - 1) / K1_TILE;
-    IX_CUDA(cudaMalloc(&d_handles, chunk_cap * 8));
-    IX_CUDA(cudaMalloc(&d_tiles, (tiles_cap + 1) * 8));
+    IX_CUDA(b_handles.alloc(chunk_cap));
+    IX_CUDA(b_tiles.alloc(tiles_cap + 1));
+    uint64_t* d_handles = b_handles.p; uint64_t* d_tiles = b_tiles.p;
     uint32_t p_lo = 0;
     for (uint64_t c0 = 0; c0 < ix->S; c0 += CH) {
         const uint64_t clen = std::min(CH, ix->S - c0);
@@ -351,13 +374,12 @@ extern "C" int gfs_index_build_shard(const uint64_t* step_handles, const uint64_
     }
     IX_CUDA(cudaStreamSynchronize(st));
     IX_CUDA(cudaGetLastError());
-    cudaFree(d_handles); cudaFree(d_tiles); cudaFree(d_path_base); cudaFree(d_carry); cudaFree(d_node_len);
+    b_handles.release(); b_tiles.release(); b_path_base.release(); b_carry.release(); b_node_len.release();   // before relabelling allocates
     if (relabel_mode == 2 && !new_of_old) { set_error("gfs_index_build: relabel_mode 2 needs a permutation"); return fail(GFS_ERR_INVALID); }
     if (relabel_mode == 1 || relabel_mode == 2) {
         rc = index_relabel(ix, relabel_mode == 2 ? new_of_old : nullptr, st);
         if (rc) return fail(rc);
     }
-    cudaStreamDestroy(st);
     ix->h2d_seconds = h2d;
     ix->build_seconds = now_s() - t_begin;
     *out = ix;
@@ -400,16 +422,15 @@ extern "C" int gfs_index_export(const gfs_index* ix, uint64_t* step_pos, uint64_
     if (!ix) { set_error("gfs_index_export: null index"); return GFS_ERR_INVALID; }
     GFS_CUDA(cudaSetDevice(ix->device));
     if (step_pos && ix->S) {
-        uint64_t* d = nullptr;
+        DevBuf<uint64_t> d;
         const uint64_t CH = 1ull << 26;
-        GFS_CUDA(cudaMalloc(&d, std::min(CH, ix->S) * 8));
+        GFS_CUDA(d.alloc(std::min(CH, ix->S)));
         for (uint64_t c0 = 0; c0 < ix->S; c0 += CH) {
             const uint64_t n = std::min(CH, ix->S - c0);
-            k1_export_pos<<<(unsigned)((n + 255) / 256), 256>>>(ix->d_recs + c0, n, d);
-            cudaError_t e = cudaMemcpy(step_pos + c0, d, n * 8, cudaMemcpyDeviceToHost);
-            if (e != cudaSuccess) { cudaFree(d); set_error(std::string("export copy failed: ") + cudaGetErrorString(e)); return GFS_ERR_CUDA; }
+            k1_export_pos<<<(unsigned)((n + 255) / 256), 256>>>(ix->d_recs + c0, n, d.p);
+            GFS_CUDA(cudaGetLastError());
+            GFS_CUDA(cudaMemcpy(step_pos + c0, d.p, n * 8, cudaMemcpyDeviceToHost));
         }
-        cudaFree(d);
     }
     if (path_len && ix->P) GFS_CUDA(cudaMemcpy(path_len, ix->d_path_len, ix->P * 8, cudaMemcpyDeviceToHost));
     return GFS_OK;
@@ -419,19 +440,18 @@ extern "C" int gfs_index_export_records(const gfs_index* ix, uint64_t* step_hand
     if (!ix || !step_handle || !step_node_len) { set_error("gfs_index_export_records: null argument"); return GFS_ERR_INVALID; }
     GFS_CUDA(cudaSetDevice(ix->device));
     if (!ix->S) return GFS_OK;
-    uint64_t* dh = nullptr; uint32_t* dl = nullptr;
+    DevBuf<uint64_t> dh; DevBuf<uint32_t> dl;
     const uint64_t CH = 1ull << 26;
     const uint64_t cap = std::min(CH, ix->S);
-    GFS_CUDA(cudaMalloc(&dh, cap * 8));
-    GFS_CUDA(cudaMalloc(&dl, cap * 4));
+    GFS_CUDA(dh.alloc(cap));
+    GFS_CUDA(dl.alloc(cap));
     for (uint64_t c0 = 0; c0 < ix->S; c0 += CH) {
         const uint64_t n = std::min(CH, ix->S - c0);
-        k1_export_hl<<<(unsigned)((n + 255) / 256), 256>>>(ix->d_recs + c0, n, (uint32_t)ix->N, ix->d_old_of_new, dh, dl);
-        cudaError_t e1 = cudaMemcpy(step_handle + c0, dh, n * 8, cudaMemcpyDeviceToHost);
-        cudaError_t e2 = cudaMemcpy(step_node_len + c0, dl, n * 4, cudaMemcpyDeviceToHost);
-        if (e1 != cudaSuccess || e2 != cudaSuccess) { cudaFree(dh); cudaFree(dl); set_error("export copy failed"); return GFS_ERR_CUDA; }
+        k1_export_hl<<<(unsigned)((n + 255) / 256), 256>>>(ix->d_recs + c0, n, (uint32_t)ix->N, ix->d_old_of_new, dh.p, dl.p);
+        GFS_CUDA(cudaGetLastError());
+        GFS_CUDA(cudaMemcpy(step_handle + c0, dh.p, n * 8, cudaMemcpyDeviceToHost));
+        GFS_CUDA(cudaMemcpy(step_node_len + c0, dl.p, n * 4, cudaMemcpyDeviceToHost));
     }
-    cudaFree(dh); cudaFree(dl);
     return GFS_OK;
 }
 
@@ -799,21 +819,18 @@ extern "C" int gfs_stress(const gfs_index* ix, uint32_t dims, int32_t layout_ord
     if (counted) *counted = 0;
     if (ix->S < 2 || samples == 0) return GFS_OK;            // sgd.rs:1220-1222
     const uint32_t stride = layout_order ? 2 * dims : dims;
-    double* d_coords = nullptr; double* d_partial = nullptr;
-    const size_t bytes = (size_t)ix->N * stride * 8;
-    GFS_CUDA(cudaMalloc(&d_coords, bytes));
-    cudaError_t e = cudaMemcpy(d_coords, coords, bytes, cudaMemcpyHostToDevice);
-    if (e != cudaSuccess) { cudaFree(d_coords); set_error(std::string("gfs_stress copy: ") + cudaGetErrorString(e)); return GFS_ERR_CUDA; }
+    DevBuf<double> d_coords, d_partial;
+    const size_t n_coords = (size_t)ix->N * stride;
+    GFS_CUDA(d_coords.alloc(n_coords));
+    GFS_CUDA(d_coords.up(coords, n_coords));
     const unsigned grid = (unsigned)std::min<uint64_t>((samples + STRESS_BLOCK - 1) / STRESS_BLOCK, 148 * 8);
-    e = cudaMalloc(&d_partial, (size_t)grid * 3 * 8);
-    if (e != cudaSuccess) { cudaFree(d_coords); set_error("gfs_stress alloc"); return GFS_ERR_CUDA; }
+    GFS_CUDA(d_partial.alloc((size_t)grid * 3));
     gfs_sgd_params dummy{};
     KernelGraph g = make_kgraph(ix, dummy, nullptr, 0);
-    stress_kernel<<<grid, STRESS_BLOCK>>>(g, ix->d_old_of_new, d_coords, dims, stride, samples, (uint32_t)seed, (uint32_t)(seed >> 32), d_partial);
+    stress_kernel<<<grid, STRESS_BLOCK>>>(g, ix->d_old_of_new, d_coords.p, dims, stride, samples, (uint32_t)seed, (uint32_t)(seed >> 32), d_partial.p);
+    GFS_CUDA(cudaGetLastError());
     std::vector<double> part((size_t)grid * 3);
-    e = cudaMemcpy(part.data(), d_partial, part.size() * 8, cudaMemcpyDeviceToHost);
-    cudaFree(d_coords); cudaFree(d_partial);
-    if (e != cudaSuccess) { set_error(std::string("gfs_stress kernel: ") + cudaGetErrorString(e)); return GFS_ERR_CUDA; }
+    GFS_CUDA(d_partial.down(part.data(), part.size()));
     double s0 = 0, s1 = 0, c = 0;
     for (unsigned b = 0; b < grid; ++b) { s0 += part[b * 3]; s1 += part[b * 3 + 1]; c += part[b * 3 + 2]; }
     if (c > 0) {
@@ -827,14 +844,6 @@ extern "C" int gfs_stress(const gfs_index* ix, uint32_t dims, int32_t layout_ord
 // ---------------------------------------------------------------------------------------------
 // debug / parity hooks
 // ---------------------------------------------------------------------------------------------
-template <typename T> struct DevBuf {
-    T* p = nullptr;
-    ~DevBuf() { cudaFree(p); }
-    cudaError_t alloc(size_t n) { return cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T)); }
-    cudaError_t up(const T* h, size_t n) { return cudaMemcpy(p, h, n * sizeof(T), cudaMemcpyHostToDevice); }
-    cudaError_t down(T* h, size_t n) { return cudaMemcpy(h, p, n * sizeof(T), cudaMemcpyDeviceToHost); }
-};
-
 extern "C" int gfs_debug_fast_precise_pow(const double* a, const double* b, double* out, uint64_t n) {
     int rc = select_device(-1); if (rc) return rc;
     DevBuf<double> da, db, dout;
@@ -932,9 +941,10 @@ static int sort_positions_device(const double* d_x, uint64_t n, uint32_t* d_orde
     if (n == 0) return GFS_OK;
     if (n >= (1ull << 32)) { set_error("sort: n must be < 2^32"); return GFS_ERR_INVALID; }
     const uint32_t n_blocks = (uint32_t)((n + RS_TILE - 1) / RS_TILE);
-    uint64_t *k0 = nullptr, *k1 = nullptr; uint32_t *v1 = nullptr, *hist = nullptr;
-    GFS_CUDA(cudaMalloc(&k0, n * 8)); GFS_CUDA(cudaMalloc(&k1, n * 8));
-    GFS_CUDA(cudaMalloc(&v1, n * 4)); GFS_CUDA(cudaMalloc(&hist, (size_t)256 * n_blocks * 4));
+    DevBuf<uint64_t> b_k0, b_k1; DevBuf<uint32_t> b_v1, b_hist;
+    GFS_CUDA(b_k0.alloc(n)); GFS_CUDA(b_k1.alloc(n));
+    GFS_CUDA(b_v1.alloc(n)); GFS_CUDA(b_hist.alloc((size_t)256 * n_blocks));
+    uint64_t *k0 = b_k0.p, *k1 = b_k1.p; uint32_t *v1 = b_v1.p, *hist = b_hist.p;
     uint32_t* v0 = d_order;
     rs_make_keys<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_x, n, k0, v0);
     uint64_t nl = 1;
@@ -948,7 +958,6 @@ static int sort_positions_device(const double* d_x, uint64_t n, uint32_t* d_orde
     // 8 passes: the result is back in the buffers it started in (v0 == d_order)
     cudaError_t e = cudaStreamSynchronize(st);
     if (e == cudaSuccess) e = cudaGetLastError();
-    cudaFree(k0); cudaFree(k1); cudaFree(v1 == d_order ? v0 : v1); cudaFree(hist);
     if (e != cudaSuccess) { set_error(std::string("sort failed: ") + cudaGetErrorString(e)); return GFS_ERR_CUDA; }
     if (launches) *launches += nl;
     return GFS_OK;

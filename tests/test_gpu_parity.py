@@ -671,3 +671,102 @@ def test_session_save_restore(gfs):
     lib().gfs_sgd_session_destroy(h)
     ix.close()
     assert not np.array_equal(moved, x0) and np.array_equal(back, x0)
+
+
+# ------------------------------------------------------------------------------------------------
+# BASELINE.json config 3 / 4 at full size (10M nodes, 90 paths, 0.83e9 steps): size-independent
+# properties — the oracle needs half an hour of CPU for one such run, so there is no direct comparison.
+# ------------------------------------------------------------------------------------------------
+def test_config3_full_size_properties(gfs):
+    from gfasort_b200._cabi import Stats, check, f64p, lib, u32p
+    G = gfs
+    sg = G.SynthGraph(10_000_000, 90, seed=42)
+    S, P, N = sg.S, sg.P, sg.N
+    assert N == 10_000_000 and P == 90 and S > 800_000_000
+    h, first, nlen = sg.step_handles, sg.path_first, sg.node_len
+    ix = G.PathIndex.from_arrays(h, first, nlen)
+    try:
+        # ---- K1: the index is the per-path exclusive prefix sum of the node lengths -------------------
+        pos = ix.step_positions()
+        plen = ix.path_lengths()
+        starts = first[:-1].astype(np.int64)
+        ends = first[1:].astype(np.int64) - 1
+        assert np.all(pos[starts] == 0)
+        assert np.array_equal(pos[ends] + nlen[(h[ends] >> np.uint64(1)).astype(np.int64)], plen)
+
+        def check_window(lo, hi):          # pos[s+1] - pos[s] == len(node of s) inside a path, for s in [lo, hi)
+            lo, hi = max(lo, 0), min(hi, S - 1)
+            if hi <= lo:
+                return
+            lens = nlen[(h[lo:hi] >> np.uint64(1)).astype(np.int64)].astype(np.uint64)
+            d = pos[lo + 1:hi + 1] - pos[lo:hi]
+            inside = np.ones(hi - lo, dtype=bool)
+            b = ends[(ends >= lo) & (ends < hi)] - lo      # last step of a path: the next step starts a new path
+            inside[b] = False
+            assert np.array_equal(d[inside], lens[inside])
+
+        for c in range(1 << 28, S, 1 << 28):              # the build's chunk seams (carry across chunks)
+            check_window(c - (1 << 20), c + (1 << 20))
+        for s0 in starts:                                 # path seams
+            check_window(int(s0) - 4096, int(s0) + 4096)
+        rng = np.random.default_rng(7)
+        for lo in rng.integers(0, S - (1 << 20), 12):     # and a dozen random 1M-step windows
+            check_window(int(lo), int(lo) + (1 << 20))
+        del pos
+
+        # ---- Y at the reference's full budget: exact update count, finite, ordered, low stress ----------
+        counts = np.diff(first)
+        mx = int(counts.max())
+        p = G.PathSGDParams(iter_max=100, min_term_updates=int(counts.sum()), eta_max=float(mx * mx),
+                            space=int(plen.max()), space_max=100, space_quantization_step=100)
+        x0 = sg.initial_positions()
+        before = G.layout_stress(None, x0, 1, 1_000_000, ix, layout_order=False)
+        x = x0.copy()
+        order = np.zeros(N, dtype=np.uint32)
+        st = Stats()
+        cp = p.c()
+        check(lib().gfs_sgd_sort_1d(ix.handle, C.byref(cp), _p(x, f64p), _p(order, u32p), C.byref(st)))
+        assert st.applied_updates == 101 * S                     # (iter_max + 1) x min_term_updates, exactly
+        assert st.attempts >= st.applied_updates
+        assert np.all(np.isfinite(x))
+        assert np.array_equal(np.sort(order), np.arange(N, dtype=np.uint32))      # a permutation of all nodes
+        xs = x[order.astype(np.int64)]
+        assert np.all(xs[1:] >= xs[:-1])                         # ordered by position
+        assert np.array_equal(G.sort_positions(x), order)        # the device sort is a function of x alone
+        after = G.layout_stress(None, x, 1, 1_000_000, ix, layout_order=False)
+        # ids are randomly permuted, so the initial layout is noise (relative error of order 1 and more); the
+        # sorted layout measured on B200 is 3.5e-5 (profiles/r1_bench.md) for both sampling schedules
+        print("config3 Y stress before/after:", before, after)
+        assert before[1] > 0.5 and after[1] < 1e-4, (before, after)
+        assert after[2] > 900_000
+
+        # ---- L (2D, float2) on the same graph, first 4 epochs of the 31-epoch schedule -----------------
+        lp = G.LayoutSGDParams(dimensions=2, iter_max=30, min_term_updates=10 * int(counts.sum()),
+                               eta_max=float(mx * mx), space=mx, space_max=1000, space_quantization_step=100)
+        n = N
+        c0 = np.zeros((n, 2, 2), dtype=np.float64)
+        c0[:, 0, 0] = x0
+        c0[:, 1, 0] = x0 + nlen
+        c0[:, :, 1] = np.random.default_rng(1).standard_normal((n, 2)) * np.sqrt(2.0 * n)
+        c0 = c0.reshape(-1)
+        lbefore = G.layout_stress(None, c0, 2, 1_000_000, ix)
+        sess = C.c_void_p()
+        lcp = lp.c()
+        check(lib().gfs_sgd_session_create(ix.handle, C.byref(lcp), 2, None, C.byref(sess)))
+        try:
+            check(lib().gfs_sgd_session_upload(sess, _p(c0, f64p)))
+            check(lib().gfs_sgd_session_run(sess, 0, 4, 0, 1))
+            c1 = np.zeros_like(c0)
+            check(lib().gfs_sgd_session_download(sess, _p(c1, f64p)))
+            lst = Stats()
+            check(lib().gfs_sgd_session_stats(sess, C.byref(lst)))
+        finally:
+            lib().gfs_sgd_session_destroy(sess)
+        assert lst.applied_updates == 4 * lp.min_term_updates and lst.coord_bytes == 4
+        assert np.all(np.isfinite(c1))
+        lafter = G.layout_stress(None, c1, 2, 1_000_000, ix)
+        print("config4 L stress before / after 4 of 31 epochs:", lbefore, lafter)
+        assert lafter[1] < 0.5 * lbefore[1], (lbefore, lafter)
+    finally:
+        ix.close()
+        sg.close()
