@@ -123,7 +123,7 @@ k1_path_base(const uint64_t* __restrict__ handles /*chunk-local*/, const uint32_
 __device__ __forceinline__ int k1_pad32(int j) { return j + (j >> 5); }
 __device__ __forceinline__ int k1_pad16(int j) { return j + (j >> 4); }
 
-__global__ void __launch_bounds__(K1_THREADS)
+__global__ void __launch_bounds__(K1_THREADS, 4)      // <= 64 registers: 4 blocks per SM
 k1_write_recs(const uint64_t* __restrict__ handles /*chunk-local*/, const uint32_t* __restrict__ node_len,
               uint64_t N, const uint64_t* __restrict__ first_step, uint32_t P, uint64_t chunk_begin,
               uint64_t chunk_len, const uint64_t* __restrict__ tile_prefix, const uint64_t* __restrict__ path_base,
@@ -138,6 +138,28 @@ k1_write_recs(const uint64_t* __restrict__ handles /*chunk-local*/, const uint32
         const uint64_t i = tbase + (uint64_t)(k * K1_THREADS + threadIdx.x);
         hh[k] = i < chunk_len ? __ldg(handles + i) : ~0ull;      // past the end: node >= N => length 0
     }
+    // path of the tile's first and last step (most tiles lie inside one path), found while the handle
+    // loads are in flight: with few paths every thread tests one first_step entry and the block counts
+    // the entries <= step (one load round trip); with many paths, a binary search.
+    const uint64_t g_first = chunk_begin + tbase;
+    const uint64_t g_last = chunk_begin + (tbase + K1_TILE <= chunk_len ? tbase + K1_TILE : chunk_len) - 1;
+    uint32_t p_first, p_last;
+    if (P <= 8 * K1_THREADS) {
+        int c_first = 0, c_last = 0;
+        for (uint32_t p0 = 0; p0 < P; p0 += K1_THREADS) {          // block-uniform trip count
+            const uint32_t p = p0 + threadIdx.x;
+            const uint64_t f = p < P ? __ldg(first_step + p) : ~0ull;
+            c_first += __syncthreads_count(f <= g_first);
+            c_last += __syncthreads_count(f <= g_last);
+        }
+        p_first = (uint32_t)c_first - 1;                            // first_step[0] = 0 <= step: count >= 1
+        p_last = (uint32_t)c_last - 1;
+    } else {
+        p_first = find_path(first_step, P, g_first);
+        p_last = find_path(first_step, P, g_last);
+    }
+    const uint64_t base_first = __ldg(path_base + p_first);
+    const uint64_t tile_pre = __ldg(tile_prefix + blockIdx.x);
     uint32_t len[K1_ITEMS], nr[K1_ITEMS];
 #pragma unroll
     for (int k = 0; k < K1_ITEMS; ++k) {
@@ -164,16 +186,10 @@ k1_write_recs(const uint64_t* __restrict__ handles /*chunk-local*/, const uint32
     uint64_t woff = 0;
 #pragma unroll
     for (int k = 0; k < K1_THREADS / 32; ++k) woff += (k < w) ? wsum[k] : 0;
-    const uint64_t texcl = tile_prefix[blockIdx.x] + woff + (inc - tsum);
+    const uint64_t texcl = tile_pre + woff + (inc - tsum);
 #pragma unroll
     for (int k = 0; k < K1_ITEMS; ++k) s_pos[k1_pad16(threadIdx.x * K1_ITEMS + k)] = texcl + loc[k];
     __syncthreads();
-    // path of the tile's first and last step; most tiles lie inside one path
-    const uint64_t g_first = chunk_begin + tbase;
-    const uint64_t last_local = (tbase + K1_TILE <= chunk_len ? tbase + K1_TILE : chunk_len) - 1;
-    const uint32_t p_first = find_path(first_step, P, g_first);
-    const uint32_t p_last = find_path(first_step, P, chunk_begin + last_local);
-    const uint64_t base_first = path_base[p_first];
 #pragma unroll
     for (int k = 0; k < K1_ITEMS; ++k) {
         const int j = k * K1_THREADS + threadIdx.x;
@@ -249,10 +265,24 @@ rl_tile_count(const StepRec* __restrict__ recs, const unsigned long long* __rest
     __shared__ uint64_t wb[32];
     const uint64_t base = (uint64_t)blockIdx.x * K1_TILE;
     uint64_t c = 0;
+    if (MODE == 0) {                        // all node loads first, then all first_occ gathers
+        uint32_t node[K1_ITEMS];
 #pragma unroll
-    for (int k = 0; k < K1_ITEMS; ++k) {
-        const uint64_t i = base + (uint64_t)k * K1_THREADS + threadIdx.x;
-        if (i < n_items) c += rl_flag<MODE>(recs, first_occ, N, i) ? 1 : 0;
+        for (int k = 0; k < K1_ITEMS; ++k) {
+            const uint64_t i = base + (uint64_t)k * K1_THREADS + threadIdx.x;
+            node[k] = i < n_items ? (recs[i].node_rev >> 1) : N;          // N: never a first occurrence
+        }
+#pragma unroll
+        for (int k = 0; k < K1_ITEMS; ++k) {
+            const uint64_t i = base + (uint64_t)k * K1_THREADS + threadIdx.x;
+            c += (node[k] < N && first_occ[node[k]] == i) ? 1 : 0;
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < K1_ITEMS; ++k) {
+            const uint64_t i = base + (uint64_t)k * K1_THREADS + threadIdx.x;
+            if (i < n_items) c += rl_flag<MODE>(recs, first_occ, N, i) ? 1 : 0;
+        }
     }
     c = block_sum_u64(c, wb);
     if (threadIdx.x == 0) tile_cnt[blockIdx.x] = c;
@@ -264,16 +294,28 @@ rl_assign(const StepRec* __restrict__ recs, const unsigned long long* __restrict
     __shared__ uint32_t wsum[K1_THREADS / 32];
     const uint64_t base = (uint64_t)blockIdx.x * K1_TILE + (uint64_t)threadIdx.x * K1_ITEMS;   // 8 consecutive items
     bool f[K1_ITEMS];
+    uint32_t node[K1_ITEMS];
     uint32_t cnt = 0;
+    if (MODE == 0) {                        // all node loads first, then all first_occ gathers
 #pragma unroll
-    for (int k = 0; k < K1_ITEMS; ++k) { f[k] = (base + k < n_items) && rl_flag<MODE>(recs, first_occ, N, base + k); cnt += f[k]; }
+        for (int k = 0; k < K1_ITEMS; ++k) node[k] = base + k < n_items ? (recs[base + k].node_rev >> 1) : N;
+#pragma unroll
+        for (int k = 0; k < K1_ITEMS; ++k) { f[k] = node[k] < N && first_occ[node[k]] == base + k; cnt += f[k]; }
+    } else {
+#pragma unroll
+        for (int k = 0; k < K1_ITEMS; ++k) {
+            node[k] = (uint32_t)(base + k);
+            f[k] = (base + k < n_items) && rl_flag<MODE>(recs, first_occ, N, base + k);
+            cnt += f[k];
+        }
+    }
     uint32_t total;
     uint32_t off = block_excl_scan_u32(cnt, wsum, &total);
     uint64_t rank = tile_prefix[blockIdx.x] + off;
 #pragma unroll
     for (int k = 0; k < K1_ITEMS; ++k) {
         if (f[k]) {
-            const uint32_t old = MODE == 0 ? (recs[base + k].node_rev >> 1) : (uint32_t)(base + k);
+            const uint32_t old = node[k];
             new_of_old[old] = (uint32_t)rank;
             old_of_new[rank] = old;
             ++rank;

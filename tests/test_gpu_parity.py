@@ -92,6 +92,34 @@ def test_path_index_edge_cases(gfs, oracle):
     assert ref["length"].tolist() == [0, 15, 11, 0, 17]
 
 
+@pytest.mark.parametrize("n_paths", [1, 255, 256, 257, 700, 2048, 2049, 5000])
+def test_path_index_many_ragged_paths(n_paths, gfs):
+    """Ragged path tables: hundreds to thousands of short paths (many per 2048-step tile), empty paths
+    in between and at both ends, one long path crossing several tiles — every path-lookup branch of K1."""
+    rng = np.random.default_rng(n_paths)
+    n_nodes = 997
+    node_len = rng.integers(1, 50, n_nodes).astype(np.uint32)
+    counts = rng.integers(0, 40, n_paths).astype(np.uint64)
+    counts[rng.random(n_paths) < 0.2] = 0
+    counts[n_paths // 2] = 9000                      # spans more than four tiles
+    if n_paths > 2:
+        counts[0] = 0
+        counts[-1] = 0
+    first = np.zeros(n_paths + 1, dtype=np.uint64)
+    np.cumsum(counts, out=first[1:])
+    S = int(first[-1])
+    steps = (rng.integers(0, n_nodes + 3, S).astype(np.uint64) << np.uint64(1)) | rng.integers(0, 2, S).astype(np.uint64)
+    ix = gfs.PathIndex.from_arrays(steps, first, node_len)
+    node = (steps >> np.uint64(1)).astype(np.int64)
+    lens = np.where(node < n_nodes, node_len[np.minimum(node, n_nodes - 1)], 0).astype(np.uint64)   # missing node => +0
+    cs = np.cumsum(lens) - lens
+    want = cs - np.repeat(cs[np.minimum(first[:-1], max(S - 1, 0)).astype(np.int64)], counts.astype(np.int64))
+    want_len = np.array([lens[int(a):int(b)].sum() for a, b in zip(first[:-1], first[1:])], dtype=np.uint64)
+    assert np.array_equal(ix.step_positions(), want)
+    assert np.array_equal(ix.path_lengths(), want_len)
+    ix.close()
+
+
 def test_index_shard_matches_whole(gfs):
     s = gfs.SynthGraph(20_000, 6, seed=3)
     whole = gfs.PathIndex.from_arrays(s.step_handles, s.path_first, s.node_len)
@@ -737,7 +765,7 @@ def test_config3_full_size_properties(gfs):
         # ids are randomly permuted, so the initial layout is noise (relative error of order 1 and more); the
         # sorted layout measured on B200 is 3.5e-5 (profiles/r1_bench.md) for both sampling schedules
         print("config3 Y stress before/after:", before, after)
-        assert before[1] > 0.5 and after[1] < 1e-4, (before, after)
+        assert before[1] > 1.0 and after[1] < 5e-5, (before, after)       # measured: 23.5 -> 3.54e-5
         assert after[2] > 900_000
 
         # ---- L (2D, float2) on the same graph, first 4 epochs of the 31-epoch schedule -----------------
@@ -766,7 +794,7 @@ def test_config3_full_size_properties(gfs):
         assert np.all(np.isfinite(c1))
         lafter = G.layout_stress(None, c1, 2, 1_000_000, ix)
         print("config4 L stress before / after 4 of 31 epochs:", lbefore, lafter)
-        assert lafter[1] < 0.5 * lbefore[1], (lbefore, lafter)
+        assert lbefore[1] > 1.0 and lafter[1] < 0.01, (lbefore, lafter)     # measured: 23.5 -> 1.09e-3
     finally:
         ix.close()
         sg.close()
