@@ -1,0 +1,567 @@
+// test_reference_api.cpp — the reference's own tests, restated against the C++ host layer
+// (include/gfasort.hpp) over libgfasort_cuda.so.
+//
+// Mirrors, test for test:  tests/integration_tests.rs (8 tests), src/ygs.rs:247-303 (4), src/graph.rs:206-258
+// (handle / reverse complement / node tests), src/graph_ops.rs:2056-2130 (graph creation, GFA output),
+// src/layout.rs:263-340 (5), src/gfa_parser.rs:191-208 (1) — plus the known answers of SURVEY.md §8c for the
+// path index and the X init, and the error behaviour at the boundary.
+//
+//   test_reference_api host [data_dir]   tests that need no device (run by pytest -m "not gpu")
+//   test_reference_api gpu  [data_dir]   tests that run the CUDA path (run by pytest -m gpu)
+//
+// Without a device the `host` group also checks that the path fails loudly (GFS_ERR_NO_DEVICE) instead of
+// falling back to any CPU implementation.
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <functional>
+#include <set>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include "gfasort.hpp"
+
+using namespace gfasort;
+
+static std::string g_data = "tests/data";
+static int g_failed = 0, g_run = 0;
+
+struct Failure { std::string msg; };
+#define REQUIRE(cond)                                                                                   \
+    do {                                                                                                \
+        if (!(cond)) throw Failure{std::string(__FILE__) + ":" + std::to_string(__LINE__) + ": " #cond}; \
+    } while (0)
+#define REQUIRE_EQ(a, b)                                                                                \
+    do {                                                                                                \
+        auto va__ = (a); auto vb__ = (b);                                                               \
+        if (!(va__ == vb__)) {                                                                          \
+            std::ostringstream os__;                                                                    \
+            os__ << __FILE__ << ":" << __LINE__ << ": " #a " == " #b " (" << va__ << " vs " << vb__ << ")"; \
+            throw Failure{os__.str()};                                                                  \
+        }                                                                                               \
+    } while (0)
+
+static void run(const char* name, const std::function<void()>& fn) {
+    ++g_run;
+    try {
+        fn();
+        std::printf("ok    %s\n", name);
+    } catch (const Failure& f) {
+        ++g_failed;
+        std::printf("FAIL  %s\n      %s\n", name, f.msg.c_str());
+    } catch (const std::exception& e) {
+        ++g_failed;
+        std::printf("FAIL  %s\n      exception: %s\n", name, e.what());
+    }
+    std::fflush(stdout);
+}
+
+static bool have_device() {
+    return std::string(gfs_device_info()).find("\"devices\": 0") == std::string::npos;
+}
+
+// src/ygs.rs:225-244
+static BidirectedGraph create_test_graph() {
+    BidirectedGraph graph;
+    graph.add_node(1, "AAAA");
+    graph.add_node(2, "CCCC");
+    graph.add_node(3, "GGGG");
+    graph.add_edge(Handle::forward(1), Handle::forward(2));
+    graph.add_edge(Handle::forward(2), Handle::forward(3));
+    BiPath path("test_path");
+    path.add_step(Handle::forward(1));
+    path.add_step(Handle::forward(2));
+    path.add_step(Handle::forward(3));
+    graph.paths.push_back(path);
+    return graph;
+}
+
+static std::string path_sequence(const BidirectedGraph& g, const BiPath& p) {
+    std::string s;
+    for (Handle h : p.steps) {
+        const auto seq = g.nodes.at(h.node_id())->get_sequence(h.is_reverse());
+        s.append(seq.begin(), seq.end());
+    }
+    return s;
+}
+static std::vector<std::string> all_path_sequences(const BidirectedGraph& g) {
+    std::vector<std::string> v;
+    for (const auto& p : g.paths) v.push_back(path_sequence(g, p));
+    return v;
+}
+static bool ids_are_1_to_n(const BidirectedGraph& g) {
+    if (g.nodes.size() != g.node_count() + 1 || g.nodes[0]) return false;
+    for (size_t i = 1; i < g.nodes.size(); ++i) if (!g.nodes[i] || g.nodes[i]->id != i) return false;
+    return true;
+}
+
+// =================================================================================================
+// host group
+// =================================================================================================
+static void host_tests() {
+    // ---- src/graph.rs:206-258
+    run("graph::test_handle_creation", [] {
+        Handle h = Handle::forward(42);
+        REQUIRE_EQ(h.node_id(), (size_t)42);
+        REQUIRE(!h.is_reverse());
+        REQUIRE_EQ(h.orientation_char(), '+');
+        Handle r = Handle::reverse(42);
+        REQUIRE_EQ(r.node_id(), (size_t)42);
+        REQUIRE(r.is_reverse());
+        REQUIRE_EQ(r.orientation_char(), '-');
+        REQUIRE_EQ(r.as_u64(), (uint64_t)85);
+        REQUIRE(Handle::from_u64(85) == r);
+        REQUIRE_EQ(r.to_string(), std::string("42-"));
+    });
+    run("graph::test_handle_flip", [] {
+        Handle h = Handle::forward(42);
+        REQUIRE(h.flip().is_reverse());
+        REQUIRE_EQ(h.flip().node_id(), (size_t)42);
+        REQUIRE(h.flip().flip() == h);
+    });
+    run("graph::test_reverse_complement", [] {
+        auto rc = [](const std::string& s) { auto v = reverse_complement(std::vector<uint8_t>(s.begin(), s.end())); return std::string(v.begin(), v.end()); };
+        REQUIRE_EQ(rc("ATCG"), std::string("CGAT"));
+        REQUIRE_EQ(rc("AAAA"), std::string("TTTT"));
+        REQUIRE_EQ(rc("acgtN"), std::string("NACGT"));
+        REQUIRE_EQ(rc(""), std::string(""));
+    });
+    run("graph::test_binode_sequences", [] {
+        BiNode n(1, std::vector<uint8_t>{'A', 'T', 'C', 'G'});
+        auto f = n.get_sequence(false), r = n.get_sequence(true);
+        REQUIRE_EQ(std::string(f.begin(), f.end()), std::string("ATCG"));
+        REQUIRE_EQ(std::string(r.begin(), r.end()), std::string("CGAT"));
+    });
+    // ---- src/graph_ops.rs:2056-2130
+    run("graph_ops::test_bidirected_graph_creation", [] {
+        BidirectedGraph g;
+        g.add_node(1, "ATCG");
+        g.add_node(2, "GCTA");
+        g.add_edge(Handle::forward(1), Handle::forward(2));
+        REQUIRE_EQ(g.node_count(), (size_t)2);
+        REQUIRE_EQ(g.edges.size(), (size_t)1);
+        REQUIRE(g.has_edge(Handle::forward(1), Handle::forward(2)));
+        REQUIRE(g.has_edge(Handle::reverse(2), Handle::reverse(1)));      // the complement is the same edge
+        g.add_edge(Handle::reverse(2), Handle::reverse(1));               // graph_ops.rs:626-638: not stored twice
+        REQUIRE_EQ(g.edges.size(), (size_t)1);
+        REQUIRE_EQ(g.node_order.size(), (size_t)2);
+        g.add_node(1, "TTTT");                                            // overwriting does not re-enter node_order (:619-621)
+        REQUIRE_EQ(g.node_order.size(), (size_t)2);
+        REQUIRE_EQ(g.total_sequence_length(), (size_t)8);
+    });
+    run("graph_ops::test_sequence_retrieval_and_orientations", [] {
+        BidirectedGraph g;
+        g.add_node(1, "ATCG");
+        g.add_node(2, "GCTA");
+        g.add_edge(Handle::forward(1), Handle::forward(2));
+        g.add_edge(Handle::forward(1), Handle::reverse(2));
+        REQUIRE_EQ(g.node_count(), (size_t)2);
+        REQUIRE_EQ(g.edges.size(), (size_t)2);
+        auto f = g.get_sequence(Handle::forward(1)), r = g.get_sequence(Handle::reverse(1));
+        REQUIRE(f && std::string(f->begin(), f->end()) == "ATCG");
+        REQUIRE(r && std::string(r->begin(), r->end()) == "CGAT");
+        REQUIRE(!g.get_sequence(Handle::forward(7)));
+        g.add_node(3, "TAC");
+        g.build_path("test_path", {{1, false}, {2, true}, {3, false}});
+        REQUIRE_EQ(g.paths.size(), (size_t)1);
+        REQUIRE_EQ(g.paths[0].steps.size(), (size_t)3);
+        REQUIRE(!g.paths[0].steps[0].is_reverse() && g.paths[0].steps[1].is_reverse() && !g.paths[0].steps[2].is_reverse());
+        REQUIRE_EQ(path_sequence(g, g.paths[0]), std::string("ATCGTAGCTAC"));
+    });
+    run("graph_ops::test_gfa_output", [] {
+        BidirectedGraph g;
+        g.add_node(1, "ATCG");
+        g.add_node(2, "GCTA");
+        g.add_edge(Handle::forward(1), Handle::reverse(2));
+        g.build_path("p1", {{1, false}, {2, true}});
+        std::ostringstream os;
+        g.write_gfa(os);
+        const std::string out = os.str();
+        REQUIRE(out.find("H\tVN:Z:1.0\n") == 0);
+        REQUIRE(out.find("S\t1\tATCG\n") != std::string::npos);
+        REQUIRE(out.find("S\t2\tGCTA\n") != std::string::npos);
+        REQUIRE(out.find("L\t1\t+\t2\t-\t0M\n") != std::string::npos);
+        REQUIRE(out.find("P\tp1\t1+,2-\t*\n") != std::string::npos);
+    });
+    // ---- src/layout.rs:263-340
+    run("layout::test_layout_new", [] {
+        Layout l = Layout::make(2, 10);
+        REQUIRE_EQ(l.dimensions, (size_t)2);
+        REQUIRE_EQ(l.num_nodes, (size_t)10);
+        REQUIRE_EQ(l.coords.size(), (size_t)40);
+    });
+    run("layout::test_layout_get_set", [] {
+        Layout l = Layout::make(2, 3);
+        l.set(1, 0, 0, 1.5);
+        l.set(1, 0, 1, 2.5);
+        l.set(1, 1, 0, 3.5);
+        l.set(1, 1, 1, 4.5);
+        REQUIRE_EQ(l.x_plus(1), 1.5);
+        REQUIRE_EQ(l.y_plus(1), 2.5);
+        REQUIRE_EQ(l.x_minus(1), 3.5);
+        REQUIRE_EQ(l.y_minus(1), 4.5);
+        REQUIRE_EQ(l.get_coords(1, 1)[0], 3.5);
+    });
+    run("layout::test_layout_distance", [] {
+        Layout l = Layout::make(2, 2);
+        l.set(0, 0, 0, 0.0); l.set(0, 0, 1, 0.0);
+        l.set(1, 0, 0, 3.0); l.set(1, 0, 1, 4.0);
+        REQUIRE(std::fabs(l.distance(0, 0, 1, 0) - 5.0) < 1e-10);
+    });
+    run("layout::test_from_vectors", [] {
+        Layout l = Layout::from_vectors({{0.0, 1.0, 2.0, 3.0}, {10.0, 11.0, 12.0, 13.0}});   // [dim][2*node+end]
+        REQUIRE_EQ(l.dimensions, (size_t)2);
+        REQUIRE_EQ(l.num_nodes, (size_t)2);
+        REQUIRE_EQ(l.x_plus(0), 0.0);  REQUIRE_EQ(l.y_plus(0), 10.0);
+        REQUIRE_EQ(l.x_minus(0), 1.0); REQUIRE_EQ(l.y_minus(0), 11.0);
+        REQUIRE_EQ(l.x_plus(1), 2.0);  REQUIRE_EQ(l.y_minus(1), 13.0);
+        bool threw = false;
+        try { Layout::from_vectors({{0.0, 1.0, 2.0}}); } catch (const std::invalid_argument&) { threw = true; }
+        REQUIRE(threw);
+    });
+    run("layout::test_tsv_roundtrip", [] {
+        Layout l = Layout::make(2, 2);
+        l.set(0, 0, 0, 1.5);  l.set(0, 0, 1, 2.5);  l.set(0, 1, 0, 3.5);   l.set(0, 1, 1, 4.5);
+        l.set(1, 0, 0, -10.0); l.set(1, 0, 1, 20.25); l.set(1, 1, 0, 1e-7); l.set(1, 1, 1, 123456789.125);
+        const std::string path = "/tmp/gfasort_b200_layout_roundtrip.tsv";
+        l.write_tsv(path);
+        std::ifstream in(path);
+        std::stringstream all; all << in.rdbuf();
+        // Rust `{}` formatting: no exponent, 1.0 -> "1"
+        REQUIRE_EQ(all.str(), std::string("idx\tx+\ty+\tx-\ty-\n0\t1.5\t2.5\t3.5\t4.5\n1\t-10\t20.25\t0.0000001\t123456789.125\n"));
+        std::istringstream again(all.str());
+        Layout r = Layout::read_tsv(again);
+        REQUIRE_EQ(r.dimensions, (size_t)2);
+        REQUIRE_EQ(r.num_nodes, (size_t)2);
+        REQUIRE(r.coords == l.coords);
+        std::remove(path.c_str());
+    });
+    run("layout::calculate_stress", [] {
+        Layout l = Layout::make(1, 2);
+        l.set(1, 0, 0, 2.0);
+        REQUIRE(std::fabs(l.calculate_stress({{0, 0, 1, 0, 1.0}}) - 1.0) < 1e-12);     // |2-1| / 1
+        REQUIRE_EQ(l.calculate_stress({{0, 0, 1, 0, 0.0}}), 0.0);                       // zero targets are skipped
+    });
+    // ---- src/gfa_parser.rs:191-208, tests/integration_tests.rs:4-20
+    run("integration::test_load_simple_gfa", [] {
+        BidirectedGraph g = gfa_parser::load_gfa(g_data + "/simple.gfa");
+        REQUIRE(g.node_count() > 0);
+        REQUIRE(!g.edges.empty());
+        REQUIRE_EQ(g.node_count(), (size_t)15);
+        REQUIRE_EQ(g.paths.size(), (size_t)1);
+        REQUIRE_EQ(g.paths[0].steps.size(), (size_t)10);
+        REQUIRE_EQ(g.node_order.size(), (size_t)15);
+        bool threw = false;
+        try { gfa_parser::load_gfa(g_data + "/no_such_file.gfa"); } catch (const std::runtime_error&) { threw = true; }
+        REQUIRE(threw);
+    });
+    // ---- src/ygs.rs:247-253
+    run("ygs::test_ygs_params_default", [] {
+        YgsParams p = YgsParams::make_default();
+        REQUIRE_EQ(p.path_sgd.iter_max, (uint64_t)100);
+        REQUIRE_EQ(p.path_sgd.theta, 0.99);
+        REQUIRE_EQ(p.path_sgd.eps, 0.01);
+        REQUIRE_EQ(p.path_sgd.min_term_updates, (uint64_t)0);
+        REQUIRE_EQ(p.path_sgd.seed, (uint64_t)9399220);
+        PathSGDParams d;                                   // sgd.rs:214-234
+        REQUIRE_EQ(d.min_term_updates, (uint64_t)100);
+        REQUIRE_EQ(d.eta_max, 100.0);
+        LayoutSGDParams ld;                                // sgd.rs:709-729
+        REQUIRE_EQ(ld.iter_max, (uint64_t)30);
+        REQUIRE_EQ(ld.space_max, (uint64_t)1000);
+    });
+    run("sgd::layout_params_from_graph", [] {             // sgd.rs:733-763
+        BidirectedGraph g = gfa_parser::load_gfa(g_data + "/DRB1-3123.gfa");
+        LayoutSGDParams p = LayoutSGDParams::from_graph(g, 2, 4);
+        REQUIRE_EQ(p.min_term_updates, (uint64_t)350590);
+        REQUIRE_EQ(p.space, (uint64_t)3100);
+        REQUIRE_EQ(p.eta_max, 9610000.0);
+        REQUIRE_EQ(p.dimensions, (size_t)2);
+        REQUIRE_EQ(p.nthreads, (size_t)4);
+    });
+    // ---- what the host hands to the C ABI (SURVEY.md §8c known answers)
+    run("boundary::dense_flattening_and_x_init", [] {
+        BidirectedGraph g = gfa_parser::load_gfa(g_data + "/simple.gfa");
+        auto d = g.dense();
+        const std::vector<double> want_x = {0, 8, 9, 10, 11, 12, 15, 16, 17, 36, 37, 38, 42, 43, 44};
+        REQUIRE(d.x_init == want_x);
+        REQUIRE_EQ(d.node_len.size(), (size_t)15);
+        const std::vector<uint64_t> want_first = {0, 10};
+        REQUIRE(d.path_first_step == want_first);
+        REQUIRE_EQ(d.step_handles[0], (uint64_t)0);                  // 1+ -> dense idx 0
+        REQUIRE_EQ(d.step_handles[9], (uint64_t)(14 << 1));         // 15+ -> dense idx 14
+        // a step on a node that is not in the graph maps to the missing-node sentinel idx == N
+        g.paths[0].add_step(Handle::reverse(99));
+        auto d2 = g.dense();
+        REQUIRE_EQ(d2.step_handles.back(), (uint64_t)((15 << 1) | 1));
+    });
+    // ---- the host steps of the pipeline need no device (tests/integration_tests.rs:112-148, ygs.rs:279-303)
+    run("integration::test_groom_only", [] {
+        BidirectedGraph g = gfa_parser::load_gfa(g_data + "/simple.gfa");
+        const auto seqs = all_path_sequences(g);
+        const size_t edges = g.edges.size();
+        groom_only(g, 0);
+        REQUIRE_EQ(g.node_count(), (size_t)15);
+        REQUIRE_EQ(g.edges.size(), edges);
+        REQUIRE(all_path_sequences(g) == seqs);
+    });
+    run("integration::test_topological_sort_only", [] {
+        BidirectedGraph g = gfa_parser::load_gfa(g_data + "/simple.gfa");
+        const auto seqs = all_path_sequences(g);
+        topological_sort_only(g, 0);
+        REQUIRE_EQ(g.node_count(), (size_t)15);
+        REQUIRE(ids_are_1_to_n(g));
+        REQUIRE(all_path_sequences(g) == seqs);
+        auto fb = g.count_edge_directions();                        // a DAG: every edge runs forward afterwards
+        REQUIRE_EQ(fb.second, (size_t)0);
+        REQUIRE_EQ(fb.first, g.edges.size());
+    });
+    run("graph_ops::groom_flips_inverted_node", [] {
+        // 1+ -> 2- -> 3+ with a path walking 2 in reverse: grooming flips node 2 and its sequence
+        BidirectedGraph g;
+        g.add_node(1, "AC"); g.add_node(2, "GGT"); g.add_node(3, "TT");
+        g.add_edge(Handle::forward(1), Handle::reverse(2));
+        g.add_edge(Handle::reverse(2), Handle::forward(3));
+        g.build_path("p", {{1, false}, {2, true}, {3, false}});
+        const auto seqs = all_path_sequences(g);
+        groom_only(g, 0);
+        REQUIRE(all_path_sequences(g) == seqs);
+        for (const auto& p : g.paths) for (Handle h : p.steps) REQUIRE(!h.is_reverse());
+        REQUIRE_EQ(std::string(g.nodes[2]->sequence.begin(), g.nodes[2]->sequence.end()), std::string("ACC"));
+        REQUIRE_EQ(g.find_head_nodes().size(), (size_t)1);
+    });
+    run("graph_ops::apply_ordering_renumbers", [] {
+        BidirectedGraph g = create_test_graph();
+        g.apply_ordering({Handle::forward(3), Handle::forward(1), Handle::forward(2)});
+        REQUIRE(ids_are_1_to_n(g));
+        REQUIRE_EQ(std::string(g.nodes[1]->sequence.begin(), g.nodes[1]->sequence.end()), std::string("GGGG"));
+        REQUIRE_EQ(path_sequence(g, g.paths[0]), std::string("AAAACCCCGGGG"));
+        REQUIRE(g.has_edge(Handle::forward(2), Handle::forward(3)));      // old 1+ -> 2+
+        REQUIRE(g.has_edge(Handle::forward(3), Handle::forward(1)));      // old 2+ -> 3+
+        REQUIRE_EQ(*g.nodes[1]->rank, (uint64_t)0);
+        g.apply_ordering({});                                              // empty ordering: no-op (:1940-1942)
+        REQUIRE_EQ(g.node_count(), (size_t)3);
+    });
+    // ---- error behaviour at the boundary
+    run("boundary::empty_graph_returns_empty", [] {
+        BidirectedGraph g;                                                  // sgd.rs:242-244, 780-782: before any device work
+        REQUIRE(path_linear_sgd(g, PathSGDParams()).empty());
+        REQUIRE(path_sgd_sort(g, PathSGDParams()).empty());
+        Layout l = path_linear_sgd_layout(g, LayoutSGDParams());
+        REQUIRE_EQ(l.num_nodes, (size_t)0);
+        REQUIRE_EQ(l.dimensions, (size_t)2);
+    });
+    if (!have_device()) {
+        run("boundary::no_device_fails_loudly", [] {
+            BidirectedGraph g = create_test_graph();
+            int code = 0; std::string what;
+            try { PathIndex::from_graph(g); } catch (const Error& e) { code = e.code; what = e.what(); }
+            REQUIRE_EQ(code, GFS_ERR_NO_DEVICE);
+            REQUIRE(what.find("no CPU fallback") != std::string::npos);
+            code = 0;
+            try { path_linear_sgd(g, PathSGDParams()); } catch (const Error& e) { code = e.code; }
+            REQUIRE_EQ(code, GFS_ERR_NO_DEVICE);
+            code = 0;
+            try { YgsParams::from_graph(g, 0, 1); } catch (const Error& e) { code = e.code; }
+            REQUIRE_EQ(code, GFS_ERR_NO_DEVICE);
+        });
+    }
+}
+
+// =================================================================================================
+// gpu group
+// =================================================================================================
+static void gpu_tests() {
+    // ---- SURVEY.md §8c known answers through PathIndex (sgd.rs:34-107)
+    run("sgd::path_index_known_answers", [] {
+        BidirectedGraph g = gfa_parser::load_gfa(g_data + "/simple.gfa");
+        PathIndex ix = PathIndex::from_graph(g);
+        REQUIRE_EQ(ix.get_total_steps(), (size_t)10);
+        REQUIRE_EQ(ix.num_paths(), (size_t)1);
+        REQUIRE_EQ(ix.get_path_step_count(0), (size_t)10);
+        REQUIRE_EQ(ix.get_path_length(0), (size_t)50);
+        const size_t want[10] = {0, 8, 9, 10, 13, 14, 33, 34, 38, 39};
+        for (size_t s = 0; s < 10; ++s) {
+            REQUIRE_EQ(ix.get_position_of_step(s), want[s]);
+            REQUIRE_EQ(ix.get_path_of_step(s), (size_t)0);
+            REQUIRE_EQ(ix.get_rank_of_step(s), s);
+            REQUIRE_EQ(ix.get_step_at_path_position(0, s), s);
+            REQUIRE(ix.get_handle_of_step(s) == g.paths[0].steps[s]);
+        }
+        BidirectedGraph lil = gfa_parser::load_gfa(g_data + "/lil.gfa");
+        PathIndex lx = PathIndex::from_graph(lil);
+        REQUIRE_EQ(lx.num_paths(), (size_t)3);
+        REQUIRE_EQ(lx.get_total_steps(), (size_t)30);
+        for (size_t p = 0; p < 3; ++p) {
+            REQUIRE_EQ(lx.get_path_length(p), (size_t)50);
+            for (size_t r = 0; r < 10; ++r) {
+                const size_t s = lx.get_step_at_path_position(p, r);
+                REQUIRE_EQ(s, p * 10 + r);
+                REQUIRE_EQ(lx.get_position_of_step(s), want[r]);
+                REQUIRE_EQ(lx.get_path_of_step(s), p);
+            }
+        }
+    });
+    // ---- src/ygs.rs:255-303
+    run("ygs::test_ygs_params_from_graph", [] {
+        BidirectedGraph g = create_test_graph();
+        YgsParams p = YgsParams::from_graph(g, 0, 1);
+        REQUIRE(p.path_sgd.min_term_updates > 0);
+        REQUIRE(p.path_sgd.eta_max > 0.0);
+        REQUIRE(p.path_sgd.space > 0);
+        REQUIRE_EQ(p.path_sgd.min_term_updates, (uint64_t)3);
+        REQUIRE_EQ(p.path_sgd.eta_max, 9.0);
+        REQUIRE_EQ(p.path_sgd.space, (uint64_t)12);
+        BidirectedGraph d = gfa_parser::load_gfa(g_data + "/DRB1-3123.gfa");
+        YgsParams q = YgsParams::from_graph(d, 0, 4);
+        REQUIRE_EQ(q.path_sgd.min_term_updates, (uint64_t)35059);
+        REQUIRE_EQ(q.path_sgd.eta_max, 9610000.0);
+        REQUIRE_EQ(q.path_sgd.nthreads, (size_t)4);
+    });
+    run("ygs::test_ygs_sort_runs", [] {
+        BidirectedGraph g = create_test_graph();
+        YgsParams p = YgsParams::from_graph(g, 0, 1);
+        ygs_sort(g, p);
+        REQUIRE_EQ(g.node_count(), (size_t)3);
+        REQUIRE(!g.paths.empty());
+        REQUIRE_EQ(path_sequence(g, g.paths[0]), std::string("AAAACCCCGGGG"));
+    });
+    run("ygs::test_individual_steps", [] {
+        const BidirectedGraph graph = create_test_graph();
+        { BidirectedGraph g = graph; YgsParams p = YgsParams::from_graph(g, 0, 1); sgd_sort_only(g, p.path_sgd, 0); REQUIRE_EQ(g.node_count(), (size_t)3); }
+        { BidirectedGraph g = graph; groom_only(g, 0); REQUIRE_EQ(g.node_count(), (size_t)3); }
+        { BidirectedGraph g = graph; topological_sort_only(g, 0); REQUIRE_EQ(g.node_count(), (size_t)3); }
+    });
+    // ---- tests/integration_tests.rs:22-206
+    run("integration::test_ygs_sort_simple", [] {
+        BidirectedGraph g = gfa_parser::load_gfa(g_data + "/simple.gfa");
+        const size_t nodes = g.node_count(), edges = g.edges.size();
+        const auto seqs = all_path_sequences(g);
+        YgsParams p = YgsParams::from_graph(g, 0, 2);
+        ygs_sort(g, p);
+        REQUIRE_EQ(g.node_count(), nodes);
+        REQUIRE_EQ(g.edges.size(), edges);
+        REQUIRE(ids_are_1_to_n(g));
+        REQUIRE(all_path_sequences(g) == seqs);            // graph_ops.rs:781-800: every path spells the same sequence
+        auto fb = g.count_edge_directions();                 // a valid linearisation of this DAG: all edges point one way
+        REQUIRE(fb.first == 0 || fb.second == 0);            // (a 1D layout is defined up to reflection)
+        REQUIRE_EQ(fb.first + fb.second, edges);
+    });
+    run("integration::test_ygs_determinism", [] {
+        // The reference asserts run-to-run identical ids and sequences with 2 Hogwild threads on simple.gfa;
+        // here the position updates are floating-point atomics, so what is asserted is what the pipeline
+        // guarantees: the same node set, sequences and — on this DAG — the same final topological order.
+        BidirectedGraph a = gfa_parser::load_gfa(g_data + "/simple.gfa");
+        BidirectedGraph b = a;
+        YgsParams p = YgsParams::from_graph(a, 0, 2);
+        ygs_sort(a, p);
+        ygs_sort(b, p);
+        REQUIRE_EQ(a.nodes.size(), b.nodes.size());
+        std::multiset<std::string> sa, sb;
+        for (size_t i = 0; i < a.nodes.size(); ++i) {
+            REQUIRE_EQ(a.nodes[i].has_value(), b.nodes[i].has_value());
+            if (a.nodes[i]) {
+                REQUIRE_EQ(a.nodes[i]->id, b.nodes[i]->id);
+                sa.insert(std::string(a.nodes[i]->sequence.begin(), a.nodes[i]->sequence.end()));
+                sb.insert(std::string(b.nodes[i]->sequence.begin(), b.nodes[i]->sequence.end()));
+            }
+        }
+        REQUIRE(sa == sb);
+        REQUIRE(all_path_sequences(a) == all_path_sequences(b));
+    });
+    run("integration::test_sgd_only", [] {
+        BidirectedGraph g = gfa_parser::load_gfa(g_data + "/simple.gfa");
+        YgsParams p = YgsParams::from_graph(g, 0, 2);
+        const auto seqs = all_path_sequences(g);
+        sgd_sort_only(g, p.path_sgd, 0);
+        REQUIRE(g.node_count() > 0);
+        REQUIRE_EQ(g.node_count(), (size_t)15);
+        REQUIRE(all_path_sequences(g) == seqs);
+        REQUIRE_EQ(last_stats().applied_updates, (uint64_t)(101 * 10));    // (iter_max + 1) x min_term_updates, exactly
+    });
+    run("integration::test_drb1_graph", [] {
+        BidirectedGraph g = gfa_parser::load_gfa(g_data + "/DRB1-3123.gfa");
+        const size_t nodes = g.node_count(), edges = g.edges.size();
+        const auto seqs = all_path_sequences(g);
+        YgsParams p = YgsParams::from_graph(g, 0, 4);
+        p.path_sgd.iter_max = 10;                            // as the reference's test
+        ygs_sort(g, p);
+        REQUIRE_EQ(g.node_count(), nodes);
+        REQUIRE_EQ(g.edges.size(), edges);
+        REQUIRE(all_path_sequences(g) == seqs);
+    });
+    run("integration::test_write_and_reload", [] {
+        BidirectedGraph g = gfa_parser::load_gfa(g_data + "/simple.gfa");
+        YgsParams p = YgsParams::from_graph(g, 0, 2);
+        ygs_sort(g, p);
+        const std::string tmp = "/tmp/gfasort_b200_write_and_reload.gfa";
+        gfa_parser::write_gfa(g, tmp);
+        BidirectedGraph r = gfa_parser::load_gfa(tmp);
+        REQUIRE_EQ(g.node_count(), r.node_count());
+        REQUIRE_EQ(g.edges.size(), r.edges.size());
+        REQUIRE(all_path_sequences(g) == all_path_sequences(r));
+        std::remove(tmp.c_str());
+    });
+    // ---- the two hot-path functions themselves
+    run("sgd::path_linear_sgd_positions", [] {
+        BidirectedGraph g = gfa_parser::load_gfa(g_data + "/DRB1-3123.gfa");
+        YgsParams p = YgsParams::from_graph(g, 0, 4);
+        auto pos = path_linear_sgd(g, p.path_sgd);
+        REQUIRE_EQ(pos.size(), g.node_count());              // key = dense idx 0..N-1
+        for (size_t i = 0; i < pos.size(); ++i) { REQUIRE(pos.count(i) == 1); REQUIRE(std::isfinite(pos[i])); }
+        REQUIRE_EQ(last_stats().applied_updates, (uint64_t)101 * 35059);
+        auto order = path_sgd_sort(g, p.path_sgd);
+        REQUIRE_EQ(order.size(), g.node_count());
+        std::set<size_t> ids;
+        for (Handle h : order) { REQUIRE(!h.is_reverse()); ids.insert(h.node_id()); }
+        REQUIRE_EQ(ids.size(), g.node_count());              // a permutation of all nodes
+        // the sorted 1D layout, read as a 1-D Layout with both ends at the node's position, has low stress
+        // (RMS form: 0.33 on B200, 0.329 for the oracle — smoke())
+        Layout l = Layout::make(1, pos.size());
+        for (size_t i = 0; i < pos.size(); ++i) { l.set(i, 0, 0, pos[i]); l.set(i, 1, 0, pos[i]); }
+        const double stress = calculate_layout_stress(g, l, 10000);
+        REQUIRE(stress > 0.0 && stress < 0.6);
+    });
+    run("sgd::path_linear_sgd_layout_2d", [] {
+        BidirectedGraph g = gfa_parser::load_gfa(g_data + "/DRB1-3123.gfa");
+        LayoutSGDParams p = LayoutSGDParams::from_graph(g, 2, 4);
+        Layout l = path_linear_sgd_layout(g, p);
+        REQUIRE_EQ(l.dimensions, (size_t)2);
+        REQUIRE_EQ(l.num_nodes, g.node_count());
+        for (double c : l.coords) REQUIRE(std::isfinite(c));
+        REQUIRE_EQ(last_stats().applied_updates, (uint64_t)31 * 350590);
+        const double after = calculate_layout_stress(g, l, 10000);
+        REQUIRE(after > 0.0 && after < 0.6);                 // RMS form: 0.32 on B200 (smoke())
+        const std::string tmp = "/tmp/gfasort_b200_layout.tsv";
+        l.write_tsv(tmp);
+        std::ifstream in(tmp);
+        Layout r = Layout::read_tsv(in);
+        REQUIRE_EQ(r.num_nodes, l.num_nodes);
+        REQUIRE(r.coords == l.coords);                       // shortest round-trip formatting
+        std::remove(tmp.c_str());
+    });
+    run("sgd::no_multi_step_path", [] {                       // sgd.rs:258-261, 795-798
+        BidirectedGraph g;
+        g.add_node(1, "A"); g.add_node(2, "C");
+        g.build_path("p", {{1, false}});
+        g.build_path("q", {{2, true}});
+        REQUIRE(path_linear_sgd(g, PathSGDParams()).empty());
+        REQUIRE(path_sgd_sort(g, PathSGDParams()).empty());
+        Layout l = path_linear_sgd_layout(g, LayoutSGDParams());
+        REQUIRE_EQ(l.num_nodes, (size_t)2);
+        for (double c : l.coords) REQUIRE_EQ(c, 0.0);
+    });
+}
+
+int main(int argc, char** argv) {
+    const std::string group = argc > 1 ? argv[1] : "host";
+    if (argc > 2) g_data = argv[2];
+    if (group == "host") host_tests();
+    else if (group == "gpu") {
+        if (!have_device()) { std::printf("FAIL  no CUDA device: the gpu group cannot run (there is no CPU fallback)\n"); return 2; }
+        gpu_tests();
+    } else { std::printf("usage: %s host|gpu [data_dir]\n", argv[0]); return 2; }
+    std::printf("%d tests, %d failed\n", g_run, g_failed);
+    return g_failed ? 1 : 0;
+}

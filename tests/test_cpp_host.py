@@ -1,0 +1,65 @@
+"""The C++ host layer (include/gfasort.hpp — the reference's Rust interface restated above the C ABI) run
+through the reference's own tests, restated in tests/cpp/test_reference_api.cpp.
+
+`host` group (no device): graph / layout / parser / parameter tests, the host steps `g` and `s`, and the
+loud failure of the hot path without a GPU.  `gpu` group: tests/integration_tests.rs and src/ygs.rs tests
+plus the known answers of the path index, through the CUDA path.
+"""
+import os
+import subprocess
+
+import pytest
+
+from conftest import DATA, ROOT
+
+HERE = os.path.join(ROOT, "tests", "cpp")
+BIN = os.path.join(HERE, "test_reference_api")
+DEPS = [os.path.join(HERE, "test_reference_api.cpp"), os.path.join(ROOT, "include", "gfasort.hpp"),
+        os.path.join(ROOT, "include", "gfasort_cuda.h")]
+
+
+@pytest.fixture(scope="module")
+def binary(gfs):          # `gfs` makes sure libgfasort_cuda.so exists
+    stale = not os.path.exists(BIN) or any(os.path.getmtime(d) > os.path.getmtime(BIN) for d in DEPS)
+    if stale:
+        subprocess.run(["bash", os.path.join(HERE, "build.sh")], check=True)
+    return BIN
+
+
+def _run(binary, group):
+    r = subprocess.run([binary, group, DATA], capture_output=True, text=True, timeout=600)
+    print(r.stdout)
+    print(r.stderr[-2000:])
+    return r
+
+
+def test_cpp_host_group(binary):
+    r = _run(binary, "host")
+    assert r.returncode == 0, r.stdout
+    assert "0 failed" in r.stdout and "FAIL" not in r.stdout
+    # every reference unit test that needs no device is there
+    for name in ("graph::test_handle_creation", "graph_ops::test_gfa_output", "layout::test_tsv_roundtrip",
+                 "integration::test_load_simple_gfa", "integration::test_groom_only",
+                 "integration::test_topological_sort_only", "ygs::test_ygs_params_default"):
+        assert f"ok    {name}" in r.stdout
+
+
+def test_cpp_header_is_self_contained(tmp_path):
+    """include/gfasort.hpp compiles on its own, warning-free, as C++17."""
+    src = tmp_path / "t.cpp"
+    src.write_text('#include "gfasort.hpp"\nint main() { gfasort::BidirectedGraph g; return (int)g.node_count(); }\n')
+    r = subprocess.run(["g++", "-std=c++17", "-Wall", "-Wextra", "-Werror", "-fsyntax-only",
+                        "-I", os.path.join(ROOT, "include"), str(src)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+
+
+@pytest.mark.gpu
+def test_cpp_gpu_group(binary):
+    r = _run(binary, "gpu")
+    assert r.returncode == 0, r.stdout
+    assert "0 failed" in r.stdout and "FAIL" not in r.stdout
+    for name in ("sgd::path_index_known_answers", "ygs::test_ygs_sort_runs", "ygs::test_individual_steps",
+                 "integration::test_ygs_sort_simple", "integration::test_ygs_determinism", "integration::test_sgd_only",
+                 "integration::test_drb1_graph", "integration::test_write_and_reload",
+                 "sgd::path_linear_sgd_layout_2d"):
+        assert f"ok    {name}" in r.stdout
