@@ -23,14 +23,25 @@
 #include <cstdint>
 #include <cstring>
 #include <functional>
+#include <new>
 #include <queue>
 #include <set>
+#include <stdexcept>
 #include <string>
 #include <vector>
 
 #include "../../include/gfasort_cuda.h"
 
 namespace gfs { void set_error(const std::string& s); }
+
+// An exception (std::bad_alloc on a huge node id, ...) must not unwind through the C ABI.
+static int gfs_host_exception(const char* where) noexcept {
+    try { throw; }
+    catch (const std::bad_alloc&) { try { gfs::set_error(std::string(where) + ": out of host memory"); } catch (...) {} }
+    catch (const std::exception& e) { try { gfs::set_error(std::string(where) + ": " + e.what()); } catch (...) {} }
+    catch (...) { try { gfs::set_error(std::string(where) + ": unknown exception"); } catch (...) {} }
+    return GFS_ERR_INVALID;
+}
 
 namespace {
 
@@ -107,7 +118,7 @@ int make_graph(HostGraph& g, const uint8_t* present, uint64_t nodes_len, const u
 
 extern "C" int gfs_find_head_nodes(const uint8_t* present, uint64_t nodes_len, const uint64_t* edge_from,
                                    const uint64_t* edge_to, uint64_t E, const uint64_t* steps, const uint64_t* path_first,
-                                   uint64_t P, uint64_t* heads_out, uint64_t* n_heads) {
+                                   uint64_t P, uint64_t* heads_out, uint64_t* n_heads) try {
     HostGraph g;
     int rc = make_graph(g, present, nodes_len, edge_from, edge_to, E, steps, path_first, P);
     if (rc) return rc;
@@ -115,14 +126,14 @@ extern "C" int gfs_find_head_nodes(const uint8_t* present, uint64_t nodes_len, c
     if (n_heads) *n_heads = hs.size();
     if (heads_out) std::memcpy(heads_out, hs.data(), hs.size() * 8);
     return GFS_OK;
-}
+} catch (...) { return gfs_host_exception("gfs_find_head_nodes"); }
 
 // groom(use_bfs = true) (groom.rs:49-199 + groom_bfs_majority :202-275): BFS from the heads over both
 // edge forms, neighbours in (node id, orientation) order; a node reached through its reverse handle is
 // flipped.  Output: every present node in increasing id, as a reverse handle when flipped.
 extern "C" int gfs_groom_order(const uint8_t* present, uint64_t nodes_len, const uint64_t* edge_from,
                                const uint64_t* edge_to, uint64_t E, const uint64_t* steps, const uint64_t* path_first,
-                               uint64_t P, uint64_t* order_out /* one per present node */, uint64_t* n_flipped) {
+                               uint64_t P, uint64_t* order_out /* one per present node */, uint64_t* n_flipped) try {
     HostGraph g;
     int rc = make_graph(g, present, nodes_len, edge_from, edge_to, E, steps, path_first, P);
     if (rc) return rc;
@@ -164,7 +175,7 @@ extern "C" int gfs_groom_order(const uint8_t* present, uint64_t nodes_len, const
         if (present[id]) { order_out[k++] = (id << 1) | flipped[id]; nf += flipped[id]; }
     if (n_flipped) *n_flipped = nf;
     return GFS_OK;
-}
+} catch (...) { return gfs_host_exception("gfs_groom_order"); }
 
 // exact_odgi_topological_order(use_heads = true, use_tails = false) (graph_ops.rs:1232-1485): the modified
 // Kahn's algorithm — heads first, the ready set processed smallest handle first, every node handled through
@@ -172,7 +183,7 @@ extern "C" int gfs_groom_order(const uint8_t* present, uint64_t nodes_len, const
 // as cycle-breaking seeds (smallest (node, orientation) first), then any unvisited handle in the same order.
 extern "C" int gfs_topological_order(const uint8_t* present, uint64_t nodes_len, const uint64_t* edge_from,
                                      const uint64_t* edge_to, uint64_t E, const uint64_t* steps, const uint64_t* path_first,
-                                     uint64_t P, uint64_t* order_out /* one per present node */, uint64_t* n_out) {
+                                     uint64_t P, uint64_t* order_out /* one per present node */, uint64_t* n_out) try {
     HostGraph g;
     int rc = make_graph(g, present, nodes_len, edge_from, edge_to, E, steps, path_first, P);
     if (rc) return rc;
@@ -230,4 +241,4 @@ extern "C" int gfs_topological_order(const uint8_t* present, uint64_t nodes_len,
     }
     if (n_out) *n_out = k;
     return GFS_OK;
-}
+} catch (...) { return gfs_host_exception("gfs_topological_order"); }

@@ -14,6 +14,9 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <memory>
+#include <new>
+#include <stdexcept>
 #include <string>
 #include <unordered_set>
 #include <vector>
@@ -21,6 +24,15 @@
 #include "../../include/gfasort_cuda.h"
 
 namespace gfs { void set_error(const std::string& s); }
+
+// An exception (std::bad_alloc on a huge node id, ...) must not unwind through the C ABI.
+static int gfs_host_exception(const char* where) noexcept {
+    try { throw; }
+    catch (const std::bad_alloc&) { try { gfs::set_error(std::string(where) + ": out of host memory"); } catch (...) {} }
+    catch (const std::exception& e) { try { gfs::set_error(std::string(where) + ": " + e.what()); } catch (...) {} }
+    catch (...) { try { gfs::set_error(std::string(where) + ": unknown exception"); } catch (...) {} }
+    return GFS_ERR_INVALID;
+}
 
 struct gfs_gfa {
     std::string text;                          // the file; sequences and names point into it
@@ -172,34 +184,35 @@ struct BufWriter {
 
 }  // namespace
 
-extern "C" int gfs_gfa_parse_text(const char* text, uint64_t len, gfs_gfa** out) {
+extern "C" int gfs_gfa_parse_text(const char* text, uint64_t len, gfs_gfa** out) try {
     if (!out || (len && !text)) { gfs::set_error("gfs_gfa_parse_text: null argument"); return GFS_ERR_INVALID; }
-    gfs_gfa* g = new gfs_gfa();
+    *out = nullptr;
+    std::unique_ptr<gfs_gfa> g(new gfs_gfa());
     g->text.assign(text, len);
-    int rc = parse_text(g);
-    if (rc) { delete g; *out = nullptr; return rc; }
-    *out = g;
+    int rc = parse_text(g.get());
+    if (rc) return rc;
+    *out = g.release();
     return GFS_OK;
-}
+} catch (...) { return gfs_host_exception("gfs_gfa_parse_text"); }
 
-extern "C" int gfs_gfa_parse_file(const char* path, gfs_gfa** out) {
+extern "C" int gfs_gfa_parse_file(const char* path, gfs_gfa** out) try {
     if (!out || !path) { gfs::set_error("gfs_gfa_parse_file: null argument"); return GFS_ERR_INVALID; }
     *out = nullptr;
-    FILE* f = fopen(path, "rb");
+    std::unique_ptr<FILE, int (*)(FILE*)> f(fopen(path, "rb"), &fclose);
     if (!f) { gfs::set_error(std::string("cannot open ") + path); return GFS_ERR_INVALID; }
-    gfs_gfa* g = new gfs_gfa();
-    fseek(f, 0, SEEK_END);
-    const long sz = ftell(f);
-    fseek(f, 0, SEEK_SET);
+    std::unique_ptr<gfs_gfa> g(new gfs_gfa());
+    fseek(f.get(), 0, SEEK_END);
+    const long sz = ftell(f.get());
+    fseek(f.get(), 0, SEEK_SET);
     g->text.resize(sz > 0 ? (size_t)sz : 0);
-    const size_t got = sz > 0 ? fread(&g->text[0], 1, (size_t)sz, f) : 0;
-    fclose(f);
-    if (got != g->text.size()) { delete g; gfs::set_error(std::string("short read on ") + path); return GFS_ERR_INVALID; }
-    int rc = parse_text(g);
-    if (rc) { delete g; return rc; }
-    *out = g;
+    const size_t got = sz > 0 ? fread(&g->text[0], 1, (size_t)sz, f.get()) : 0;
+    f.reset();
+    if (got != g->text.size()) { gfs::set_error(std::string("short read on ") + path); return GFS_ERR_INVALID; }
+    int rc = parse_text(g.get());
+    if (rc) return rc;
+    *out = g.release();
     return GFS_OK;
-}
+} catch (...) { return gfs_host_exception("gfs_gfa_parse_file"); }
 
 extern "C" int gfs_gfa_dims(const gfs_gfa* g, uint64_t* nodes_len, uint64_t* n_nodes, uint64_t* n_edges, uint64_t* n_steps,
                             uint64_t* n_paths) {
@@ -240,7 +253,7 @@ extern "C" void gfs_gfa_free(gfs_gfa* g) { delete g; }
 
 // Layout::write_tsv (src/layout.rs:138-163).  coords in Layout order [node][end][dim].
 extern "C" int gfs_layout_write_tsv(const double* coords, uint64_t num_nodes, uint32_t dims, const char* path,
-                                    uint64_t* bytes_written) {
+                                    uint64_t* bytes_written) try {
     if (!path || (num_nodes && !coords) || dims == 0) { gfs::set_error("gfs_layout_write_tsv: bad argument"); return GFS_ERR_INVALID; }
     FILE* f = fopen(path, "wb");
     if (!f) { gfs::set_error(std::string("cannot create ") + path); return GFS_ERR_INVALID; }
@@ -261,18 +274,19 @@ extern "C" int gfs_layout_write_tsv(const double* coords, uint64_t num_nodes, ui
         w.advance(p);
     }
     w.flush();
-    const bool ok = w.ok && fclose(f) == 0;
+    const bool closed = fclose(f) == 0;
+    const bool ok = w.ok && closed;
     if (bytes_written) *bytes_written = w.total;
     if (!ok) { gfs::set_error(std::string("write failed on ") + path); return GFS_ERR_INVALID; }
     return GFS_OK;
-}
+} catch (...) { return gfs_host_exception("gfs_layout_write_tsv"); }
 
 // BidirectedGraph::write_gfa (src/graph_ops.rs:693-738): header, S lines by increasing id, L lines in the
 // stored edge order (the reference iterates a HashSet: compare as sets), P lines.
 extern "C" int gfs_gfa_write(const char* path, const uint8_t* present, uint64_t nodes_len, const char* seq_blob,
                              const uint64_t* seq_off, const uint64_t* seq_len, const uint64_t* edge_from,
                              const uint64_t* edge_to, uint64_t E, const uint64_t* steps, const uint64_t* path_first, uint64_t P,
-                             const char* name_blob, const uint64_t* name_off, const uint64_t* name_len, uint64_t* bytes_written) {
+                             const char* name_blob, const uint64_t* name_off, const uint64_t* name_len, uint64_t* bytes_written) try {
     if (!path) { gfs::set_error("gfs_gfa_write: null path"); return GFS_ERR_INVALID; }
     FILE* f = fopen(path, "wb");
     if (!f) { gfs::set_error(std::string("cannot create ") + path); return GFS_ERR_INVALID; }
@@ -306,8 +320,9 @@ extern "C" int gfs_gfa_write(const char* path, const uint8_t* present, uint64_t 
         w.put("\t*\n", 3);
     }
     w.flush();
-    const bool ok = w.ok && fclose(f) == 0;
+    const bool closed = fclose(f) == 0;
+    const bool ok = w.ok && closed;
     if (bytes_written) *bytes_written = w.total;
     if (!ok) { gfs::set_error(std::string("write failed on ") + path); return GFS_ERR_INVALID; }
     return GFS_OK;
-}
+} catch (...) { return gfs_host_exception("gfs_gfa_write"); }

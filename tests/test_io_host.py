@@ -55,6 +55,9 @@ def test_flat_ingest_odd_inputs(gfs, tmp_path):
     _same_graph(a, c)
     with pytest.raises(gfs.GfsError):
         gfs.load_gfa_flat(text=b"S\tx1\tACGT\n")         # non-numeric id: the CLI errors out too
+    # an absurd node id must come back as an error, not as an exception unwinding through the C ABI
+    with pytest.raises(gfs.GfsError, match="out of host memory"):
+        gfs.load_gfa_flat(text=b"S\t9999999999999999\tA\n")
 
 
 def test_layout_tsv_bytes_match_rust_formatting(gfs, tmp_path):
