@@ -417,7 +417,7 @@ def main():
     ap.add_argument("--workload", default=os.environ.get("GFASORT_BENCH_WORKLOAD", "y10m"), choices=sorted(WORKLOADS))
     ap.add_argument("--seed", type=int, default=42)
     ap.add_argument("--syncs", type=int, default=int(os.environ.get("GFASORT_SYNCS", "1")), help="replica reconciles per epoch (N > 1)")
-    ap.add_argument("--reconcile", default=os.environ.get("GFASORT_RECONCILE", "tavg"), choices=["avg", "tavg", "delta"])
+    ap.add_argument("--reconcile", default=os.environ.get("GFASORT_RECONCILE", "tavg"), choices=["avg", "tavg", "delta", "p2p"])
     ap.add_argument("--stress-paths", type=int, default=0, help="N = 1: also report the stress over the first K paths only (to compare with rank 0 of a multi-GPU run)")
     ap.add_argument("--e2e-epochs", type=int, default=-1, help="-1 = the full schedule, 0 = skip the e2e leg")
     ap.add_argument("--stress", type=int, default=1, help="report the sampled path stress of the e2e result")

@@ -119,6 +119,14 @@ SIGNATURES = {
     "gfs_debug_philox": (C.c_int, [u32p, u32p, u32p, C.c_uint64]),
     "gfs_debug_trace_terms": (C.c_int, [C.c_void_p, C.POINTER(SgdParams), C.c_int32, C.c_uint64, C.c_uint32,
                                         C.c_uint64, C.c_uint64, u8p, u64p, u64p, u8p, f64p]),
+    "gfs_p2p_region_create": (C.c_int, [C.c_int32, C.c_uint64, C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p)]),
+    "gfs_p2p_region_ptrs": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), u64p]),
+    "gfs_p2p_region_ipc_handle": (C.c_int, [C.c_void_p, u8p]),
+    "gfs_p2p_region_connect_ipc": (C.c_int, [C.c_void_p, u8p, C.c_uint32, C.c_uint32]),
+    "gfs_p2p_region_connect_local": (C.c_int, [C.POINTER(C.c_void_p), C.c_uint32]),
+    "gfs_p2p_reconcile": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "gfs_p2p_region_check": (C.c_int, [C.c_void_p]),
+    "gfs_p2p_region_free": (None, [C.c_void_p]),
     "gfs_debug_schedule": (C.c_int, [C.POINTER(SgdParams), f64p]),
     "gfs_debug_zetas": (C.c_int, [C.c_void_p, C.POINTER(SgdParams), f64p, C.c_uint64, u64p]),
 }

@@ -10,7 +10,9 @@ lives inside one path (reference src/sgd.rs:445, 502-503) — positions do not. 
     uniform over steps (src/sgd.rs:435, 444);
   * replicas are reconciled `syncs_per_epoch` times per epoch by an all-reduce over the position
     array: "avg" (north star: mean of the replicas), "tavg" (mean over the replicas that moved the
-    node since the last sync) or "delta" (sum of the replicas' displacements, i.e. Hogwild with staleness).
+    node since the last sync) or "delta" (sum of the replicas' displacements, i.e. Hogwild with staleness);
+    "p2p" is "tavg" done by ONE kernel per rank over NVLink peer memory instead of pack + NCCL all-reduce +
+    apply (gfs_p2p_*; opt-in until measured).
 
 Everything here is host logic over torch tensors; it runs unchanged on CPU tensors with the gloo
 backend, which is how tests/test_multi_gloo.py covers it without GPUs.
@@ -108,6 +110,92 @@ def reconcile(x, x_sync, mode: str, group=None, scratch=None):
 
 
 # ------------------------------------------------------------------------------------------------
+# peer-memory regions (mode "p2p")
+# ------------------------------------------------------------------------------------------------
+class _DeviceArray:
+    """A raw device pointer as something torch.as_tensor understands (__cuda_array_interface__)."""
+
+    def __init__(self, ptr: int, n: int, typestr: str):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
+
+
+class PeerRegion:
+    """One rank's replica + snapshot + barrier flags in one allocation that the other ranks map
+    (gfs_p2p_region_*).  `x` / `x_sync` are torch views of the library's memory: valid until close()."""
+
+    def __init__(self, device: int, n_elems: int, f64: bool, max_blocks: int = 0):
+        import ctypes as C
+
+        import torch
+
+        from ._cabi import check, lib
+        self._h = C.c_void_p()
+        self.n, self.f64, self.device = int(n_elems), bool(f64), device
+        check(lib().gfs_p2p_region_create(device, self.n, 8 if f64 else 4, max_blocks, C.byref(self._h)))
+        px, pxs, nbytes = C.c_void_p(), C.c_void_p(), C.c_uint64()
+        check(lib().gfs_p2p_region_ptrs(self._h, C.byref(px), C.byref(pxs), C.byref(nbytes)))
+        self.x_ptr, self.x_sync_ptr, self.nbytes = px.value, pxs.value, nbytes.value
+        ts = "<f8" if f64 else "<f4"
+        dev = f"cuda:{device}"
+        self.x = torch.as_tensor(_DeviceArray(self.x_ptr, self.n, ts), device=dev)
+        self.x_sync = torch.as_tensor(_DeviceArray(self.x_sync_ptr, self.n, ts), device=dev)
+        if self.n and (self.x.data_ptr() != self.x_ptr or self.x_sync.data_ptr() != self.x_sync_ptr):
+            raise RuntimeError("PeerRegion: torch copied the region instead of viewing it")
+
+    def ipc_handle(self) -> bytes:
+        import ctypes as C
+
+        from ._cabi import check, lib, u8p
+        buf = (C.c_uint8 * 64)()
+        check(lib().gfs_p2p_region_ipc_handle(self._h, C.cast(buf, u8p)))
+        return bytes(buf)
+
+    def connect_ipc(self, handles: list, rank: int) -> None:
+        """handles: the 64-byte blobs of all ranks in rank order (one process per GPU)."""
+        import ctypes as C
+
+        from ._cabi import check, lib, u8p
+        assert all(len(h) == 64 for h in handles)
+        blob = (C.c_uint8 * (64 * len(handles))).from_buffer_copy(b"".join(handles))
+        check(lib().gfs_p2p_region_connect_ipc(self._h, C.cast(blob, u8p), len(handles), rank))
+
+    @staticmethod
+    def connect_local(regions: list) -> None:
+        """All replicas live in this process (several GPUs with peer access, or several replicas on one GPU)."""
+        import ctypes as C
+
+        from ._cabi import check, lib
+        arr = (C.c_void_p * len(regions))(*[r._h for r in regions])
+        check(lib().gfs_p2p_region_connect_local(arr, len(regions)))
+
+    def reconcile(self, stream_ptr: int) -> None:
+        from ._cabi import check, lib
+        check(lib().gfs_p2p_reconcile(self._h, stream_ptr))
+
+    def check(self) -> None:
+        from ._cabi import check, lib
+        check(lib().gfs_p2p_region_check(self._h))
+
+    def close(self) -> None:
+        from ._cabi import lib
+        if self._h:
+            self.x = self.x_sync = None
+            lib().gfs_p2p_region_free(self._h)
+            self._h = None
+
+
+def connect_peer_regions(region: PeerRegion, rank: int, world: int, group=None) -> None:
+    """One process per GPU: all-gather the IPC handles over torch.distributed and map the peers."""
+    import torch
+    import torch.distributed as dist
+    mine = torch.tensor(list(region.ipc_handle()), dtype=torch.uint8, device=f"cuda:{region.device}")
+    allh = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(allh, mine, group=group)
+    region.connect_ipc([bytes(t.cpu().tolist()) for t in allh], rank)
+    dist.barrier(group=group)            # nobody reconciles before everybody has mapped everybody
+
+
+# ------------------------------------------------------------------------------------------------
 # one rank of a replicated run (GPU only: drives the C-ABI session API)
 # ------------------------------------------------------------------------------------------------
 _DS = {0: 1, 1: 1, 2: 2, 3: 4, 4: 4, 5: 8, 6: 8, 7: 8, 8: 8}     # coordinate stride per node end (gfs_lib.cu pick_nd)
@@ -136,9 +224,20 @@ class ReplicaRun:
         self.N = int(n_nodes)
         f64 = dims == 0 or layout_f64
         n_elems = self.N if dims == 0 else self.N * 2 * _DS[dims]
-        self.x = torch.zeros(n_elems, dtype=torch.float64 if f64 else torch.float32, device=f"cuda:{device}")
-        self.x_sync = torch.empty_like(self.x) if mode in ("delta", "tavg") else None
-        self.scratch = torch.empty(2 * n_elems, dtype=torch.float32, device=self.x.device) if mode == "tavg" else None
+        self.region = None
+        if mode == "p2p":
+            import torch.distributed as dist
+            world = dist.get_world_size(group) if dist.is_initialized() else 1
+            self.region = PeerRegion(device, n_elems, f64)
+            if world > 1:
+                connect_peer_regions(self.region, shard.rank, world, group)
+            else:
+                PeerRegion.connect_local([self.region])
+            self.x, self.x_sync, self.scratch = self.region.x, self.region.x_sync, None
+        else:
+            self.x = torch.zeros(n_elems, dtype=torch.float64 if f64 else torch.float32, device=f"cuda:{device}")
+            self.x_sync = torch.empty_like(self.x) if mode in ("delta", "tavg") else None
+            self.scratch = torch.empty(2 * n_elems, dtype=torch.float32, device=self.x.device) if mode == "tavg" else None
         self.stream = torch.cuda.Stream(device=device)
         from dataclasses import replace
         self.params = replace(params, min_term_updates=epoch_quota(params.min_term_updates, shard, total_steps))
@@ -190,7 +289,10 @@ class ReplicaRun:
         with torch.cuda.stream(self.stream):
             for k in range(self.syncs):
                 check(lib().gfs_sgd_session_run(self._h, epoch, epoch + 1, k, self.syncs))
-                reconcile(self.x, self.x_sync, self.mode, self.group, self.scratch)
+                if self.region is not None:
+                    self.region.reconcile(self.stream.cuda_stream)      # one kernel: barrier, reduce + scatter over NVLink, barrier
+                else:
+                    reconcile(self.x, self.x_sync, self.mode, self.group, self.scratch)
 
     def stats(self) -> dict:
         import ctypes as C
@@ -198,6 +300,8 @@ class ReplicaRun:
         from ._cabi import Stats, check, lib
         st = Stats()
         check(lib().gfs_sgd_session_stats(self._h, C.byref(st)))
+        if self.region is not None:
+            self.region.check()          # a timed-out peer barrier is an error, never a silent skip
         return st.as_dict()
 
     def close(self):
@@ -205,6 +309,10 @@ class ReplicaRun:
         if self._h:
             lib().gfs_sgd_session_destroy(self._h)
             self._h = None
+        if self.region is not None:
+            self.x = self.x_sync = None
+            self.region.close()
+            self.region = None
 
 
 def build_shard_index(shard_handles, shard_first, node_len, device: int = 0, rank: int = 0, world: int = 1, group=None):

@@ -245,6 +245,31 @@ int gfs_gfa_write(const char* path, const uint8_t* present, uint64_t nodes_len, 
 int gfs_reconcile_pack(const void* x, const void* x_sync, uint64_t n, uint32_t elem_bytes, float* buf, void* stream);
 int gfs_reconcile_apply(void* x, void* x_sync, uint64_t n, uint32_t elem_bytes, const float* buf, void* stream);
 
+/* ---- replica reconcile over peer memory (multi-GPU; opt-in) -------
+ * The same exchange as pack -> all-reduce -> apply, as ONE kernel per rank over NVLink peer memory: every rank
+ * maps every other rank's replica, reduces its 1/G slice of the elements across the G replicas and stores the
+ * result into all of them, between two in-kernel barriers (flags in peer memory, bounded spins).
+ * A region holds one rank's replica x[n], its snapshot x_sync[n] (elem_bytes = 8: f64 positions, 4: f32
+ * coordinates) and the barrier flags in one allocation; give gfs_p2p_region_ptrs()'s x to the session as
+ * gfs_launch_cfg.device_positions.  One process per GPU: exchange gfs_p2p_region_ipc_handle() blobs (all-gather)
+ * and call gfs_p2p_region_connect_ipc; one process driving several GPUs (or several replicas on one GPU):
+ * gfs_p2p_region_connect_local.  max_blocks = 0: one block per SM. */
+#define GFS_P2P_MAX_RANKS 16
+#define GFS_P2P_HANDLE_BYTES 64
+typedef struct gfs_p2p_region gfs_p2p_region;
+int gfs_p2p_region_create(int32_t device, uint64_t n, uint32_t elem_bytes, uint32_t max_blocks, gfs_p2p_region** out);
+int gfs_p2p_region_ptrs(gfs_p2p_region* r, void** x, void** x_sync, uint64_t* region_bytes);
+int gfs_p2p_region_ipc_handle(gfs_p2p_region* r, uint8_t* handle /*GFS_P2P_HANDLE_BYTES*/);
+int gfs_p2p_region_connect_ipc(gfs_p2p_region* r, const uint8_t* handles /*world x GFS_P2P_HANDLE_BYTES, rank order*/,
+                               uint32_t world, uint32_t rank);
+int gfs_p2p_region_connect_local(gfs_p2p_region* const* regions /*world, rank order*/, uint32_t world);
+/* Asynchronous on `stream`: x <- x_sync + (sum of the replicas' displacements) / (#replicas that moved the element)
+ * on every replica, then x_sync <- x.  Every rank calls it once per reconcile, in the same order. */
+int gfs_p2p_reconcile(gfs_p2p_region* r, void* stream);
+/* Blocking: GFS_ERR_CUDA if a barrier of an earlier reconcile timed out (a rank missing, kernels not co-resident). */
+int gfs_p2p_region_check(gfs_p2p_region* r);
+void gfs_p2p_region_free(gfs_p2p_region* r);
+
 /* ---- synthetic pangenome graphs (bench / tests input) -------------------------
  * Seeded bubble-chain generator writing the C-ABI's own flat inputs.  Two calls: sizes, then fill. */
 typedef struct gfs_synth_spec {
