@@ -63,6 +63,15 @@ def test_no_device_fails_loudly(gfs):
     assert b"no CPU fallback" in lib().gfs_last_error()
     with pytest.raises(gfs.GfsError):
         gfs.PathIndex.from_arrays(steps, first, nl)
+    # every other device entry point says the same
+    x = np.zeros(4)
+    order = np.zeros(4, dtype=np.uint32)
+    from gfasort_b200._cabi import f64p
+    assert lib().gfs_sort_positions(x.ctypes.data_as(f64p), 4, order.ctypes.data_as(u32p)) == GFS_ERR_NO_DEVICE
+    assert lib().gfs_debug_fast_precise_pow(x.ctypes.data_as(f64p), x.ctypes.data_as(f64p), x.ctypes.data_as(f64p), 4) == GFS_ERR_NO_DEVICE
+    r = C.c_void_p()
+    assert lib().gfs_p2p_region_create(-1, 16, 8, 0, C.byref(r)) == GFS_ERR_NO_DEVICE and not r.value
+    assert b"no CPU fallback" in lib().gfs_last_error()
 
 
 def test_index_build_rejects_bad_arguments(gfs):
