@@ -14,6 +14,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <algorithm>
 #include <functional>
 #include <set>
 #include <sstream>
@@ -554,8 +555,38 @@ static void gpu_tests() {
     });
 }
 
+// `dump <op> <in.gfa>`: apply a host step and print the graph canonically (nodes by id, sorted edges, paths),
+// so that tests/test_cpp_host.py can compare this host layer with the Python one step by step.
+static int dump(const std::string& op, const std::string& in) {
+    BidirectedGraph g = gfa_parser::load_gfa(in);
+    if (op == "groom") groom_only(g, 0);
+    else if (op == "topo") topological_sort_only(g, 0);
+    else if (op == "groom+topo") { groom_only(g, 0); topological_sort_only(g, 0); }
+    else if (op == "reverse") {                           // apply_ordering with the ids reversed
+        std::vector<Handle> order;
+        for (size_t id = g.nodes.size(); id-- > 0;) if (g.nodes[id]) order.push_back(Handle::forward(id));
+        g.apply_ordering(order);
+    } else if (op != "load") { std::printf("unknown op %s\n", op.c_str()); return 2; }
+    for (size_t id = 0; id < g.nodes.size(); ++id)
+        if (g.nodes[id]) std::printf("S %zu %s\n", id, std::string(g.nodes[id]->sequence.begin(), g.nodes[id]->sequence.end()).c_str());
+    std::vector<std::pair<uint64_t, uint64_t>> es;
+    for (const auto& e : g.edges) es.emplace_back(e.from.value, e.to.value);
+    std::sort(es.begin(), es.end());
+    for (auto& e : es) std::printf("L %llu %llu\n", (unsigned long long)e.first, (unsigned long long)e.second);
+    for (const auto& p : g.paths) {
+        std::printf("P %s", p.name.c_str());
+        for (Handle h : p.steps) std::printf(" %llu", (unsigned long long)h.value);
+        std::printf("\n");
+    }
+    std::printf("O");
+    for (size_t id : g.node_order) std::printf(" %zu", id);
+    std::printf("\n");
+    return 0;
+}
+
 int main(int argc, char** argv) {
     const std::string group = argc > 1 ? argv[1] : "host";
+    if (group == "dump" && argc == 4) return dump(argv[2], argv[3]);
     if (argc > 2) g_data = argv[2];
     if (group == "host") host_tests();
     else if (group == "gpu") {
