@@ -101,3 +101,35 @@ def test_cpp_and_python_host_layers_agree(op, name, binary, gfs):
         ids = np.nonzero(g.present)[0][::-1].astype(np.uint64)
         g.apply_ordering(ids << np.uint64(1))
     assert r.stdout.split("\n")[:-1] == _canonical(g)
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_cpp_and_python_host_layers_agree_on_random_graphs(seed, binary, gfs, tmp_path):
+    """Random bidirected graphs (cycles, inversions, self loops, tips) as GFA text through both host layers."""
+    import numpy as np
+    rng = np.random.default_rng(1000 + seed)
+    n = int(rng.integers(2, 40))
+    p_rev = [0.0, 0.2, 0.5][seed % 3]
+    lines = ["H\tVN:Z:1.0"]
+    for i in range(1, n + 1):
+        lines.append(f"S\t{i}\t" + "".join(rng.choice(list("ACGT"), int(rng.integers(1, 7)))))
+    for _ in range(int(rng.integers(n // 2, 3 * n))):
+        a, b = int(rng.integers(1, n + 1)), int(rng.integers(1, n + 1))
+        lines.append(f"L\t{a}\t{'-' if rng.random() < p_rev else '+'}\t{b}\t{'-' if rng.random() < p_rev else '+'}\t0M")
+    for p in range(int(rng.integers(0, 4))):
+        steps = [f"{int(rng.integers(1, n + 1))}{'-' if rng.random() < p_rev else '+'}" for _ in range(int(rng.integers(1, 15)))]
+        lines.append(f"P\tpath{p}\t" + ",".join(steps) + "\t*")
+    path = tmp_path / "random.gfa"
+    path.write_text("\n".join(lines) + "\n")
+    for op in ("load", "groom", "topo", "groom+topo", "reverse"):
+        r = subprocess.run([binary, "dump", op, str(path)], capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stdout + r.stderr
+        g = gfs.load_gfa(str(path))
+        if op in ("groom", "groom+topo"):
+            gfs.groom_only(g, 0)
+        if op in ("topo", "groom+topo"):
+            gfs.topological_sort_only(g, 0)
+        if op == "reverse":
+            ids = np.nonzero(g.present)[0][::-1].astype(np.uint64)
+            g.apply_ordering(ids << np.uint64(1))
+        assert r.stdout.split("\n")[:-1] == _canonical(g), (seed, op)
