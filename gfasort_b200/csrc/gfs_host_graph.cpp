@@ -28,6 +28,7 @@
 #include <set>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/gfasort_cuda.h"
@@ -242,3 +243,30 @@ extern "C" int gfs_topological_order(const uint8_t* present, uint64_t nodes_len,
     if (n_out) *n_out = k;
     return GFS_OK;
 } catch (...) { return gfs_host_exception("gfs_topological_order"); }
+
+// Flat form of the handle rewrites that follow every pipeline step — apply_ordering (graph_ops.rs:1939-2025),
+// apply_node_id_mapping (:36-84) and the orientation flips of apply_grooming_with_reorder (groom.rs:533-605) —
+// over path steps or edge ends, in place: id -> new_id[id] where id < table_len and new_id[id] != UINT64_MAX
+// (other handles keep their id), then orientation ^= flip[id] (flip indexed by the OLD id, may be NULL).
+// The reference does this through HashMap<usize, usize> lookups per step (1e9 SipHash probes at config 3).
+extern "C" int gfs_remap_handles(uint64_t* handles, uint64_t n, const uint64_t* new_id, uint64_t table_len,
+                                 const uint8_t* flip, uint64_t flip_len) try {
+    if (n && !handles) { gfs::set_error("gfs_remap_handles: null handles"); return GFS_ERR_INVALID; }
+    if (table_len && !new_id) { gfs::set_error("gfs_remap_handles: null table"); return GFS_ERR_INVALID; }
+    auto work = [&](uint64_t lo, uint64_t hi) {
+        for (uint64_t i = lo; i < hi; ++i) {
+            const uint64_t h = handles[i];
+            uint64_t id = h >> 1, rev = h & 1;
+            if (flip && id < flip_len) rev ^= (uint64_t)(flip[id] & 1);
+            if (id < table_len && new_id[id] != ~0ull) id = new_id[id];
+            handles[i] = (id << 1) | rev;
+        }
+    };
+    unsigned hw = std::thread::hardware_concurrency();
+    const unsigned nt = (unsigned)std::min<uint64_t>(hw ? hw : 4, std::max<uint64_t>(n >> 20, 1));   // >= 1M handles per thread
+    if (nt <= 1) { work(0, n); return GFS_OK; }
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < nt; ++t) th.emplace_back(work, n * t / nt, n * (t + 1) / nt);
+    for (auto& x : th) x.join();
+    return GFS_OK;
+} catch (...) { return gfs_host_exception("gfs_remap_handles"); }

@@ -101,45 +101,70 @@ class BidirectedGraph:
 
         Follows src/graph_ops.rs:1939-2025: new id = rank + 1, orientations are kept, steps/edges on
         ids not in the ordering are left/dropped as the reference does, and `node_order` is NOT
-        updated (SURVEY.md §8 quirk 7 — harmless for contiguous ids)."""
+        updated (SURVEY.md §8 quirk 7 — harmless for contiguous ids).  The per-step rewrite is the
+        library's flat, multi-threaded gfs_remap_handles (the reference: one HashMap probe per step)."""
         ordering = np.asarray(ordering, dtype=np.uint64)
         if len(ordering) == 0:
             return
         old_ids = (ordering >> np.uint64(1)).astype(np.int64)
         new_ids = np.arange(1, len(ordering) + 1, dtype=np.uint64)
         size = max(len(self.present), int(old_ids.max()) + 1)
-        old_to_new = np.zeros(size, dtype=np.uint64)          # 0 = not remapped
-        old_to_new[old_ids] = new_ids
-        max_new = len(ordering)
-        present = np.zeros(max_new + 1, dtype=np.uint8)
-        seq_len = np.zeros(max_new + 1, dtype=np.uint64)
+        old_to_new = np.full(size, UNMAPPED, dtype=np.uint64)
+        old_to_new[old_ids] = new_ids                          # a repeated node keeps its LAST rank (HashMap insert)
         in_range = old_ids < len(self.present)
         live = np.zeros(len(old_ids), dtype=bool)
         live[in_range] = self.present[old_ids[in_range]] != 0
-        present[new_ids[live].astype(np.int64)] = 1
-        seq_len[new_ids[live].astype(np.int64)] = self.seq_len[old_ids[live]]
+        # a node listed twice lands where its last entry says
+        dst = old_to_new[old_ids[live]].astype(np.int64)
+        present = np.zeros(len(ordering) + 1, dtype=np.uint8)
+        seq_len = np.zeros(len(ordering) + 1, dtype=np.uint64)
+        present[dst] = 1
+        seq_len[dst] = self.seq_len[old_ids[live]]
         if self.sequences:
-            self.sequences = {int(n): self.sequences[int(o)] for o, n in zip(old_ids[live], new_ids[live])
+            self.sequences = {int(n): self.sequences[int(o)] for o, n in zip(old_ids[live], dst)
                               if int(o) in self.sequences}
         self.present, self.seq_len = present, seq_len
-        sid = (self.steps >> np.uint64(1)).astype(np.int64)
-        mapped = np.zeros(len(sid), dtype=np.uint64)
-        ok = sid < size
-        mapped[ok] = old_to_new[sid[ok]]
-        keep_old = mapped == 0
-        self.steps = np.where(keep_old, self.steps, (mapped << np.uint64(1)) | (self.steps & np.uint64(1)))
+        self.steps = remap_handles(self.steps, old_to_new)
         if len(self.edges):
             f = (self.edges[:, 0] >> np.uint64(1)).astype(np.int64)
             t = (self.edges[:, 1] >> np.uint64(1)).astype(np.int64)
-            okf = (f < size) & (t < size)
-            nf = np.zeros(len(f), dtype=np.uint64)
-            nt = np.zeros(len(t), dtype=np.uint64)
-            nf[okf] = old_to_new[f[okf]]
-            nt[okf] = old_to_new[t[okf]]
-            keep = (nf != 0) & (nt != 0)
-            e = np.stack([(nf << np.uint64(1)) | (self.edges[:, 0] & np.uint64(1)),
-                          (nt << np.uint64(1)) | (self.edges[:, 1] & np.uint64(1))], axis=1)[keep]
-            self.edges = np.unique(e, axis=0) if len(e) else e
+            keep = (f < size) & (t < size)
+            keep[keep] = (old_to_new[f[keep]] != UNMAPPED) & (old_to_new[t[keep]] != UNMAPPED)   # an unmapped end drops the edge
+            e = np.ascontiguousarray(self.edges[keep].T)       # (2, E'): one contiguous array per end
+            self.edges = unique_rows(remap_handles(e[0], old_to_new), remap_handles(e[1], old_to_new), sort=True)
+
+
+UNMAPPED = np.uint64(0xFFFFFFFFFFFFFFFF)
+
+
+def remap_handles(handles: np.ndarray, new_id: np.ndarray, flip: np.ndarray | None = None) -> np.ndarray:
+    """A rewritten copy of `handles`: orientation ^= flip[id], id -> new_id[id] unless new_id[id] == UNMAPPED or
+    id >= len(new_id).  gfs_remap_handles: flat and multi-threaded."""
+    import ctypes as C
+
+    from ._cabi import check, lib, u8p, u64p
+    out = np.array(handles, dtype=np.uint64, copy=True, order="C")
+    new_id = np.ascontiguousarray(new_id, dtype=np.uint64)
+    fl = None if flip is None else np.ascontiguousarray(flip, dtype=np.uint8)
+    check(lib().gfs_remap_handles(out.ctypes.data_as(u64p), len(out), new_id.ctypes.data_as(u64p), len(new_id),
+                                  fl.ctypes.data_as(u8p) if fl is not None else None, len(fl) if fl is not None else 0))
+    return out
+
+
+def unique_rows(a: np.ndarray, b: np.ndarray, sort: bool = False) -> np.ndarray:
+    """HashSet<BiEdge> semantics for the pairs (a[i], b[i]): exact duplicates collapse.  (E', 2) array; rows in
+    increasing (a, b) order when `sort`, else in order of first occurrence."""
+    if len(a) == 0:
+        return np.zeros((0, 2), dtype=np.uint64)
+    if sort and int(a.max()) < (1 << 32) and int(b.max()) < (1 << 32):
+        key = np.sort((a.astype(np.uint64) << np.uint64(32)) | b.astype(np.uint64))     # one 1-D sort, then adjacent dedupe
+        keep = np.ones(len(key), dtype=bool)
+        keep[1:] = key[1:] != key[:-1]
+        key = key[keep]
+        return np.stack([key >> np.uint64(32), key & np.uint64(0xFFFFFFFF)], axis=1)
+    idx = unique_pair_index(a, b)
+    e = np.stack([a[idx], b[idx]], axis=1)
+    return e[np.lexsort((e[:, 1], e[:, 0]))] if sort else e
 
 
 def edges_from_paths(steps: np.ndarray, path_first: np.ndarray) -> np.ndarray:
@@ -167,7 +192,11 @@ def unique_pair_index(a: np.ndarray, b: np.ndarray) -> np.ndarray:
         return np.zeros(0, dtype=np.int64)
     if int(a.max()) < (1 << 32) and int(b.max()) < (1 << 32):
         key = (a.astype(np.uint64) << np.uint64(32)) | b.astype(np.uint64)          # one 1-D sort instead of a row sort
-        _, idx = np.unique(key, return_index=True)
+        order = np.argsort(key, kind="stable")                                      # stable: the first occurrence leads its run
+        sk = key[order]
+        lead = np.ones(len(sk), dtype=bool)
+        lead[1:] = sk[1:] != sk[:-1]
+        idx = order[lead]
     else:
         _, idx = np.unique(np.stack([a, b], axis=1), axis=0, return_index=True)
     idx.sort()

@@ -63,62 +63,47 @@ def groom(graph: BidirectedGraph, verbose: bool = False) -> np.ndarray:
 
 def apply_grooming_with_reorder(graph: BidirectedGraph, groomed: np.ndarray, reorder: bool = True) -> None:
     """src/groom.rs:533-605: reverse-complement flipped nodes, XOR the orientation of every edge end and
-    path step on them, then renumber 1..N in the order given (apply_node_id_mapping, graph_ops.rs:36-84)."""
+    path step on them, then renumber 1..N in the order given (apply_node_id_mapping, graph_ops.rs:36-84).
+    Flip and renumbering are one pass of gfs_remap_handles over the steps and one over the edge ends."""
+    from .graph import UNMAPPED, remap_handles, unique_rows
     groomed = np.asarray(groomed, dtype=np.uint64)
     flip_ids = (groomed[(groomed & np.uint64(1)) == 1] >> np.uint64(1)).astype(np.int64)
     size = len(graph.present)
-    flip = np.zeros(size + 1, dtype=np.uint64)
-    flip[flip_ids[flip_ids < size]] = 1
+    flip = np.zeros(max(size, int(flip_ids.max()) + 1 if len(flip_ids) else 0), dtype=np.uint8)
+    flip[flip_ids] = 1                                       # the flip set holds ids, live or not (groom.rs:535-541)
     for nid in flip_ids.tolist():
         if nid in graph.sequences:
             graph.sequences[nid] = reverse_complement(graph.sequences[nid])
-
-    def xor(h):
-        ids = np.minimum((h >> np.uint64(1)).astype(np.int64), size)
-        return h ^ flip[ids]
-
-    if len(graph.edges):
-        e = np.stack([xor(graph.edges[:, 0]), xor(graph.edges[:, 1])], axis=1)
-        graph.edges = _unique_rows(e)
-    graph.steps = xor(graph.steps)
+    mapping = np.full(size, UNMAPPED, dtype=np.uint64)      # unmapped ids keep their id (graph_ops.rs:44, 58-59, 78)
+    max_new = 0
     if reorder:
         old_ids = (groomed >> np.uint64(1)).astype(np.int64)
-        mapping = np.arange(size + 1, dtype=np.uint64)          # unmapped ids keep their id
-        mapping[old_ids[old_ids < size]] = np.arange(1, len(groomed) + 1, dtype=np.uint64)[old_ids < size]
-        _apply_node_id_mapping(graph, mapping, int(len(groomed)))
+        ranks = np.arange(1, len(groomed) + 1, dtype=np.uint64)
+        if len(old_ids) and int(old_ids.max()) >= size:
+            mapping = np.concatenate([mapping, np.full(int(old_ids.max()) + 1 - size, UNMAPPED, dtype=np.uint64)])
+        mapping[old_ids] = ranks
+        max_new = len(groomed)
+        _renumber_nodes(graph, mapping, max_new)
+    graph.steps = remap_handles(graph.steps, mapping, flip)
+    if len(graph.edges):
+        e = np.ascontiguousarray(graph.edges.T)
+        graph.edges = unique_rows(remap_handles(e[0], mapping, flip), remap_handles(e[1], mapping, flip))
 
 
-def _unique_rows(e: np.ndarray) -> np.ndarray:
-    """HashSet<BiEdge> semantics: exact duplicates collapse (first occurrence kept, order otherwise preserved)."""
-    if len(e) == 0:
-        return e
-    from .graph import unique_pair_index
-    return e[unique_pair_index(e[:, 0], e[:, 1])]
-
-
-def _apply_node_id_mapping(graph: BidirectedGraph, mapping: np.ndarray, max_new: int) -> None:
-    size = len(graph.present)
+def _renumber_nodes(graph: BidirectedGraph, mapping: np.ndarray, max_new: int) -> None:
+    """The node-table half of apply_node_id_mapping (graph_ops.rs:36-50)."""
+    from .graph import UNMAPPED
     live = np.nonzero(graph.present)[0]
-    new_ids = mapping[live].astype(np.int64)
+    new_ids = mapping[live]
+    new_ids = np.where(new_ids == UNMAPPED, live.astype(np.uint64), new_ids).astype(np.int64)
     n_len = max(max_new, int(new_ids.max()) if len(new_ids) else 0) + 1
     present = np.zeros(n_len, dtype=np.uint8)
     seq_len = np.zeros(n_len, dtype=np.uint64)
     present[new_ids] = 1
     seq_len[new_ids] = graph.seq_len[live]
     if graph.sequences:
-        graph.sequences = {int(mapping[o]): s for o, s in graph.sequences.items() if o < size}
+        graph.sequences = {int(n): graph.sequences[int(o)] for o, n in zip(live, new_ids) if int(o) in graph.sequences}
     graph.present, graph.seq_len = present, seq_len
-
-    def remap(h):
-        ids = (h >> np.uint64(1)).astype(np.int64)
-        ok = ids < size
-        out = h.copy()
-        out[ok] = (mapping[ids[ok]] << np.uint64(1)) | (h[ok] & np.uint64(1))
-        return out
-
-    if len(graph.edges):
-        graph.edges = _unique_rows(np.stack([remap(graph.edges[:, 0]), remap(graph.edges[:, 1])], axis=1))
-    graph.steps = remap(graph.steps)
 
 
 def groom_only(graph: BidirectedGraph, verbose: int = 0) -> None:

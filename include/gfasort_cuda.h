@@ -211,6 +211,13 @@ int gfs_topological_order(const uint8_t* present, uint64_t nodes_len, const uint
                           uint64_t E, const uint64_t* steps, const uint64_t* path_first, uint64_t P,
                           uint64_t* order_out, uint64_t* n_out);
 
+/* Flat form of the handle rewrites after every pipeline step — apply_ordering (src/graph_ops.rs:1939-2025),
+ * apply_node_id_mapping (:36-84), the flips of apply_grooming_with_reorder (src/groom.rs:533-605) — in place over
+ * n handles (path steps or edge ends): orientation ^= flip[id] (flip may be NULL; indexed by the old id), then
+ * id -> new_id[id] where id < table_len and new_id[id] != UINT64_MAX (other handles keep their id).  Multi-threaded. */
+int gfs_remap_handles(uint64_t* handles, uint64_t n, const uint64_t* new_id, uint64_t table_len, const uint8_t* flip,
+                      uint64_t flip_len);
+
 /* ---- flat ingest and buffered writers (CPU code) ------------------------------
  * gfs_gfa_parse_*: the CLI's parse_gfa (src/bin/gfasort.rs:88-167) in one pass, straight into flat arrays:
  * present / seq_len indexed by node id, node_order (add_node order, src/graph_ops.rs:613-623), edges unique

@@ -141,3 +141,108 @@ def test_linear_time_at_scale(gfs):
     ids = (g.steps >> np.uint64(1)).astype(np.int64)
     p0 = ids[int(g.path_first[0]):int(g.path_first[1])]
     assert (np.diff(p0) > 0).mean() > 0.9       # and the paths run (mostly) left to right
+
+
+# ------------------------------------------------------------------------------------------------
+# apply_ordering / apply_grooming_with_reorder (the flat gfs_remap_handles passes) against a literal,
+# dict-based restatement of the reference (src/graph_ops.rs:36-84, 1939-2025; src/groom.rs:533-605)
+# ------------------------------------------------------------------------------------------------
+def _ref_state(g):
+    nodes = {int(i): (int(g.seq_len[i]), g.sequences.get(int(i))) for i in np.nonzero(g.present)[0]}
+    edges = {(int(a), int(b)) for a, b in g.edges.tolist()}
+    return nodes, len(g.present), edges, [int(h) for h in g.steps.tolist()]
+
+
+def _ref_apply_ordering(state, ordering):
+    nodes, nodes_len, edges, steps = state
+    if not ordering:
+        return state
+    old_to_new = {}
+    for i, h in enumerate(ordering):
+        old_to_new[h >> 1] = i + 1                                   # HashMap insert: the last rank wins
+    max_new = max(old_to_new.values())
+    new_nodes = {new: nodes[old] for old, new in old_to_new.items() if old in nodes}
+    new_edges = {((old_to_new[f >> 1] << 1) | (f & 1), (old_to_new[t >> 1] << 1) | (t & 1))
+                 for f, t in edges if (f >> 1) in old_to_new and (t >> 1) in old_to_new}
+    new_steps = [((old_to_new[h >> 1] << 1) | (h & 1)) if (h >> 1) in old_to_new else h for h in steps]
+    return new_nodes, max_new + 1, new_edges, new_steps
+
+
+def _ref_apply_grooming(state, groomed, reorder, rc):
+    nodes, nodes_len, edges, steps = state
+    flips = {h >> 1 for h in groomed if h & 1}
+    nodes = {i: (l, rc(s) if (i in flips and s is not None) else s) for i, (l, s) in nodes.items()}
+    fl = lambda h: h ^ 1 if (h >> 1) in flips else h
+    edges = {(fl(f), fl(t)) for f, t in edges}
+    steps = [fl(h) for h in steps]
+    if reorder:
+        m = {h >> 1: i + 1 for i, h in enumerate(groomed)}
+        mp = lambda h: (m.get(h >> 1, h >> 1) << 1) | (h & 1)
+        max_new = max(m.values()) if m else 0
+        nodes = {m.get(i, i): v for i, v in nodes.items()}
+        nodes_len = max(max_new, max(nodes) if nodes else 0) + 1      # the reference would panic past max_new
+        edges = {(mp(f), mp(t)) for f, t in edges}
+        steps = [mp(h) for h in steps]
+    return nodes, nodes_len, edges, steps
+
+
+def _check_state(g, want, tag):
+    nodes, nodes_len, edges, steps = want
+    got_nodes, got_len, got_edges, got_steps = _ref_state(g)
+    assert got_nodes == nodes, tag
+    assert got_len == nodes_len, tag
+    assert got_edges == edges, tag
+    assert got_steps == steps, tag
+    assert len(g.edges) == len(edges), tag                           # HashSet semantics: no duplicate rows
+
+
+@pytest.mark.parametrize("seed", range(80))
+def test_apply_ordering_and_grooming_match_reference_semantics(seed, gfs):
+    rng = np.random.default_rng(seed)
+    g = _random_graph(gfs, rng, int(rng.integers(2, 50)), int(rng.integers(0, 120)), int(rng.integers(0, 5)),
+                      p_present=0.85, p_rev=0.3, p_missing_edge=0.1)
+    live = np.nonzero(g.present)[0]
+    g.sequences = {int(i): bytes(rng.choice(list(b"ACGT"), int(g.seq_len[i])).tolist()) for i in live}
+    # steps on ids that are not in the graph, too
+    extra = (rng.integers(1, len(g.present) + 4, 5).astype(np.uint64) << np.uint64(1)) | rng.integers(0, 2, 5).astype(np.uint64)
+    g.steps = np.concatenate([g.steps, extra]); g.path_first = np.append(g.path_first, np.uint64(len(g.steps)))
+    kind = seed % 4
+    if kind == 0:
+        ids = rng.permutation(live)                                             # a full permutation
+    elif kind == 1:
+        ids = rng.permutation(live)[:max(1, len(live) // 2)]                    # partial: unmapped nodes / steps / edges
+    elif kind == 2:
+        ids = np.concatenate([rng.permutation(live), rng.choice(live, 2)])      # a node listed twice: the last rank wins
+    else:
+        ids = np.concatenate([rng.permutation(live), [len(g.present) + 3]])     # an id that is not in the graph
+    order = (ids.astype(np.uint64) << np.uint64(1)) | (rng.random(len(ids)) < 0.3).astype(np.uint64)
+    import copy
+    for reorder in (None, True, False):
+        h = copy.deepcopy(g)
+        before = _ref_state(h)
+        if reorder is None:
+            h.apply_ordering(order)
+            _check_state(h, _ref_apply_ordering(before, [int(x) for x in order]), ("apply_ordering", seed))
+        else:
+            groomed = (rng.permutation(live).astype(np.uint64) << np.uint64(1)) | (rng.random(len(live)) < 0.4).astype(np.uint64)
+            gfs.apply_grooming_with_reorder(h, groomed, reorder)
+            _check_state(h, _ref_apply_grooming(before, [int(x) for x in groomed], reorder, gfs.ygs.reverse_complement),
+                         ("apply_grooming", seed, reorder))
+
+
+def test_remap_handles_native(gfs):
+    from gfasort_b200.graph import UNMAPPED, remap_handles
+    rng = np.random.default_rng(3)
+    n = 3_000_000                                                   # several threads
+    h = rng.integers(0, 2 * 1000 + 40, n).astype(np.uint64)
+    table = rng.integers(1, 5000, 1000).astype(np.uint64)
+    table[rng.random(1000) < 0.2] = UNMAPPED
+    flip = (rng.random(1010) < 0.5).astype(np.uint8)
+    got = remap_handles(h, table, flip)
+    ids = (h >> np.uint64(1)).astype(np.int64)
+    rev = h & np.uint64(1)
+    rev = np.where(ids < 1010, rev ^ flip[np.minimum(ids, 1009)], rev)
+    mapped = np.where((ids < 1000) & (table[np.minimum(ids, 999)] != UNMAPPED), table[np.minimum(ids, 999)], ids.astype(np.uint64))
+    assert np.array_equal(got, (mapped << np.uint64(1)) | rev)
+    assert np.array_equal(remap_handles(h[:7], table), ((np.where((ids[:7] < 1000) & (table[np.minimum(ids[:7], 999)] != UNMAPPED), table[np.minimum(ids[:7], 999)], ids[:7].astype(np.uint64))) << np.uint64(1)) | (h[:7] & np.uint64(1)))
+    assert len(remap_handles(np.zeros(0, dtype=np.uint64), table)) == 0
