@@ -229,6 +229,23 @@ struct BidirectedGraph {
         return d;
     }
 
+    /// The per-step half of every renumbering: one flat, multi-threaded pass of the library's gfs_remap_handles over
+    /// each path (the reference probes a HashMap per step).  table[id] == UINT64_MAX / id >= table.size(): id kept.
+    static std::vector<uint64_t> flat_table(const std::unordered_map<size_t, size_t>& mapping) {
+        size_t top = 0;
+        for (auto& kv : mapping) top = std::max(top, kv.first + 1);
+        std::vector<uint64_t> t(top, ~0ull);
+        for (auto& kv : mapping) t[kv.first] = kv.second;
+        return t;
+    }
+    void remap_path_steps(const std::vector<uint64_t>& table, const std::vector<uint8_t>* flip) {
+        static_assert(sizeof(Handle) == sizeof(uint64_t), "Handle is one u64");
+        for (auto& p : paths)
+            if (!p.steps.empty())
+                check(gfs_remap_handles(reinterpret_cast<uint64_t*>(p.steps.data()), p.steps.size(), table.data(), table.size(),
+                                        flip ? flip->data() : nullptr, flip ? flip->size() : 0));
+    }
+
     /// graph_ops.rs:36-84.  Unmapped ids keep their id.
     void apply_node_id_mapping(const std::unordered_map<size_t, size_t>& mapping) {
         size_t max_new = 0;
@@ -248,7 +265,7 @@ struct BidirectedGraph {
         for (const auto& e : edges)
             ne.insert(BiEdge(Handle::make(map_id(e.from.node_id()), e.from.is_reverse()), Handle::make(map_id(e.to.node_id()), e.to.is_reverse())));
         edges = std::move(ne);
-        for (auto& p : paths) for (auto& h : p.steps) h = Handle::make(map_id(h.node_id()), h.is_reverse());
+        remap_path_steps(flat_table(mapping), nullptr);
     }
 
     /// graph_ops.rs:1939-2025: new id = rank + 1; edges with an unmapped end are dropped, steps on unmapped
@@ -276,11 +293,7 @@ struct BidirectedGraph {
                 ne.insert(BiEdge(Handle::make(f->second, e.from.is_reverse()), Handle::make(t->second, e.to.is_reverse())));
         }
         edges = std::move(ne);
-        for (auto& p : paths)
-            for (auto& h : p.steps) {
-                auto it = old_to_new.find(h.node_id());
-                if (it != old_to_new.end()) h = Handle::make(it->second, h.is_reverse());
-            }
+        remap_path_steps(flat_table(old_to_new), nullptr);
         if (verbose) std::cerr << "\n[apply_ordering] Applied ordering: renumbered " << old_to_new.size() << " nodes\n\n";
     }
 
@@ -338,7 +351,13 @@ struct BidirectedGraph {
         for (const auto& e : edges)
             ne.insert(BiEdge(flips.count(e.from.node_id()) ? e.from.flip() : e.from, flips.count(e.to.node_id()) ? e.to.flip() : e.to));
         edges = std::move(ne);
-        for (auto& p : paths) for (auto& h : p.steps) if (flips.count(h.node_id())) h = h.flip();
+        {
+            size_t top = 0;
+            for (size_t id : flips) top = std::max(top, id + 1);
+            std::vector<uint8_t> flip(top, 0);
+            for (size_t id : flips) flip[id] = 1;
+            remap_path_steps({}, &flip);
+        }
         if (reorder) {
             std::unordered_map<size_t, size_t> m;
             for (size_t i = 0; i < groomed.size(); ++i) m[groomed[i].node_id()] = i + 1;
