@@ -22,6 +22,28 @@ def _p(a, t):
     return a.ctypes.data_as(t)
 
 
+_GOLDEN = None
+
+
+def _golden():
+    """tests/golden/term_traces.json (made by tests/golden/make_golden.py from the oracle)."""
+    global _GOLDEN
+    if _GOLDEN is None:
+        import json
+        from conftest import GOLDEN
+        with open(os.path.join(GOLDEN, "term_traces.json")) as f:
+            _GOLDEN = json.load(f)
+    return _GOLDEN
+
+
+def _digest(*arrays):
+    import hashlib
+    h = hashlib.sha256()
+    for a in arrays:
+        h.update(np.ascontiguousarray(a).tobytes())
+    return h.hexdigest()
+
+
 def _cparams(op, G):
     """oracle params -> gfs_sgd_params (same field order)."""
     from gfasort_b200._cabi import SgdParams
@@ -46,6 +68,10 @@ def test_path_index_fixtures_bit_exact(name, gfs, oracle):
     assert np.array_equal(ix.path_lengths(), ref["length"])
     assert np.array_equal(ix.path_step_counts(), ref["step_count"])
     assert ix.get_total_steps() == len(ref["step_to_handle"])
+    gold = _golden()["index"][name]                         # and against the committed golden digests
+    assert _digest(ix.step_positions().astype(np.uint64)) == gold["step_to_position_sha256"]
+    assert ix.path_lengths().tolist() == gold["path_length"]
+    assert _digest(gfs.initial_positions(gfs.load_gfa(path))) == gold["x_init_sha256"]
     # accessors
     for s in (0, ix.get_total_steps() // 2, ix.get_total_steps() - 1):
         assert ix.get_path_of_step(s) == ref["step_to_path"][s]
@@ -222,6 +248,7 @@ def test_term_sampling_bit_exact(name, nd, gfs, oracle):
     op = oracle.params_from_graph(og, layout=nd)
     cp = _cparams(op, gfs)
     count = 20000
+    n_gold = 0
     first_cooling = int(np.floor(op.cooling_start * op.iter_max))
     for epoch in (0, first_cooling + 1):
         cooling = epoch > first_cooling
@@ -238,6 +265,11 @@ def test_term_sampling_bit_exact(name, nd, gfs, oracle):
             assert np.array_equal(fl, rfl)
             assert np.array_equal(d.view(np.uint64), rd.view(np.uint64))
             assert v.mean() > 0.9
+            key = f"{name}|{'nd' if nd else '1d'}|epoch{epoch}|tid{tid}|a{a0}"
+            if key in _golden()["traces"]:                   # committed golden digest of the same trace
+                assert _digest(v, sa, sb, fl, d.view(np.uint64)) == _golden()["traces"][key]["sha256"], key
+                n_gold += 1
+    assert n_gold == (4 if name in ("lil", "DRB1-3123") else 0)
     ix.close()
 
 

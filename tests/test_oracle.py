@@ -260,3 +260,22 @@ def test_xoshiro_float_and_bounded_draws(oracle):
     d = oracle.xoshiro_below(7, 10, 20000)
     cnt = np.bincount(d.astype(np.int64), minlength=10)
     assert ((cnt - 2000.0) ** 2 / 2000.0).sum() < 27.9
+
+
+# ---- committed golden vectors (tests/golden/term_traces.json, made by tests/golden/make_golden.py) ------
+def test_oracle_matches_committed_golden_vectors(oracle):
+    """The oracle reproduces the committed digests of the path index and of the sampled terms (warm and cooling
+    epoch, 1D and nD, two Philox streams): integer / IEEE-exact work, independent of the host CPU."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(GOLDEN, "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    with open(os.path.join(GOLDEN, "term_traces.json")) as f:
+        want = json.load(f)
+    got = mg.build(oracle)
+    assert got["index"] == want["index"]
+    assert got["traces"].keys() == want["traces"].keys() and len(want["traces"]) == 16
+    for k, v in want["traces"].items():
+        assert got["traces"][k] == v, k
+    # the hand-derived known answers and the golden file agree where they overlap
+    assert want["index"]["simple"]["path_length"] == [50] and want["index"]["lil"]["path_length"] == [50, 50, 50]
