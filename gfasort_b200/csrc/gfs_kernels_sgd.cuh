@@ -318,11 +318,9 @@ __device__ __forceinline__ void apply_nd(CT* C, unsigned warp_mask, int lane, bo
 }
 
 // D == 0: 1D `Y` (CT must be double).  D >= 1: nD `L`.  K: terms in flight per thread.
+constexpr int SGD_MIN_BLOCKS_K1 = 4, SGD_MIN_BLOCKS_K2 = 3;     // resident blocks per SM the register budget is set for
 template <typename CT, int D, int DS, bool AGG, int K>
-#ifndef GFS_K1_BLOCKS
-#define GFS_K1_BLOCKS 4
-#endif
-__global__ void __launch_bounds__(SGD_BLOCK, (K > 1 ? 3 : GFS_K1_BLOCKS))
+__global__ void __launch_bounds__(SGD_BLOCK, (K > 1 ? SGD_MIN_BLOCKS_K2 : SGD_MIN_BLOCKS_K1))
 sgd_kernel(const SgdArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // shared: first_step (P+1 u64) + path-of-block table (BLK_TABLE u16) when the path table fits
@@ -458,11 +456,6 @@ sgd_kernel(const SgdArgs a) {
         bool any_ok = false;
 #pragma unroll
         for (int k = 0; k < K; ++k) any_ok = any_ok || xs[k].ok;
-#ifdef GFS_EXP_NOAPPLY
-#pragma unroll
-        for (int k = 0; k < K; ++k) { done += xs[k].ok ? 1u : 0u; if (xs[k].dist == 1.2345e-300) ((double*)a.positions)[0] = (double)xs[k].ci[0] + (double)xs[k].cj[0]; }
-        any_ok = false;
-#endif
         if (__any_sync(warp_mask, any_ok)) {
 #pragma unroll
             for (int k = 0; k < K; ++k) {
