@@ -23,11 +23,8 @@ enum : uint32_t { STREAM_SGD = 1, STREAM_STRESS = 2 };
 
 // ---- Philox4x32-10 (Salmon et al. SC'11) -------------------------------------------------------
 __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
-#ifndef GFS_PHILOX_ROUNDS
-#define GFS_PHILOX_ROUNDS 10
-#endif
 #pragma unroll
-    for (int r = 0; r < GFS_PHILOX_ROUNDS; ++r) {
+    for (int r = 0; r < 10; ++r) {
         const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
         const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
         c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
