@@ -88,15 +88,23 @@ struct HostGraph {
     // find_head_nodes (graph_ops.rs:1138-1183): forward handles with no edge going to them, sorted by
     // (earliest rank in any path, node id); nodes on no path sort last (usize::MAX).
     std::vector<uint64_t> heads() const {
-        std::vector<uint64_t> min_pos(nodes_len, ~0ull);                       // build_path_position_map :1111-1125
-        for (uint64_t p = 0; p < P; ++p)
-            for (uint64_t s = path_first[p]; s < path_first[p + 1]; ++s) {
-                const uint64_t id = steps[s] >> 1, r = s - path_first[p];
-                if (id < nodes_len && r < min_pos[id]) min_pos[id] = r;
-            }
         std::vector<uint64_t> hs;
         for (uint64_t id = 0; id < nodes_len; ++id)
             if (present[id] && in_first[(id << 1) + 1] == in_first[id << 1]) hs.push_back(id << 1);
+        // earliest rank in any path (build_path_position_map :1111-1125) — needed for the heads only, and the heads
+        // are few: one sequential pass over the steps against a byte map, instead of a random 8-byte read per step
+        std::vector<uint8_t> is_head(nodes_len, 0);
+        for (uint64_t h : hs) is_head[h >> 1] = 1;
+        std::vector<uint64_t> min_pos(hs.empty() ? 0 : nodes_len, ~0ull);
+        if (!hs.empty())
+            for (uint64_t p = 0; p < P; ++p)
+                for (uint64_t s = path_first[p]; s < path_first[p + 1]; ++s) {
+                    const uint64_t id = steps[s] >> 1;
+                    if (id < nodes_len && is_head[id]) {
+                        const uint64_t r = s - path_first[p];
+                        if (r < min_pos[id]) min_pos[id] = r;
+                    }
+                }
         std::stable_sort(hs.begin(), hs.end(), [&](uint64_t a, uint64_t b) {
             const uint64_t pa = min_pos[a >> 1], pb = min_pos[b >> 1];
             return pa != pb ? pa < pb : a < b;
