@@ -93,6 +93,9 @@ SIGNATURES = {
     "gfs_sort_positions": (C.c_int, [f64p, C.c_uint64, u32p]),
     "gfs_sgd_session_sort": (C.c_int, [C.c_void_p, u32p]),
     "gfs_sgd_sort_1d": (C.c_int, [C.c_void_p, C.POINTER(SgdParams), f64p, u32p, C.POINTER(Stats)]),
+    "gfs_edges_from_paths": (C.c_int, [u64p, u64p, C.c_uint64, C.POINTER(C.c_void_p)]),
+    "gfs_edge_list_get": (C.c_int, [C.c_void_p, C.POINTER(u64p), C.POINTER(u64p), u64p]),
+    "gfs_edge_list_free": (None, [C.c_void_p]),
     "gfs_remap_handles": (C.c_int, [u64p, C.c_uint64, u64p, C.c_uint64, u8p, C.c_uint64]),
     "gfs_find_head_nodes": (C.c_int, [u8p, C.c_uint64, u64p, u64p, C.c_uint64, u64p, u64p, C.c_uint64, u64p, u64p]),
     "gfs_groom_order": (C.c_int, [u8p, C.c_uint64, u64p, u64p, C.c_uint64, u64p, u64p, C.c_uint64, u64p, u64p]),

@@ -23,6 +23,7 @@
 #include <cstdint>
 #include <cstring>
 #include <functional>
+#include <memory>
 #include <new>
 #include <queue>
 #include <set>
@@ -278,3 +279,55 @@ extern "C" int gfs_remap_handles(uint64_t* handles, uint64_t n, const uint64_t* 
     for (auto& x : th) x.join();
     return GFS_OK;
 } catch (...) { return gfs_host_exception("gfs_remap_handles"); }
+
+// The edge set a graph has when only its paths are known (synthetic inputs; what a GFA writer emitting L lines in
+// path order would store): every pair of consecutive steps, one edge per {edge, complement} class as add_edge keeps
+// them (graph_ops.rs:626-638), in order of first occurrence and in the form a path first walks it.
+struct gfs_edge_list { std::vector<uint64_t> from, to; };
+
+extern "C" int gfs_edges_from_paths(const uint64_t* steps, const uint64_t* path_first, uint64_t P, gfs_edge_list** out) try {
+    if (!out || (P && !path_first)) { gfs::set_error("gfs_edges_from_paths: null argument"); return GFS_ERR_INVALID; }
+    *out = nullptr;
+    std::unique_ptr<gfs_edge_list> el(new gfs_edge_list());
+    // open addressing over the canonical (smaller) form of each class; 16-byte keys, grows at 1/2 load
+    struct Slot { uint64_t a, b; };
+    const uint64_t EMPTY = ~0ull;                             // no handle pair is (EMPTY, EMPTY): ids are < 2^63
+    std::vector<Slot> table((size_t)1 << 16, Slot{EMPTY, EMPTY});
+    uint64_t used = 0;
+    auto hash = [](uint64_t a, uint64_t b) {
+        uint64_t x = a * 0x9e3779b97f4a7c15ULL ^ (b + 0x7f4a7c15ULL + (a << 6));
+        x ^= x >> 31; x *= 0xbf58476d1ce4e5b9ULL; return x ^ (x >> 29);
+    };
+    auto insert = [&](std::vector<Slot>& t, uint64_t a, uint64_t b) -> bool {      // true when (a, b) was not there
+        const uint64_t mask = t.size() - 1;
+        for (uint64_t i = hash(a, b) & mask;; i = (i + 1) & mask) {
+            if (t[i].a == a && t[i].b == b) return false;
+            if (t[i].a == EMPTY && t[i].b == EMPTY) { t[i] = Slot{a, b}; return true; }
+        }
+    };
+    for (uint64_t p = 0; p < P; ++p)
+        for (uint64_t s = path_first[p]; s + 1 < path_first[p + 1]; ++s) {
+            const uint64_t a = steps[s], b = steps[s + 1];
+            const uint64_t ca = b ^ 1, cb = a ^ 1;            // the complement edge
+            const bool swap = ca < a || (ca == a && cb < b);
+            if (insert(table, swap ? ca : a, swap ? cb : b)) {
+                el->from.push_back(a); el->to.push_back(b);
+                if (++used * 2 > table.size()) {
+                    std::vector<Slot> bigger(table.size() * 4, Slot{EMPTY, EMPTY});
+                    for (const Slot& q : table) if (!(q.a == EMPTY && q.b == EMPTY)) insert(bigger, q.a, q.b);
+                    table.swap(bigger);
+                }
+            }
+        }
+    *out = el.release();
+    return GFS_OK;
+} catch (...) { return gfs_host_exception("gfs_edges_from_paths"); }
+
+extern "C" int gfs_edge_list_get(const gfs_edge_list* el, const uint64_t** edge_from, const uint64_t** edge_to, uint64_t* n_edges) {
+    if (!el) { gfs::set_error("gfs_edge_list_get: null list"); return GFS_ERR_INVALID; }
+    if (edge_from) *edge_from = el->from.data();
+    if (edge_to) *edge_to = el->to.data();
+    if (n_edges) *n_edges = el->from.size();
+    return GFS_OK;
+}
+extern "C" void gfs_edge_list_free(gfs_edge_list* el) { delete el; }

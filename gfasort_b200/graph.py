@@ -169,21 +169,23 @@ def unique_rows(a: np.ndarray, b: np.ndarray, sort: bool = False) -> np.ndarray:
 
 def edges_from_paths(steps: np.ndarray, path_first: np.ndarray) -> np.ndarray:
     """The edge set a GFA writer would emit for a graph given only by its paths: every pair of consecutive
-    steps, stored once per {edge, complement} like add_edge (graph_ops.rs:626-638).  For synthetic graphs."""
-    steps = np.asarray(steps, dtype=np.uint64)
-    first = np.asarray(path_first, dtype=np.int64)
-    if len(steps) < 2:
-        return np.zeros((0, 2), dtype=np.uint64)
-    a, b = steps[:-1], steps[1:]
-    keep = np.ones(len(a), dtype=bool)
-    keep[first[1:-1] - 1] = False                         # no edge across a path boundary
-    a, b = a[keep], b[keep]
-    # one edge per {a->b, b^1->a^1} class, kept in the form in which a path first walks it (what a GFA
-    # writer emitting L lines in path order would store)
-    ca, cb = b ^ np.uint64(1), a ^ np.uint64(1)
-    swap = (ca < a) | ((ca == a) & (cb < b))
-    idx = unique_pair_index(np.where(swap, ca, a), np.where(swap, cb, b))
-    return np.stack([a[idx], b[idx]], axis=1)
+    steps, stored once per {edge, complement} like add_edge (graph_ops.rs:626-638), in order of first occurrence
+    and in the form in which a path first walks it.  For synthetic graphs (gfs_edges_from_paths)."""
+    import ctypes as C
+
+    from ._cabi import check, lib, u64p
+    steps = np.ascontiguousarray(steps, dtype=np.uint64)
+    first = np.ascontiguousarray(path_first, dtype=np.uint64)
+    h = C.c_void_p()
+    check(lib().gfs_edges_from_paths(steps.ctypes.data_as(u64p), first.ctypes.data_as(u64p), len(first) - 1, C.byref(h)))
+    try:
+        pf, pt, n = u64p(), u64p(), C.c_uint64()
+        check(lib().gfs_edge_list_get(h, C.byref(pf), C.byref(pt), C.byref(n)))
+        if n.value == 0:
+            return np.zeros((0, 2), dtype=np.uint64)
+        return np.stack([np.ctypeslib.as_array(pf, shape=(n.value,)), np.ctypeslib.as_array(pt, shape=(n.value,))], axis=1).copy()
+    finally:
+        lib().gfs_edge_list_free(h)
 
 
 def unique_pair_index(a: np.ndarray, b: np.ndarray) -> np.ndarray:

@@ -218,6 +218,14 @@ int gfs_topological_order(const uint8_t* present, uint64_t nodes_len, const uint
 int gfs_remap_handles(uint64_t* handles, uint64_t n, const uint64_t* new_id, uint64_t table_len, const uint8_t* flip,
                       uint64_t flip_len);
 
+/* The edge set of a graph given only by its paths (synthetic inputs): every pair of consecutive steps, one edge per
+ * {edge, complement} class as add_edge keeps them (src/graph_ops.rs:626-638), in order of first occurrence and in the form
+ * a path first walks it.  Pointers from gfs_edge_list_get stay valid until gfs_edge_list_free. */
+typedef struct gfs_edge_list gfs_edge_list;
+int gfs_edges_from_paths(const uint64_t* steps, const uint64_t* path_first, uint64_t P, gfs_edge_list** out);
+int gfs_edge_list_get(const gfs_edge_list* el, const uint64_t** edge_from, const uint64_t** edge_to, uint64_t* n_edges);
+void gfs_edge_list_free(gfs_edge_list* el);
+
 /* ---- flat ingest and buffered writers (CPU code) ------------------------------
  * gfs_gfa_parse_*: the CLI's parse_gfa (src/bin/gfasort.rs:88-167) in one pass, straight into flat arrays:
  * present / seq_len indexed by node id, node_order (add_node order, src/graph_ops.rs:613-623), edges unique

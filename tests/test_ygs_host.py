@@ -246,3 +246,23 @@ def test_remap_handles_native(gfs):
     assert np.array_equal(got, (mapped << np.uint64(1)) | rev)
     assert np.array_equal(remap_handles(h[:7], table), ((np.where((ids[:7] < 1000) & (table[np.minimum(ids[:7], 999)] != UNMAPPED), table[np.minimum(ids[:7], 999)], ids[:7].astype(np.uint64))) << np.uint64(1)) | (h[:7] & np.uint64(1)))
     assert len(remap_handles(np.zeros(0, dtype=np.uint64), table)) == 0
+
+
+@pytest.mark.parametrize("seed", range(40))
+def test_edges_from_paths_matches_add_edge_semantics(seed, gfs):
+    """gfs_edges_from_paths == add_edge (graph_ops.rs:626-638) applied to every consecutive step pair in path order:
+    one edge per {edge, complement} class, first occurrence wins, kept as first walked; empty / single-step paths."""
+    from gfasort_b200.graph import edges_from_paths
+    rng = np.random.default_rng(seed)
+    steps, first = [], [0]
+    for _ in range(int(rng.integers(0, 6))):
+        steps += [(int(rng.integers(1, 8)) << 1) | int(rng.random() < 0.4) for _ in range(int(rng.integers(0, 15)))]
+        first.append(len(steps))
+    seen, want = set(), []
+    for p in range(len(first) - 1):
+        for s in range(first[p], first[p + 1] - 1):
+            a, b = steps[s], steps[s + 1]
+            if (a, b) not in seen and (b ^ 1, a ^ 1) not in seen:
+                seen.add((a, b)); want.append((a, b))
+    got = edges_from_paths(np.array(steps, dtype=np.uint64), np.array(first, dtype=np.uint64))
+    assert got.shape == (len(want), 2) and got.tolist() == [list(e) for e in want]
