@@ -128,6 +128,7 @@ SIGNATURES = {
     "gfs_p2p_region_ipc_handle": (C.c_int, [C.c_void_p, u8p]),
     "gfs_p2p_region_connect_ipc": (C.c_int, [C.c_void_p, u8p, C.c_uint32, C.c_uint32]),
     "gfs_p2p_region_connect_local": (C.c_int, [C.POINTER(C.c_void_p), C.c_uint32]),
+    "gfs_p2p_region_snapshot": (C.c_int, [C.c_void_p, C.c_void_p]),
     "gfs_p2p_reconcile": (C.c_int, [C.c_void_p, C.c_void_p]),
     "gfs_p2p_region_check": (C.c_int, [C.c_void_p]),
     "gfs_p2p_region_free": (None, [C.c_void_p]),

@@ -262,6 +262,15 @@ extern "C" int gfs_p2p_region_connect_local(gfs_p2p_region* const* regions, uint
     return GFS_OK;
 }
 
+// Asynchronous on `stream`: x_sync <- x.  Called once after the initial positions have been uploaded into x
+// (every replica starts from the same positions, so the snapshots start equal — the invariant the kernel relies on).
+extern "C" int gfs_p2p_region_snapshot(gfs_p2p_region* r, void* stream) {
+    if (!r) { gfs::set_error("gfs_p2p_region_snapshot: null region"); return GFS_ERR_INVALID; }
+    P2P_CUDA(cudaSetDevice(r->device));
+    P2P_CUDA(cudaMemcpyAsync(r->base + r->off_xs, r->base, r->n * r->elem_bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return GFS_OK;
+}
+
 // Asynchronous on `stream`.  Every rank calls it once per reconcile, in the same order.
 extern "C" int gfs_p2p_reconcile(gfs_p2p_region* r, void* stream) {
     if (!r) { gfs::set_error("gfs_p2p_reconcile: null region"); return GFS_ERR_INVALID; }

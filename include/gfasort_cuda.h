@@ -278,6 +278,9 @@ int gfs_p2p_region_ipc_handle(gfs_p2p_region* r, uint8_t* handle /*GFS_P2P_HANDL
 int gfs_p2p_region_connect_ipc(gfs_p2p_region* r, const uint8_t* handles /*world x GFS_P2P_HANDLE_BYTES, rank order*/,
                                uint32_t world, uint32_t rank);
 int gfs_p2p_region_connect_local(gfs_p2p_region* const* regions /*world, rank order*/, uint32_t world);
+/* Asynchronous on `stream`: x_sync <- x.  Once, after the initial positions were uploaded into x (gfs_sgd_session_upload
+ * with the region's x as gfs_launch_cfg.device_positions): all replicas start from equal snapshots. */
+int gfs_p2p_region_snapshot(gfs_p2p_region* r, void* stream);
 /* Asynchronous on `stream`: x <- x_sync + (sum of the replicas' displacements) / (#replicas that moved the element)
  * on every replica, then x_sync <- x.  Every rank calls it once per reconcile, in the same order. */
 int gfs_p2p_reconcile(gfs_p2p_region* r, void* stream);
