@@ -18,6 +18,7 @@ u8p = C.POINTER(C.c_uint8)
 f64p = C.POINTER(C.c_double)
 
 GFS_OK, GFS_ERR_INVALID, GFS_ERR_CUDA, GFS_ERR_NO_DEVICE, GFS_ERR_NO_VALID_PATH = 0, 1, 2, 3, 4
+GFS_P2P_HANDLE_BYTES = 80
 
 
 class GfsError(RuntimeError):
@@ -50,10 +51,17 @@ class Stats(C.Structure):
     _fields_ = [("applied_updates", C.c_uint64), ("attempts", C.c_uint64), ("epochs", C.c_uint64),
                 ("launches", C.c_uint64), ("kernel_seconds", C.c_double), ("h2d_seconds", C.c_double),
                 ("d2h_seconds", C.c_double), ("total_seconds", C.c_double), ("grid", C.c_uint32),
-                ("block", C.c_uint32), ("coord_bytes", C.c_uint32), ("reserved", C.c_uint32)]
+                ("block", C.c_uint32), ("coord_bytes", C.c_uint32), ("n_devices", C.c_uint32),
+                ("window_steps", C.c_uint64), ("coherent", C.c_uint32), ("syncs_per_epoch", C.c_uint32)]
 
     def as_dict(self) -> dict:
-        return {n: getattr(self, n) for n, _ in self._fields_ if n != "reserved"}
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+class ShardPlan(C.Structure):
+    """gfs_shard_plan: who samples what in a replicated multi-GPU run."""
+    _fields_ = [("sample_begin", C.c_uint64), ("sample_end", C.c_uint64), ("path_begin", C.c_uint64),
+                ("path_end", C.c_uint64), ("first_step", C.c_uint64)]
 
 
 class SynthSpec(C.Structure):
@@ -68,7 +76,12 @@ SIGNATURES = {
     "gfs_index_build": (C.c_int, [u64p, u64p, u32p, C.c_uint64, C.c_uint64, C.c_uint64, C.POINTER(C.c_void_p)]),
     "gfs_index_build_shard": (C.c_int, [u64p, u64p, u32p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64,
                                         C.c_uint64, C.c_int32, C.c_int32, u32p, C.POINTER(C.c_void_p)]),
+    "gfs_index_build32": (C.c_int, [u32p, u64p, u32p, C.c_uint64, C.c_uint64, C.c_uint64, C.POINTER(C.c_void_p)]),
+    "gfs_index_build_shard32": (C.c_int, [u32p, u64p, u32p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64,
+                                          C.c_uint64, C.c_int32, C.c_int32, u32p, C.POINTER(C.c_void_p)]),
+    "gfs_index_build_info": (C.c_int, [C.c_void_p, f64p, f64p, f64p, u64p, u32p]),
     "gfs_index_export_relabel": (C.c_int, [C.c_void_p, u32p]),
+    "gfs_index_apply_relabel": (C.c_int, [C.c_void_p, u32p]),
     "gfs_index_export": (C.c_int, [C.c_void_p, u64p, u64p]),
     "gfs_index_export_records": (C.c_int, [C.c_void_p, u64p, u32p]),
     "gfs_index_dims": (C.c_int, [C.c_void_p, u64p, u64p, u64p, u64p]),
@@ -79,6 +92,8 @@ SIGNATURES = {
     "gfs_sgd_nd_cfg": (C.c_int, [C.c_void_p, C.POINTER(SgdParams), C.POINTER(LaunchCfg), C.c_uint32, f64p,
                                  C.POINTER(Stats)]),
     "gfs_stress": (C.c_int, [C.c_void_p, C.c_uint32, C.c_int32, f64p, C.c_uint64, C.c_uint64, f64p, f64p, u64p]),
+    "gfs_stress_partial": (C.c_int, [C.c_void_p, C.c_uint32, C.c_int32, f64p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64,
+                                     C.c_uint64, C.c_uint64, f64p]),
     "gfs_sgd_session_create": (C.c_int, [C.c_void_p, C.POINTER(SgdParams), C.c_uint32, C.POINTER(LaunchCfg),
                                          C.POINTER(C.c_void_p)]),
     "gfs_sgd_session_upload": (C.c_int, [C.c_void_p, f64p]),
@@ -130,8 +145,23 @@ SIGNATURES = {
     "gfs_p2p_region_connect_local": (C.c_int, [C.POINTER(C.c_void_p), C.c_uint32]),
     "gfs_p2p_region_snapshot": (C.c_int, [C.c_void_p, C.c_void_p]),
     "gfs_p2p_reconcile": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "gfs_p2p_reconcile_local": (C.c_int, [C.POINTER(C.c_void_p), C.c_uint32, C.c_void_p]),
     "gfs_p2p_region_check": (C.c_int, [C.c_void_p]),
     "gfs_p2p_region_free": (None, [C.c_void_p]),
+    "gfs_shard_plan_make": (C.c_int, [u64p, C.c_uint64, C.c_uint32, C.c_uint32, C.POINTER(ShardPlan)]),
+    "gfs_shard_epoch_quota": (C.c_uint64, [C.c_uint64, C.POINTER(ShardPlan), C.c_uint64]),
+    "gfs_replica_create": (C.c_int, [C.c_void_p, C.POINTER(SgdParams), C.c_uint32, C.POINTER(LaunchCfg), C.POINTER(ShardPlan),
+                                     C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p)]),
+    "gfs_replica_ipc_handle": (C.c_int, [C.c_void_p, u8p]),
+    "gfs_replica_connect_ipc": (C.c_int, [C.c_void_p, u8p, C.c_uint32, C.c_uint32]),
+    "gfs_replica_connect_local": (C.c_int, [C.POINTER(C.c_void_p), C.c_uint32]),
+    "gfs_replica_upload": (C.c_int, [C.c_void_p, f64p]),
+    "gfs_replica_run": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64]),
+    "gfs_replica_sync": (C.c_int, [C.c_void_p]),
+    "gfs_replica_download": (C.c_int, [C.c_void_p, f64p]),
+    "gfs_replica_stats": (C.c_int, [C.c_void_p, C.POINTER(Stats)]),
+    "gfs_replica_stream": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), u64p, u32p]),
+    "gfs_replica_destroy": (None, [C.c_void_p]),
     "gfs_debug_schedule": (C.c_int, [C.POINTER(SgdParams), f64p]),
     "gfs_debug_zetas": (C.c_int, [C.c_void_p, C.POINTER(SgdParams), f64p, C.c_uint64, u64p]),
 }

@@ -2,25 +2,29 @@
 // Part of libgfasort_cuda.so; included by gfs_lib.cu (one translation unit).  See DESIGN.md §4.
 #pragma once
 #include "gfs_device.cuh"
+#include "gfs_kernels_sgd.cuh"
 
 namespace gfs {
-
-#include "gfs_kernels_sgd.cuh"
 
 // =============================================================================================
 // K4 — sampled stress (sgd.rs:1196-1283)
 // =============================================================================================
 constexpr int STRESS_BLOCK = 256;
-// coords: stride_node doubles per node, the + end's `dims` coordinates first.
+// coords: stride_node doubles per node, the + end's `dims` coordinates first.  g is one index (the whole graph, or
+// one shard whose local step 0 is global step `step_offset`).
 __global__ void __launch_bounds__(STRESS_BLOCK)
 stress_kernel(KernelGraph g, const uint32_t* __restrict__ old_of_new, const double* __restrict__ coords, uint32_t dims,
-              uint32_t stride_node, uint64_t samples, uint32_t seed_lo, uint32_t seed_hi, double* __restrict__ partial /*3 per block*/) {
+              uint32_t stride_node, uint64_t samples, uint32_t seed_lo, uint32_t seed_hi, uint64_t total_steps, uint64_t step_offset,
+              uint64_t step_begin, uint64_t step_end, double* __restrict__ partial /*3 per block*/) {
     __shared__ double red[3][STRESS_BLOCK / 32];
     double sum = 0.0, sum_abs = 0.0, cnt = 0.0;
     const uint2 key = make_uint2(seed_lo, seed_hi);
     for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < samples; k += (uint64_t)gridDim.x * blockDim.x) {
         const uint4 r = philox4x32_10(make_uint4((uint32_t)k, (uint32_t)(k >> 32), 0u, STREAM_STRESS), key);
-        const uint64_t s = __umul64hi(((uint64_t)r.y << 32) | r.x, g.S);
+        // the step is drawn over the whole graph; this index evaluates the samples that land in [step_begin, step_end)
+        const uint64_t sg = __umul64hi(((uint64_t)r.y << 32) | r.x, total_steps);
+        if (sg < step_begin || sg >= step_end) continue;
+        const uint64_t s = sg - step_offset;
         const uint32_t p = find_path(g.first_step, g.P, s);
         const uint64_t f = g.first_step[p];
         const uint32_t n = (uint32_t)(g.first_step[p + 1] - f);

@@ -24,55 +24,15 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
-#include "../../include/gfasort_cuda.h"
-#include "gfs_device.cuh"
+#include "gfs_internal.h"
 
 namespace gfs {
 
 static thread_local std::string g_last_error;
 void set_error(const std::string& s) { g_last_error = s; }
-
-#define GFS_CUDA(call)                                                                              \
-    do {                                                                                            \
-        cudaError_t e__ = (call);                                                                   \
-        if (e__ != cudaSuccess) {                                                                   \
-            set_error(std::string(#call) + " failed: " + cudaGetErrorString(e__) + " (" __FILE__ ":" + \
-                      std::to_string(__LINE__) + ")");                                              \
-            return GFS_ERR_CUDA;                                                                    \
-        }                                                                                           \
-    } while (0)
-
-// Scoped device buffer / stream: transient allocations are released on every return path.
-template <typename T> struct DevBuf {
-    T* p = nullptr;
-    DevBuf() = default;
-    DevBuf(const DevBuf&) = delete;
-    DevBuf& operator=(const DevBuf&) = delete;
-    ~DevBuf() { cudaFree(p); }
-    void release() { cudaFree(p); p = nullptr; }
-    cudaError_t alloc(size_t n) { return cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T)); }
-    cudaError_t up(const T* h, size_t n) { return cudaMemcpy(p, h, n * sizeof(T), cudaMemcpyHostToDevice); }
-    cudaError_t down(T* h, size_t n) { return cudaMemcpy(h, p, n * sizeof(T), cudaMemcpyDeviceToHost); }
-};
-struct ScopedStream {
-    cudaStream_t st = nullptr;
-    ScopedStream() = default;
-    ScopedStream(const ScopedStream&) = delete;
-    ScopedStream& operator=(const ScopedStream&) = delete;
-    ~ScopedStream() { if (st) cudaStreamDestroy(st); }
-    cudaError_t create() { return cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking); }
-};
-
-static double now_s() {
-    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
-}
-static long env_long(const char* name, long dflt) {
-    const char* v = std::getenv(name);
-    if (!v || !*v) return dflt;
-    return std::strtol(v, nullptr, 10);
-}
 
 // =============================================================================================
 // Host twins of the reference's scalar helpers (schedule / zeta table / per-epoch constants).
@@ -160,55 +120,6 @@ static void h_epochs(const gfs_sgd_params& p, std::vector<EpochDesc>& out) {
 // =============================================================================================
 using namespace gfs;
 
-struct gfs_index {
-    int device = 0;
-    uint64_t S = 0, P = 0, N = 0;
-    uint64_t max_path_steps = 0;
-    bool any_multi_step = false;
-    StepRec* d_recs = nullptr;
-    uint64_t* d_first_step = nullptr;   // P+1
-    uint64_t* d_path_len = nullptr;     // P
-    uint32_t* d_new_of_old = nullptr;   // N, null when not relabelled
-    uint32_t* d_old_of_new = nullptr;   // N
-    std::vector<uint64_t> h_first_step;
-    double build_seconds = 0, h2d_seconds = 0;
-};
-
-struct gfs_sgd_session {
-    const gfs_index* ix = nullptr;
-    gfs_sgd_params params{};
-    uint32_t dims = 0;          // 0 = 1D
-    uint32_t DS = 1;            // coordinate stride per node end
-    bool f64 = true;
-    bool aggregate = true;
-    int device = 0;
-    uint32_t grid = 0, block = 0;
-    cudaStream_t stream = nullptr;
-    bool own_stream = false;
-    void* d_pos = nullptr;
-    bool own_pos = false;
-    uint64_t n_elems = 0;       // elements in d_pos
-    double* d_zetas = nullptr; uint32_t zlen = 0;
-    EpochDesc* d_epochs = nullptr; uint32_t n_epochs = 0;
-    uint64_t* d_attempts = nullptr;
-    unsigned long long* d_counters = nullptr;
-    double* d_stage = nullptr;  // f64 staging for nD conversions
-    size_t smem_bytes = 0;
-    uint64_t rng_thread_base = 0;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    double kernel_ms = 0.0;
-    uint64_t launches = 0;
-    double h2d_s = 0, d2h_s = 0;
-    bool ev_pending = false;
-    int inflight = 2;           // terms in flight per thread (kernel template parameter K)
-    bool coherent = true;       // warp-coherent step sampling in the sweep schedule
-    uint64_t window_steps = 0;  // 0 = static schedule
-    uint32_t chunk_updates = 128;
-    unsigned long long* d_work = nullptr;
-    void* d_saved = nullptr;    // gfs_sgd_session_save snapshot of the positions
-    uint64_t samp_base = 0, samp_len = 0;
-};
-
 static int select_device(int dev) {
     int n = 0;
     cudaError_t e = cudaGetDeviceCount(&n);
@@ -248,48 +159,76 @@ extern "C" const char* gfs_device_info(void) {
 // ---------------------------------------------------------------------------------------------
 // index build
 // ---------------------------------------------------------------------------------------------
+static int radix_sort_pairs(uint64_t*& k0, uint64_t*& k1, uint32_t*& v0, uint32_t*& v1, uint32_t* hist, uint64_t n, int passes,
+                            cudaStream_t st, uint64_t* launches);
 
-// Relabel the nodes of a built index.  given == nullptr: order of first appearance in this index's
-// steps (never-visited nodes last); else the caller's permutation (multi-GPU: one for all ranks).
-static int index_relabel(gfs_index* ix, const uint32_t* given, cudaStream_t st) {
-    if (ix->N == 0) return GFS_OK;
-    const uint32_t N = (uint32_t)ix->N;
-    GFS_CUDA(cudaMalloc(&ix->d_new_of_old, (size_t)N * 4));
-    GFS_CUDA(cudaMalloc(&ix->d_old_of_new, (size_t)N * 4));
-    if (given) {
-        GFS_CUDA(cudaMemcpyAsync(ix->d_new_of_old, given, (size_t)N * 4, cudaMemcpyHostToDevice, st));
-        rl_invert<<<(N + 255) / 256, 256, 0, st>>>(ix->d_new_of_old, N, ix->d_old_of_new);
-    } else {
-        DevBuf<unsigned long long> b_first; DevBuf<uint64_t> b_tiles, b_carry;
-        const uint64_t tiles_s = (ix->S + K1_TILE - 1) / K1_TILE, tiles_n = ((uint64_t)N + K1_TILE - 1) / K1_TILE;
-        GFS_CUDA(b_first.alloc(N));
-        GFS_CUDA(b_tiles.alloc(std::max(tiles_s, tiles_n) + 1));
-        GFS_CUDA(b_carry.alloc(1));
-        unsigned long long* d_first = b_first.p; uint64_t* d_tiles = b_tiles.p; uint64_t* d_carry = b_carry.p;
-        GFS_CUDA(cudaMemsetAsync(d_first, 0xff, (size_t)N * 8, st));
-        GFS_CUDA(cudaMemsetAsync(d_carry, 0, 8, st));
-        if (ix->S) {
-            rl_first_occ<<<(unsigned)((ix->S + 255) / 256), 256, 0, st>>>(ix->d_recs, ix->S, N, d_first);
-            rl_tile_count<0><<<(unsigned)tiles_s, K1_THREADS, 0, st>>>(ix->d_recs, d_first, N, ix->S, d_tiles);
-            k1_scan_tiles<<<1, 1024, 0, st>>>(d_tiles, tiles_s, d_carry);
-            rl_assign<0><<<(unsigned)tiles_s, K1_THREADS, 0, st>>>(ix->d_recs, d_first, N, ix->S, d_tiles, ix->d_new_of_old, ix->d_old_of_new);
-        }
-        rl_tile_count<1><<<(unsigned)tiles_n, K1_THREADS, 0, st>>>(nullptr, d_first, N, N, d_tiles);
-        k1_scan_tiles<<<1, 1024, 0, st>>>(d_tiles, tiles_n, d_carry);      // carry continues after the visited nodes
-        rl_assign<1><<<(unsigned)tiles_n, K1_THREADS, 0, st>>>(nullptr, d_first, N, N, d_tiles, ix->d_new_of_old, ix->d_old_of_new);
-        cudaError_t e = cudaStreamSynchronize(st);      // the scratch buffers go out of scope below
-        if (e != cudaSuccess) { set_error(std::string("relabel failed: ") + cudaGetErrorString(e)); return GFS_ERR_CUDA; }
+// Copies `bytes` with several host threads (pageable source -> pinned bounce buffer): one thread tops out
+// well below what a PCIe 5 x16 link drains.
+static void parallel_memcpy(void* dst, const void* src, size_t bytes, int threads) {
+    if (threads <= 1 || bytes < (8u << 20)) { std::memcpy(dst, src, bytes); return; }
+    std::vector<std::thread> pool;
+    const size_t per = ((bytes + threads - 1) / threads + 4095) & ~(size_t)4095;
+    for (int t = 0; t < threads; ++t) {
+        const size_t lo = std::min(bytes, per * t), hi = std::min(bytes, per * (t + 1));
+        if (hi > lo) pool.emplace_back([=] { std::memcpy((char*)dst + lo, (const char*)src + lo, hi - lo); });
     }
+    for (auto& th : pool) th.join();
+}
+
+static int relabel_rewrite(gfs_index* ix, cudaStream_t st) {
+    const uint32_t N = (uint32_t)ix->N;
     if (ix->S) rl_rewrite<<<(unsigned)((ix->S + 255) / 256), 256, 0, st>>>(ix->d_recs, ix->S, N, ix->d_new_of_old);
+    ix->launches += ix->S ? 1 : 0;
     GFS_CUDA(cudaStreamSynchronize(st));
     GFS_CUDA(cudaGetLastError());
     return GFS_OK;
 }
 
-extern "C" int gfs_index_build_shard(const uint64_t* step_handles, const uint64_t* path_first_step,
-                                     const uint32_t* node_len, uint64_t S, uint64_t P, uint64_t N,
-                                     uint64_t path_begin, uint64_t path_end, int32_t device, int32_t relabel_mode,
-                                     const uint32_t* new_of_old, gfs_index** out) {
+// Relabel a built index with the caller's permutation new_of_old[N] (host pointer).
+static int index_relabel_given(gfs_index* ix, const uint32_t* given, cudaStream_t st) {
+    if (ix->N == 0) return GFS_OK;
+    const uint32_t N = (uint32_t)ix->N;
+    GFS_CUDA(cudaMalloc(&ix->d_new_of_old, (size_t)N * 4));
+    GFS_CUDA(cudaMalloc(&ix->d_old_of_new, (size_t)N * 4));
+    GFS_CUDA(cudaMemcpyAsync(ix->d_new_of_old, given, (size_t)N * 4, cudaMemcpyHostToDevice, st));
+    rl_invert<<<(N + 255) / 256, 256, 0, st>>>(ix->d_new_of_old, N, ix->d_old_of_new);
+    ix->launches += 1;
+    return relabel_rewrite(ix, st);
+}
+
+// Relabel by order of first appearance: a stable radix sort of the N first-occurrence keys K1 left in the
+// node table (32-bit keys: 4 passes), never-visited nodes last.
+static int index_relabel_first_occ(gfs_index* ix, const NodeEnt* d_tbl, cudaStream_t st) {
+    if (ix->N == 0) return GFS_OK;
+    const uint32_t N = (uint32_t)ix->N;
+    GFS_CUDA(cudaMalloc(&ix->d_new_of_old, (size_t)N * 4));
+    GFS_CUDA(cudaMalloc(&ix->d_old_of_new, (size_t)N * 4));
+    {
+        DevBuf<uint64_t> b_k0, b_k1; DevBuf<uint32_t> b_v1, b_hist;
+        const uint32_t n_blocks = (uint32_t)(((uint64_t)N + RS_TILE - 1) / RS_TILE);
+        GFS_CUDA(b_k0.alloc(N)); GFS_CUDA(b_k1.alloc(N)); GFS_CUDA(b_v1.alloc(N)); GFS_CUDA(b_hist.alloc((size_t)256 * n_blocks));
+        uint64_t *k0 = b_k0.p, *k1 = b_k1.p; uint32_t *v0 = ix->d_old_of_new, *v1 = b_v1.p;
+        rl_keys<<<(N + 255) / 256, 256, 0, st>>>(d_tbl, N, k0, v0);
+        ix->launches += 1;
+        int rc = radix_sort_pairs(k0, k1, v0, v1, b_hist.p, N, 4, st, &ix->launches);     // even number of passes: result in v0
+        if (rc) return rc;
+        rl_invert<<<(N + 255) / 256, 256, 0, st>>>(ix->d_old_of_new, N, ix->d_new_of_old);
+        ix->launches += 1;
+        GFS_CUDA(cudaStreamSynchronize(st));        // the scratch buffers go out of scope
+    }
+    return relabel_rewrite(ix, st);
+}
+
+// PathIndex::from_graph (src/sgd.rs:34-71) for paths [path_begin, path_end) on `device`.
+// The step array is streamed through two device staging buffers in chunks: the copy of chunk c+1 (stream
+// s_copy) runs under the K1 kernel of chunk c (stream s_k).  A page-locked source is read by the copy engine
+// directly; a pageable one (a Rust Vec) goes through two pinned bounce buffers filled by several host threads,
+// so that the host-side staging of chunk c+1 also runs under the DMA of chunk c.
+// relabel_mode: 0 none, 1 first-appearance order, 2 the given permutation.
+template <typename HT>
+static int build_shard_impl(const HT* step_handles, const uint64_t* path_first_step, const uint32_t* node_len, uint64_t S,
+                            uint64_t P, uint64_t N, uint64_t path_begin, uint64_t path_end, int32_t device,
+                            int32_t relabel_mode, const uint32_t* new_of_old, gfs_index** out) {
     if (!out) { set_error("gfs_index_build: out is null"); return GFS_ERR_INVALID; }
     *out = nullptr;
     if (!path_first_step || (S && !step_handles) || (N && !node_len)) { set_error("gfs_index_build: null input array"); return GFS_ERR_INVALID; }
@@ -301,6 +240,7 @@ extern "C" int gfs_index_build_shard(const uint64_t* step_handles, const uint64_
         if (path_first_step[p + 1] - path_first_step[p] >= (1ull << 32)) { set_error("gfs_index_build: a path has >= 2^32 steps"); return GFS_ERR_INVALID; }
     }
     if (path_end - path_begin >= (1ull << 31)) { set_error("gfs_index_build: too many paths"); return GFS_ERR_INVALID; }
+    if (relabel_mode == 2 && !new_of_old) { set_error("gfs_index_build: relabel_mode 2 needs a permutation"); return GFS_ERR_INVALID; }
     int rc = select_device(device);
     if (rc) return rc;
 
@@ -319,82 +259,228 @@ extern "C" int gfs_index_build_shard(const uint64_t* step_handles, const uint64_
     auto fail = [&](int code) { gfs_index_free(ix); return code; };
 #define IX_CUDA(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { set_error(std::string(#call) + " failed: " + cudaGetErrorString(e__)); return fail(GFS_ERR_CUDA); } } while (0)
 
-    ScopedStream sst;
-    IX_CUDA(sst.create());
-    cudaStream_t st = sst.st;
-    DevBuf<uint64_t> b_path_base, b_carry, b_handles, b_tiles; DevBuf<uint32_t> b_node_len;
+    ScopedStream sk, sc;
+    IX_CUDA(sk.create());
+    IX_CUDA(sc.create());
+    cudaStream_t s_k = sk.st, s_copy = sc.st;
+    const bool first_occ = relabel_mode == 1;
+    uint32_t key_shift = 0;
+    while ((ix->S >> key_shift) >= 0xffffffffull) ++key_shift;
+
+    // chunks of at most CH steps (a multiple of the tile, so no tile straddles two chunks)
+    uint64_t CH = (uint64_t)env_long("GFASORT_INDEX_CHUNK", 1l << 24);
+    CH = std::max<uint64_t>(K1_TILE, (CH / K1_TILE) * K1_TILE);
+    const uint64_t chunk_cap = std::min<uint64_t>(CH, std::max<uint64_t>(ix->S, 1));
+    const uint64_t n_chunks = (ix->S + CH - 1) / CH;
+    const uint64_t tiles_total = (ix->S + K1_TILE - 1) / K1_TILE;
+
+    DevBuf<uint64_t> b_desc; DevBuf<unsigned int> b_ticket; DevBuf<uint32_t> b_node_len; DevBuf<NodeEnt> b_tbl;
+    DevBuf<HT> b_h[2];
     IX_CUDA(cudaMalloc(&ix->d_first_step, (ix->P + 1) * 8));
     IX_CUDA(cudaMalloc(&ix->d_path_len, std::max<uint64_t>(ix->P, 1) * 8));
     IX_CUDA(cudaMalloc(&ix->d_recs, std::max<uint64_t>(ix->S, 1) * sizeof(StepRec)));
-    IX_CUDA(b_path_base.alloc(ix->P + 1));
-    IX_CUDA(b_carry.alloc(1));
+    IX_CUDA(b_desc.alloc(tiles_total + 1));
+    IX_CUDA(b_ticket.alloc(2));
+    IX_CUDA(cudaMemsetAsync(b_ticket.p, 0, 2 * sizeof(unsigned int), s_k));
     IX_CUDA(b_node_len.alloc(N));
-    uint64_t* d_path_base = b_path_base.p; uint64_t* d_carry = b_carry.p; uint32_t* d_node_len = b_node_len.p;
-    IX_CUDA(cudaMemsetAsync(d_carry, 0, 8, st));
-    IX_CUDA(cudaMemsetAsync(d_path_base, 0, (ix->P + 1) * 8, st));
+    IX_CUDA(b_tbl.alloc(N));
+    IX_CUDA(b_h[0].alloc(chunk_cap));
+    if (n_chunks > 1) IX_CUDA(b_h[1].alloc(chunk_cap));
+    IX_CUDA(cudaMemsetAsync(b_desc.p, 0, (tiles_total + 1) * 8, s_k));
+    IX_CUDA(cudaMemsetAsync(ix->d_path_len, 0, std::max<uint64_t>(ix->P, 1) * 8, s_k));
     const double t_h2d0 = now_s();
-    IX_CUDA(cudaMemcpyAsync(ix->d_first_step, ix->h_first_step.data(), (ix->P + 1) * 8, cudaMemcpyHostToDevice, st));
-    if (N) IX_CUDA(cudaMemcpyAsync(d_node_len, node_len, N * 4, cudaMemcpyHostToDevice, st));
-    double h2d = now_s() - t_h2d0;
+    IX_CUDA(cudaMemcpyAsync(ix->d_first_step, ix->h_first_step.data(), (ix->P + 1) * 8, cudaMemcpyHostToDevice, s_k));
+    if (N) {
+        IX_CUDA(cudaMemcpyAsync(b_node_len.p, node_len, N * 4, cudaMemcpyHostToDevice, s_k));
+        k1_init_table<<<(unsigned)((N + 255) / 256), 256, 0, s_k>>>(b_node_len.p, (uint32_t)N, b_tbl.p);
+        ix->launches += 1;
+    }
 
-    // chunks of at most CH steps (multiple of the tile) so that the transient handle buffer stays small
-    uint64_t CH = (uint64_t)env_long("GFASORT_INDEX_CHUNK", 1l << 28);
-    CH = std::max<uint64_t>(K1_TILE, (CH / K1_TILE) * K1_TILE);
-    const uint64_t chunk_cap = std::min<uint64_t>(CH, std::max<uint64_t>(ix->S, 1));
-    const uint64_t tiles_cap = (chunk_cap + K1_TILE - 1) / K1_TILE;
-    IX_CUDA(b_handles.alloc(chunk_cap));
-    IX_CUDA(b_tiles.alloc(tiles_cap + 1));
-    uint64_t* d_handles = b_handles.p; uint64_t* d_tiles = b_tiles.p;
-    uint32_t p_lo = 0;
-    for (uint64_t c0 = 0; c0 < ix->S; c0 += CH) {
-        const uint64_t clen = std::min(CH, ix->S - c0);
-        const uint64_t n_tiles = (clen + K1_TILE - 1) / K1_TILE;
-        const double t0 = now_s();
-        IX_CUDA(cudaMemcpyAsync(d_handles, step_handles + s_begin + c0, clen * 8, cudaMemcpyHostToDevice, st));
-        IX_CUDA(cudaStreamSynchronize(st));
-        h2d += now_s() - t0;
-        k1_tile_sums<<<(unsigned)n_tiles, K1_THREADS, 0, st>>>(d_handles, d_node_len, clen, N, d_tiles);
-        k1_scan_tiles<<<1, 1024, 0, st>>>(d_tiles, n_tiles, d_carry);
-        // paths whose first step lies in this chunk: [p_lo, p_hi)
-        uint32_t p_hi = p_lo;
-        while (p_hi < ix->P && ix->h_first_step[p_hi] < c0 + clen) ++p_hi;
-        if (p_hi > p_lo)
-            k1_path_base<<<p_hi - p_lo, K1_THREADS, 0, st>>>(d_handles, d_node_len, N, ix->d_first_step, p_lo, p_hi, c0,
-                                                            c0 + clen, d_tiles, d_path_base);
-        k1_write_recs<<<(unsigned)n_tiles, K1_THREADS, 0, st>>>(d_handles, d_node_len, N, ix->d_first_step, (uint32_t)ix->P,
-                                                               c0, clen, d_tiles, d_path_base, ix->d_recs);
-        IX_CUDA(cudaGetLastError());
-        p_lo = p_hi;
+    // is the caller's step array page-locked?  (cudaHostAlloc / cudaHostRegister memory: the copy engine reads it directly)
+    bool src_pinned = false;
+    if (ix->S) {
+        cudaPointerAttributes attr{};
+        if (cudaPointerGetAttributes(&attr, step_handles + s_begin) == cudaSuccess) src_pinned = attr.type == cudaMemoryTypeHost;
+        else (void)cudaGetLastError();
     }
-    // paths that start at S (empty tail paths) and the sentinel base[P] = total
-    if (ix->P) {
-        // every empty path at the very end has first_step == S: base = total
-        for (uint32_t p = p_lo; p <= ix->P; ++p) k1_set_u64<<<1, 1, 0, st>>>(d_path_base, p, d_carry);
-        k1_path_len<<<(unsigned)((ix->P + 255) / 256), 256, 0, st>>>(d_path_base, (uint32_t)ix->P, ix->d_path_len);
+    struct Pinned { void* p = nullptr; ~Pinned() { if (p) cudaFreeHost(p); } } pin[2];
+    const int copy_threads = (int)std::max<long>(1, env_long("GFASORT_COPY_THREADS", std::min<long>(8, std::max<long>(1, (long)std::thread::hardware_concurrency() / 2))));
+    if (ix->S && !src_pinned) {
+        IX_CUDA(cudaHostAlloc(&pin[0].p, chunk_cap * sizeof(HT), cudaHostAllocDefault));
+        if (n_chunks > 1) IX_CUDA(cudaHostAlloc(&pin[1].p, chunk_cap * sizeof(HT), cudaHostAllocDefault));
     }
-    IX_CUDA(cudaStreamSynchronize(st));
-    IX_CUDA(cudaGetLastError());
-    b_handles.release(); b_tiles.release(); b_path_base.release(); b_carry.release(); b_node_len.release();   // before relabelling allocates
-    if (relabel_mode == 2 && !new_of_old) { set_error("gfs_index_build: relabel_mode 2 needs a permutation"); return fail(GFS_ERR_INVALID); }
-    if (relabel_mode == 1 || relabel_mode == 2) {
-        rc = index_relabel(ix, relabel_mode == 2 ? new_of_old : nullptr, st);
-        if (rc) return fail(rc);
+    cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_k[2] = {nullptr, nullptr};
+    std::vector<cudaEvent_t> ev_t;      // kernel timing: one pair per chunk
+    auto drop_events = [&]() {
+        for (int b = 0; b < 2; ++b) { if (ev_h2d[b]) cudaEventDestroy(ev_h2d[b]); if (ev_k[b]) cudaEventDestroy(ev_k[b]); }
+        for (cudaEvent_t e : ev_t) cudaEventDestroy(e);
+    };
+#define IXE_CUDA(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { set_error(std::string(#call) + " failed: " + cudaGetErrorString(e__)); drop_events(); return fail(GFS_ERR_CUDA); } } while (0)
+    for (int b = 0; b < 2; ++b) {
+        IXE_CUDA(cudaEventCreateWithFlags(&ev_h2d[b], cudaEventDisableTiming));
+        IXE_CUDA(cudaEventCreateWithFlags(&ev_k[b], cudaEventDisableTiming));
     }
-    ix->h2d_seconds = h2d;
+    for (uint64_t c = 0; c < n_chunks; ++c) {
+        const int b = (int)(c & 1);
+        const uint64_t c0 = c * CH, clen = std::min(CH, ix->S - c0);
+        const size_t bytes = clen * sizeof(HT);
+        const HT* src = step_handles + s_begin + c0;
+        if (c >= 2) IXE_CUDA(cudaStreamWaitEvent(s_copy, ev_k[b], 0));          // the kernel of chunk c-2 is done with this buffer
+        if (src_pinned) {
+            IXE_CUDA(cudaMemcpyAsync(b_h[b].p, src, bytes, cudaMemcpyHostToDevice, s_copy));
+        } else {
+            if (c >= 2) IXE_CUDA(cudaEventSynchronize(ev_h2d[b]));             // the DMA of chunk c-2 has drained this bounce buffer
+            parallel_memcpy(pin[b].p, src, bytes, copy_threads);
+            IXE_CUDA(cudaMemcpyAsync(b_h[b].p, pin[b].p, bytes, cudaMemcpyHostToDevice, s_copy));
+        }
+        IXE_CUDA(cudaEventRecord(ev_h2d[b], s_copy));
+        IXE_CUDA(cudaStreamWaitEvent(s_k, ev_h2d[b], 0));
+        IXE_CUDA(cudaMemsetAsync(b_ticket.p, 0, sizeof(unsigned int), s_k));
+        cudaEvent_t t0 = nullptr, t1 = nullptr;
+        IXE_CUDA(cudaEventCreate(&t0)); ev_t.push_back(t0);
+        IXE_CUDA(cudaEventCreate(&t1)); ev_t.push_back(t1);
+        IXE_CUDA(cudaEventRecord(t0, s_k));
+        const unsigned n_tiles = (unsigned)((clen + K1_TILE - 1) / K1_TILE);
+        if (first_occ)
+            k1_scan_write<HT, true><<<n_tiles, K1_THREADS, 0, s_k>>>(b_h[b].p, b_tbl.p, (uint32_t)N, ix->d_first_step, (uint32_t)ix->P, c0, clen,
+                                                                      b_desc.p, b_ticket.p, key_shift, ix->d_recs, ix->d_path_len);
+        else
+            k1_scan_write<HT, false><<<n_tiles, K1_THREADS, 0, s_k>>>(b_h[b].p, b_tbl.p, (uint32_t)N, ix->d_first_step, (uint32_t)ix->P, c0, clen,
+                                                                       b_desc.p, b_ticket.p, key_shift, ix->d_recs, ix->d_path_len);
+        IXE_CUDA(cudaGetLastError());
+        IXE_CUDA(cudaEventRecord(t1, s_k));
+        IXE_CUDA(cudaEventRecord(ev_k[b], s_k));
+        ix->launches += 1;
+    }
+    IXE_CUDA(cudaStreamSynchronize(s_k));
+    IXE_CUDA(cudaGetLastError());
+    {
+        unsigned int tk[2] = {0, 0};
+        IXE_CUDA(cudaMemcpy(tk, b_ticket.p, sizeof tk, cudaMemcpyDeviceToHost));
+        if (tk[1]) { set_error("gfs_index_build: the scan's look-back watchdog tripped (a tile never published its prefix)"); drop_events(); return fail(GFS_ERR_CUDA); }
+    }
+    ix->h2d_seconds = now_s() - t_h2d0;          // wall time of the streamed copy + K1 (they overlap)
+    for (size_t k = 0; k + 1 < ev_t.size(); k += 2) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, ev_t[k], ev_t[k + 1]) == cudaSuccess) ix->kernel_seconds += ms * 1e-3;
+    }
+    drop_events();
+#undef IXE_CUDA
+    b_h[0].release(); b_h[1].release(); b_desc.release(); b_ticket.release(); b_node_len.release();   // before relabelling allocates
+    if (relabel_mode == 1) rc = index_relabel_first_occ(ix, b_tbl.p, s_k);
+    else if (relabel_mode == 2) rc = index_relabel_given(ix, new_of_old, s_k);
+    if (rc) return fail(rc);
     ix->build_seconds = now_s() - t_begin;
     *out = ix;
     return GFS_OK;
 #undef IX_CUDA
 }
 
+// ---- multi-GPU index (GFASORT_GPUS > 1): one shard per device, built concurrently, one shared relabelling ----------
+template <typename HT>
+static int build_multi_impl(const HT* step_handles, const uint64_t* path_first_step, const uint32_t* node_len, uint64_t S,
+                            uint64_t P, uint64_t N, uint32_t G, int32_t relabel, gfs_index** out) {
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { set_error("no CUDA device available — libgfasort_cuda has no CPU fallback"); return GFS_ERR_NO_DEVICE; }
+    if ((int)G > ndev) { set_error("GFASORT_GPUS=" + std::to_string(G) + " but only " + std::to_string(ndev) + " CUDA devices are visible"); return GFS_ERR_INVALID; }
+    if (G > GFS_P2P_MAX_RANKS) { set_error("GFASORT_GPUS too large"); return GFS_ERR_INVALID; }
+    if (!path_first_step || path_first_step[0] != 0 || path_first_step[P] != S) { set_error("gfs_index_build: path_first_step must start at 0 and end at S"); return GFS_ERR_INVALID; }
+    const double t0 = now_s();
+    gfs_index* mix = new gfs_index();
+    mix->device = 0; mix->S = S; mix->P = P; mix->N = N;
+    mix->h_first_step.assign(path_first_step, path_first_step + P + 1);
+    for (uint64_t p = 0; p < P; ++p) {
+        const uint64_t c = path_first_step[p + 1] - path_first_step[p];
+        mix->max_path_steps = std::max(mix->max_path_steps, c);
+        if (c > 1) mix->any_multi_step = true;
+    }
+    mix->shards.assign(G, nullptr);
+    mix->plans.resize(G);
+    for (uint32_t g = 0; g < G; ++g) gfs_shard_plan_make(path_first_step, P, g, G, &mix->plans[g]);
+    std::vector<int> rcs(G, GFS_OK);
+    std::vector<std::string> errs(G);
+    {   // every device pulls its own shard over its own PCIe link; shard 0 also derives the permutation
+        std::vector<std::thread> pool;
+        for (uint32_t g = 0; g < G; ++g)
+            pool.emplace_back([&, g] {
+                const gfs_shard_plan& pl = mix->plans[g];
+                rcs[g] = build_shard_impl<HT>(step_handles, path_first_step, node_len, S, P, N, pl.path_begin, pl.path_end, (int32_t)g,
+                                              (relabel && g == 0) ? 1 : 0, nullptr, &mix->shards[g]);
+                if (rcs[g]) errs[g] = g_last_error;
+            });
+        for (auto& th : pool) th.join();
+    }
+    for (uint32_t g = 0; g < G; ++g)
+        if (rcs[g]) { set_error("shard " + std::to_string(g) + ": " + errs[g]); gfs_index_free(mix); return rcs[g]; }
+    if (relabel && N) {     // replicas are reconciled element-wise: all shards use shard 0's node order
+        std::vector<uint32_t> perm(N);
+        int rc = gfs_index_export_relabel(mix->shards[0], perm.data());
+        if (rc) { gfs_index_free(mix); return rc; }
+        std::vector<std::thread> pool;
+        for (uint32_t g = 1; g < G; ++g)
+            pool.emplace_back([&, g] {
+                rcs[g] = gfs_index_apply_relabel(mix->shards[g], perm.data());
+                if (rcs[g]) errs[g] = g_last_error;
+            });
+        for (auto& th : pool) th.join();
+        for (uint32_t g = 1; g < G; ++g)
+            if (rcs[g]) { set_error("shard " + std::to_string(g) + ": " + errs[g]); gfs_index_free(mix); return rcs[g]; }
+    }
+    for (uint32_t g = 0; g < G; ++g) {
+        mix->launches += mix->shards[g]->launches;
+        mix->kernel_seconds = std::max(mix->kernel_seconds, mix->shards[g]->kernel_seconds);
+        mix->h2d_seconds = std::max(mix->h2d_seconds, mix->shards[g]->h2d_seconds);
+    }
+    mix->build_seconds = now_s() - t0;
+    *out = mix;
+    return GFS_OK;
+}
+
+template <typename HT>
+static int index_build_env(const HT* step_handles, const uint64_t* path_first_step, const uint32_t* node_len, uint64_t S, uint64_t P,
+                           uint64_t N, gfs_index** out) {
+    if (!out) { set_error("gfs_index_build: out is null"); return GFS_ERR_INVALID; }
+    const long gpus = env_long("GFASORT_GPUS", 1);
+    const int relabel = env_long("GFASORT_RELABEL", 1) ? 1 : 0;
+    if (gpus > 1) return build_multi_impl<HT>(step_handles, path_first_step, node_len, S, P, N, (uint32_t)gpus, relabel, out);
+    return build_shard_impl<HT>(step_handles, path_first_step, node_len, S, P, N, 0, P, -1, relabel, nullptr, out);
+}
+
+extern "C" int gfs_index_build_shard(const uint64_t* step_handles, const uint64_t* path_first_step,
+                                     const uint32_t* node_len, uint64_t S, uint64_t P, uint64_t N,
+                                     uint64_t path_begin, uint64_t path_end, int32_t device, int32_t relabel_mode,
+                                     const uint32_t* new_of_old, gfs_index** out) {
+    return build_shard_impl<uint64_t>(step_handles, path_first_step, node_len, S, P, N, path_begin, path_end, device, relabel_mode, new_of_old, out);
+}
+extern "C" int gfs_index_build_shard32(const uint32_t* step_handles, const uint64_t* path_first_step,
+                                       const uint32_t* node_len, uint64_t S, uint64_t P, uint64_t N,
+                                       uint64_t path_begin, uint64_t path_end, int32_t device, int32_t relabel_mode,
+                                       const uint32_t* new_of_old, gfs_index** out) {
+    return build_shard_impl<uint32_t>(step_handles, path_first_step, node_len, S, P, N, path_begin, path_end, device, relabel_mode, new_of_old, out);
+}
 extern "C" int gfs_index_build(const uint64_t* step_handles, const uint64_t* path_first_step, const uint32_t* node_len,
                                uint64_t S, uint64_t P, uint64_t N, gfs_index** out) {
-    return gfs_index_build_shard(step_handles, path_first_step, node_len, S, P, N, 0, P, -1,
-                                 env_long("GFASORT_RELABEL", 1) ? 1 : 0, nullptr, out);
+    return index_build_env<uint64_t>(step_handles, path_first_step, node_len, S, P, N, out);
+}
+extern "C" int gfs_index_build32(const uint32_t* step_handles, const uint64_t* path_first_step, const uint32_t* node_len,
+                                 uint64_t S, uint64_t P, uint64_t N, gfs_index** out) {
+    return index_build_env<uint32_t>(step_handles, path_first_step, node_len, S, P, N, out);
+}
+
+extern "C" int gfs_index_apply_relabel(gfs_index* ix, const uint32_t* new_of_old) {
+    if (!ix || !new_of_old) { set_error("gfs_index_apply_relabel: null argument"); return GFS_ERR_INVALID; }
+    if (!ix->shards.empty()) { set_error("gfs_index_apply_relabel: not for a multi-GPU index (its shards already share one order)"); return GFS_ERR_INVALID; }
+    if (ix->d_new_of_old) { set_error("gfs_index_apply_relabel: the index is already relabelled"); return GFS_ERR_INVALID; }
+    GFS_CUDA(cudaSetDevice(ix->device));
+    ScopedStream ss;
+    GFS_CUDA(ss.create());
+    return index_relabel_given(ix, new_of_old, ss.st);
 }
 
 extern "C" int gfs_index_export_relabel(const gfs_index* ix, uint32_t* new_of_old) {
     if (!ix || !new_of_old) { set_error("gfs_index_export_relabel: null argument"); return GFS_ERR_INVALID; }
+    if (!ix->shards.empty()) return gfs_index_export_relabel(ix->shards[0], new_of_old);
     GFS_CUDA(cudaSetDevice(ix->device));
     if (ix->d_new_of_old) GFS_CUDA(cudaMemcpy(new_of_old, ix->d_new_of_old, ix->N * 4, cudaMemcpyDeviceToHost));
     else for (uint64_t i = 0; i < ix->N; ++i) new_of_old[i] = (uint32_t)i;
@@ -403,9 +489,12 @@ extern "C" int gfs_index_export_relabel(const gfs_index* ix, uint32_t* new_of_ol
 
 extern "C" void gfs_index_free(gfs_index* ix) {
     if (!ix) return;
-    cudaSetDevice(ix->device);
-    cudaFree(ix->d_recs); cudaFree(ix->d_first_step); cudaFree(ix->d_path_len);
-    cudaFree(ix->d_new_of_old); cudaFree(ix->d_old_of_new);
+    for (gfs_index* sh : ix->shards) gfs_index_free(sh);
+    if (ix->shards.empty()) {
+        cudaSetDevice(ix->device);
+        cudaFree(ix->d_recs); cudaFree(ix->d_first_step); cudaFree(ix->d_path_len);
+        cudaFree(ix->d_new_of_old); cudaFree(ix->d_old_of_new);
+    }
     delete ix;
 }
 
@@ -418,8 +507,27 @@ extern "C" int gfs_index_dims(const gfs_index* ix, uint64_t* S, uint64_t* P, uin
     return GFS_OK;
 }
 
+extern "C" int gfs_index_build_info(const gfs_index* ix, double* build_seconds, double* copy_seconds, double* kernel_seconds,
+                                    uint64_t* launches, uint32_t* n_devices) {
+    if (!ix) { set_error("gfs_index_build_info: null index"); return GFS_ERR_INVALID; }
+    if (build_seconds) *build_seconds = ix->build_seconds;
+    if (copy_seconds) *copy_seconds = ix->h2d_seconds;
+    if (kernel_seconds) *kernel_seconds = ix->kernel_seconds;
+    if (launches) *launches = ix->launches;
+    if (n_devices) *n_devices = ix->shards.empty() ? 1u : (uint32_t)ix->shards.size();
+    return GFS_OK;
+}
+
 extern "C" int gfs_index_export(const gfs_index* ix, uint64_t* step_pos, uint64_t* path_len) {
     if (!ix) { set_error("gfs_index_export: null index"); return GFS_ERR_INVALID; }
+    if (!ix->shards.empty()) {      // shard g holds paths [path_begin, path_end); a path two shards share has equal values in both
+        for (size_t g = 0; g < ix->shards.size(); ++g) {
+            const gfs_shard_plan& pl = ix->plans[g];
+            int rc = gfs_index_export(ix->shards[g], step_pos ? step_pos + pl.first_step : nullptr, path_len ? path_len + pl.path_begin : nullptr);
+            if (rc) return rc;
+        }
+        return GFS_OK;
+    }
     GFS_CUDA(cudaSetDevice(ix->device));
     if (step_pos && ix->S) {
         DevBuf<uint64_t> d;
@@ -438,6 +546,14 @@ extern "C" int gfs_index_export(const gfs_index* ix, uint64_t* step_pos, uint64_
 
 extern "C" int gfs_index_export_records(const gfs_index* ix, uint64_t* step_handle, uint32_t* step_node_len) {
     if (!ix || !step_handle || !step_node_len) { set_error("gfs_index_export_records: null argument"); return GFS_ERR_INVALID; }
+    if (!ix->shards.empty()) {
+        for (size_t g = 0; g < ix->shards.size(); ++g) {
+            const gfs_shard_plan& pl = ix->plans[g];
+            int rc = gfs_index_export_records(ix->shards[g], step_handle + pl.first_step, step_node_len + pl.first_step);
+            if (rc) return rc;
+        }
+        return GFS_OK;
+    }
     GFS_CUDA(cudaSetDevice(ix->device));
     if (!ix->S) return GFS_OK;
     DevBuf<uint64_t> dh; DevBuf<uint32_t> dl;
@@ -522,6 +638,11 @@ extern "C" int gfs_sgd_session_create(const gfs_index* ix, const gfs_sgd_params*
     if (!out) { set_error("gfs_sgd_session_create: out is null"); return GFS_ERR_INVALID; }
     *out = nullptr;
     if (!ix) { set_error("gfs_sgd_session_create: null index"); return GFS_ERR_INVALID; }
+    if (!ix->shards.empty()) {
+        set_error("gfs_sgd_session_create: this index spans several GPUs (GFASORT_GPUS); use gfs_sgd_1d / gfs_sgd_nd, or one "
+                  "gfs_replica per shard");
+        return GFS_ERR_INVALID;
+    }
     int rc = validate_params(params);
     if (rc) return rc;
     if (dims > 8) { set_error("gfs_sgd_session_create: dims must be <= 8"); return GFS_ERR_INVALID; }
@@ -607,8 +728,11 @@ extern "C" int gfs_sgd_session_create(const gfs_index* ix, const gfs_sgd_params*
         // auto: graphs whose records fit in half of L2 need no window; otherwise 2^20 steps (16 MB of
         // records, several times the number of terms in flight) but never more than 1/8 of the range
         if (w < 0) w = (ix->S * sizeof(StepRec) > (64ull << 20)) ? (long)std::min<uint64_t>(1ull << 20, s->samp_len / 8) : 0;
-        if ((uint64_t)w >= s->samp_len) w = 0;
-        s->window_steps = w > 0 ? std::max<uint64_t>((uint64_t)w, 1024) : 0;
+        // a window is at least 1024 steps; window + one warp of consecutive steps must fit in the sampled range
+        // (sample_s1 wraps a step past the end of the range exactly once), else the static schedule is used
+        uint64_t ws = w > 0 ? std::max<uint64_t>((uint64_t)w, 1024) : 0;
+        if (ws + 32 > s->samp_len) ws = 0;
+        s->window_steps = ws;
         s->chunk_updates = (uint32_t)std::max<long>(1, env_long("GFASORT_CHUNK", 256));
         s->coherent = env_long("GFASORT_COHERENT", 1) != 0;
         SS_CUDA(cudaMalloc(&s->d_work, 8));
@@ -768,12 +892,15 @@ extern "C" int gfs_sgd_session_stats(gfs_sgd_session* s, gfs_stats* st) {
     st->kernel_seconds = s->kernel_ms * 1e-3;
     st->h2d_seconds = s->h2d_s; st->d2h_seconds = s->d2h_s;
     st->grid = s->grid; st->block = s->block; st->coord_bytes = s->f64 ? 8 : 4;
+    st->n_devices = 1; st->window_steps = s->window_steps; st->coherent = (s->window_steps > 0 && s->coherent) ? 1u : 0u;
+    st->syncs_per_epoch = 0;
     return GFS_OK;
 }
 
 static int run_whole(const gfs_index* ix, const gfs_sgd_params* params, const gfs_launch_cfg* cfg, uint32_t dims,
                      double* pos_inout, gfs_stats* stats) {
     if (!pos_inout) { set_error("positions buffer is null"); return GFS_ERR_INVALID; }
+    if (ix && !ix->shards.empty()) return gfs_multi_run_whole(ix, params, cfg, dims, pos_inout, stats);    // GFASORT_GPUS > 1
     const double t0 = now_s();
     gfs_sgd_session* s = nullptr;
     int rc = gfs_sgd_session_create(ix, params, dims, cfg, &s);
@@ -810,34 +937,67 @@ extern "C" int gfs_sgd_nd(const gfs_index* ix, const gfs_sgd_params* params, uin
 // ---------------------------------------------------------------------------------------------
 // stress
 // ---------------------------------------------------------------------------------------------
-extern "C" int gfs_stress(const gfs_index* ix, uint32_t dims, int32_t layout_order, const double* coords,
-                          uint64_t samples, uint64_t seed, double* rms_rel, double* mean_abs_rel, uint64_t* counted) {
-    if (!ix || !coords || dims < 1) { set_error("gfs_stress: bad argument"); return GFS_ERR_INVALID; }
+// One index's share of the sampled stress: sample k draws a step s ~ U[0, total_steps) of the WHOLE graph; this index
+// (whose local step 0 is global step `step_offset`) evaluates the samples with s in [step_begin, step_end) and adds
+// (sum of squared relative errors, sum of absolute relative errors, count) to sums[3].  A path's steps must all lie
+// in this index, which holds for a shard and the step slice it samples.
+static int stress_partial(const gfs_index* ix, uint32_t dims, int32_t layout_order, const double* coords, uint64_t samples,
+                          uint64_t seed, uint64_t total_steps, uint64_t step_offset, uint64_t step_begin, uint64_t step_end,
+                          double* sums) {
     GFS_CUDA(cudaSetDevice(ix->device));
-    if (rms_rel) *rms_rel = 0;
-    if (mean_abs_rel) *mean_abs_rel = 0;
-    if (counted) *counted = 0;
-    if (ix->S < 2 || samples == 0) return GFS_OK;            // sgd.rs:1220-1222
+    if (total_steps < 2 || samples == 0 || step_end <= step_begin) return GFS_OK;            // sgd.rs:1220-1222
     const uint32_t stride = layout_order ? 2 * dims : dims;
     DevBuf<double> d_coords, d_partial;
     const size_t n_coords = (size_t)ix->N * stride;
     GFS_CUDA(d_coords.alloc(n_coords));
     GFS_CUDA(d_coords.up(coords, n_coords));
-    const unsigned grid = (unsigned)std::min<uint64_t>((samples + STRESS_BLOCK - 1) / STRESS_BLOCK, 148 * 8);
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ix->device);
+    const unsigned grid = (unsigned)std::min<uint64_t>((samples + STRESS_BLOCK - 1) / STRESS_BLOCK, (uint64_t)sms * 8);
     GFS_CUDA(d_partial.alloc((size_t)grid * 3));
     gfs_sgd_params dummy{};
     KernelGraph g = make_kgraph(ix, dummy, nullptr, 0);
-    stress_kernel<<<grid, STRESS_BLOCK>>>(g, ix->d_old_of_new, d_coords.p, dims, stride, samples, (uint32_t)seed, (uint32_t)(seed >> 32), d_partial.p);
+    stress_kernel<<<grid, STRESS_BLOCK>>>(g, ix->d_old_of_new, d_coords.p, dims, stride, samples, (uint32_t)seed, (uint32_t)(seed >> 32),
+                                          total_steps, step_offset, step_begin, step_end, d_partial.p);
     GFS_CUDA(cudaGetLastError());
     std::vector<double> part((size_t)grid * 3);
     GFS_CUDA(d_partial.down(part.data(), part.size()));
-    double s0 = 0, s1 = 0, c = 0;
-    for (unsigned b = 0; b < grid; ++b) { s0 += part[b * 3]; s1 += part[b * 3 + 1]; c += part[b * 3 + 2]; }
-    if (c > 0) {
-        if (rms_rel) *rms_rel = std::sqrt(s0 / c);
-        if (mean_abs_rel) *mean_abs_rel = s1 / c;
+    for (unsigned b = 0; b < grid; ++b) { sums[0] += part[b * 3]; sums[1] += part[b * 3 + 1]; sums[2] += part[b * 3 + 2]; }
+    return GFS_OK;
+}
+
+extern "C" int gfs_stress_partial(const gfs_index* ix, uint32_t dims, int32_t layout_order, const double* coords, uint64_t samples,
+                                  uint64_t seed, uint64_t total_steps, uint64_t step_offset, uint64_t step_begin, uint64_t step_end,
+                                  double* sums3) {
+    if (!ix || !coords || dims < 1 || !sums3) { set_error("gfs_stress_partial: bad argument"); return GFS_ERR_INVALID; }
+    if (!ix->shards.empty()) { set_error("gfs_stress_partial: call it on one shard (gfs_stress handles a multi-GPU index)"); return GFS_ERR_INVALID; }
+    if (step_begin < step_offset || step_end > step_offset + ix->S) { set_error("gfs_stress_partial: step range outside the index"); return GFS_ERR_INVALID; }
+    return stress_partial(ix, dims, layout_order, coords, samples, seed, total_steps, step_offset, step_begin, step_end, sums3);
+}
+
+extern "C" int gfs_stress(const gfs_index* ix, uint32_t dims, int32_t layout_order, const double* coords,
+                          uint64_t samples, uint64_t seed, double* rms_rel, double* mean_abs_rel, uint64_t* counted) {
+    if (!ix || !coords || dims < 1) { set_error("gfs_stress: bad argument"); return GFS_ERR_INVALID; }
+    if (rms_rel) *rms_rel = 0;
+    if (mean_abs_rel) *mean_abs_rel = 0;
+    if (counted) *counted = 0;
+    double sums[3] = {0, 0, 0};
+    if (!ix->shards.empty()) {      // every shard evaluates the samples that fall into its step slice: all paths, same sample as one GPU
+        for (size_t g = 0; g < ix->shards.size(); ++g) {
+            const gfs_shard_plan& pl = ix->plans[g];
+            int rc = stress_partial(ix->shards[g], dims, layout_order, coords, samples, seed, ix->S, pl.first_step, pl.sample_begin,
+                                    pl.sample_end, sums);
+            if (rc) return rc;
+        }
+    } else {
+        int rc = stress_partial(ix, dims, layout_order, coords, samples, seed, ix->S, 0, 0, ix->S, sums);
+        if (rc) return rc;
     }
-    if (counted) *counted = (uint64_t)c;
+    if (sums[2] > 0) {
+        if (rms_rel) *rms_rel = std::sqrt(sums[0] / sums[2]);
+        if (mean_abs_rel) *mean_abs_rel = sums[1] / sums[2];
+    }
+    if (counted) *counted = (uint64_t)sums[2];
     return GFS_OK;
 }
 
@@ -914,10 +1074,22 @@ extern "C" int gfs_debug_trace_terms(const gfs_index* ix, const gfs_sgd_params* 
 // ---------------------------------------------------------------------------------------------
 // replica reconcile helpers
 // ---------------------------------------------------------------------------------------------
+// the device that owns `ptr` becomes current; returns its SM count (the helpers take raw device pointers and a
+// caller stream, so nothing else says where to launch)
+static int enter_device_of(const void* ptr, int* sms) {
+    cudaPointerAttributes attr{};
+    GFS_CUDA(cudaPointerGetAttributes(&attr, ptr));
+    if (attr.type != cudaMemoryTypeDevice) { set_error("reconcile: not a device pointer"); return GFS_ERR_INVALID; }
+    GFS_CUDA(cudaSetDevice(attr.device));
+    GFS_CUDA(cudaDeviceGetAttribute(sms, cudaDevAttrMultiProcessorCount, attr.device));
+    return GFS_OK;
+}
 extern "C" int gfs_reconcile_pack(const void* x, const void* x_sync, uint64_t n, uint32_t elem_bytes, float* buf, void* stream) {
     if (!x || !x_sync || !buf || (elem_bytes != 4 && elem_bytes != 8)) { set_error("gfs_reconcile_pack: bad argument"); return GFS_ERR_INVALID; }
     if (n == 0) return GFS_OK;
-    const unsigned grid = (unsigned)std::min<uint64_t>((n + 255) / 256, 148 * 16);
+    int sms = 0, rc = enter_device_of(x, &sms);
+    if (rc) return rc;
+    const unsigned grid = (unsigned)std::min<uint64_t>((n + 255) / 256, (uint64_t)sms * 16);
     if (elem_bytes == 8) rc_pack<double><<<grid, 256, 0, (cudaStream_t)stream>>>((const double*)x, (const double*)x_sync, n, buf);
     else rc_pack<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)x, (const float*)x_sync, n, buf);
     GFS_CUDA(cudaGetLastError());
@@ -926,7 +1098,9 @@ extern "C" int gfs_reconcile_pack(const void* x, const void* x_sync, uint64_t n,
 extern "C" int gfs_reconcile_apply(void* x, void* x_sync, uint64_t n, uint32_t elem_bytes, const float* buf, void* stream) {
     if (!x || !x_sync || !buf || (elem_bytes != 4 && elem_bytes != 8)) { set_error("gfs_reconcile_apply: bad argument"); return GFS_ERR_INVALID; }
     if (n == 0) return GFS_OK;
-    const unsigned grid = (unsigned)std::min<uint64_t>((n + 255) / 256, 148 * 16);
+    int sms = 0, rc = enter_device_of(x, &sms);
+    if (rc) return rc;
+    const unsigned grid = (unsigned)std::min<uint64_t>((n + 255) / 256, (uint64_t)sms * 16);
     if (elem_bytes == 8) rc_apply<double><<<grid, 256, 0, (cudaStream_t)stream>>>((double*)x, (double*)x_sync, n, buf);
     else rc_apply<float><<<grid, 256, 0, (cudaStream_t)stream>>>((float*)x, (float*)x_sync, n, buf);
     GFS_CUDA(cudaGetLastError());
@@ -936,6 +1110,22 @@ extern "C" int gfs_reconcile_apply(void* x, void* x_sync, uint64_t n, uint32_t e
 // ---------------------------------------------------------------------------------------------
 // order by position
 // ---------------------------------------------------------------------------------------------
+// Stable LSD radix sort of n (key, value) pairs over the low 8*passes key bits (rs_* kernels).  The buffers are
+// ping-ponged: after the call (k0, v0) name the sorted arrays (with an even number of passes, the ones passed in).
+static int radix_sort_pairs(uint64_t*& k0, uint64_t*& k1, uint32_t*& v0, uint32_t*& v1, uint32_t* hist, uint64_t n, int passes,
+                            cudaStream_t st, uint64_t* launches) {
+    const uint32_t n_blocks = (uint32_t)((n + RS_TILE - 1) / RS_TILE);
+    for (int pass = 0; pass < passes; ++pass) {
+        rs_hist<<<n_blocks, RS_THREADS, 0, st>>>(k0, n, pass * 8, n_blocks, hist);
+        rs_scan<<<1, 1024, 0, st>>>(hist, (uint64_t)256 * n_blocks);
+        rs_scatter<<<n_blocks, RS_THREADS, 0, st>>>(k0, v0, n, pass * 8, n_blocks, hist, k1, v1);
+        std::swap(k0, k1); std::swap(v0, v1);
+        if (launches) *launches += 3;
+    }
+    GFS_CUDA(cudaGetLastError());
+    return GFS_OK;
+}
+
 // d_x: n positions on the device, in the caller's node order.  d_order: n dense indices.  Asynchronous on st.
 static int sort_positions_device(const double* d_x, uint64_t n, uint32_t* d_order, cudaStream_t st, uint64_t* launches) {
     if (n == 0) return GFS_OK;
@@ -944,22 +1134,15 @@ static int sort_positions_device(const double* d_x, uint64_t n, uint32_t* d_orde
     DevBuf<uint64_t> b_k0, b_k1; DevBuf<uint32_t> b_v1, b_hist;
     GFS_CUDA(b_k0.alloc(n)); GFS_CUDA(b_k1.alloc(n));
     GFS_CUDA(b_v1.alloc(n)); GFS_CUDA(b_hist.alloc((size_t)256 * n_blocks));
-    uint64_t *k0 = b_k0.p, *k1 = b_k1.p; uint32_t *v1 = b_v1.p, *hist = b_hist.p;
+    uint64_t *k0 = b_k0.p, *k1 = b_k1.p; uint32_t *v1 = b_v1.p;
     uint32_t* v0 = d_order;
     rs_make_keys<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_x, n, k0, v0);
-    uint64_t nl = 1;
-    for (int pass = 0; pass < 8; ++pass) {
-        rs_hist<<<n_blocks, RS_THREADS, 0, st>>>(k0, n, pass * 8, n_blocks, hist);
-        rs_scan<<<1, 1024, 0, st>>>(hist, (uint64_t)256 * n_blocks);
-        rs_scatter<<<n_blocks, RS_THREADS, 0, st>>>(k0, v0, n, pass * 8, n_blocks, hist, k1, v1);
-        std::swap(k0, k1); std::swap(v0, v1);
-        nl += 3;
-    }
-    // 8 passes: the result is back in the buffers it started in (v0 == d_order)
+    if (launches) *launches += 1;
+    int rc = radix_sort_pairs(k0, k1, v0, v1, b_hist.p, n, 8, st, launches);    // 8 passes: the result is back in d_order
+    if (rc) return rc;
     cudaError_t e = cudaStreamSynchronize(st);
     if (e == cudaSuccess) e = cudaGetLastError();
     if (e != cudaSuccess) { set_error(std::string("sort failed: ") + cudaGetErrorString(e)); return GFS_ERR_CUDA; }
-    if (launches) *launches += nl;
     return GFS_OK;
 }
 
@@ -1000,6 +1183,11 @@ extern "C" int gfs_sgd_session_sort(gfs_sgd_session* s, uint32_t* order) {
 extern "C" int gfs_sgd_sort_1d(const gfs_index* ix, const gfs_sgd_params* params, double* x_inout, uint32_t* order_out,
                                gfs_stats* stats) {
     if (!x_inout || !order_out) { set_error("gfs_sgd_sort_1d: null buffer"); return GFS_ERR_INVALID; }
+    if (ix && !ix->shards.empty()) {                 // multi-GPU index: the replicated run, then the sort on one device
+        int rc = gfs_sgd_1d(ix, params, x_inout, stats);
+        if (!rc) rc = gfs_sort_positions(x_inout, ix->N, order_out);
+        return rc;
+    }
     const double t0 = now_s();
     gfs_sgd_session* s = nullptr;
     int rc = gfs_sgd_session_create(ix, params, 0, nullptr, &s);

@@ -1,0 +1,226 @@
+// gfs_multi.cu — replicated multi-GPU runs behind the C ABI.
+//
+// Terms shard, positions do not: every term lives inside one path (reference src/sgd.rs:445, 502-503), any path can
+// touch any node.  So rank r of G samples only the steps of its slice [S r/G, S (r+1)/G) of the concatenated step
+// array, holds the records of just the paths that slice overlaps (partners never leave them), runs its share
+// min_term_updates |slice| / S of every epoch (exact in sum; the global sampling distribution stays uniform over
+// steps, src/sgd.rs:435, 444), and keeps a full replica of the positions.  Replicas are reconciled `syncs` times per
+// epoch by the peer-memory kernel of gfs_p2p.cu (moved-replica mean over NVLink).
+//
+//   gfs_shard_plan_make / gfs_shard_epoch_quota   who samples what (host arithmetic, no device)
+//   gfs_replica_*                                  one rank: session + peer region + the epoch loop, for hosts that run
+//                                                  one process per GPU (exchange gfs_replica_ipc_handle blobs, connect)
+//   gfs_multi_run_whole                            all ranks driven from ONE process: what gfs_sgd_1d / gfs_sgd_nd do on
+//                                                  an index built under GFASORT_GPUS=G (the frozen reference CLI has no
+//                                                  flag for it, so the GPU count is an environment variable)
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "gfs_internal.h"
+
+using namespace gfs;
+
+// ---------------------------------------------------------------------------------------------
+// shard plan
+// ---------------------------------------------------------------------------------------------
+extern "C" int gfs_shard_plan_make(const uint64_t* path_first_step, uint64_t P, uint32_t rank, uint32_t world, gfs_shard_plan* out) {
+    if (!path_first_step || !out || world == 0 || rank >= world) { set_error("gfs_shard_plan_make: bad argument"); return GFS_ERR_INVALID; }
+    std::memset(out, 0, sizeof *out);
+    const uint64_t S = path_first_step[P];
+    const uint64_t b = (uint64_t)(((unsigned __int128)S * rank) / world);
+    const uint64_t e = (uint64_t)(((unsigned __int128)S * (rank + 1)) / world);
+    out->sample_begin = out->sample_end = b;
+    if (e <= b) return GFS_OK;                                   // more ranks than steps: an empty shard
+    // path of step b and of step e-1: the last p with first_step[p] <= step
+    const uint64_t* fs = path_first_step;
+    const uint64_t pb = (uint64_t)(std::upper_bound(fs, fs + P + 1, b) - fs) - 1;
+    const uint64_t pe = (uint64_t)(std::upper_bound(fs, fs + P + 1, e - 1) - fs);
+    out->sample_end = e;
+    out->path_begin = pb; out->path_end = pe;
+    out->first_step = fs[pb];
+    return GFS_OK;
+}
+
+extern "C" uint64_t gfs_shard_epoch_quota(uint64_t min_term_updates, const gfs_shard_plan* plan, uint64_t total_steps) {
+    if (!plan || total_steps == 0) return 0;
+    const unsigned __int128 M = min_term_updates;
+    return (uint64_t)(M * plan->sample_end / total_steps) - (uint64_t)(M * plan->sample_begin / total_steps);
+}
+
+// ---------------------------------------------------------------------------------------------
+// one rank of a replicated run
+// ---------------------------------------------------------------------------------------------
+struct gfs_replica {
+    gfs_sgd_session* s = nullptr;
+    gfs_p2p_region* region = nullptr;
+    uint32_t rank = 0, world = 1, syncs = 1;
+    uint64_t reconciles = 0;
+    uint64_t n_epochs = 0;
+};
+
+extern "C" void gfs_replica_destroy(gfs_replica* r) {
+    if (!r) return;
+    if (r->s) gfs_sgd_session_destroy(r->s);
+    if (r->region) gfs_p2p_region_free(r->region);
+    delete r;
+}
+
+extern "C" int gfs_replica_create(const gfs_index* shard, const gfs_sgd_params* params, uint32_t dims, const gfs_launch_cfg* cfg,
+                                  const gfs_shard_plan* plan, uint64_t total_steps, uint32_t rank, uint32_t world,
+                                  uint32_t syncs_per_epoch, gfs_replica** out) {
+    if (!out) { set_error("gfs_replica_create: out is null"); return GFS_ERR_INVALID; }
+    *out = nullptr;
+    if (!shard || !params || !plan || world == 0 || rank >= world || world > GFS_P2P_MAX_RANKS) { set_error("gfs_replica_create: bad argument"); return GFS_ERR_INVALID; }
+    if (!shard->shards.empty()) { set_error("gfs_replica_create: pass one shard, not a multi-GPU index"); return GFS_ERR_INVALID; }
+    if (dims > 8) { set_error("gfs_replica_create: dims must be <= 8"); return GFS_ERR_INVALID; }
+    if (plan->sample_end < plan->sample_begin || plan->sample_begin < plan->first_step ||
+        plan->sample_end - plan->first_step > shard->S) { set_error("gfs_replica_create: the plan's step slice is outside the shard"); return GFS_ERR_INVALID; }
+    gfs_replica* r = new gfs_replica();
+    r->rank = rank; r->world = world; r->syncs = std::max(1u, syncs_per_epoch);
+    auto fail = [&](int code) { gfs_replica_destroy(r); return code; };
+    const int f64 = dims == 0 ? 1 : (cfg && cfg->layout_f64 >= 0 ? cfg->layout_f64 : (int)env_long("GFASORT_LAYOUT_F64", 0));
+    const uint64_t n_elems = dims == 0 ? shard->N : shard->N * 2 * coord_stride(dims);
+    int rc = gfs_p2p_region_create(shard->device, n_elems, f64 ? 8 : 4, 0, &r->region);
+    if (rc) return fail(rc);
+    void* x = nullptr;
+    rc = gfs_p2p_region_ptrs(r->region, &x, nullptr, nullptr);
+    if (rc) return fail(rc);
+    gfs_sgd_params p = *params;
+    p.min_term_updates = gfs_shard_epoch_quota(params->min_term_updates, plan, total_steps);
+    gfs_launch_cfg c{};
+    c.device = shard->device; c.total_threads = cfg ? cfg->total_threads : 0;
+    c.aggregate = cfg ? cfg->aggregate : -1; c.layout_f64 = f64;
+    c.rng_thread_base = (uint64_t)rank << 24;                       // disjoint Philox streams: the analogue of seed + tid (sgd.rs:431)
+    c.stream = nullptr;
+    c.device_positions = x;
+    c.sample_begin = plan->sample_begin - plan->first_step;        // index-local step range
+    c.sample_end = plan->sample_end - plan->first_step;
+    if (c.sample_end <= c.sample_begin) { set_error("gfs_replica_create: rank " + std::to_string(rank) + " has no steps to sample (more GPUs than steps)"); return fail(GFS_ERR_INVALID); }
+    rc = gfs_sgd_session_create(shard, &p, dims, &c, &r->s);
+    if (rc) return fail(rc);
+    r->n_epochs = params->iter_max + 1;
+    *out = r;
+    return GFS_OK;
+}
+
+extern "C" int gfs_replica_ipc_handle(gfs_replica* r, uint8_t* blob) {
+    if (!r) { set_error("gfs_replica_ipc_handle: null replica"); return GFS_ERR_INVALID; }
+    return gfs_p2p_region_ipc_handle(r->region, blob);
+}
+extern "C" int gfs_replica_connect_ipc(gfs_replica* r, const uint8_t* blobs, uint32_t world, uint32_t rank) {
+    if (!r) { set_error("gfs_replica_connect_ipc: null replica"); return GFS_ERR_INVALID; }
+    if (world != r->world || rank != r->rank) { set_error("gfs_replica_connect_ipc: world / rank differ from gfs_replica_create"); return GFS_ERR_INVALID; }
+    return gfs_p2p_region_connect_ipc(r->region, blobs, world, rank);
+}
+extern "C" int gfs_replica_connect_local(gfs_replica* const* replicas, uint32_t world) {
+    if (!replicas || world == 0 || world > GFS_P2P_MAX_RANKS) { set_error("gfs_replica_connect_local: bad argument"); return GFS_ERR_INVALID; }
+    std::vector<gfs_p2p_region*> regs(world);
+    for (uint32_t g = 0; g < world; ++g) {
+        if (!replicas[g] || replicas[g]->world != world || replicas[g]->rank != g) { set_error("gfs_replica_connect_local: replicas must come in rank order"); return GFS_ERR_INVALID; }
+        regs[g] = replicas[g]->region;
+        for (uint32_t h = 0; h < g; ++h)
+            if (replicas[h]->s->device == replicas[g]->s->device) {
+                set_error("gfs_replica_connect_local: two replicas share a device (their reconcile kernels would wait on one another inside one GPU)");
+                return GFS_ERR_INVALID;
+            }
+    }
+    return gfs_p2p_region_connect_local(regs.data(), world);
+}
+
+extern "C" int gfs_replica_upload(gfs_replica* r, const double* positions) {
+    if (!r) { set_error("gfs_replica_upload: null replica"); return GFS_ERR_INVALID; }
+    int rc = gfs_sgd_session_upload(r->s, positions);
+    // the snapshot is taken on the session's stream, behind the upload: a snapshot racing the first SGD launch would
+    // leave the ranks with different x_sync, which this reconcile (it never re-reads absolute positions) cannot repair
+    if (!rc) rc = gfs_p2p_region_snapshot(r->region, r->s->stream);
+    if (!rc) rc = gfs_sgd_session_sync(r->s);
+    return rc;
+}
+
+// Asynchronous: epochs [epoch_begin, epoch_end) of this rank's share, `syncs` slices per epoch, replicas reconciled
+// after every slice.  Every rank must enqueue the same epochs in the same order.
+extern "C" int gfs_replica_run(gfs_replica* r, uint64_t epoch_begin, uint64_t epoch_end) {
+    if (!r) { set_error("gfs_replica_run: null replica"); return GFS_ERR_INVALID; }
+    for (uint64_t e = epoch_begin; e < epoch_end; ++e)
+        for (uint32_t k = 0; k < r->syncs; ++k) {
+            int rc = gfs_sgd_session_run(r->s, e, e + 1, k, r->syncs);
+            if (rc) return rc;
+            if (r->world > 1) {
+                rc = gfs_p2p_reconcile(r->region, r->s->stream);
+                if (rc) return rc;
+                r->reconciles += 1;
+            }
+        }
+    return GFS_OK;
+}
+
+// Blocking: waits for everything enqueued; a reconcile barrier that timed out on ANY rank is an error here.
+extern "C" int gfs_replica_sync(gfs_replica* r) {
+    if (!r) { set_error("gfs_replica_sync: null replica"); return GFS_ERR_INVALID; }
+    int rc = gfs_sgd_session_sync(r->s);
+    if (!rc) rc = gfs_p2p_region_check(r->region);
+    return rc;
+}
+extern "C" int gfs_replica_download(gfs_replica* r, double* positions) {
+    if (!r) { set_error("gfs_replica_download: null replica"); return GFS_ERR_INVALID; }
+    int rc = gfs_replica_sync(r);
+    if (!rc) rc = gfs_sgd_session_download(r->s, positions);
+    return rc;
+}
+extern "C" int gfs_replica_stats(gfs_replica* r, gfs_stats* st) {
+    if (!r || !st) { set_error("gfs_replica_stats: null argument"); return GFS_ERR_INVALID; }
+    int rc = gfs_replica_sync(r);
+    if (!rc) rc = gfs_sgd_session_stats(r->s, st);
+    if (!rc) { st->launches += r->reconciles; st->n_devices = r->world; st->syncs_per_epoch = r->syncs; }
+    return rc;
+}
+extern "C" int gfs_replica_stream(gfs_replica* r, void** stream, void** dev_positions, uint64_t* n_elems, uint32_t* elem_bytes) {
+    if (!r) { set_error("gfs_replica_stream: null replica"); return GFS_ERR_INVALID; }
+    if (stream) *stream = r->s->stream;
+    return gfs_sgd_session_positions(r->s, dev_positions, n_elems, elem_bytes);
+}
+
+// ---------------------------------------------------------------------------------------------
+// all ranks from one process
+// ---------------------------------------------------------------------------------------------
+int gfs_multi_run_whole(const gfs_index* ix, const gfs_sgd_params* params, const gfs_launch_cfg* cfg, uint32_t dims,
+                        double* pos_inout, gfs_stats* stats) {
+    const double t0 = now_s();
+    const uint32_t G = (uint32_t)ix->shards.size();
+    if (!params) { set_error("params is null"); return GFS_ERR_INVALID; }
+    if (!ix->any_multi_step) { set_error("no paths with multiple steps found"); return GFS_ERR_NO_VALID_PATH; }
+    const uint32_t syncs = (uint32_t)std::max<long>(1, env_long("GFASORT_SYNCS", 1));
+    std::vector<gfs_replica*> reps(G, nullptr);
+    auto cleanup = [&]() { for (gfs_replica* r : reps) gfs_replica_destroy(r); };
+    int rc = GFS_OK;
+    for (uint32_t g = 0; g < G && !rc; ++g)
+        rc = gfs_replica_create(ix->shards[g], params, dims, cfg, &ix->plans[g], ix->S, g, G, syncs, &reps[g]);
+    if (!rc) rc = gfs_replica_connect_local(reps.data(), G);
+    for (uint32_t g = 0; g < G && !rc; ++g) rc = gfs_replica_upload(reps[g], pos_inout);
+    // one epoch at a time over all devices: no device's queue runs far ahead of a peer it will wait for
+    const uint64_t n_epochs = params->iter_max + 1;
+    for (uint64_t e = 0; e < n_epochs && !rc; ++e)
+        for (uint32_t g = 0; g < G && !rc; ++g) rc = gfs_replica_run(reps[g], e, e + 1);
+    for (uint32_t g = 0; g < G && !rc; ++g) rc = gfs_replica_sync(reps[g]);
+    if (!rc) rc = gfs_replica_download(reps[0], pos_inout);        // the replicas are identical after the last reconcile
+    gfs_stats tot{};
+    for (uint32_t g = 0; g < G && !rc; ++g) {
+        gfs_stats st{};
+        rc = gfs_replica_stats(reps[g], &st);
+        if (rc) break;
+        tot.applied_updates += st.applied_updates; tot.attempts += st.attempts; tot.launches += st.launches;
+        tot.kernel_seconds = std::max(tot.kernel_seconds, st.kernel_seconds);
+        tot.h2d_seconds += st.h2d_seconds; tot.d2h_seconds += st.d2h_seconds;
+        tot.epochs = st.epochs; tot.grid = st.grid; tot.block = st.block; tot.coord_bytes = st.coord_bytes;
+        tot.window_steps = st.window_steps; tot.coherent = st.coherent;
+    }
+    tot.n_devices = G; tot.syncs_per_epoch = syncs;
+    tot.total_seconds = now_s() - t0;
+    if (!rc && stats) *stats = tot;
+    cleanup();
+    return rc;
+}

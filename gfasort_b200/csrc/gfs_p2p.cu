@@ -1,29 +1,32 @@
 // gfs_p2p.cu — K5b: replica reconcile as ONE kernel over NVLink peer memory.
 //
-// The default reconcile of a multi-GPU run is rc_pack -> NCCL all-reduce -> rc_apply: three passes over the
-// replica, a 2n-float staging buffer and two kernel boundaries around a library collective.  Here every rank
-// maps every other rank's replica (CUDA IPC between the one-process-per-GPU ranks, or plain peer access inside
-// one process) and one kernel per rank does the whole exchange:
+// The exchange step of a replicated multi-GPU run.  Every rank maps every other rank's replica (CUDA IPC between
+// one-process-per-GPU ranks, plain peer access inside one process) and one kernel per rank does the whole exchange:
 //
 //   start barrier   block b of rank r signals block b of every peer: "my SGD slice is complete" (it is: the kernel
 //                   is stream-ordered after the SGD kernel) and waits for theirs;
-//   reduce+scatter  rank r owns elements [n r/G, n (r+1)/G): for each it loads the G replicas' values (G-1 of them
-//                   over NVLink, coalesced), forms x_sync + sum of displacements / #replicas that moved the element
-//                   (the "moved-replica mean" of DESIGN.md §6, in f64 instead of a f32 staging buffer), and stores
-//                   the result into all G replicas;
+//   reduce+scatter  rank r owns the 16-byte vectors [nvec r/G, nvec (r+1)/G): for each it loads the G replicas' values
+//                   (G-1 of them over NVLink: one 16-byte load per peer, all G issued before the first use), forms
+//                   x_sync + sum of displacements / #replicas that moved the element (the "moved-replica mean" of
+//                   DESIGN.md §6, in f64) and stores the result into all G replicas (16-byte stores);
 //   end barrier     all of this rank's peer stores are visible (fence.sys + release) before any peer goes on;
 //   refresh         x_sync <- x over the whole local replica (local HBM traffic only).
 //
-// Per rank and reconcile: n(G-1)/G elements read and written over NVLink — the volume of a ring all-reduce — in one
-// launch, with no staging buffer and 3 local passes (read x_sync slice, read x, write x_sync) instead of 7.
+// Per rank and reconcile: n(G-1)/G elements read and n(G-1)/G written over NVLink — the volume of a ring all-reduce —
+// in one launch, no staging buffer, 3 local passes instead of the 7 of pack + NCCL all-reduce + apply.
 //
 // Barrier flags live in the region itself, one u32 per (phase, block, source rank), written by the source with
 // st.release.sys and polled by the owner with ld.acquire.sys; tags increase by one per reconcile, so no reset is
-// needed.  Every spin is bounded: a barrier that does not complete within `spin_cap` polls raises the region's
-// error flag and the kernel returns without touching any replica (gfs_p2p_region_check turns it into an error).
+// needed.  Every spin is bounded.  A barrier that does not complete within `spin_cap` polls FAILS THE RUN: the block
+// raises the error word of every rank's region (its own and, over NVLink, its peers'), every later reconcile kernel
+// returns at once when it sees the word set, and gfs_p2p_region_check — called by the replica runner after every
+// schedule it enqueues and before any result is handed out — turns it into GFS_ERR_CUDA.  After a timeout the
+// replicas are in an undefined state (other blocks may already have scattered); the contract is "an error, never a
+// hang and never a silently wrong result", not "untouched replicas".
 //
-// STATUS: opt-in (`--reconcile p2p` / ReplicaRun(mode="p2p")); the NCCL path stays the default until this one
-// has been measured on 2 and 8 GPUs.
+// One device, several replicas (tests): kernels that wait on one another must not be separate launches on one GPU
+// (nothing guarantees they run at the same time), so gfs_p2p_reconcile_local runs all ranks as ONE cooperative
+// launch in which block group g plays rank g.
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -43,15 +46,16 @@ constexpr uint32_t P2P_MAX_RANKS = GFS_P2P_MAX_RANKS;
 constexpr uint32_t P2P_MAX_BLOCKS = 256;
 constexpr uint32_t P2P_THREADS = 512;
 constexpr uint64_t P2P_ALIGN = 256;
+constexpr uint32_t P2P_EMU_MAX = 4;         // ranks one emulated launch can hold (kernel parameter space)
 
 struct P2pArgs {
-    void* x[P2P_MAX_RANKS];            // replicas, by rank (own entry = local pointer)
-    uint32_t* flags[P2P_MAX_RANKS];    // [phase 0/1][block][source rank]
-    void* xs;                          // local x_sync
-    unsigned long long* err;           // local watchdog counter
-    uint64_t n;
+    void* x[P2P_MAX_RANKS];                  // replicas, by rank (own entry = local pointer)
+    uint32_t* flags[P2P_MAX_RANKS];          // [phase 0/1][block][source rank]
+    unsigned long long* err[P2P_MAX_RANKS];  // every rank's error word
+    void* xs;                                // local x_sync
+    uint64_t nvec;                           // 16-byte vectors per replica (arrays are padded to 256 B)
     uint64_t spin_cap;
-    uint32_t rank, world, tag;
+    uint32_t rank, world, tag, blocks;
 };
 
 __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
@@ -62,33 +66,55 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
     asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
-template <typename T> __device__ __forceinline__ T ld_peer(const T* p);
-template <> __device__ __forceinline__ double ld_peer<double>(const double* p) {
-    double v;
-    asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
-    return v;
-}
-template <> __device__ __forceinline__ float ld_peer<float>(const float* p) {
-    float v;
-    asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+__device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
 
-// elements [slice_begin(r), slice_begin(r + 1)) belong to rank r: n/G each, the first n%G ranks one more
-__device__ __forceinline__ uint64_t slice_begin(uint64_t n, uint32_t world, uint32_t r) {
+// one 16-byte vector of T
+template <typename T> struct V16;
+template <> struct V16<double> {
+    static constexpr int N = 2;
+    double v[2];
+    static __device__ __forceinline__ V16 ld_sys(const void* p) {       // peer (or local) replica: bypass L1
+        V16 r;
+        asm volatile("ld.relaxed.sys.global.v2.f64 {%0,%1}, [%2];" : "=d"(r.v[0]), "=d"(r.v[1]) : "l"(p) : "memory");
+        return r;
+    }
+    static __device__ __forceinline__ void st(void* p, const V16& r) {
+        asm volatile("st.global.v2.f64 [%0], {%1,%2};" ::"l"(p), "d"(r.v[0]), "d"(r.v[1]) : "memory");
+    }
+};
+template <> struct V16<float> {
+    static constexpr int N = 4;
+    float v[4];
+    static __device__ __forceinline__ V16 ld_sys(const void* p) {
+        V16 r;
+        asm volatile("ld.relaxed.sys.global.v4.f32 {%0,%1,%2,%3}, [%4];"
+                     : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]) : "l"(p) : "memory");
+        return r;
+    }
+    static __device__ __forceinline__ void st(void* p, const V16& r) {
+        asm volatile("st.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(r.v[0]), "f"(r.v[1]), "f"(r.v[2]), "f"(r.v[3]) : "memory");
+    }
+};
+
+// vectors [slice_begin(r), slice_begin(r + 1)) belong to rank r: n/G each, the first n%G ranks one more
+__device__ __host__ __forceinline__ uint64_t slice_begin(uint64_t n, uint32_t world, uint32_t r) {
     const uint64_t q = n / world, rem = n % world;
     return q * r + (r < rem ? r : rem);
 }
 
 // Block b of this rank meets block b of every peer.  PHASE 1 (end) publishes this block's peer stores first.
 template <int PHASE>
-__device__ bool p2p_barrier(const P2pArgs& a) {
+__device__ bool p2p_barrier(const P2pArgs& a, uint32_t b) {
     if (PHASE == 1) __threadfence_system();
     __syncthreads();
     bool ok = true;
     if (threadIdx.x < a.world) {
         const uint32_t peer = threadIdx.x;
-        const size_t slot = ((size_t)PHASE * P2P_MAX_BLOCKS + blockIdx.x) * P2P_MAX_RANKS;
+        const size_t slot = ((size_t)PHASE * P2P_MAX_BLOCKS + b) * P2P_MAX_RANKS;
         st_release_sys(a.flags[peer] + slot + a.rank, a.tag);
         const uint32_t* mine = a.flags[a.rank] + slot + peer;
         uint64_t spins = 0;
@@ -100,40 +126,85 @@ __device__ bool p2p_barrier(const P2pArgs& a) {
     return __syncthreads_and(ok) != 0;
 }
 
-template <typename T>
-__global__ void __launch_bounds__(P2P_THREADS) rc_p2p(const P2pArgs a) {
-    if (!p2p_barrier<0>(a)) {
-        if (threadIdx.x == 0) atomicAdd(a.err, 1ull);
-        return;
-    }
-    T* const xs = static_cast<T*>(a.xs);
-    const uint64_t lo = slice_begin(a.n, a.world, a.rank), hi = slice_begin(a.n, a.world, a.rank + 1);
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    const uint64_t first = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    for (uint64_t i = lo + first; i < hi; i += stride) {
-        const T s = xs[i];                                    // identical on every replica (invariant of the reconcile)
-        double sum = 0.0;
-        uint32_t moved = 0;
-        T only = s;                                           // the value of the one replica that moved it, if just one did
-        for (uint32_t g = 0; g < a.world; ++g) {
-            const T v = ld_peer<T>(static_cast<const T*>(a.x[g]) + i);
-            if (v != s) { sum += (double)v - (double)s; ++moved; only = v; }
+// a barrier timed out: fail the run on every rank (see the header)
+__device__ void p2p_raise(const P2pArgs& a) {
+    if (threadIdx.x < a.world) atomicAdd_system(a.err[threadIdx.x], 1ull);
+}
+
+// the moved-replica mean of one 16-byte vector; W > 0: world known at compile time (all loads issued up front)
+template <typename T, int W>
+__device__ __forceinline__ void reduce_scatter_vec(const P2pArgs& a, uint64_t i) {
+    using V = V16<T>;
+    const V s = *reinterpret_cast<const V*>(static_cast<const char*>(a.xs) + i * 16);   // identical on every replica
+    V nv;
+    if constexpr (W > 0) {
+        V v[W];
+#pragma unroll
+        for (int g = 0; g < W; ++g) v[g] = V::ld_sys(static_cast<const char*>(a.x[g]) + i * 16);
+#pragma unroll
+        for (int k = 0; k < V::N; ++k) {
+            double sum = 0.0; uint32_t moved = 0; T only = s.v[k];
+#pragma unroll
+            for (int g = 0; g < W; ++g)
+                if (v[g].v[k] != s.v[k]) { sum += (double)v[g].v[k] - (double)s.v[k]; ++moved; only = v[g].v[k]; }
+            nv.v[k] = moved <= 1 ? only : (T)((double)s.v[k] + sum / (double)moved);    // exact when 0 or 1 replicas moved it
         }
-        const T nv = moved <= 1 ? only : (T)((double)s + sum / (double)moved);      // exact when 0 or 1 replicas moved it
-        for (uint32_t g = 0; g < a.world; ++g) static_cast<T*>(a.x[g])[i] = nv;
+#pragma unroll
+        for (int g = 0; g < W; ++g) V::st(static_cast<char*>(a.x[g]) + i * 16, nv);
+    } else {
+        double sum[V::N]; uint32_t moved[V::N]; T only[V::N];
+#pragma unroll
+        for (int k = 0; k < V::N; ++k) { sum[k] = 0.0; moved[k] = 0; only[k] = s.v[k]; }
+        for (uint32_t g = 0; g < a.world; ++g) {
+            const V v = V::ld_sys(static_cast<const char*>(a.x[g]) + i * 16);
+#pragma unroll
+            for (int k = 0; k < V::N; ++k)
+                if (v.v[k] != s.v[k]) { sum[k] += (double)v.v[k] - (double)s.v[k]; ++moved[k]; only[k] = v.v[k]; }
+        }
+#pragma unroll
+        for (int k = 0; k < V::N; ++k) nv.v[k] = moved[k] <= 1 ? only[k] : (T)((double)s.v[k] + sum[k] / (double)moved[k]);
+        for (uint32_t g = 0; g < a.world; ++g) V::st(static_cast<char*>(a.x[g]) + i * 16, nv);
     }
-    if (!p2p_barrier<1>(a)) {
-        if (threadIdx.x == 0) atomicAdd(a.err, 1ull);
-        return;
+}
+
+template <typename T>
+__device__ void rc_p2p_body(const P2pArgs& a, uint32_t b) {
+    using V = V16<T>;
+    __shared__ int s_dead;
+    if (threadIdx.x == 0) s_dead = ld_relaxed_sys_u64(a.err[a.rank]) != 0;     // an earlier reconcile failed: the run is over
+    __syncthreads();
+    if (s_dead) return;
+    if (!p2p_barrier<0>(a, b)) { p2p_raise(a); return; }
+    const uint64_t lo = slice_begin(a.nvec, a.world, a.rank), hi = slice_begin(a.nvec, a.world, a.rank + 1);
+    const uint64_t stride = (uint64_t)a.blocks * blockDim.x;
+    const uint64_t first = (uint64_t)b * blockDim.x + threadIdx.x;
+    switch (a.world) {
+        case 2: for (uint64_t i = lo + first; i < hi; i += stride) reduce_scatter_vec<T, 2>(a, i); break;
+        case 4: for (uint64_t i = lo + first; i < hi; i += stride) reduce_scatter_vec<T, 4>(a, i); break;
+        case 8: for (uint64_t i = lo + first; i < hi; i += stride) reduce_scatter_vec<T, 8>(a, i); break;
+        default: for (uint64_t i = lo + first; i < hi; i += stride) reduce_scatter_vec<T, 0>(a, i); break;
     }
+    if (!p2p_barrier<1>(a, b)) { p2p_raise(a); return; }
     // Refresh the local snapshot (local traffic only).  The barriers pair block b with block b of every peer, so
     // this thread may only read what the SAME (block, thread) of rank g wrote: walk every rank's slice with the
     // partition the data phase used.
-    const T* const x = static_cast<const T*>(a.x[a.rank]);
+    const char* const x = static_cast<const char*>(a.x[a.rank]);
+    char* const xs = static_cast<char*>(a.xs);
     for (uint32_t g = 0; g < a.world; ++g) {
-        const uint64_t glo = slice_begin(a.n, a.world, g), ghi = slice_begin(a.n, a.world, g + 1);
-        for (uint64_t i = glo + first; i < ghi; i += stride) xs[i] = ld_peer<T>(x + i);
+        const uint64_t glo = slice_begin(a.nvec, a.world, g), ghi = slice_begin(a.nvec, a.world, g + 1);
+        for (uint64_t i = glo + first; i < ghi; i += stride) *reinterpret_cast<V*>(xs + i * 16) = V::ld_sys(x + i * 16);
     }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(P2P_THREADS) rc_p2p(const P2pArgs a) { rc_p2p_body<T>(a, blockIdx.x); }
+
+// all ranks in one cooperative launch (replicas on one device): block group g plays rank g
+struct P2pEmuArgs { P2pArgs r[P2P_EMU_MAX]; };
+template <typename T>
+__global__ void __launch_bounds__(P2P_THREADS) rc_p2p_emulated(const P2pEmuArgs e) {
+    const uint32_t blocks = e.r[0].blocks;
+    rc_p2p_body<T>(e.r[blockIdx.x / blocks], blockIdx.x % blocks);
 }
 
 uint64_t align_up(uint64_t v) { return (v + P2P_ALIGN - 1) / P2P_ALIGN * P2P_ALIGN; }
@@ -183,7 +254,7 @@ extern "C" int gfs_p2p_region_create(int32_t device, uint64_t n, uint32_t elem_b
     r->blocks = std::max(1u, std::min(blocks, P2P_MAX_BLOCKS));
     const char* cap = std::getenv("GFASORT_P2P_SPIN_CAP");
     r->spin_cap = cap && *cap ? std::strtoull(cap, nullptr, 10) : (1ull << 24);   // x >= 64 ns: seconds, not forever
-    const uint64_t arr = align_up(std::max<uint64_t>(n, 1) * elem_bytes);
+    const uint64_t arr = align_up(std::max<uint64_t>(n, 1) * elem_bytes);  // padded: the kernel works on whole 16-byte vectors
     r->off_xs = arr;
     r->off_flags = 2 * arr;
     r->off_err = r->off_flags + align_up((uint64_t)2 * P2P_MAX_BLOCKS * P2P_MAX_RANKS * 4);
@@ -205,21 +276,38 @@ extern "C" int gfs_p2p_region_ptrs(gfs_p2p_region* r, void** x, void** x_sync, u
     return GFS_OK;
 }
 
+// blob = cudaIpcMemHandle_t (64 bytes) + n (u64) + elem_bytes (u32) + blocks (u32): what a peer must agree on
 extern "C" int gfs_p2p_region_ipc_handle(gfs_p2p_region* r, uint8_t* handle /*GFS_P2P_HANDLE_BYTES*/) {
     if (!r || !handle) { gfs::set_error("gfs_p2p_region_ipc_handle: null argument"); return GFS_ERR_INVALID; }
-    static_assert(sizeof(cudaIpcMemHandle_t) == GFS_P2P_HANDLE_BYTES, "cudaIpcMemHandle_t is 64 bytes");
+    static_assert(sizeof(cudaIpcMemHandle_t) + 16 == GFS_P2P_HANDLE_BYTES, "blob = 64-byte IPC handle + 16 bytes of shape");
     P2P_CUDA(cudaSetDevice(r->device));
     cudaIpcMemHandle_t h;
     P2P_CUDA(cudaIpcGetMemHandle(&h, r->base));
     std::memcpy(handle, &h, sizeof h);
+    std::memcpy(handle + 64, &r->n, 8);
+    std::memcpy(handle + 72, &r->elem_bytes, 4);
+    std::memcpy(handle + 76, &r->blocks, 4);
     return GFS_OK;
 }
 
-extern "C" int gfs_p2p_region_connect_ipc(gfs_p2p_region* r, const uint8_t* handles /*world x 64, rank order*/, uint32_t world,
-                                          uint32_t rank) {
+extern "C" int gfs_p2p_region_connect_ipc(gfs_p2p_region* r, const uint8_t* handles /*world x GFS_P2P_HANDLE_BYTES, rank order*/,
+                                          uint32_t world, uint32_t rank) {
     if (!r || !handles) { gfs::set_error("gfs_p2p_region_connect_ipc: null argument"); return GFS_ERR_INVALID; }
     if (world == 0 || world > P2P_MAX_RANKS || rank >= world) { gfs::set_error("gfs_p2p_region_connect_ipc: bad world / rank"); return GFS_ERR_INVALID; }
     if (r->connected) { gfs::set_error("gfs_p2p_region_connect_ipc: region already connected"); return GFS_ERR_INVALID; }
+    // every peer must have the same element count, element type and grid: a mismatch would leave blocks without
+    // a partner at the barriers (a guaranteed timeout) or reduce different elements
+    for (uint32_t g = 0; g < world; ++g) {
+        const uint8_t* b = handles + (size_t)g * GFS_P2P_HANDLE_BYTES;
+        uint64_t n; uint32_t eb, bl;
+        std::memcpy(&n, b + 64, 8); std::memcpy(&eb, b + 72, 4); std::memcpy(&bl, b + 76, 4);
+        if (n != r->n || eb != r->elem_bytes || bl != r->blocks) {
+            gfs::set_error("gfs_p2p_region_connect_ipc: rank " + std::to_string(g) + " differs in size, element type or grid (n " +
+                           std::to_string(n) + " vs " + std::to_string(r->n) + ", elem_bytes " + std::to_string(eb) + " vs " +
+                           std::to_string(r->elem_bytes) + ", blocks " + std::to_string(bl) + " vs " + std::to_string(r->blocks) + ")");
+            return GFS_ERR_INVALID;
+        }
+    }
     P2P_CUDA(cudaSetDevice(r->device));
     r->rank = rank; r->world = world;
     for (uint32_t g = 0; g < world; ++g) {
@@ -271,35 +359,71 @@ extern "C" int gfs_p2p_region_snapshot(gfs_p2p_region* r, void* stream) {
     return GFS_OK;
 }
 
-// Asynchronous on `stream`.  Every rank calls it once per reconcile, in the same order.
-extern "C" int gfs_p2p_reconcile(gfs_p2p_region* r, void* stream) {
-    if (!r) { gfs::set_error("gfs_p2p_reconcile: null region"); return GFS_ERR_INVALID; }
-    if (!r->connected) { gfs::set_error("gfs_p2p_reconcile: region is not connected to its peers"); return GFS_ERR_INVALID; }
-    P2P_CUDA(cudaSetDevice(r->device));
+static P2pArgs make_args(gfs_p2p_region* r, uint32_t blocks) {
     P2pArgs a{};
     for (uint32_t g = 0; g < r->world; ++g) {
         a.x[g] = r->peer_base[g];
         a.flags[g] = reinterpret_cast<uint32_t*>(r->peer_base[g] + r->off_flags);
+        a.err[g] = reinterpret_cast<unsigned long long*>(r->peer_base[g] + r->off_err);
     }
     a.xs = r->base + r->off_xs;
-    a.err = reinterpret_cast<unsigned long long*>(r->base + r->off_err);
-    a.n = r->n; a.spin_cap = r->spin_cap;
+    a.nvec = (r->n * r->elem_bytes + 15) / 16;
+    a.spin_cap = r->spin_cap;
     a.rank = r->rank; a.world = r->world;
     a.tag = ++r->tag;
+    a.blocks = blocks;
+    return a;
+}
+
+// Asynchronous on `stream`.  Every rank calls it once per reconcile, in the same order.  Ranks must be on
+// DIFFERENT devices (kernels of one device that wait on one another may never run together): replicas that
+// share a device go through gfs_p2p_reconcile_local.
+extern "C" int gfs_p2p_reconcile(gfs_p2p_region* r, void* stream) {
+    if (!r) { gfs::set_error("gfs_p2p_reconcile: null region"); return GFS_ERR_INVALID; }
+    if (!r->connected) { gfs::set_error("gfs_p2p_reconcile: region is not connected to its peers"); return GFS_ERR_INVALID; }
+    P2P_CUDA(cudaSetDevice(r->device));
+    const P2pArgs a = make_args(r, r->blocks);
     if (r->elem_bytes == 8) rc_p2p<double><<<r->blocks, P2P_THREADS, 0, (cudaStream_t)stream>>>(a);
     else rc_p2p<float><<<r->blocks, P2P_THREADS, 0, (cudaStream_t)stream>>>(a);
     P2P_CUDA(cudaGetLastError());
     return GFS_OK;
 }
 
-// Blocking: non-zero (GFS_ERR_CUDA) when a barrier of any earlier reconcile timed out.
+// All `world` replicas live on ONE device and were connected with gfs_p2p_region_connect_local: one cooperative
+// launch in which block group g plays rank g (same barriers, same partition, same arithmetic as G ranks on G GPUs).
+extern "C" int gfs_p2p_reconcile_local(gfs_p2p_region* const* regions, uint32_t world, void* stream) {
+    if (!regions || world == 0 || world > P2P_EMU_MAX) { gfs::set_error("gfs_p2p_reconcile_local: 1..4 regions"); return GFS_ERR_INVALID; }
+    for (uint32_t g = 0; g < world; ++g) {
+        if (!regions[g] || !regions[g]->connected || regions[g]->world != world || regions[g]->rank != g ||
+            regions[g]->device != regions[0]->device) {
+            gfs::set_error("gfs_p2p_reconcile_local: regions must be connected to each other, in rank order, on one device");
+            return GFS_ERR_INVALID;
+        }
+    }
+    P2P_CUDA(cudaSetDevice(regions[0]->device));
+    const bool f64 = regions[0]->elem_bytes == 8;
+    const void* fn = f64 ? (const void*)rc_p2p_emulated<double> : (const void*)rc_p2p_emulated<float>;
+    int per_sm = 0, sms = 0;
+    P2P_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, P2P_THREADS, 0));
+    P2P_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, regions[0]->device));
+    const uint32_t blocks = std::min<uint32_t>(regions[0]->blocks, (uint32_t)(per_sm * sms) / world);
+    if (blocks == 0) { gfs::set_error("gfs_p2p_reconcile_local: the device cannot hold all ranks at once"); return GFS_ERR_INVALID; }
+    P2pEmuArgs e{};
+    for (uint32_t g = 0; g < world; ++g) e.r[g] = make_args(regions[g], blocks);
+    void* kargs[] = {(void*)&e};
+    P2P_CUDA(cudaLaunchCooperativeKernel(fn, dim3(blocks * world), dim3(P2P_THREADS), kargs, 0, (cudaStream_t)stream));
+    return GFS_OK;
+}
+
+// Blocking: non-zero (GFS_ERR_CUDA) when a barrier of any earlier reconcile — on any rank — timed out.
 extern "C" int gfs_p2p_region_check(gfs_p2p_region* r) {
     if (!r) { gfs::set_error("gfs_p2p_region_check: null region"); return GFS_ERR_INVALID; }
     P2P_CUDA(cudaSetDevice(r->device));
     unsigned long long err = 0;
     P2P_CUDA(cudaMemcpy(&err, r->base + r->off_err, 8, cudaMemcpyDeviceToHost));
     if (err) {
-        gfs::set_error("peer-memory reconcile: a barrier timed out (a rank did not reach the reconcile, or its kernel was not resident)");
+        gfs::set_error("peer-memory reconcile: a barrier timed out (a rank did not reach the reconcile, or its kernel was not "
+                       "resident); the replicas are in an undefined state and the run has failed");
         return GFS_ERR_CUDA;
     }
     return GFS_OK;

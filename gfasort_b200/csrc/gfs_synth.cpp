@@ -19,11 +19,23 @@
 #include <thread>
 #include <vector>
 
+#ifndef GFS_SYNTH_STANDALONE
 #include <cuda_runtime.h>
+#endif
 
 #include "../../include/gfasort_cuda.h"
 
+#ifdef GFS_SYNTH_STANDALONE
+// libgfs_synth.so: the generator alone, host code only (no CUDA, nothing of the product library), so that the
+// CPU reference arm of bench.py and the oracle tools can make the SAME graphs without mapping libgfasort_cuda.so.
+namespace gfs {
+static thread_local std::string g_synth_error;
+void set_error(const std::string& s) { g_synth_error = s; }
+}
+extern "C" const char* gfs_synth_last_error(void) { return gfs::g_synth_error.c_str(); }
+#else
 namespace gfs { void set_error(const std::string& s); }
+#endif
 
 namespace {
 
@@ -152,7 +164,11 @@ struct gfs_synth_graph {
     std::vector<uint64_t> path_first;   // path_end - path_begin + 1 entries, local to the generated range
     uint64_t* steps = nullptr;          // S handles (malloc'd: avoid value-initialising tens of GB)
     bool pinned = false;                // steps came from cudaHostAlloc
+#ifndef GFS_SYNTH_STANDALONE
     ~gfs_synth_graph() { if (pinned) cudaFreeHost(steps); else std::free(steps); }
+#else
+    ~gfs_synth_graph() { std::free(steps); }
+#endif
 };
 
 extern "C" int gfs_synth_create_range(const gfs_synth_spec* spec, uint64_t path_begin, uint64_t path_end,
@@ -202,11 +218,13 @@ extern "C" int gfs_synth_create_range(const gfs_synth_spec* spec, uint64_t path_
     for (uint64_t k = 0; k < np; ++k) g->path_first[k + 1] = g->path_first[k] + count[k];
     g->S = g->path_first[np];
     const size_t step_bytes = std::max<uint64_t>(g->S, 1) * sizeof(uint64_t);
+#ifndef GFS_SYNTH_STANDALONE
     if (spec->pinned) {
         void* ptr = nullptr;
         if (cudaHostAlloc(&ptr, step_bytes, cudaHostAllocDefault) == cudaSuccess) { g->steps = (uint64_t*)ptr; g->pinned = true; }
         else cudaGetLastError();   // no device / no pinned memory: fall back to pageable
     }
+#endif
     if (!g->steps) g->steps = (uint64_t*)std::malloc(step_bytes);
     if (!g->steps) { delete g; gfs::set_error("gfs_synth_create: out of memory for steps"); return GFS_ERR_INVALID; }
     parallel_paths([&](uint64_t k) { walk(path_begin + k, g->steps + g->path_first[k]); });

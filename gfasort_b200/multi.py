@@ -1,21 +1,25 @@
 """Multi-GPU `Y` / `L`: replicated positions, sharded term sampling.
 
-One process per GPU (torch.distributed, NCCL over NVLink).  Terms shard naturally — every term
-lives inside one path (reference src/sgd.rs:445, 502-503) — positions do not.  So:
+The run itself lives behind the C ABI (gfasort_b200/csrc/gfs_multi.cu): `gfs_shard_plan_make` says which step
+slice a rank samples and which paths' records it needs, `gfs_replica_*` is one rank (session + peer-memory
+region + the epoch loop with its reconciles), and `gfs_sgd_1d` / `gfs_sgd_nd` on an index built under
+GFASORT_GPUS=G drive all G GPUs from one process.  This module is the thin host side of the
+one-process-per-GPU form: torch.distributed carries the 80-byte region handles, the shared node order and the
+timing / stress reductions — plumbing, no data-path collective.
 
   * rank r samples only the steps of its slice [S*r/G, S*(r+1)/G) of the concatenated step array
     and holds the records of just the paths that slice overlaps (its partners never leave them);
   * every rank keeps a full replica of the positions and runs its share
     min_term_updates * |slice| / S of every epoch, which keeps the global sampling distribution
     uniform over steps (src/sgd.rs:435, 444);
-  * replicas are reconciled `syncs_per_epoch` times per epoch by an all-reduce over the position
-    array: "avg" (north star: mean of the replicas), "tavg" (mean over the replicas that moved the
-    node since the last sync) or "delta" (sum of the replicas' displacements, i.e. Hogwild with staleness);
-    "p2p" is "tavg" done by ONE kernel per rank over NVLink peer memory instead of pack + NCCL all-reduce +
-    apply (gfs_p2p_*; opt-in until measured).
+  * replicas are reconciled `syncs_per_epoch` times per epoch.  "p2p" (default): ONE kernel per rank over
+    NVLink peer memory forms the mean of the displacements over the replicas that moved the element
+    (gfs_p2p.cu).  For comparison the same rule as pack + NCCL all-reduce + apply ("tavg"), the plain replica
+    mean the north star names ("avg") and the displacement sum ("delta") remain, driven from here through
+    torch.distributed.
 
-Everything here is host logic over torch tensors; it runs unchanged on CPU tensors with the gloo
-backend, which is how tests/test_multi_gloo.py covers it without GPUs.
+`reconcile` runs unchanged on CPU tensors with the gloo backend, which is how tests/test_multi_gloo.py covers
+the host logic without GPUs.
 """
 from __future__ import annotations
 
@@ -40,23 +44,29 @@ class Shard:
 
 
 def shard_steps(path_first: np.ndarray, rank: int, world: int) -> Shard:
-    """Step-balanced slice for `rank` and the path range covering it."""
-    path_first = np.asarray(path_first, dtype=np.uint64)
-    S = int(path_first[-1])
-    b = (S * rank) // world
-    e = (S * (rank + 1)) // world
-    if e <= b:
-        return Shard(rank, world, b, b, 0, 0, 0)
-    pb = int(np.searchsorted(path_first, b, side="right") - 1)
-    pe = int(np.searchsorted(path_first, e - 1, side="right"))
-    return Shard(rank, world, b, e, pb, pe, int(path_first[pb]))
+    """Step-balanced slice for `rank` and the path range covering it (gfs_shard_plan_make)."""
+    import ctypes as C
+
+    from ._cabi import ShardPlan, check, lib, u64p
+    path_first = np.ascontiguousarray(path_first, dtype=np.uint64)
+    pl = ShardPlan()
+    check(lib().gfs_shard_plan_make(path_first.ctypes.data_as(u64p), len(path_first) - 1, rank, world, C.byref(pl)))
+    return Shard(rank, world, pl.sample_begin, pl.sample_end, pl.path_begin, pl.path_end, pl.first_step)
+
+
+def _plan(shard: Shard):
+    from ._cabi import ShardPlan
+    return ShardPlan(shard.sample_begin, shard.sample_end, shard.path_begin, shard.path_end, shard.first_step_of_path_begin)
 
 
 def epoch_quota(min_term_updates: int, shard: Shard, total_steps: int) -> int:
-    """This rank's share of one epoch: floor/ceil split of M in proportion to the slice, exact in sum."""
-    lo = (min_term_updates * shard.sample_begin) // total_steps
-    hi = (min_term_updates * shard.sample_end) // total_steps
-    return hi - lo
+    """This rank's share of one epoch: floor/ceil split of M in proportion to the slice, exact in sum
+    (gfs_shard_epoch_quota)."""
+    import ctypes as C
+
+    from ._cabi import lib
+    pl = _plan(shard)
+    return int(lib().gfs_shard_epoch_quota(min_term_updates, C.byref(pl), total_steps))
 
 
 def reconcile(x, x_sync, mode: str, group=None, scratch=None):
@@ -145,18 +155,18 @@ class PeerRegion:
     def ipc_handle(self) -> bytes:
         import ctypes as C
 
-        from ._cabi import check, lib, u8p
-        buf = (C.c_uint8 * 64)()
+        from ._cabi import GFS_P2P_HANDLE_BYTES, check, lib, u8p
+        buf = (C.c_uint8 * GFS_P2P_HANDLE_BYTES)()
         check(lib().gfs_p2p_region_ipc_handle(self._h, C.cast(buf, u8p)))
         return bytes(buf)
 
     def connect_ipc(self, handles: list, rank: int) -> None:
-        """handles: the 64-byte blobs of all ranks in rank order (one process per GPU)."""
+        """handles: the blobs of all ranks in rank order (one process per GPU)."""
         import ctypes as C
 
-        from ._cabi import check, lib, u8p
-        assert all(len(h) == 64 for h in handles)
-        blob = (C.c_uint8 * (64 * len(handles))).from_buffer_copy(b"".join(handles))
+        from ._cabi import GFS_P2P_HANDLE_BYTES, check, lib, u8p
+        assert all(len(h) == GFS_P2P_HANDLE_BYTES for h in handles)
+        blob = (C.c_uint8 * (GFS_P2P_HANDLE_BYTES * len(handles))).from_buffer_copy(b"".join(handles))
         check(lib().gfs_p2p_region_connect_ipc(self._h, C.cast(blob, u8p), len(handles), rank))
 
     @staticmethod
@@ -169,8 +179,18 @@ class PeerRegion:
         check(lib().gfs_p2p_region_connect_local(arr, len(regions)))
 
     def reconcile(self, stream_ptr: int) -> None:
+        """This rank's reconcile kernel (ranks on DIFFERENT devices)."""
         from ._cabi import check, lib
         check(lib().gfs_p2p_reconcile(self._h, stream_ptr))
+
+    @staticmethod
+    def reconcile_local(regions: list, stream_ptr: int) -> None:
+        """All ranks of replicas that share ONE device, as one cooperative launch (tests)."""
+        import ctypes as C
+
+        from ._cabi import check, lib
+        arr = (C.c_void_p * len(regions))(*[r._h for r in regions])
+        check(lib().gfs_p2p_reconcile_local(arr, len(regions), stream_ptr))
 
     def check(self) -> None:
         from ._cabi import check, lib
@@ -184,34 +204,41 @@ class PeerRegion:
             self._h = None
 
 
-def connect_peer_regions(region: PeerRegion, rank: int, world: int, group=None) -> None:
-    """One process per GPU: all-gather the IPC handles over torch.distributed and map the peers."""
+def _all_gather_bytes(blob: bytes, world: int, device: int, group=None) -> list:
     import torch
     import torch.distributed as dist
-    mine = torch.tensor(list(region.ipc_handle()), dtype=torch.uint8, device=f"cuda:{region.device}")
+    mine = torch.tensor(list(blob), dtype=torch.uint8, device=f"cuda:{device}")
     allh = [torch.empty_like(mine) for _ in range(world)]
     dist.all_gather(allh, mine, group=group)
-    region.connect_ipc([bytes(t.cpu().tolist()) for t in allh], rank)
+    return [bytes(t.cpu().tolist()) for t in allh]
+
+
+def connect_peer_regions(region: PeerRegion, rank: int, world: int, group=None) -> None:
+    """One process per GPU: all-gather the IPC handles over torch.distributed and map the peers."""
+    import torch.distributed as dist
+    region.connect_ipc(_all_gather_bytes(region.ipc_handle(), world, region.device, group), rank)
     dist.barrier(group=group)            # nobody reconciles before everybody has mapped everybody
 
 
 # ------------------------------------------------------------------------------------------------
-# one rank of a replicated run (GPU only: drives the C-ABI session API)
+# one rank of a replicated run (GPU only)
 # ------------------------------------------------------------------------------------------------
-_DS = {0: 1, 1: 1, 2: 2, 3: 4, 4: 4, 5: 8, 6: 8, 7: 8, 8: 8}     # coordinate stride per node end (gfs_lib.cu pick_nd)
+_DS = {0: 1, 1: 1, 2: 2, 3: 4, 4: 4, 5: 8, 6: 8, 7: 8, 8: 8}     # coordinate stride per node end (gfs_internal.h coord_stride)
 
 
 class ReplicaRun:
     """This rank's share of a `Y` (dims = 0) or `L` (dims >= 1) run.
 
     index: the PathIndex of paths [shard.path_begin, shard.path_end) only (build_shard_index) — a
-    rank never needs the other ranks' records.  The positions live in a torch tensor (so
-    torch.distributed can all-reduce them in place) that the library's session uses as its position
-    buffer; the session launches on `self.stream`.
+    rank never needs the other ranks' records.
+
+    mode "p2p" (default): the whole rank — session, peer-memory replica, epoch loop, reconciles — is one
+    `gfs_replica` behind the C ABI; this class only exchanges the region handles.  The other modes keep the
+    positions in a torch tensor that torch.distributed all-reduces between the library's SGD launches.
     """
 
     def __init__(self, index, n_nodes: int, shard: Shard, total_steps: int, params, dims: int = 0,
-                 device: int = 0, syncs_per_epoch: int = 1, mode: str = "avg", group=None,
+                 device: int = 0, syncs_per_epoch: int = 1, mode: str = "p2p", group=None,
                  layout_f64: bool = False):
         import ctypes as C
 
@@ -222,29 +249,47 @@ class ReplicaRun:
         self.dims, self.device = dims, device
         self.index = index
         self.N = int(n_nodes)
+        self.n_epochs = params.iter_max + 1
+        self.global_updates_per_epoch = params.min_term_updates
+        self._h = self._rep = None
         f64 = dims == 0 or layout_f64
         n_elems = self.N if dims == 0 else self.N * 2 * _DS[dims]
-        self.region = None
-        if mode == "p2p":
-            import torch.distributed as dist
-            world = dist.get_world_size(group) if dist.is_initialized() else 1
-            self.region = PeerRegion(device, n_elems, f64)
-            if world > 1:
-                connect_peer_regions(self.region, shard.rank, world, group)
-            else:
-                PeerRegion.connect_local([self.region])
-            self.x, self.x_sync, self.scratch = self.region.x, self.region.x_sync, None
-        else:
-            self.x = torch.zeros(n_elems, dtype=torch.float64 if f64 else torch.float32, device=f"cuda:{device}")
-            self.x_sync = torch.empty_like(self.x) if mode in ("delta", "tavg") else None
-            self.scratch = torch.empty(2 * n_elems, dtype=torch.float32, device=self.x.device) if mode == "tavg" else None
-        self.stream = torch.cuda.Stream(device=device)
-        from dataclasses import replace
-        self.params = replace(params, min_term_updates=epoch_quota(params.min_term_updates, shard, total_steps))
-        self.global_updates_per_epoch = params.min_term_updates
+        import torch.distributed as dist
+        world = dist.get_world_size(group) if dist.is_initialized() else 1
+        assert world == shard.world, "the shard plan was made for another world size"
         cfg = LaunchCfg.default()
         cfg.device = device
         cfg.layout_f64 = int(layout_f64)
+        if mode == "p2p":
+            from ._cabi import u8p
+            pl = _plan(shard)
+            cp = params.c()
+            self._rep = C.c_void_p()
+            check(lib().gfs_replica_create(index.handle, C.byref(cp), dims, C.byref(cfg), C.byref(pl), total_steps,
+                                           shard.rank, world, self.syncs, C.byref(self._rep)))
+            if world > 1:
+                from ._cabi import GFS_P2P_HANDLE_BYTES
+                buf = (C.c_uint8 * GFS_P2P_HANDLE_BYTES)()
+                check(lib().gfs_replica_ipc_handle(self._rep, C.cast(buf, u8p)))
+                handles = _all_gather_bytes(bytes(buf), world, device, group)
+                blob = (C.c_uint8 * (GFS_P2P_HANDLE_BYTES * world)).from_buffer_copy(b"".join(handles))
+                check(lib().gfs_replica_connect_ipc(self._rep, C.cast(blob, u8p), world, shard.rank))
+                dist.barrier(group=group)        # nobody reconciles before everybody has mapped everybody
+            else:
+                arr = (C.c_void_p * 1)(self._rep)
+                check(lib().gfs_replica_connect_local(arr, 1))
+            st, px, ne, eb = C.c_void_p(), C.c_void_p(), C.c_uint64(), C.c_uint32()
+            check(lib().gfs_replica_stream(self._rep, C.byref(st), C.byref(px), C.byref(ne), C.byref(eb)))
+            self.stream = torch.cuda.ExternalStream(st.value, device=device)
+            self.x = torch.as_tensor(_DeviceArray(px.value, ne.value, "<f8" if eb.value == 8 else "<f4"), device=f"cuda:{device}")
+            self.x_sync = self.scratch = None
+            return
+        self.x = torch.zeros(n_elems, dtype=torch.float64 if f64 else torch.float32, device=f"cuda:{device}")
+        self.x_sync = torch.empty_like(self.x) if mode in ("delta", "tavg") else None
+        self.scratch = torch.empty(2 * n_elems, dtype=torch.float32, device=self.x.device) if mode == "tavg" else None
+        self.stream = torch.cuda.Stream(device=device)
+        from dataclasses import replace
+        self.params = replace(params, min_term_updates=epoch_quota(params.min_term_updates, shard, total_steps))
         cfg.rng_thread_base = shard.rank << 24
         cfg.stream = self.stream.cuda_stream
         cfg.device_positions = self.x.data_ptr()
@@ -253,7 +298,6 @@ class ReplicaRun:
         self._h = C.c_void_p()
         cp = self.params.c()
         check(lib().gfs_sgd_session_create(self.index.handle, C.byref(cp), dims, C.byref(cfg), C.byref(self._h)))
-        self.n_epochs = params.iter_max + 1
         torch.cuda.synchronize(device)        # allocations / zero fills on torch's stream are done before the session's stream runs
 
     def upload(self, positions):
@@ -263,6 +307,9 @@ class ReplicaRun:
         from ._cabi import check, f64p, lib
         positions = np.ascontiguousarray(positions, dtype=np.float64)
         import torch
+        if self._rep is not None:
+            check(lib().gfs_replica_upload(self._rep, positions.ctypes.data_as(f64p)))
+            return
         check(lib().gfs_sgd_session_upload(self._h, positions.ctypes.data_as(f64p)))
         if self.x_sync is not None:
             # on the session's stream: torch's default stream does not order against it (non-blocking
@@ -278,20 +325,25 @@ class ReplicaRun:
         from ._cabi import check, f64p, lib
         ends, d = (1, 1) if self.dims == 0 else (2, self.dims)
         out = np.zeros(self.N * ends * d, dtype=np.float64)
-        check(lib().gfs_sgd_session_download(self._h, out.ctypes.data_as(f64p)))
+        if self._rep is not None:
+            check(lib().gfs_replica_download(self._rep, out.ctypes.data_as(f64p)))
+        else:
+            check(lib().gfs_sgd_session_download(self._h, out.ctypes.data_as(f64p)))
         return out
 
     def run_epoch(self, epoch: int):
-        """One epoch of the schedule: `syncs` slices of this rank's quota, replicas reconciled after each."""
+        """One epoch of the schedule: `syncs` slices of this rank's quota, replicas reconciled after each.
+        Asynchronous on self.stream."""
         import torch
 
         from ._cabi import check, lib
+        if self._rep is not None:
+            check(lib().gfs_replica_run(self._rep, epoch, epoch + 1))      # SGD slices + peer-memory reconciles, one C call
+            return
         with torch.cuda.stream(self.stream):
             for k in range(self.syncs):
                 check(lib().gfs_sgd_session_run(self._h, epoch, epoch + 1, k, self.syncs))
-                if self.region is not None:
-                    self.region.reconcile(self.stream.cuda_stream)      # one kernel: barrier, reduce + scatter over NVLink, barrier
-                else:
+                if self.shard.world > 1:
                     reconcile(self.x, self.x_sync, self.mode, self.group, self.scratch)
 
     def stats(self) -> dict:
@@ -299,26 +351,28 @@ class ReplicaRun:
 
         from ._cabi import Stats, check, lib
         st = Stats()
-        check(lib().gfs_sgd_session_stats(self._h, C.byref(st)))
-        if self.region is not None:
-            self.region.check()          # a timed-out peer barrier is an error, never a silent skip
+        if self._rep is not None:
+            check(lib().gfs_replica_stats(self._rep, C.byref(st)))     # a timed-out peer barrier is an error here, never a silent skip
+        else:
+            check(lib().gfs_sgd_session_stats(self._h, C.byref(st)))
         return st.as_dict()
 
     def close(self):
         from ._cabi import lib
+        self.x = self.x_sync = None
+        if self._rep is not None:
+            lib().gfs_replica_destroy(self._rep)
+            self._rep = None
         if self._h:
             lib().gfs_sgd_session_destroy(self._h)
             self._h = None
-        if self.region is not None:
-            self.x = self.x_sync = None
-            self.region.close()
-            self.region = None
 
 
 def build_shard_index(shard_handles, shard_first, node_len, device: int = 0, rank: int = 0, world: int = 1, group=None):
-    """PathIndex of this rank's paths, with ONE node relabelling for all ranks: rank 0 derives the
-    first-appearance order from its own records and broadcasts it, so that the position replicas
-    line up element-wise for the all-reduce.  shard_first is local to the shard (starts at 0)."""
+    """PathIndex of this rank's paths, with ONE node relabelling for all ranks so that the position replicas
+    line up element-wise: every rank runs K1 at the same time (rank 0 with the first-appearance relabelling,
+    the others without), then rank 0's permutation is broadcast and the others adopt it
+    (gfs_index_apply_relabel).  shard_first is local to the shard (starts at 0)."""
     import os
 
     import numpy as np
@@ -330,15 +384,39 @@ def build_shard_index(shard_handles, shard_first, node_len, device: int = 0, ran
     import torch
     import torch.distributed as dist
     relabel = os.environ.get("GFASORT_RELABEL", "1") != "0"
+    ix = PathIndex.from_arrays(shard_handles, shard_first, node_len, device=device, relabel=1 if (relabel and rank == 0) else 0)
     if not relabel:
-        return PathIndex.from_arrays(shard_handles, shard_first, node_len, device=device, relabel=0)
+        return ix
     perm = torch.empty(len(node_len), dtype=torch.int32, device=f"cuda:{device}")
-    ix = None
     if rank == 0:
-        ix = PathIndex.from_arrays(shard_handles, shard_first, node_len, device=device, relabel=1)
         perm.copy_(torch.from_numpy(ix.relabel_permutation().view(np.int32)))
     dist.broadcast(perm, src=0, group=group)
     if rank != 0:
-        ix = PathIndex.from_arrays(shard_handles, shard_first, node_len, device=device,
-                                   new_of_old=perm.cpu().numpy().view(np.uint32))
+        ix.apply_relabel(perm.cpu().numpy().view(np.uint32))
     return ix
+
+
+def all_paths_stress(index, shard: Shard, total_steps: int, positions, dims: int, samples: int, layout_order: bool,
+                     device: int = 0, group=None, seed: int = 12345):
+    """Sampled path stress over ALL paths of a sharded graph: every rank evaluates the samples that land in its
+    step slice (gfs_stress_partial), the three sums are all-reduced.  Same sample, same value as gfs_stress on
+    one GPU holding the whole graph.  Returns (rms_rel, mean_abs_rel, counted)."""
+    import ctypes as C
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from ._cabi import check, f64p, lib
+    positions = np.ascontiguousarray(positions, dtype=np.float64)
+    sums = (C.c_double * 3)(0.0, 0.0, 0.0)
+    if shard.steps > 0:
+        check(lib().gfs_stress_partial(index.handle, max(dims, 1), int(layout_order), positions.ctypes.data_as(f64p), samples, seed,
+                                       total_steps, shard.first_step_of_path_begin, shard.sample_begin, shard.sample_end, sums))
+    t = torch.tensor(list(sums), dtype=torch.float64, device=f"cuda:{device}")
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    s0, s1, c = (float(v) for v in t.tolist())
+    if c <= 0:
+        return 0.0, 0.0, 0
+    return float(np.sqrt(s0 / c)), s1 / c, int(c)

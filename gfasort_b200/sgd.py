@@ -55,27 +55,38 @@ class PathIndex:
     @staticmethod
     def from_graph(graph: BidirectedGraph) -> "PathIndex":
         handles, first, node_len = graph.dense()
-        return PathIndex.from_arrays(handles, first, node_len, graph)
+        return PathIndex.from_arrays(handles, first, node_len, graph, env=True)     # gfs_index_build: what the Rust host calls
 
     @staticmethod
     def from_arrays(step_handles: np.ndarray, path_first: np.ndarray, node_len: np.ndarray, graph=None,
                     path_begin: int = 0, path_end: int | None = None, device: int = -1,
-                    relabel: int | None = None, new_of_old: np.ndarray | None = None) -> "PathIndex":
-        step_handles = np.ascontiguousarray(step_handles, dtype=np.uint64)
+                    relabel: int | None = None, new_of_old: np.ndarray | None = None, env: bool = False) -> "PathIndex":
+        """step_handles: uint64 (Handle as the reference stores it) or uint32 (same value, half the copy).
+        env=True: gfs_index_build / gfs_index_build32 — the whole graph, device / GPU count / relabelling from the
+        environment (GFASORT_DEVICE, GFASORT_GPUS, GFASORT_RELABEL), i.e. what the Rust host's call does."""
+        h32 = np.asarray(step_handles).dtype == np.uint32
+        step_handles = np.ascontiguousarray(step_handles, dtype=np.uint32 if h32 else np.uint64)
+        hp = u32p if h32 else u64p
         path_first = np.ascontiguousarray(path_first, dtype=np.uint64)
         node_len = np.ascontiguousarray(node_len, dtype=np.uint32)
         P = len(path_first) - 1
         if path_end is None:
             path_end = P
         h = C.c_void_p()
+        if env:
+            assert path_begin == 0 and path_end == P and new_of_old is None and relabel is None
+            fn = lib().gfs_index_build32 if h32 else lib().gfs_index_build
+            check(fn(_p(step_handles, hp), _p(path_first, u64p), _p(node_len, u32p), len(step_handles), P, len(node_len), C.byref(h)))
+            return PathIndex(h, step_handles, path_first, len(node_len), graph)
         if relabel is None:
             relabel = 2 if new_of_old is not None else int(os.environ.get("GFASORT_RELABEL", "1") != "0")
         perm = None
         if new_of_old is not None:
             perm = np.ascontiguousarray(new_of_old, dtype=np.uint32)
-        check(lib().gfs_index_build_shard(_p(step_handles, u64p), _p(path_first, u64p), _p(node_len, u32p),
-                                          len(step_handles), P, len(node_len), path_begin, path_end, device,
-                                          relabel, _p(perm, u32p) if perm is not None else None, C.byref(h)))
+        fn = lib().gfs_index_build_shard32 if h32 else lib().gfs_index_build_shard
+        check(fn(_p(step_handles, hp), _p(path_first, u64p), _p(node_len, u32p),
+                 len(step_handles), P, len(node_len), path_begin, path_end, device,
+                 relabel, _p(perm, u32p) if perm is not None else None, C.byref(h)))
         s0, s1 = int(path_first[path_begin]), int(path_first[path_end])
         return PathIndex(h, step_handles[s0:s1], path_first[path_begin:path_end + 1] - path_first[path_begin],
                          len(node_len), graph)
@@ -84,6 +95,17 @@ class PathIndex:
         if self._h:
             lib().gfs_index_free(self._h)
             self._h = None
+
+    def apply_relabel(self, new_of_old: np.ndarray) -> None:
+        """Adopt another rank's node order (an index built with relabel=0; gfs_index_apply_relabel)."""
+        perm = np.ascontiguousarray(new_of_old, dtype=np.uint32)
+        check(lib().gfs_index_apply_relabel(self._h, _p(perm, u32p)))
+
+    def build_info(self) -> dict:
+        """Wall / copy / K1-kernel seconds, launches and devices of the build (gfs_index_build_info)."""
+        b, c, k, n, d = C.c_double(), C.c_double(), C.c_double(), C.c_uint64(), C.c_uint32()
+        check(lib().gfs_index_build_info(self._h, C.byref(b), C.byref(c), C.byref(k), C.byref(n), C.byref(d)))
+        return {"build_seconds": b.value, "copy_seconds": c.value, "kernel_seconds": k.value, "launches": n.value, "devices": d.value}
 
     def relabel_permutation(self) -> np.ndarray:
         """new_of_old[N]: the library's internal node order (identity when relabelling is off)."""

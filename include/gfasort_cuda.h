@@ -100,7 +100,11 @@ typedef struct gfs_stats {
     double total_seconds;      /* wall time of the call */
     uint32_t grid, block;      /* launch shape used */
     uint32_t coord_bytes;      /* 8 = f64 positions, 4 = f32 */
-    uint32_t reserved;
+    uint32_t n_devices;        /* GPUs the call ran on (GFASORT_GPUS) */
+    uint64_t window_steps;     /* sampling schedule used: 0 = every step ~ U[0,S) (the reference's), else the
+                                  sliding window's length in steps */
+    uint32_t coherent;         /* 1 = warps sampled 32 consecutive steps (window mode only) */
+    uint32_t syncs_per_epoch;  /* replica reconciles per epoch (n_devices > 1) */
 } gfs_stats;
 
 const char* gfs_last_error(void);
@@ -114,11 +118,30 @@ const char* gfs_device_info(void);
  * record per step {node<<1|rev, node_len, offset}.  Each path must have < 2^32 steps. */
 int gfs_index_build(const uint64_t* step_handles, const uint64_t* path_first_step, const uint32_t* node_len,
                     uint64_t S, uint64_t P, uint64_t N, gfs_index** out);
-/* As above, on `device` and on a sub-range of paths [path_begin, path_end): the shard one GPU of a
+/* Same with 32-bit step handles ((dense_idx << 1) | is_reverse still fits: N < 2^31): half the host->device
+ * copy, which is what the index build costs end to end.  The host flattens Vec<Handle> once either way. */
+int gfs_index_build32(const uint32_t* step_handles, const uint64_t* path_first_step, const uint32_t* node_len,
+                      uint64_t S, uint64_t P, uint64_t N, gfs_index** out);
+/* Multi-GPU: under GFASORT_GPUS=G (G > 1; the reference CLI is frozen) gfs_index_build /
+ * gfs_index_build32 build one shard per device 0..G-1 (concurrently, each device pulling its own steps), with one
+ * node order for all shards, and gfs_sgd_1d / gfs_sgd_nd / gfs_sgd_sort_1d / gfs_stress / gfs_index_export on the
+ * returned index drive all G GPUs from this one process: replicated positions, terms sharded by step slice,
+ * replicas reconciled GFASORT_SYNCS (default 1) times per epoch over NVLink peer memory.
+ * The step array is streamed in chunks (GFASORT_INDEX_CHUNK steps, default 2^24) with the copy of chunk c+1 under
+ * the kernel of chunk c; a pageable source goes through pinned bounce buffers filled by GFASORT_COPY_THREADS
+ * host threads. */
+/* How the last build went: wall seconds of the whole call, of the streamed copy + K1 phase, K1 kernel seconds
+ * (CUDA events; max over shards), kernels launched, devices used.  Any pointer may be NULL. */
+int gfs_index_build_info(const gfs_index* ix, double* build_seconds, double* copy_seconds, double* kernel_seconds,
+                         uint64_t* launches, uint32_t* n_devices);
+/* As gfs_index_build, on `device` and on a sub-range of paths [path_begin, path_end): the shard one GPU of a
  * multi-GPU run owns.  step_handles/path_first_step still describe the whole graph. */
 int gfs_index_build_shard(const uint64_t* step_handles, const uint64_t* path_first_step, const uint32_t* node_len,
                           uint64_t S, uint64_t P, uint64_t N, uint64_t path_begin, uint64_t path_end,
                           int32_t device, int32_t relabel_mode, const uint32_t* new_of_old, gfs_index** out);
+int gfs_index_build_shard32(const uint32_t* step_handles, const uint64_t* path_first_step, const uint32_t* node_len,
+                            uint64_t S, uint64_t P, uint64_t N, uint64_t path_begin, uint64_t path_end,
+                            int32_t device, int32_t relabel_mode, const uint32_t* new_of_old, gfs_index** out);
 /* Internal node numbering.  The library stores positions in the order in which nodes first appear
  * along the paths (path-adjacent nodes then share cache lines); uploads and downloads permute, so
  * callers never see it.  relabel_mode: 0 = keep the caller's dense order, 1 = first-appearance
@@ -126,6 +149,9 @@ int gfs_index_build_shard(const uint64_t* step_handles, const uint64_t* path_fir
  * permutation new_of_old[N] supplied by the caller — ranks of a multi-GPU run must share one
  * permutation so that their position replicas can be all-reduced element-wise. */
 int gfs_index_export_relabel(const gfs_index* ix, uint32_t* new_of_old /*N*/);
+/* Relabels an index that was built with relabel_mode 0 (so all ranks can run K1 at the same time and adopt
+ * rank 0's order afterwards). */
+int gfs_index_apply_relabel(gfs_index* ix, const uint32_t* new_of_old /*N*/);
 /* Copies back what PathIndex holds: step_to_position (src/sgd.rs:18) and PathInfo.length (:29).
  * Either pointer may be NULL.  step_to_path / step_to_rank / first_step / step_count are functions
  * of path_first_step alone and stay on the host. */
@@ -161,6 +187,14 @@ int gfs_sgd_nd_cfg(const gfs_index* ix, const gfs_sgd_params* params, const gfs_
  * dims >= 1 with layout_order != 0 takes a Layout-order array (N*2*dims). */
 int gfs_stress(const gfs_index* ix, uint32_t dims, int32_t layout_order, const double* coords, uint64_t samples,
                uint64_t seed, double* rms_rel, double* mean_abs_rel, uint64_t* counted);
+
+/* One shard's share of the same measurement (one process per GPU): sample k draws its step over the WHOLE graph
+ * (total_steps); this index — whose local step 0 is global step step_offset — evaluates the samples that land in
+ * [step_begin, step_end) and ADDS {sum (dl-dp)^2/dp^2, sum |dl-dp|/dp, count} to sums3.  Summing the ranks' triples
+ * gives exactly the single-GPU sample over all paths. */
+int gfs_stress_partial(const gfs_index* ix, uint32_t dims, int32_t layout_order, const double* coords, uint64_t samples,
+                       uint64_t seed, uint64_t total_steps, uint64_t step_offset, uint64_t step_begin, uint64_t step_end,
+                       double* sums3);
 
 /* ---- session API (device-resident runs, multi-GPU) -------------------------------------------
  * A session holds the positions on the device between calls so that the host can run the schedule
@@ -270,7 +304,7 @@ int gfs_reconcile_apply(void* x, void* x_sync, uint64_t n, uint32_t elem_bytes, 
  * and call gfs_p2p_region_connect_ipc; one process driving several GPUs (or several replicas on one GPU):
  * gfs_p2p_region_connect_local.  max_blocks = 0: one block per SM. */
 #define GFS_P2P_MAX_RANKS 16
-#define GFS_P2P_HANDLE_BYTES 64
+#define GFS_P2P_HANDLE_BYTES 80    /* cudaIpcMemHandle_t + {n, elem_bytes, blocks}: peers must agree on the shape */
 typedef struct gfs_p2p_region gfs_p2p_region;
 int gfs_p2p_region_create(int32_t device, uint64_t n, uint32_t elem_bytes, uint32_t max_blocks, gfs_p2p_region** out);
 int gfs_p2p_region_ptrs(gfs_p2p_region* r, void** x, void** x_sync, uint64_t* region_bytes);
@@ -284,9 +318,47 @@ int gfs_p2p_region_snapshot(gfs_p2p_region* r, void* stream);
 /* Asynchronous on `stream`: x <- x_sync + (sum of the replicas' displacements) / (#replicas that moved the element)
  * on every replica, then x_sync <- x.  Every rank calls it once per reconcile, in the same order. */
 int gfs_p2p_reconcile(gfs_p2p_region* r, void* stream);
-/* Blocking: GFS_ERR_CUDA if a barrier of an earlier reconcile timed out (a rank missing, kernels not co-resident). */
+/* Replicas that share ONE device (tests): all `world` (<= 4) ranks as one cooperative launch, block group g playing
+ * rank g — kernels of one GPU that wait on one another must not be separate launches. */
+int gfs_p2p_reconcile_local(gfs_p2p_region* const* regions /*world, rank order, one device*/, uint32_t world, void* stream);
+/* Blocking: GFS_ERR_CUDA if a barrier of an earlier reconcile timed out on ANY rank (a rank missing, kernels not
+ * co-resident).  After a timeout the replicas are undefined and every later reconcile returns at once: the run failed. */
 int gfs_p2p_region_check(gfs_p2p_region* r);
 void gfs_p2p_region_free(gfs_p2p_region* r);
+
+/* ---- replicated multi-GPU runs -------------------------------------------------
+ * Terms shard, positions do not.  Rank r of G samples the steps of its slice [S r/G, S (r+1)/G) of the concatenated
+ * step array and needs the records of just the paths that slice overlaps; it applies its share of every epoch's
+ * min_term_updates (exact in sum over ranks) to its own full replica of the positions; replicas are reconciled
+ * (moved-replica mean, gfs_p2p_*) syncs_per_epoch times per epoch. */
+typedef struct gfs_shard_plan {
+    uint64_t sample_begin, sample_end;   /* global step range this rank samples from */
+    uint64_t path_begin, path_end;       /* paths whose records it needs (gfs_index_build_shard) */
+    uint64_t first_step;                 /* global step index of path_begin's first step */
+} gfs_shard_plan;
+int gfs_shard_plan_make(const uint64_t* path_first_step /*P+1*/, uint64_t P, uint32_t rank, uint32_t world, gfs_shard_plan* out);
+uint64_t gfs_shard_epoch_quota(uint64_t min_term_updates, const gfs_shard_plan* plan, uint64_t total_steps);
+/* One rank: a session on `shard` (built for plan->path_begin..path_end) whose positions live in a peer region.
+ * `params` are the WHOLE run's (the quota is derived here); cfg may be NULL (total_threads, aggregate, layout_f64 are
+ * honoured).  One process per GPU: create, exchange gfs_replica_ipc_handle blobs (GFS_P2P_HANDLE_BYTES each, rank
+ * order), gfs_replica_connect_ipc.  One process, G devices: gfs_replica_connect_local — or simply GFASORT_GPUS. */
+typedef struct gfs_replica gfs_replica;
+int gfs_replica_create(const gfs_index* shard, const gfs_sgd_params* params, uint32_t dims, const gfs_launch_cfg* cfg,
+                       const gfs_shard_plan* plan, uint64_t total_steps, uint32_t rank, uint32_t world,
+                       uint32_t syncs_per_epoch, gfs_replica** out);
+int gfs_replica_ipc_handle(gfs_replica* r, uint8_t* blob /*GFS_P2P_HANDLE_BYTES*/);
+int gfs_replica_connect_ipc(gfs_replica* r, const uint8_t* blobs /*world x GFS_P2P_HANDLE_BYTES*/, uint32_t world, uint32_t rank);
+int gfs_replica_connect_local(gfs_replica* const* replicas /*world, rank order, distinct devices*/, uint32_t world);
+int gfs_replica_upload(gfs_replica* r, const double* positions);            /* every rank uploads the same positions */
+/* Asynchronous: epochs [epoch_begin, epoch_end), syncs_per_epoch (SGD slice, reconcile) pairs each. */
+int gfs_replica_run(gfs_replica* r, uint64_t epoch_begin, uint64_t epoch_end);
+int gfs_replica_sync(gfs_replica* r);                                        /* blocking; reports reconcile time-outs */
+int gfs_replica_download(gfs_replica* r, double* positions);
+int gfs_replica_stats(gfs_replica* r, gfs_stats* stats);                     /* this rank's share; synchronises first */
+/* The stream the rank's kernels run on and its replica (device pointer, element count, element bytes): for timing
+ * with CUDA events on the launching stream and for checks.  Any pointer may be NULL. */
+int gfs_replica_stream(gfs_replica* r, void** stream, void** dev_positions, uint64_t* n_elems, uint32_t* elem_bytes);
+void gfs_replica_destroy(gfs_replica* r);
 
 /* ---- synthetic pangenome graphs (bench / tests input) -------------------------
  * Seeded bubble-chain generator writing the C-ABI's own flat inputs.  Two calls: sizes, then fill. */

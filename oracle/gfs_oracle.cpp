@@ -516,6 +516,11 @@ struct Barrier {   // reusable barrier for the exact-count mode (C++17)
 enum { MODE_REFERENCE = 0, MODE_EXACT = 1 };
 enum { DRAW_XOSHIRO = 0, DRAW_PHILOX = 1 };
 
+// bench.py's bounded CPU samples run single epochs of the reference's schedule (same eta, same cooling state as
+// the epoch the GPU arm times): epochs [g_epoch_begin, min(g_epoch_end, iter_max + 1)) of the run are executed,
+// the schedule itself (etas, first cooling epoch) is always the full one.  Default: the whole run, i.e. the reference.
+static uint64_t g_epoch_begin = 0, g_epoch_end = ~0ull;
+
 // One SGD run, 1D (dims == 0 -> X) or nD (dims >= 1 -> C).  mode REFERENCE = checker thread polling
 // every 1 ms + free-running workers (sgd.rs:355-593 / 912-1164); mode EXACT = every epoch applies
 // exactly min_term_updates updates (thread t does floor(M/T) + (t < M%T)), barrier between epochs.
@@ -540,9 +545,12 @@ void run_sgd(const GraphView& g, const Params& P, int mode, uint64_t dims, uint3
     // NOTE: the clamp `space_idx.min(zetas.len()-1)` (sgd.rs:469) can only bind when the table is
     // full-size; with the capped table every reachable index is < zalloc-1, so results are identical.
 
+    const uint64_t e_begin = std::min<uint64_t>(g_epoch_begin, P.iter_max), e_end = std::min<uint64_t>(g_epoch_end, P.iter_max + 1);
     Control ctl;
-    ctl.eta_bits.store(f64_bits(etas[0]));
-    ctl.theta_bits.store(f64_bits(P.theta));
+    ctl.iteration.store(e_begin);
+    ctl.eta_bits.store(f64_bits(etas[e_begin]));
+    ctl.theta_bits.store(f64_bits(e_begin > first_cooling_iteration ? 0.001 : P.theta));
+    ctl.cooling.store(e_begin > first_cooling_iteration);
     std::atomic<uint64_t> applied_total{0}, attempts_total{0};
     auto t0 = std::chrono::steady_clock::now();
     const uint64_t T = P.nthreads;
@@ -558,7 +566,7 @@ void run_sgd(const GraphView& g, const Params& P, int mode, uint64_t dims, uint3
                 uint64_t cur = ctl.term_updates.load(std::memory_order_relaxed);
                 if (cur >= P.min_term_updates) {
                     uint64_t new_iter = ctl.iteration.fetch_add(1, std::memory_order_relaxed) + 1;
-                    if (new_iter > P.iter_max) {
+                    if (new_iter > P.iter_max || new_iter >= e_end) {
                         ctl.work_todo.store(false, std::memory_order_relaxed);
                     } else {
                         if (new_iter < etas.size()) ctl.eta_bits.store(f64_bits(etas[new_iter]), std::memory_order_relaxed);
@@ -608,7 +616,7 @@ void run_sgd(const GraphView& g, const Params& P, int mode, uint64_t dims, uint3
                 std::vector<double> deltas(std::max<uint64_t>(dims, 1));
                 uint64_t applied = 0, attempts = 0;
                 Term t;
-                for (uint64_t it = 0; it <= P.iter_max; ++it) {
+                for (uint64_t it = e_begin; it < e_end; ++it) {
                     double eta = etas[it];
                     bool cooling = it > first_cooling_iteration;
                     double theta = cooling ? 0.001 : P.theta;
@@ -634,7 +642,7 @@ void run_sgd(const GraphView& g, const Params& P, int mode, uint64_t dims, uint3
     if (st) {
         st->applied = applied_total; st->attempts = attempts_total;
         st->seconds = std::chrono::duration<double>(t1 - t0).count();
-        st->epochs = P.iter_max + 1;
+        st->epochs = e_end - e_begin;
     }
 }
 
@@ -682,6 +690,7 @@ static Params conv(const oracle_params* p) {
                   p->cooling_start, p->nthreads, p->progress, p->seed};
 }
 
+void oracle_set_epoch_window(uint64_t epoch_begin, uint64_t epoch_end) { g_epoch_begin = epoch_begin; g_epoch_end = epoch_end; }
 double oracle_fast_precise_pow(double a, double b) { return fast_precise_pow(a, b); }
 uint64_t oracle_dirty_zipf(uint64_t zmin, uint64_t zmax, double theta, double zeta, double zeta2theta, double u) {
     return dirty_zipf(zmin, zmax, theta, zeta, zeta2theta, u);

@@ -87,6 +87,8 @@ def lib():
         L.oracle_zetas.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_double, f64p, C.c_uint64, C.c_uint64]
         L.oracle_philox4x32_10.restype = None
         L.oracle_philox4x32_10.argtypes = [u32p, u32p, u32p]
+        L.oracle_set_epoch_window.restype = None
+        L.oracle_set_epoch_window.argtypes = [C.c_uint64, C.c_uint64]
         L.oracle_xoshiro_u64.restype = None
         L.oracle_xoshiro_u64.argtypes = [C.c_uint64, C.c_uint64, u64p]
         L.oracle_xoshiro_below.restype = None
@@ -381,6 +383,12 @@ class PrebuiltIndex:
             self.close()
         except Exception:
             pass
+
+
+def set_epoch_window(epoch_begin: int = 0, epoch_end: int | None = None):
+    """Run only epochs [epoch_begin, epoch_end) of the schedule in the following SGD calls (bench.py's bounded CPU
+    samples); no arguments = the whole run, as the reference."""
+    lib().oracle_set_epoch_window(epoch_begin, (1 << 64) - 1 if epoch_end is None else epoch_end)
 
 
 def path_linear_sgd(g: Graph, p: OracleParams, mode=MODE_REFERENCE, draw=DRAW_XOSHIRO, x0=None,

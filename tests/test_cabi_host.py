@@ -34,7 +34,7 @@ def test_header_symbols_all_exported(gfs):
 def test_struct_layouts_match_header(gfs):
     from gfasort_b200 import _cabi
     assert C.sizeof(_cabi.SgdParams) == 14 * 8
-    assert C.sizeof(_cabi.Stats) == 8 * 8 + 4 * 4
+    assert C.sizeof(_cabi.Stats) == 8 * 8 + 4 * 4 + 8 + 2 * 4
     assert C.sizeof(_cabi.SynthSpec) == 3 * 8 + 2 * 4
     assert C.sizeof(_cabi.LaunchCfg) == 4 * 4 + 8 + 8 + 8 + 8 + 8
 

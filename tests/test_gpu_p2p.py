@@ -1,7 +1,13 @@
-"""GPU tests (-m gpu) of the peer-memory reconcile kernel (gfasort_b200/csrc/gfs_p2p.cu, K5b) on ONE device:
-G replicas live on the same GPU and are connected with gfs_p2p_region_connect_local, one stream per "rank",
-so the G kernels run concurrently and meet at their in-kernel barriers exactly as G ranks over NVLink would.
-(The IPC path between processes needs >= 2 GPUs: bench.py --gpus N --reconcile p2p.)"""
+"""GPU tests (-m gpu) of the peer-memory reconcile kernel (gfasort_b200/csrc/gfs_p2p.cu, K5b) and of the replicated
+multi-GPU run behind the C ABI (gfs_multi.cu).
+
+One device: G replicas live on the same GPU, are connected with gfs_p2p_region_connect_local and reconciled by
+gfs_p2p_reconcile_local — ONE cooperative launch in which block group g plays rank g, so the ranks meet at the same
+in-kernel barriers, use the same partition and the same arithmetic as G ranks over NVLink, without ever having two
+kernels of one GPU wait on one another.  Two or more devices (skipped otherwise): the real thing — one process
+driving G GPUs through GFASORT_GPUS, and tools/p2p_ipc_check.py covers one process per GPU."""
+import os
+
 import numpy as np
 import pytest
 
@@ -22,7 +28,8 @@ def _expected(xs, xr):
     return out
 
 
-@pytest.mark.parametrize("dtype,G,n", [("float64", 2, 100_003), ("float64", 4, 1_000_000), ("float32", 3, 65_537), ("float64", 1, 999)])
+@pytest.mark.parametrize("dtype,G,n", [("float64", 2, 100_003), ("float64", 4, 1_000_000), ("float32", 3, 65_537),
+                                       ("float32", 2, 1_000_001), ("float64", 1, 999)])
 def test_p2p_reconcile_matches_moved_replica_mean(dtype, G, n, gfs, monkeypatch):
     import torch
     from gfasort_b200.multi import PeerRegion
@@ -31,7 +38,7 @@ def test_p2p_reconcile_matches_moved_replica_mean(dtype, G, n, gfs, monkeypatch)
     regions = [PeerRegion(0, n, f64, max_blocks=8) for _ in range(G)]
     try:
         PeerRegion.connect_local(regions)
-        streams = [torch.cuda.Stream(device=0) for _ in range(G)]
+        stream = torch.cuda.Stream(device=0)
         rng = np.random.default_rng(5)
         xs = (rng.standard_normal(n) * 1e6).astype(dtype)
         for r in regions:
@@ -46,8 +53,7 @@ def test_p2p_reconcile_matches_moved_replica_mean(dtype, G, n, gfs, monkeypatch)
                 xr.append(x)
                 r.x.copy_(torch.from_numpy(x))
             torch.cuda.synchronize()
-            for g, r in enumerate(regions):
-                r.reconcile(streams[g].cuda_stream)
+            PeerRegion.reconcile_local(regions, stream.cuda_stream)    # all ranks, one cooperative launch
             torch.cuda.synchronize()
             for r in regions:
                 r.check()
@@ -66,33 +72,129 @@ def test_p2p_reconcile_matches_moved_replica_mean(dtype, G, n, gfs, monkeypatch)
             r.close()
 
 
-def test_p2p_missing_peer_is_an_error_not_a_hang(gfs, monkeypatch):
+def test_p2p_missing_peer_fails_the_run_on_every_rank(gfs, monkeypatch):
+    """A rank that never shows up: the barrier's bounded spin gives up, the error word of EVERY rank is raised
+    (the run failed; nobody may use its replica), and later reconciles return at once instead of timing out again."""
+    import time
+
     import torch
     from gfasort_b200.multi import PeerRegion
     monkeypatch.setenv("GFASORT_P2P_SPIN_CAP", str(1 << 12))          # a few ms
     regions = [PeerRegion(0, 1000, True, max_blocks=2) for _ in range(2)]
     try:
         PeerRegion.connect_local(regions)
-        x0 = regions[0].x.clone()
-        regions[0].reconcile(torch.cuda.current_stream().cuda_stream)  # rank 1 never shows up
+        st = torch.cuda.current_stream().cuda_stream
+        regions[0].reconcile(st)                                       # rank 1 never launches: a lone kernel with a bounded spin
         torch.cuda.synchronize()
-        with pytest.raises(gfs.GfsError, match="barrier timed out"):
-            regions[0].check()
-        assert torch.equal(regions[0].x, x0)                           # nothing was touched
-        regions[1].check()
+        for r in regions:
+            with pytest.raises(gfs.GfsError, match="barrier timed out"):
+                r.check()
+        t0 = time.perf_counter()
+        regions[0].reconcile(st)                                       # sticky: returns without waiting
+        torch.cuda.synchronize()
+        assert time.perf_counter() - t0 < 0.5
     finally:
         for r in regions:
             r.close()
 
 
 def test_p2p_region_argument_checks(gfs):
+    import ctypes as C
+
+    from gfasort_b200._cabi import GFS_P2P_HANDLE_BYTES, lib, u8p
     from gfasort_b200.multi import PeerRegion
     a = PeerRegion(0, 10, True, max_blocks=2)
     b = PeerRegion(0, 11, True, max_blocks=2)
+    c = PeerRegion(0, 10, True, max_blocks=3)
     try:
         with pytest.raises(gfs.GfsError):
             a.reconcile(0)                                             # not connected
         with pytest.raises(gfs.GfsError):
             PeerRegion.connect_local([a, b])                           # sizes differ
+        with pytest.raises(gfs.GfsError):
+            PeerRegion.connect_local([a, c])                           # grids differ
+        # the IPC path checks the same agreement from the exchanged blobs, before opening any handle
+        ha, hb, hc = a.ipc_handle(), b.ipc_handle(), c.ipc_handle()
+        assert len(ha) == GFS_P2P_HANDLE_BYTES
+        for other in (hb, hc):
+            blob = (C.c_uint8 * (2 * GFS_P2P_HANDLE_BYTES)).from_buffer_copy(ha + other)
+            assert lib().gfs_p2p_region_connect_ipc(a._h, C.cast(blob, u8p), 2, 0) != 0
+            assert b"differs in size, element type or grid" in lib().gfs_last_error()
     finally:
-        a.close(); b.close()
+        a.close(); b.close(); c.close()
+
+
+# ------------------------------------------------------------------------------------------------
+# the replicated run behind the C ABI
+# ------------------------------------------------------------------------------------------------
+def _synth(gfs, nodes, paths):
+    s = gfs.SynthGraph(nodes, paths, seed=42)
+    counts = np.diff(s.path_first)
+    x0 = s.initial_positions()
+    return s, counts, x0
+
+
+def test_replica_world_one_equals_plain_run(gfs):
+    """A gfs_replica with world = 1 is the plain session: same applied count, finite positions, same stress."""
+    from gfasort_b200 import multi
+    s, counts, x0 = _synth(gfs, 50_000, 8)
+    ix = gfs.PathIndex.from_arrays(s.step_handles, s.path_first, s.node_len)
+    p = gfs.PathSGDParams(iter_max=30, min_term_updates=int(counts.sum()), eta_max=float(int(counts.max()) ** 2),
+                          space=int(ix.path_lengths().max()), space_max=100)
+    shard = multi.shard_steps(s.path_first, 0, 1)
+    run = multi.ReplicaRun(ix, s.N, shard, s.S, p, dims=0, device=0, mode="p2p")
+    run.upload(x0)
+    for e in range(p.iter_max + 1):
+        run.run_epoch(e)
+    x = run.download()
+    st = run.stats()
+    run.close()
+    assert st["applied_updates"] == (p.iter_max + 1) * p.min_term_updates
+    assert np.all(np.isfinite(x))
+    graph = gfs.BidirectedGraph.from_dense(s.step_handles, s.path_first, s.node_len)
+    x1 = gfs.path_linear_sgd_array(graph, p, ix)
+    a, b = gfs.sort_stress(graph, x, 200_000, ix)[1], gfs.sort_stress(graph, x1, 200_000, ix)[1]
+    assert abs(a - b) <= 0.05 * b
+    ix.close()
+
+
+def _n_gpus():
+    import torch
+    return torch.cuda.device_count()
+
+
+@pytest.mark.skipif("_n_gpus() < 2")
+@pytest.mark.parametrize("dims", [0, 2])
+def test_one_call_multi_gpu_through_the_cabi(dims, gfs, monkeypatch):
+    """GFASORT_GPUS=2: gfs_index_build builds one shard per device, gfs_sgd_1d / gfs_sgd_nd run the replicated
+    schedule from this one process, gfs_stress covers all paths.  Index bit-identical to one GPU; stress within 2 %
+    (1D) / 10 % (2D float) of the one-GPU run."""
+    s, counts, x0 = _synth(gfs, 200_000, 16)
+    graph = gfs.BidirectedGraph.from_dense(s.step_handles, s.path_first, s.node_len)
+    ix1 = gfs.PathIndex.from_arrays(s.step_handles, s.path_first, s.node_len)
+    monkeypatch.setenv("GFASORT_GPUS", "2")
+    ix2 = gfs.PathIndex.from_arrays(s.step_handles, s.path_first, s.node_len, env=True)
+    assert ix2.build_info()["devices"] == 2
+    assert np.array_equal(ix1.step_positions(), ix2.step_positions())
+    assert np.array_equal(ix1.path_lengths(), ix2.path_lengths())
+    if dims == 0:
+        p = gfs.PathSGDParams(iter_max=100, min_term_updates=int(counts.sum()), eta_max=float(int(counts.max()) ** 2),
+                              space=int(ix1.path_lengths().max()), space_max=100)
+        xa = gfs.path_linear_sgd_array(graph, p, ix1)
+        xb = gfs.path_linear_sgd_array(graph, p, ix2)
+        st = dict(gfs.sgd.last_stats)
+        assert st["applied_updates"] == (p.iter_max + 1) * p.min_term_updates
+        sa, sb = gfs.sort_stress(graph, xa, 500_000, ix1), gfs.sort_stress(graph, xb, 500_000, ix2)
+        sb1 = gfs.sort_stress(graph, xb, 500_000, ix1)
+        assert sb[2] == sb1[2] and abs(sb[1] - sb1[1]) <= 1e-9 * sb1[1]       # sharded stress == one-GPU stress, same sample
+        print(f"1D stress one GPU {sa[1]:.5e} vs GFASORT_GPUS=2 {sb[1]:.5e}")
+        assert abs(sb[1] - sa[1]) <= 0.02 * sa[1]
+    else:
+        p = gfs.LayoutSGDParams(dimensions=2, iter_max=30, min_term_updates=10 * int(counts.sum()),
+                                eta_max=float(int(counts.max()) ** 2), space=int(counts.max()), space_max=1000)
+        la = gfs.path_linear_sgd_layout(graph, p, ix1)
+        lb = gfs.path_linear_sgd_layout(graph, p, ix2, coords0=gfs.initial_layout(graph, 2, p.seed))
+        sa, sb = gfs.layout_stress(graph, la.coords, 2, 500_000, ix1), gfs.layout_stress(graph, lb.coords, 2, 500_000, ix2)
+        print(f"2D stress one GPU {sa[1]:.5e} vs GFASORT_GPUS=2 {sb[1]:.5e}")
+        assert abs(sb[1] - sa[1]) <= 0.10 * sa[1]
+    ix1.close(); ix2.close()

@@ -448,10 +448,15 @@ def test_sgd_1d_stress_parity_synth(mode, iter_max, gfs, oracle, monkeypatch):
         assert g_mar <= c_mar * 1.02 + 1e-5
         assert g_rms <= c_rms * 1.08
     else:
-        # mid-schedule (not a reference configuration; printed for the record): the layout is still moving,
-        # the measure varies by 10-20 % between runs on either side, and the sweep schedule trails the oracle
-        # by a few percent before catching up — so only a gross-error bound here
-        assert g_mar <= c_mar * 1.5
+        # mid-schedule (not a reference configuration): the layout is still moving and the measure varies by
+        # 10-20 % between runs on either side.  Measured on B200 (round 1, gpurun_out/pytest_r1l.log): iid equal to
+        # the oracle; the sweep schedule FORCED on this 200k-node graph (a 32768-step window holds 1/45 of all
+        # steps and ~40 % of them are in flight at once — not a configuration the library ever picks) trails by
+        # 13 % on the mean form (3.4e-4 vs 3.0e-4) and 2.5x on the RMS form (9.0e-3 vs 3.6e-3), and has caught up
+        # by iter_max = 100.  The bound below is that measured gap plus the run-to-run spread.
+        bound = 1.10 if mode == "iid" else 1.30
+        assert g_mar <= c_mar * bound, (f"mid-schedule stress: gpu {g_mar:.3e} vs oracle {c_mar:.3e} "
+                                        f"(ratio {g_mar / c_mar:.3f}, bound {bound}; measured in round 1: 1.00 iid / 1.13 forced sweep)")
     ix.close()
 
 
@@ -481,9 +486,10 @@ def test_sgd_2d_stress_parity_synth(mode, gfs, oracle, monkeypatch):
     # After only 31 epochs these synthetic layouts are still settling: the ORACLE's own median over 3 seeds
     # moves between 0.00129 and 0.00170 (20k nodes) from one run to the next (16 free-running threads), the
     # GPU's between 0.00124 and 0.00145.  A 2 % statement is not testable here — DRB1 (stable to 0.2 %) carries
-    # it for `L` (test_sgd_nd_stress_parity_drb1); this test guards against gross regressions of either schedule.
-    assert g_mar <= c_mar * 1.25
-    assert g_rms <= c_rms * 1.25
+    # it for `L` (test_sgd_nd_stress_parity_drb1) and test_default_schedule_hard_graph_vs_oracle for the default
+    # schedule at a size where it engages; this test guards against gross regressions of either schedule.
+    assert g_mar <= c_mar * 1.25, f"2D synth stress: gpu {g_mar:.3e} vs oracle {c_mar:.3e} (ratio {g_mar / c_mar:.3f}; oracle's own run-to-run spread is +-15 %)"
+    assert g_rms <= c_rms * 1.25, f"2D synth rms: gpu {g_rms:.3e} vs oracle {c_rms:.3e}"
     ix.close()
 
 
@@ -517,6 +523,114 @@ def test_sgd_nd_stress_parity_drb1(dims, f64, gfs, oracle):
     print(f"DRB1 L(D={dims}, f64={f64}) stress: gpu mean_abs {g_mar:.5f} rms {g_rms:.5f} | oracle mean_abs {c_mar:.5f} rms {c_rms:.5f}")
     assert g_mar <= c_mar * 1.02
     assert g_rms <= c_rms * 1.02
+    ix.close()
+
+
+# ------------------------------------------------------------------------------------------------
+# the DEFAULT schedule at the sizes where it engages (records > 64 MB: sliding 2^20-step window + 32 consecutive
+# steps per warp) against the oracle, which samples every step from U[0, S) like the reference (sgd.rs:444)
+# ------------------------------------------------------------------------------------------------
+def _oracle_fixture():
+    """tests/golden/oracle_stress.json: stress reached by the oracle (all host cores, exact budget) on the named
+    graphs, on the same Philox sample gfs_stress uses — made by tools/oracle_config3.py (commands inside)."""
+    import json
+    from conftest import GOLDEN
+    with open(os.path.join(GOLDEN, "oracle_stress.json")) as f:
+        return json.load(f)
+
+
+def _gpu_1d(gfs, graph, ix, p, seed, window=None, monkeypatch=None):
+    from dataclasses import replace
+    if window is not None:
+        monkeypatch.setenv("GFASORT_WINDOW", str(window))
+    x = gfs.path_linear_sgd_array(graph, replace(p, seed=seed), ix)
+    st = dict(gfs.sgd.last_stats)
+    assert st["applied_updates"] == (p.iter_max + 1) * p.min_term_updates
+    if window is not None:
+        monkeypatch.delenv("GFASORT_WINDOW")
+    return x, st
+
+
+def test_default_schedule_hard_graph_vs_oracle(gfs, oracle, monkeypatch):
+    """Tiled / perturbed DRB1 (tests/hard_graph.py): 743k nodes, 12 paths, 5.8M steps with recombining haplotypes,
+    whole-tile and nested inversions, tandem repeats (path-revisited nodes, cycles).  93 MB of records, so the library
+    picks the sweep + coherent schedule by itself.  Medians over 3 seeds, live oracle at the same exact budget:
+    <= 2 % on the mean form (BASELINE.json), and the same for the reference-exact iid schedule."""
+    from hard_graph import tiled_drb1
+    h, first, nl = tiled_drb1(gfs, 150)
+    og = oracle.Graph.from_dense(h, first.copy(), nl)
+    graph = gfs.BidirectedGraph.from_dense(h, first, nl)
+    ix = gfs.PathIndex.from_arrays(h, first, nl)
+    op = oracle.params_from_graph(og, nthreads=os.cpu_count() or 4)
+    p = _pyparams(op, gfs)
+    seeds = [9399220 + 1000 * k for k in range(3)]
+    samples = 500_000
+
+    def cpu(seed):
+        q = op.copy(); q.seed = seed
+        x, st, _ = oracle.path_linear_sgd(og, q, mode=oracle.MODE_EXACT)
+        assert st.applied == (op.iter_max + 1) * op.min_term_updates
+        return gfs.sort_stress(graph, x, samples, ix)
+
+    def gpu_default(seed):
+        x, st = _gpu_1d(gfs, graph, ix, p, seed)
+        assert st["window_steps"] > 0 and st["coherent"] == 1, "the default schedule did not engage on a 93 MB step table"
+        return gfs.sort_stress(graph, x, samples, ix)
+
+    def gpu_iid(seed):
+        x, st = _gpu_1d(gfs, graph, ix, p, seed, window=0, monkeypatch=monkeypatch)
+        assert st["window_steps"] == 0
+        return gfs.sort_stress(graph, x, samples, ix)
+
+    c_rms, c_mar = _median_stress_1d(cpu, seeds)
+    d_rms, d_mar = _median_stress_1d(gpu_default, seeds)
+    i_rms, i_mar = _median_stress_1d(gpu_iid, seeds)
+    x0 = gfs.initial_positions(graph)
+    print(f"hard graph (tiled DRB1 x150, S={len(h)}) Y stress: init {gfs.sort_stress(graph, x0, samples, ix)[1]:.4f} | "
+          f"gpu default(sweep+coherent) mean_abs {d_mar:.5f} rms {d_rms:.5f} | gpu iid mean_abs {i_mar:.5f} rms {i_rms:.5f} | "
+          f"oracle mean_abs {c_mar:.5f} rms {c_rms:.5f}")
+    assert d_mar <= c_mar * 1.02, f"default schedule {d_mar:.5f} vs oracle {c_mar:.5f}"
+    assert i_mar <= c_mar * 1.02, f"iid schedule {i_mar:.5f} vs oracle {c_mar:.5f}"
+    assert d_rms <= c_rms * 1.05 and i_rms <= c_rms * 1.05
+    ix.close()
+
+
+def test_default_schedule_config2_vs_oracle(gfs, oracle):
+    """BASELINE.json config 2's graph (1M nodes / 32 paths / 29.6M steps; 474 MB of records: sweep + coherent by
+    default), reference budget (iter_max 100).  GPU medians over 3 seeds against (i) the committed oracle results
+    for the same 3 seeds (tests/golden/oracle_stress.json: 3 x ~3e9 updates, minutes of CPU) and (ii) ONE live
+    oracle run here, which also guards the fixture."""
+    s = gfs.SynthGraph(1_000_000, 32, seed=42)
+    graph = gfs.BidirectedGraph.from_dense(s.step_handles, s.path_first, s.node_len)
+    ix = gfs.PathIndex.from_arrays(s.step_handles, s.path_first, s.node_len)
+    counts = np.diff(s.path_first)
+    p = gfs.PathSGDParams(iter_max=100, min_term_updates=int(counts.sum()), eta_max=float(int(counts.max()) ** 2),
+                          space=int(ix.path_lengths().max()), space_max=100)
+    fx = _oracle_fixture()["config2_1M_32"]
+    assert fx["steps"] == s.S and fx["params"]["min_term_updates"] == p.min_term_updates and fx["params"]["space"] == p.space
+    seeds = [r["sgd_seed"] for r in fx["runs"]]
+    samples = fx["stress_sample"]["samples"]
+    gvals = []
+    for sd in seeds:
+        x, st = _gpu_1d(gfs, graph, ix, p, sd)
+        assert st["window_steps"] > 0 and st["coherent"] == 1
+        gvals.append(gfs.sort_stress(graph, x, samples, ix))
+    g_mar, g_rms = float(np.median([v[1] for v in gvals])), float(np.median([v[0] for v in gvals]))
+    f_mar = float(np.median([r["final"]["mean_abs_rel"] for r in fx["runs"]]))
+    f_rms = float(np.median([r["final"]["rms_rel"] for r in fx["runs"]]))
+    # one live oracle run (all host cores, exact budget) on the first seed
+    og = oracle.Graph.from_dense(s.step_handles, s.path_first.copy(), s.node_len)
+    op = oracle.params_from_graph(og, nthreads=os.cpu_count() or 4)
+    op.seed = seeds[0]
+    xo, ost, _ = oracle.path_linear_sgd(og, op, mode=oracle.MODE_EXACT)
+    live = gfs.sort_stress(graph, xo, samples, ix)
+    print(f"config 2 Y stress (default schedule, window {st['window_steps']}): gpu mean_abs {g_mar:.6e} rms {g_rms:.6e} | "
+          f"oracle fixture mean_abs {f_mar:.6e} rms {f_rms:.6e} | oracle live (seed {seeds[0]}, {ost.applied / ost.seconds / 1e6:.0f} M upd/s) "
+          f"mean_abs {live[1]:.6e} rms {live[0]:.6e}")
+    assert abs(live[1] - fx["runs"][0]["final"]["mean_abs_rel"]) <= 0.03 * live[1], "the committed oracle result is not what the oracle produces here"
+    assert g_mar <= f_mar * 1.02, f"gpu {g_mar:.4e} vs oracle fixture {f_mar:.4e}"
+    assert g_mar <= live[1] * 1.03
+    assert g_rms <= f_rms * 1.10
     ix.close()
 
 
@@ -765,8 +879,8 @@ def test_config3_full_size_properties(gfs):
             inside[b] = False
             assert np.array_equal(d[inside], lens[inside])
 
-        for c in range(1 << 28, S, 1 << 28):              # the build's chunk seams (carry across chunks)
-            check_window(c - (1 << 20), c + (1 << 20))
+        for c in range(1 << 24, S, 1 << 24):              # the build's chunk seams (the scan carries across chunks)
+            check_window(c - (1 << 14), c + (1 << 14))
         for s0 in starts:                                 # path seams
             check_window(int(s0) - 4096, int(s0) + 4096)
         rng = np.random.default_rng(7)
@@ -799,6 +913,32 @@ def test_config3_full_size_properties(gfs):
         print("config3 Y stress before/after:", before, after)
         assert before[1] > 1.0 and after[1] < 5e-5, (before, after)       # measured: 23.5 -> 3.54e-5
         assert after[2] > 900_000
+        assert st.window_steps > 0 and st.coherent == 1          # that was the default (sweep + coherent) schedule
+
+        # ---- the same budget with the reference's own sampling (every step ~ U[0,S)), and the oracle ----
+        # transitive parity: the iid schedule is bit-faithful to the oracle's sampling (test_term_sampling_bit_exact)
+        # and within 2 % of it wherever both were run; here sweep vs iid at FULL size, both forms, plus the one
+        # committed oracle run at this size (tests/golden/oracle_stress.json, ~1 h of 8 cores)
+        os.environ["GFASORT_WINDOW"] = "0"
+        try:
+            xi = x0.copy()
+            sti = Stats()
+            check(lib().gfs_sgd_1d(ix.handle, C.byref(cp), _p(xi, f64p), C.byref(sti)))
+        finally:
+            del os.environ["GFASORT_WINDOW"]
+        assert sti.applied_updates == 101 * S and sti.window_steps == 0
+        iid = G.layout_stress(None, xi, 1, 1_000_000, ix, layout_order=False)
+        print(f"config3 Y stress: sweep+coherent mean_abs {after[1]:.4e} rms {after[0]:.4e} ({st.kernel_seconds:.2f} s) | "
+              f"iid mean_abs {iid[1]:.4e} rms {iid[0]:.4e} ({sti.kernel_seconds:.2f} s)")
+        assert after[1] <= iid[1] * 1.02, "default schedule more than 2 % above the reference-exact sampling (mean form)"
+        assert after[0] <= iid[0] * 1.02 or after[0] <= iid[0] + 2e-5, "default schedule more than 2 % above iid (RMS form)"
+        fx = _oracle_fixture().get("config3_10M_90")
+        if fx:
+            assert fx["steps"] == S
+            o = fx["runs"][0]["final"]
+            print(f"config3 Y stress: oracle (committed run, {fx['runs'][0]['threads']} threads) mean_abs {o['mean_abs_rel']:.4e} rms {o['rms_rel']:.4e}")
+            assert after[1] <= o["mean_abs_rel"] * 1.02, "default schedule more than 2 % above the oracle at config 3"
+            assert iid[1] <= o["mean_abs_rel"] * 1.02
 
         # ---- L (2D, float2) on the same graph, first 4 epochs of the 31-epoch schedule -----------------
         lp = G.LayoutSGDParams(dimensions=2, iter_max=30, min_term_updates=10 * int(counts.sum()),

@@ -1,0 +1,117 @@
+"""One full-budget run of the CPU oracle (the C++ restatement of reference src/sgd.rs:237-614) on a
+synthetic graph of a named shape, and the sampled path stress of its result on the SAME Philox sample
+gfs_stress uses on the GPU (stream 2, counter k, seed 12345) — SURVEY.md §8d: "stress-parity runs use the
+full budget on DRB1, config 2 and (once) config 3".
+
+    python tools/oracle_config3.py [--nodes 10000000 --paths 90 --threads 8 --seed 9399220 --out DIR]
+
+The index of the oracle is the reference's four 8-byte-per-step arrays (27 GB at config 3), so the stress
+is evaluated here with numpy from per-path prefix sums instead of oracle_layout_stress (which would build
+a second index).  Writes <out>/x.npy (final positions, dense node order) and <out>/result.json.
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+
+def philox_stress(step_handles, path_first, node_len, x, samples, seed=12345):
+    """gfs_stress / stress_kernel restated with numpy: returns (rms_rel, mean_abs_rel, counted)."""
+    from oracle import oracle as O
+    S = int(path_first[-1])
+    P = len(path_first) - 1
+    sa = np.zeros(samples, dtype=np.int64)
+    r23 = np.zeros(samples, dtype=object)
+    key = (seed & 0xffffffff, seed >> 32)
+    for k in range(samples):
+        r = O.philox((k & 0xffffffff, k >> 32, 0, O.STREAM_STRESS), key)
+        sa[k] = ((int(r[1]) << 32 | int(r[0])) * S) >> 64
+        r23[k] = int(r[3]) << 32 | int(r[2])
+    pa = np.searchsorted(path_first, sa.astype(np.uint64), side="right") - 1
+    f = path_first[pa].astype(np.int64)
+    n = (path_first[pa + 1] - path_first[pa]).astype(np.int64)
+    ra = sa - f
+    rb = np.array([(int(r23[k]) * int(n[k])) >> 64 for k in range(samples)], dtype=np.int64)
+    sb = f + rb
+    ok = (n >= 2) & (ra != rb)
+    pos_a = np.zeros(samples, dtype=np.float64)
+    pos_b = np.zeros(samples, dtype=np.float64)
+    for p in range(P):
+        lo, hi = int(path_first[p]), int(path_first[p + 1])
+        sel = np.nonzero(pa == p)[0]
+        if not len(sel) or hi <= lo:
+            continue
+        lens = node_len[(step_handles[lo:hi] >> np.uint64(1)).astype(np.int64)].astype(np.uint64)
+        pos = np.zeros(hi - lo, dtype=np.uint64)
+        np.cumsum(lens[:-1], out=pos[1:])
+        pos_a[sel] = pos[ra[sel]].astype(np.float64)
+        pos_b[sel] = pos[np.minimum(rb[sel], hi - lo - 1)].astype(np.float64)
+    dp = np.abs(pos_a - pos_b)
+    ok &= dp != 0
+    ia = (step_handles[sa] >> np.uint64(1)).astype(np.int64)
+    ib = (step_handles[np.where(ok, sb, sa)] >> np.uint64(1)).astype(np.int64)
+    dl = np.abs(x[ia] - x[ib])
+    err = (dl - dp)[ok]
+    d = dp[ok]
+    cnt = int(ok.sum())
+    return float(np.sqrt(np.sum(err * err / (d * d)) / cnt)), float(np.sum(np.abs(err) / d) / cnt), cnt
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--nodes", type=int, default=10_000_000)
+    ap.add_argument("--paths", type=int, default=90)
+    ap.add_argument("--graph-seed", type=int, default=42)
+    ap.add_argument("--seed", type=int, default=9399220)
+    ap.add_argument("--threads", type=int, default=os.cpu_count() or 1)
+    ap.add_argument("--iter-max", type=int, default=100)
+    ap.add_argument("--samples", type=int, default=1_000_000)
+    ap.add_argument("--mode", default="exact", choices=["exact", "reference"])
+    ap.add_argument("--out", default="oracle/_runs/config3")
+    a = ap.parse_args()
+    os.makedirs(a.out, exist_ok=True)
+    import gfasort_b200 as G
+    from oracle import oracle as O
+    t0 = time.time()
+    s = G.SynthGraph(a.nodes, a.paths, seed=a.graph_seed)
+    handles = np.array(s.step_handles)
+    path_first = np.array(s.path_first)
+    node_len = np.array(s.node_len)
+    s.close()
+    x0 = np.zeros(a.nodes)
+    np.cumsum(node_len[:-1], dtype=np.float64, out=x0[1:])
+    print(f"graph N={a.nodes} P={a.paths} S={len(handles)} in {time.time()-t0:.0f}s", flush=True)
+    st0 = philox_stress(handles, path_first, node_len, x0, a.samples)
+    print(f"initial stress: rms {st0[0]:.6e} mean_abs {st0[1]:.6e} counted {st0[2]}", flush=True)
+    og = O.Graph.from_dense(handles, path_first.copy(), node_len)
+    op = O.params_from_graph(og, nthreads=a.threads)
+    op.iter_max = a.iter_max
+    op.seed = a.seed
+    t1 = time.time()
+    x, st, rc = O.path_linear_sgd(og, op, mode=O.MODE_EXACT if a.mode == "exact" else O.MODE_REFERENCE, x0=x0)
+    assert rc == 0
+    dt = time.time() - t1
+    print(f"oracle {a.mode}: {st.applied} updates in {st.seconds:.0f}s ({st.applied/st.seconds/1e6:.1f} M/s), wall {dt:.0f}s", flush=True)
+    np.save(os.path.join(a.out, "x.npy"), x)
+    del og
+    st1 = philox_stress(handles, path_first, node_len, x, a.samples)
+    print(f"final stress: rms {st1[0]:.6e} mean_abs {st1[1]:.6e} counted {st1[2]}", flush=True)
+    res = {"nodes": a.nodes, "paths": a.paths, "steps": int(len(handles)), "graph_seed": a.graph_seed, "sgd_seed": a.seed,
+           "threads": a.threads, "mode": a.mode, "iter_max": a.iter_max, "applied": int(st.applied),
+           "sgd_seconds": st.seconds, "updates_per_s": st.applied / st.seconds,
+           "stress_sample": {"samples": a.samples, "seed": 12345, "draw": "philox stream 2 (same sample as gfs_stress)"},
+           "initial": {"rms_rel": st0[0], "mean_abs_rel": st0[1], "counted": st0[2]},
+           "final": {"rms_rel": st1[0], "mean_abs_rel": st1[1], "counted": st1[2]},
+           "params": op.as_dict()}
+    with open(os.path.join(a.out, "result.json"), "w") as f:
+        json.dump(res, f, indent=1)
+    print(json.dumps(res), flush=True)
+
+
+if __name__ == "__main__":
+    main()
