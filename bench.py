@@ -131,8 +131,11 @@ def nvlink_bytes(gpu: int):
                 tx += int(ln.split("Data Tx:")[1].split()[0]); found = True
             elif "Data Rx:" in ln:
                 rx += int(ln.split("Data Rx:")[1].split()[0]); found = True
+        if not found:
+            log("[bench] nvidia-smi nvlink -gt d: no data counters in the output: " + " | ".join(out.splitlines()[:4]))
         return (tx * 1024, rx * 1024) if found else None
-    except Exception:
+    except Exception as e:
+        log(f"[bench] nvidia-smi nvlink failed: {e}")
         return None
 
 
@@ -294,8 +297,9 @@ def measure_workload(a, wl, name, rank, world, local, dev, K, W, with_cpu, e2e_e
     pin_keep = None
     if a.handles == 32:
         if a.pinned:
-            pin_keep = torch.empty(max(sg.S, 1), dtype=torch.int32, pin_memory=True)
-            handles = pin_keep.numpy().view(np.uint32)[:sg.S]
+            from gfasort_b200.sgd import PinnedArray
+            pin_keep = PinnedArray(sg.S, np.uint32)              # gfs_host_alloc: what the binding flattens into
+            handles = pin_keep.array
             handles[:] = sg.step_handles
         else:
             handles = sg.step_handles.astype(np.uint32)
@@ -334,8 +338,8 @@ def measure_workload(a, wl, name, rank, world, local, dev, K, W, with_cpu, e2e_e
     barrier()
     st0 = run.stats()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    nv0 = nvlink_bytes(local) if (world > 1 and rank == 0) else None     # a subprocess: BEFORE the barrier, or the peers would wait for it inside the timed region
     barrier()
-    nv0 = nvlink_bytes(local) if (world > 1 and rank == 0) else None
     c_lo = clocks.mark()
     with torch.cuda.stream(run.stream):
         ev0.record()

@@ -79,7 +79,9 @@ SIGNATURES = {
     "gfs_index_build32": (C.c_int, [u32p, u64p, u32p, C.c_uint64, C.c_uint64, C.c_uint64, C.POINTER(C.c_void_p)]),
     "gfs_index_build_shard32": (C.c_int, [u32p, u64p, u32p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64,
                                           C.c_uint64, C.c_int32, C.c_int32, u32p, C.POINTER(C.c_void_p)]),
-    "gfs_index_build_info": (C.c_int, [C.c_void_p, f64p, f64p, f64p, u64p, u32p]),
+    "gfs_host_alloc": (C.c_int, [C.c_uint64, C.POINTER(C.c_void_p)]),
+    "gfs_host_free": (None, [C.c_void_p]),
+    "gfs_index_build_info": (C.c_int, [C.c_void_p, f64p, f64p, f64p, f64p, f64p, u64p, u32p]),
     "gfs_index_export_relabel": (C.c_int, [C.c_void_p, u32p]),
     "gfs_index_apply_relabel": (C.c_int, [C.c_void_p, u32p]),
     "gfs_index_export": (C.c_int, [C.c_void_p, u64p, u64p]),

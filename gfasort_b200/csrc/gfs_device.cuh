@@ -101,10 +101,13 @@ __device__ __forceinline__ ZipfPre dirty_zipf_pre(uint32_t jump_space, const Zip
     p.num = __dsub_rn(1.0, f1);
     return p;
 }
+// den = 1 - zeta2theta / zeta (sgd.rs:133-134): a function of the zeta table entry and the epoch's theta alone, so the
+// kernels read it from the table ({zeta, den} pairs, one table per theta, filled on the host with the same two IEEE
+// operations) instead of running a second dependent division behind the zeta load.
 __device__ __forceinline__ uint32_t dirty_zipf_post(uint32_t jump_space, const ZipfConsts& zc, const ZipfPre& p,
-                                                    double zeta, double u) {
+                                                    double zeta, double den, double u) {
     const double uz = __dmul_rn(u, zeta);
-    const double eta = __ddiv_rn(p.num, __dsub_rn(1.0, __ddiv_rn(zc.z2, zeta)));
+    const double eta = __ddiv_rn(p.num, den);
     const double base = __dadd_rn(__dsub_rn(__dmul_rn(eta, u), eta), 1.0);
     double ip;
     if (zc.alpha_e == 99) ip = int_pow_fixed<99>(base);  // warp-uniform branches (per-epoch constant)
@@ -119,7 +122,7 @@ __device__ __forceinline__ uint32_t dirty_zipf_post(uint32_t jump_space, const Z
     return z;
 }
 __device__ __forceinline__ uint32_t dirty_zipf(uint32_t jump_space, const ZipfConsts& zc, double zeta, double u) {
-    return dirty_zipf_post(jump_space, zc, dirty_zipf_pre(jump_space, zc), zeta, u);
+    return dirty_zipf_post(jump_space, zc, dirty_zipf_pre(jump_space, zc), zeta, __dsub_rn(1.0, __ddiv_rn(zc.z2, zeta)), u);
 }
 
 // exact u64 -> f64 for v < 2^52 (step offsets; gfs_index_build rejects longer paths): one DADD
@@ -175,7 +178,7 @@ struct EpochDesc {
     ZipfConsts zc;
     uint64_t updates;     // min_term_updates
     uint32_t cooling;
-    uint32_t pad;
+    uint32_t ztab;        // which {zeta, den} table this epoch's theta uses (0 = params.theta, 1 = the cooling theta)
 };
 
 }  // namespace gfs

@@ -72,8 +72,9 @@ struct gfs_index {
     uint64_t* d_path_len = nullptr;     // P
     uint32_t* d_new_of_old = nullptr;   // N, null when not relabelled
     uint32_t* d_old_of_new = nullptr;   // N
+    void* d_build_arena = nullptr;      // the build's transient device memory, released with the index
     std::vector<uint64_t> h_first_step;
-    double build_seconds = 0, h2d_seconds = 0, kernel_seconds = 0;
+    double build_seconds = 0, h2d_seconds = 0, kernel_seconds = 0, alloc_seconds = 0, relabel_seconds = 0;
     uint64_t launches = 0;
     // A multi-GPU index (gfs_index_build under GFASORT_GPUS > 1) is a directory of per-device shards:
     // shard g holds the records of the paths that step slice g overlaps.  The fields above
@@ -96,20 +97,24 @@ struct gfs_sgd_session {
     void* d_pos = nullptr;
     bool own_pos = false;
     uint64_t n_elems = 0;       // elements in d_pos
-    double* d_zetas = nullptr; uint32_t zlen = 0;
+    double2* d_zetas = nullptr; uint32_t zlen = 0;      // 2 x zlen {zeta, den} pairs (gfs_lib.cu h_zeta_tables)
     gfs::EpochDesc* d_epochs = nullptr; uint32_t n_epochs = 0;
     uint64_t* d_attempts = nullptr;
     unsigned long long* d_counters = nullptr;
     double* d_stage = nullptr;  // f64 staging for nD conversions
     size_t smem_bytes = 0;
+    uint32_t zeta_smem = 0;     // experiment: zeta entries per theta staged in shared memory (GFASORT_ZETA_SMEM)
     uint64_t rng_thread_base = 0;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // kernel timing: a ring of event pairs, so that enqueueing a launch never waits for the previous one (a host that
+    // blocks per launch leaves the GPU idle between an epoch's reconcile and the next epoch's kernel)
+    static constexpr int EV_RING = 16;
+    cudaEvent_t ev0[EV_RING] = {}, ev1[EV_RING] = {};
+    uint32_t ev_head = 0, ev_tail = 0;      // pairs [ev_tail, ev_head) are recorded and not yet read
     double kernel_ms = 0.0;
     uint64_t launches = 0;
     double h2d_s = 0, d2h_s = 0;
-    bool ev_pending = false;
     int inflight = 2;           // terms in flight per thread (kernel template parameter K)
-    bool coherent = true;       // warp-coherent step sampling in the sweep schedule
+    uint32_t coherent = 32;     // sweep schedule: groups of this many lanes sample consecutive steps (0 = off)
     uint64_t window_steps = 0;  // 0 = static schedule
     uint32_t chunk_updates = 128;
     unsigned long long* d_work = nullptr;

@@ -256,7 +256,7 @@ __global__ void dbg_trace(KernelGraph g, const EpochDesc* epochs, uint32_t epoch
                                   make_uint2(seed_lo, seed_hi));
     Slot t;
     PathLookup pl;
-    pl.fs = g.first_step; pl.blk = nullptr; pl.shift = 0; pl.P = g.P;
+    pl.fs = g.first_step; pl.blk = nullptr; pl.shift = 0; pl.P = g.P; pl.zs = nullptr; pl.zs_n = 0;
     sample_s1(g, pl, ep, r, g.samp_base, g.samp_len, true, 0u, 0, t);      // g.coherent == 0 here
     sample_s2(g, ep, t);
     t.a = load_rec(g.recs + t.step_a);

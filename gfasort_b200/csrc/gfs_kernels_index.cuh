@@ -11,28 +11,31 @@ namespace gfs {
 // PathIndex::from_graph (src/sgd.rs:41-62) is, per path, an exclusive prefix sum of node lengths along
 // the steps.  Over the concatenated step array that is a SEGMENTED exclusive scan with a segment start at
 // every path's first step.  k1_scan_write does it in one pass: every tile of 2048 steps
-//   loads its handles once (coalesced), gathers {node length, first-occurrence key} (one 8-byte entry per
-//   node, L2-resident), scans the lengths in shared memory, publishes its aggregate in a per-tile
+//   loads its handles once (16-byte streaming loads), gathers the node lengths (4 bytes per step from an
+//   L2-resident table), scans them in registers and with warp shuffles, publishes its aggregate in a per-tile
 //   descriptor, looks back over its predecessors' descriptors for its exclusive prefix (Merrill & Garland's
 //   decoupled look-back, with the segmented twist: a tile that contains a path start publishes its
 //   INCLUSIVE value at once — the scan restarts inside it, so nothing before it matters to its successors),
 //   and writes one 16-byte record per step {node<<1|rev, node_len, offset}.
 // Fused into the same pass: the per-path lengths (PathInfo.length, sgd.rs:29) and, when the index is going
-// to be relabelled, the first-occurrence key of every node (atomicMin, almost always skipped after the
-// first path thanks to the key that came with the length gather).
+// to be relabelled, the first-occurrence key of every node (a visited bitmap gates an atomicMin that almost only
+// the first path ever executes).
 // Algorithmic bytes per step: 8 (handle; 4 with 32-bit handles) + 4 (gathered length) + 16 (record).
 constexpr int K1_THREADS = 256;
 constexpr int K1_ITEMS = 8;
 constexpr int K1_TILE = K1_THREADS * K1_ITEMS;
 
-// per-node table the kernel gathers from: node length and the node's first-occurrence key
-// (step index >> key_shift of the first step that visits it; 0xffffffff = not visited yet)
-struct __align__(8) NodeEnt { uint32_t len; uint32_t key; };
+// What the kernel gathers per step is node_len[node] alone (4 bytes: the 40 MB table of config 3 stays L2-resident
+// next to the streamed handles and records).  First occurrences use two more arrays: a bitmap of visited nodes (1 bit
+// per node, 1.25 MB at config 3 — read per step, cached) and first_key[node] = (step index >> key_shift) of the first
+// step that visits the node, 0xffffffff = never visited (atomicMin, touched only while a node's bit is still clear,
+// i.e. almost only during the first path).
 
 constexpr uint64_t K1_ST_AGG = 1ull << 62;      // descriptor holds the tile's sum; the tile has no path start
 constexpr uint64_t K1_ST_INCL = 2ull << 62;     // descriptor holds the offset, in its path, of the step after the tile
 constexpr uint64_t K1_VAL_MASK = (1ull << 62) - 1;
-constexpr uint32_t K1_SPIN_CAP = 1u << 27;      // look-back polls before the kernel gives up (ticket[1] = 1: the build fails)
+constexpr int K1_LB_WINDOWS = 4;                // look-back: 4 x 32 descriptors per round
+constexpr uint32_t K1_SPIN_CAP = 1u << 27;      // look-back polls before the kernel gives up (flags[0] = 1: the build fails)
 
 __device__ __forceinline__ uint64_t ld_desc(const uint64_t* p) {
     uint64_t v;
@@ -42,178 +45,224 @@ __device__ __forceinline__ uint64_t ld_desc(const uint64_t* p) {
 __device__ __forceinline__ void st_desc(uint64_t* p, uint64_t v) {
     asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
-__device__ __forceinline__ NodeEnt ld_node_ent(const NodeEnt* p) {
-    NodeEnt e;
-    asm volatile("ld.global.cg.v2.u32 {%0,%1}, [%2];" : "=r"(e.len), "=r"(e.key) : "l"(p));
-    return e;
+// streamed once: handles in (evict-first), records out (evict-first) — keep L2 for the node-length table
+__device__ __forceinline__ uint4 ld_stream_v4(const void* p) {
+    uint4 v;
+    asm volatile("ld.global.cs.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void st_stream_v4(void* p, uint4 v) {
+    asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
-__global__ void k1_init_table(const uint32_t* __restrict__ node_len, uint32_t N, NodeEnt* __restrict__ tbl) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < N) { NodeEnt e; e.len = node_len[i]; e.key = 0xffffffffu; tbl[i] = e; }
+// warp-level "largest p with first_step[p] <= g" for p in [0, P): every lane tests one entry per round and the warp
+// counts them (first_step[0] = 0 <= g, so the count is >= 1).  Few paths: 1-3 rounds, no block barrier.
+__device__ __forceinline__ uint32_t warp_find_path(const uint64_t* __restrict__ first_step, uint32_t P, uint64_t g, int lane) {
+    if (P > 1024) return find_path(first_step, P, g);
+    uint32_t c = 0;
+    for (uint32_t p0 = 0; p0 < P; p0 += 32) {                       // warp-uniform trip count
+        const uint32_t p = p0 + lane;
+        const uint64_t f = p < P ? __ldg(first_step + p) : ~0ull;
+        c += __popc(__ballot_sync(0xffffffffu, f <= g));
+    }
+    return c - 1;
 }
 
-// shared-memory views: loads and stores are strided (thread t owns items k*256 + t: coalesced handle loads,
-// one 16-byte store per record), the scan is blocked (thread t sums items [8t, 8t+8)); padded by one word per
-// 32 (lengths) / one entry per 16 (offsets) so that neither view has bank conflicts.
-__device__ __forceinline__ int k1_pad32(int j) { return j + (j >> 5); }
-__device__ __forceinline__ int k1_pad16(int j) { return j + (j >> 4); }
+template <typename HT> struct K1Load;
+template <> struct K1Load<uint64_t> {       // 8 handles = 64 bytes = 4 x LDG.128
+    static __device__ __forceinline__ void load(const uint64_t* p, uint64_t (&h)[K1_ITEMS]) {
+        const uint4* q = reinterpret_cast<const uint4*>(p);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint4 v = ld_stream_v4(q + k);
+            h[2 * k] = ((uint64_t)v.y << 32) | v.x;
+            h[2 * k + 1] = ((uint64_t)v.w << 32) | v.z;
+        }
+    }
+};
+template <> struct K1Load<uint32_t> {       // 8 handles = 32 bytes = 2 x LDG.128
+    static __device__ __forceinline__ void load(const uint32_t* p, uint64_t (&h)[K1_ITEMS]) {
+        const uint4* q = reinterpret_cast<const uint4*>(p);
+        const uint4 a = ld_stream_v4(q), b = ld_stream_v4(q + 1);
+        h[0] = a.x; h[1] = a.y; h[2] = a.z; h[3] = a.w; h[4] = b.x; h[5] = b.y; h[6] = b.z; h[7] = b.w;
+    }
+};
+// a padding handle (steps past the end of the index): 32-bit handles are widened, so test the narrow all-ones too
+template <typename HT> __device__ __forceinline__ uint64_t k1_node_of(uint64_t h) {
+    return sizeof(HT) == 4 && h == 0xffffffffull ? ~0ull : (h >> 1);
+}
 
 // HT: handle type of the caller's step array (uint64_t = Handle as the reference stores it; uint32_t = the
 // same value in 32 bits, dense idx < 2^31).  FIRST_OCC: maintain the first-occurrence keys.
-// handles: this chunk's steps; chunk_begin (a multiple of K1_TILE): index-local step of handles[0].
-// ticket[0]: tile counter of this launch (zeroed by the host before it); ticket[1]: look-back watchdog flag.
+// Block = 8 worker warps + 1 look-back warp.  Worker thread t owns the 8 CONSECUTIVE steps [8t, 8t+8) of the tile:
+// 16-byte handle loads, eight gathers in flight, a register scan, one warp-shuffle scan, warp totals through shared
+// memory, one 16-byte store per record.  The ninth warp runs the decoupled look-back from the start, under the
+// workers' loads and gathers, so that the tile's exclusive prefix is normally there when the workers need it.
+// handles: this chunk's steps, PADDED to a whole number of tiles with all-ones handles (node >= N: length 0);
+// recs is padded likewise (records past the last step are written and never read).
+// chunk_begin (a multiple of K1_TILE): index-local step of handles[0];  S: steps in the index.
+// flags[0]: look-back watchdog.
+constexpr int K1_BLOCK = K1_THREADS + 32;
 template <typename HT, bool FIRST_OCC>
-__global__ void __launch_bounds__(K1_THREADS, 4)
-k1_scan_write(const HT* __restrict__ handles, NodeEnt* __restrict__ tbl, uint32_t N, const uint64_t* __restrict__ first_step,
-              uint32_t P, uint64_t chunk_begin, uint64_t chunk_len, uint64_t* __restrict__ desc, unsigned int* __restrict__ ticket,
+__global__ void __launch_bounds__(K1_BLOCK, 4)
+k1_scan_write(const HT* __restrict__ handles, const uint32_t* __restrict__ node_len, uint32_t* __restrict__ visited,
+              uint32_t* __restrict__ first_key, uint32_t N, const uint64_t* __restrict__ first_step,
+              uint32_t P, uint64_t chunk_begin, uint64_t S, uint64_t* __restrict__ desc, unsigned int* __restrict__ flags,
               uint32_t key_shift, StepRec* __restrict__ recs, uint64_t* __restrict__ path_len) {
-    __shared__ uint32_t s_len[K1_TILE + K1_TILE / 32];
-    __shared__ uint64_t s_pos[K1_TILE + K1_TILE / 16];
-    __shared__ uint64_t wsum[K1_THREADS / 32];
+    __shared__ uint64_t s_wsum[K1_THREADS / 32];
     __shared__ uint64_t s_prefix;
-    __shared__ unsigned int s_tile;
-    // tiles are handed out in order, so every predecessor of a running tile is running or done: the
-    // look-back below can never wait for a block that has not been scheduled
-    if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
-    __syncthreads();
-    const uint64_t tbase = (uint64_t)s_tile * K1_TILE;              // chunk-local
-    if (tbase >= chunk_len) return;
-    const uint64_t gtile = (chunk_begin + tbase) / K1_TILE;
-    uint64_t hh[K1_ITEMS];
-#pragma unroll
-    for (int k = 0; k < K1_ITEMS; ++k) {
-        const uint64_t i = tbase + (uint64_t)(k * K1_THREADS + threadIdx.x);
-        hh[k] = i < chunk_len ? (uint64_t)__ldg(handles + i) : ~0ull;      // past the end: node >= N => length 0
-    }
-    // path of the tile's first and last step (most tiles lie inside one path), found while the handle
-    // loads are in flight: with few paths every thread tests one first_step entry and the block counts
-    // the entries <= step (one load round trip); with many paths, a binary search.
-    const uint64_t g_first = chunk_begin + tbase;
-    const uint32_t n_here = (uint32_t)(tbase + K1_TILE <= chunk_len ? K1_TILE : chunk_len - tbase);
-    const uint64_t g_last = g_first + n_here - 1;
-    uint32_t p_first, p_last;
-    if (P <= 8 * K1_THREADS) {
-        int c_first = 0, c_last = 0;
-        for (uint32_t p0 = 0; p0 < P; p0 += K1_THREADS) {          // block-uniform trip count
-            const uint32_t p = p0 + threadIdx.x;
-            const uint64_t f = p < P ? __ldg(first_step + p) : ~0ull;
-            c_first += __syncthreads_count(f <= g_first);
-            c_last += __syncthreads_count(f <= g_last);
-        }
-        p_first = (uint32_t)c_first - 1;                            // first_step[0] = 0 <= step: count >= 1
-        p_last = (uint32_t)c_last - 1;
-    } else {
-        p_first = find_path(first_step, P, g_first);
-        p_last = find_path(first_step, P, g_last);
-    }
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    // blocks are dispatched in index order, so every predecessor of a running tile is running or done: the
+    // look-back can never wait for a block that has not been scheduled (and a watchdog bounds it anyway)
+    const uint64_t g_first = chunk_begin + (uint64_t)blockIdx.x * K1_TILE;
+    const uint64_t gtile = g_first / K1_TILE;
+    const uint64_t g_last = (g_first + K1_TILE <= S ? g_first + K1_TILE : S) - 1;
+    // path of the tile's first and last step (most tiles lie inside one path): every warp finds them for itself
+    const uint32_t p_first = warp_find_path(first_step, P, g_first, lane);
+    const uint32_t p_last = warp_find_path(first_step, P, g_last, lane);
     const uint64_t fs_first = __ldg(first_step + p_first);
     const bool start_first = fs_first == g_first;                   // the tile begins exactly at a path start
     const bool has_start = start_first || p_last != p_first;
-    uint32_t len[K1_ITEMS], nr[K1_ITEMS];
-    NodeEnt ent[K1_ITEMS];
+
+    if (w == K1_THREADS / 32) {
+        // ---- look-back warp ------------------------------------------------------------------------------
+        // Every round reads K1_LB_WINDOWS x 32 predecessor descriptors at once (all loads in flight together) and
+        // consumes them nearest window first, up to the nearest inclusive value.  The wider the round, the fewer L2
+        // round trips separate a tile from the inclusive front — with hundreds of tiles in flight that chain, not
+        // bandwidth, is what bounds a chained scan (32 per round capped this kernel at ~27 tiles/us).
+        uint64_t T = 0;
+        if (!start_first) {
+            int64_t look = (int64_t)gtile - 1;
+            bool found = false;
+            while (!found) {
+                uint64_t d[K1_LB_WINDOWS];
 #pragma unroll
-    for (int k = 0; k < K1_ITEMS; ++k) {                            // all eight gathers in flight before the first use
-        const uint64_t node = hh[k] >> 1;
-        ent[k].len = 0; ent[k].key = 0;
-        if (node < N) ent[k] = ld_node_ent(tbl + node);             // missing node => +0 (src/sgd.rs:52-54)
+                for (int j = 0; j < K1_LB_WINDOWS; ++j) {
+                    const int64_t t = look - 32 * j - lane;
+                    d[j] = t >= 0 ? ld_desc(desc + t) : K1_ST_INCL;     // before the first tile: offset 0
+                }
+#pragma unroll
+                for (int j = 0; j < K1_LB_WINDOWS; ++j) {
+                    if (found) break;
+                    const int64_t t = look - 32 * j - lane;
+                    uint32_t spins = 0;
+                    while ((d[j] >> 62) == 0) {                         // not published yet: poll
+                        d[j] = ld_desc(desc + t);
+                        if (++spins > K1_SPIN_CAP) { atomicExch(flags, 1u); d[j] = K1_ST_INCL; break; }   // watchdog: never a hang
+                    }
+                    const unsigned incl = __ballot_sync(0xffffffffu, (d[j] >> 62) == 2);
+                    const int stop = incl ? __ffs(incl) - 1 : 32;       // nearest predecessor with an inclusive value
+                    uint64_t v = lane <= stop ? (d[j] & K1_VAL_MASK) : 0;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                    T += v;
+                    found = incl != 0;
+                }
+                look -= 32 * K1_LB_WINDOWS;
+            }
+        }
+        if (lane == 0) s_prefix = T;
+        asm volatile("bar.sync 2, %0;" ::"n"(K1_BLOCK) : "memory");     // the workers' warp totals are in s_wsum (they passed barrier 1)
+        if (lane == 0 && !has_start) {
+            uint64_t tile_sum = 0;
+#pragma unroll
+            for (int k = 0; k < K1_THREADS / 32; ++k) tile_sum += s_wsum[k];
+            st_desc(desc + gtile, K1_ST_INCL | (T + tile_sum));
+        }
+        return;
     }
+    // ---- worker warps ------------------------------------------------------------------------------------
+    const uint64_t my_first = g_first + (uint64_t)threadIdx.x * K1_ITEMS;      // this thread's first step
+    uint64_t hh[K1_ITEMS];
+    K1Load<HT>::load(handles + (my_first - chunk_begin), hh);
+    uint32_t len[K1_ITEMS], vis[K1_ITEMS];
 #pragma unroll
-    for (int k = 0; k < K1_ITEMS; ++k) {
-        const uint64_t node = hh[k] >> 1;
-        len[k] = ent[k].len;
-        nr[k] = (uint32_t)(((node < N ? node : N) << 1) | (hh[k] & 1));
-        s_len[k1_pad32(k * K1_THREADS + threadIdx.x)] = ent[k].len;
-        if (FIRST_OCC && node < N) {
-            const uint64_t gi = g_first + (uint64_t)(k * K1_THREADS + threadIdx.x);
-            const uint32_t key = (uint32_t)(gi >> key_shift);
-            if (key < ent[k].key) atomicMin(&tbl[node].key, key);
+    for (int k = 0; k < K1_ITEMS; ++k) {                            // all gathers in flight before the first use
+        const uint64_t node = k1_node_of<HT>(hh[k]);
+        len[k] = 0; vis[k] = ~0u;
+        if (node < N) {
+            len[k] = __ldg(node_len + node);                        // missing node => +0 (src/sgd.rs:52-54)
+            if (FIRST_OCC) vis[k] = visited[node >> 5];             // plain load: a stale clear bit only costs a redundant atomicMin
         }
     }
-    __syncthreads();
-    // blocked view: thread t owns items [t*8, t*8+8)
+    uint32_t nr[K1_ITEMS];
     uint64_t loc[K1_ITEMS];
     uint64_t tsum = 0;
 #pragma unroll
-    for (int k = 0; k < K1_ITEMS; ++k) { loc[k] = tsum; tsum += s_len[k1_pad32(threadIdx.x * K1_ITEMS + k)]; }
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int k = 0; k < K1_ITEMS; ++k) {
+        const uint64_t node = k1_node_of<HT>(hh[k]);
+        nr[k] = (uint32_t)(((node < N ? node : N) << 1) | (hh[k] & 1));
+        loc[k] = tsum;
+        tsum += len[k];
+        if (FIRST_OCC && node < N && !((vis[k] >> (node & 31)) & 1u)) {
+            atomicOr(visited + (node >> 5), 1u << (node & 31));
+            atomicMin(first_key + node, (uint32_t)((my_first + k) >> key_shift));
+        }
+    }
     uint64_t inc = tsum;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
         const uint64_t t = __shfl_up_sync(0xffffffffu, inc, o);
         if (lane >= o) inc += t;
     }
-    if (lane == 31) wsum[w] = inc;
-    __syncthreads();
+    if (lane == 31) s_wsum[w] = inc;
+    asm volatile("bar.sync 1, %0;" ::"n"(K1_THREADS) : "memory");        // workers only
     uint64_t woff = 0, tile_sum = 0;
 #pragma unroll
-    for (int k = 0; k < K1_THREADS / 32; ++k) { const uint64_t v = wsum[k]; woff += (k < w) ? v : 0; tile_sum += v; }
-    const uint64_t texcl = woff + (inc - tsum);                     // tile-local exclusive prefix of item t*8
+    for (int k = 0; k < K1_THREADS / 32; ++k) { const uint64_t v = s_wsum[k]; woff += (k < w) ? v : 0; tile_sum += v; }
+    const uint64_t texcl = woff + (inc - tsum);                     // tile-local exclusive prefix of this thread's first step
+    // publish at once what the successors can use: the tile's sum, or — when the scan restarts inside the tile — the
+    // offset after its last path start (nothing before the tile matters to them then)
+    uint32_t j_ls = 0;
+    if (has_start) j_ls = (uint32_t)(__ldg(first_step + p_last) - g_first);      // p_last's first step is in the tile
+    if (has_start) {
+        // the thread that owns step j_ls knows its local prefix
+        if (j_ls / K1_ITEMS == threadIdx.x) {
+            uint64_t lp = 0;                                        // loc[j_ls % 8] without indexing a register array
 #pragma unroll
-    for (int k = 0; k < K1_ITEMS; ++k) s_pos[k1_pad16(threadIdx.x * K1_ITEMS + k)] = texcl + loc[k];
-    __syncthreads();
-    // ---- publish, look back ---------------------------------------------------------------------
-    if (w == 0) {
-        if (has_start) {
-            // the scan restarts at the tile's last path start: what follows the tile depends on nothing before it
-            if (lane == 0) {
-                const uint32_t j_ls = (uint32_t)(__ldg(first_step + p_last) - g_first);     // p_last's first step is in the tile
-                st_desc(desc + gtile, K1_ST_INCL | (tile_sum - s_pos[k1_pad16((int)j_ls)]));
-            }
-        } else if (lane == 0) {
-            st_desc(desc + gtile, K1_ST_AGG | tile_sum);
+            for (int k = 0; k < K1_ITEMS; ++k) lp += k < (int)(j_ls % K1_ITEMS) ? len[k] : 0u;
+            st_desc(desc + gtile, K1_ST_INCL | (tile_sum - (texcl + lp)));
         }
-        uint64_t T = 0;
-        if (!start_first) {
-            int64_t look = (int64_t)gtile - 1;
-            for (;;) {
-                const int64_t t = look - lane;
-                uint64_t d = K1_ST_INCL;                            // before the first tile: offset 0
-                if (t >= 0) {
-                    uint32_t spins = 0;
-                    do {
-                        d = ld_desc(desc + t);
-                        if (++spins > K1_SPIN_CAP) { atomicExch(ticket + 1, 1u); d = K1_ST_INCL; break; }   // watchdog: never a hang
-                    } while ((d >> 62) == 0);
-                }
-                const unsigned incl = __ballot_sync(0xffffffffu, (d >> 62) == 2);
-                const int stop = incl ? __ffs(incl) - 1 : 32;       // nearest predecessor with an inclusive value
-                uint64_t v = lane <= stop ? (d & K1_VAL_MASK) : 0;
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-                T += v;
-                if (incl) break;
-                look -= 32;
-            }
-        }
-        if (lane == 0) {
-            if (!has_start) st_desc(desc + gtile, K1_ST_INCL | (T + tile_sum));
-            s_prefix = T;
-        }
+    } else if (threadIdx.x == 0) {
+        st_desc(desc + gtile, K1_ST_AGG | tile_sum);
     }
-    __syncthreads();
-    const uint64_t T = s_prefix;
+    asm volatile("bar.sync 2, %0;" ::"n"(K1_BLOCK) : "memory");          // the look-back warp has delivered s_prefix
+    const uint64_t base = s_prefix + texcl;                          // s_prefix == 0 when the tile begins at a path start
     const uint64_t fs_next = __ldg(first_step + p_first + 1);       // single-path tiles: where the path ends
+    StepRec* out = recs + my_first;
+    // Offsets as if the whole tile continued p_first's path.  That is exact for every step of a single-path tile (all
+    // but at most P tiles) and for p_first's steps in a tile where other paths start; the steps after such a start
+    // are off by the tile-local prefix at that start, which k1_fix_path_starts subtracts afterwards.
 #pragma unroll
     for (int k = 0; k < K1_ITEMS; ++k) {
-        const int j = k * K1_THREADS + threadIdx.x;
-        if (j < (int)n_here) {
-            const uint64_t gi = g_first + j;
-            uint64_t pos, next_first;
-            uint32_t q = p_first;
-            if (p_first == p_last || gi < fs_next) {
-                pos = T + s_pos[k1_pad16(j)];                        // T == 0 when the tile begins at a path start
-                next_first = fs_next;
-            } else {
-                q = find_path(first_step, P, gi);
-                const uint64_t fq = first_step[q];
-                pos = s_pos[k1_pad16(j)] - s_pos[k1_pad16((int)(fq - g_first))];
-                next_first = first_step[q + 1];
-            }
-            // StepRec {node_rev, node_len, pos} as one 16-byte store (see load_rec)
-            *reinterpret_cast<uint4*>(recs + gi) = make_uint4(nr[k], len[k], (uint32_t)pos, (uint32_t)(pos >> 32));
-            if (gi + 1 == next_first) path_len[q] = pos + len[k];   // the path's last step: PathInfo.length (sgd.rs:64-68)
-        }
+        const uint64_t pos = base + loc[k];
+        // StepRec {node_rev, node_len, pos} as one 16-byte store (see load_rec)
+        st_stream_v4(out + k, make_uint4(nr[k], len[k], (uint32_t)pos, (uint32_t)(pos >> 32)));
+        if (my_first + k + 1 == fs_next) path_len[p_first] = pos + len[k];         // the path's last step: PathInfo.length (sgd.rs:64-68)
+    }
+}
+
+// The paths that start INSIDE a tile (not at its first step): k1_scan_write gave the steps from such a start to the
+// end of the tile (or of the path) offsets that continue the previous path; subtract the offset it gave the start.
+// One block per path; at most P - 1 blocks do anything, each touches < K1_TILE records.  Launched after the
+// k1_scan_write of the chunk [c_begin, c_end) that holds the start.
+__global__ void __launch_bounds__(K1_THREADS)
+k1_fix_path_starts(const uint64_t* __restrict__ first_step, uint32_t P, uint64_t c_begin, uint64_t c_end, StepRec* __restrict__ recs,
+                   uint64_t* __restrict__ path_len) {
+    __shared__ uint64_t s0;
+    const uint32_t p = blockIdx.x + 1;
+    if (p >= P) return;
+    const uint64_t fs = first_step[p], fe = first_step[p + 1];
+    if (fs == fe || fs < c_begin || fs >= c_end || fs % K1_TILE == 0) return;       // empty / not this chunk / tile-aligned start (already exact)
+    const uint64_t tile_end = (fs / K1_TILE + 1) * K1_TILE;
+    const uint64_t end = fe < tile_end ? fe : tile_end;
+    if (threadIdx.x == 0) s0 = recs[fs].pos;
+    __syncthreads();
+    const uint64_t off = s0;
+    for (uint64_t i = fs + threadIdx.x; i < end; i += blockDim.x) {
+        const uint64_t pos = recs[i].pos - off;
+        recs[i].pos = pos;
+        if (i + 1 == fe) path_len[p] = pos + recs[i].node_len;
     }
 }
 
@@ -240,9 +289,9 @@ __global__ void k1_export_hl(const StepRec* __restrict__ recs, uint64_t S, uint3
 // (rs_* kernels, gfs_kernels_aux.cuh) of the N first-occurrence keys K1 left in the node table:
 // never-visited nodes (key 0xffffffff) sort last, ties (key_shift > 0) by dense idx.
 // ---------------------------------------------------------------------------------------------
-__global__ void rl_keys(const NodeEnt* __restrict__ tbl, uint32_t N, uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+__global__ void rl_keys(const uint32_t* __restrict__ first_key, uint32_t N, uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < N) { keys[i] = tbl[i].key; vals[i] = i; }
+    if (i < N) { keys[i] = first_key[i]; vals[i] = i; }
 }
 __global__ void rl_rewrite(StepRec* __restrict__ recs, uint64_t S, uint32_t N, const uint32_t* __restrict__ new_of_old) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -11,7 +11,7 @@ namespace gfs {
 struct KernelGraph {
     const StepRec* recs;
     const uint64_t* first_step;   // P+1 (global memory copy)
-    const double* zetas;          // zlen entries (global)
+    const double2* zetas;         // 2 tables (one per theta, EpochDesc::ztab) of zlen {zeta, 1 - zeta2theta/zeta} pairs (global)
     uint64_t S;
     uint32_t P;
     uint32_t N;
@@ -21,7 +21,8 @@ struct KernelGraph {
     uint32_t q;
     uint32_t q_is_100;            // 1: the quantisation step is the reference's 100 (constant division)
     uint32_t blk_shift;           // path-of-block table granularity: block = step >> blk_shift
-    uint32_t coherent;            // 1: the lanes of a warp sample 32 consecutive steps (see sample_s1)
+    uint32_t coherent;            // 0: every lane draws its own step; G = 2..32 (power of two): groups of G lanes
+                                  // sample G consecutive steps (see sample_s1)
     uint64_t samp_base, samp_len; // sampled steps are drawn from [samp_base, samp_base + samp_len) (default 0, S)
 };
 
@@ -35,6 +36,10 @@ struct PathLookup {
     const uint16_t* blk;          // BLK_TABLE entries in shared memory, or nullptr
     uint32_t shift;
     uint32_t P;
+    // experiment (GFASORT_ZETA_SMEM, profiles/r2_experiments.md): the first zs_n entries of both zeta tables staged in
+    // shared memory ([table][entry]); null = every zeta read goes to L2 through the read-only path (the default)
+    const double2* zs;
+    uint32_t zs_n;
     __device__ __forceinline__ uint32_t path_of(uint64_t s) const {
         if (blk) {
             uint32_t p = blk[(uint32_t)(s >> shift)];
@@ -53,7 +58,7 @@ struct Slot {
     uint64_t step_a, step_b;   // step indices
     uint64_t f;                // first step of the path
     uint64_t r23;              // second half of the Philox block
-    double zeta;
+    double zeta, den;          // table entry: zeta and 1 - zeta2theta/zeta
     uint32_t n, ra, J;
     uint32_t coins;            // r.z
     bool zipf, back, live;     // live: a partner is drawn (n > 1 and the Zipf branch has room to move)
@@ -74,11 +79,16 @@ __device__ __forceinline__ void sample_s1(const KernelGraph& g, const PathLookup
     // (samp_base, samp_len) = (0, S) is the reference's U[0, S) (sgd.rs:444)
     uint64_t s = win_base + __umul64hi(r01, win_len);
     if (g.coherent) {
-        // warp-coherent sampling (sweep schedule only): the warp's first lane draws the step, lane l takes
-        // the l-th step after it.  Every step is still drawn with the same probability over a sweep, but
-        // the 32 sampled records — and, with the node relabelling, most of their nodes' positions — are
-        // adjacent in memory: one coalesced request instead of 32.  Partners stay independent per lane.
-        s = __shfl_sync(warp_mask, s, __ffs(warp_mask) - 1) + (uint32_t)lane;
+        // warp-coherent sampling (sweep schedule only): the first lane of every group of G lanes draws the step,
+        // lane l of the group takes the l-th step after it.  Every step is still drawn with the same probability
+        // over a sweep, but the G sampled records — and, with the node relabelling, most of their nodes'
+        // positions — are adjacent in memory: one coalesced request instead of G.  Partners stay independent
+        // per lane.  (A partial warp — only with a hand-picked thread count — falls back to one group led by
+        // its first active lane.)
+        const uint32_t G = g.coherent;
+        const bool full = warp_mask == 0xffffffffu;
+        const int src = full ? (lane & ~(int)(G - 1)) : __ffs(warp_mask) - 1;
+        s = __shfl_sync(warp_mask, s, src) + (uint32_t)(full ? (lane & (int)(G - 1)) : lane);
     }
     if (s >= g.samp_base + g.samp_len) s -= g.samp_len;
     t.step_a = s;
@@ -101,8 +111,11 @@ __device__ __forceinline__ void sample_s1(const KernelGraph& g, const PathLookup
     }
     k = k < g.zlen - 1 ? k : g.zlen - 1;                                                   // sgd.rs:469
     t.live = active && n > 1 && (!t.zipf || moves);        // n == 1 => continue (sgd.rs:448)
-    t.zeta = 1.0;
-    if (t.live && t.zipf) t.zeta = __ldg(g.zetas + k);
+    t.zeta = 1.0; t.den = 1.0;
+    if (t.live && t.zipf) {
+        const double2 zd = (pl.zs && k < pl.zs_n) ? pl.zs[ep.ztab * pl.zs_n + k] : __ldg(g.zetas + (size_t)ep.ztab * g.zlen + k);
+        t.zeta = zd.x; t.den = zd.y;
+    }
 }
 
 __device__ __forceinline__ void sample_s2(const KernelGraph& g, const EpochDesc& ep, Slot& t) {
@@ -110,7 +123,7 @@ __device__ __forceinline__ void sample_s2(const KernelGraph& g, const EpochDesc&
     // u = (r23 >> 11) * 2^-53 (sgd.rs:136 through PhiloxDraw::unit)
     const double u = __dmul_rn((double)(t.r23 >> 11), 1.0 / 9007199254740992.0);
     const ZipfPre pre = dirty_zipf_pre(t.J, ep.zc);
-    const uint32_t z = dirty_zipf_post(t.J, ep.zc, pre, t.zeta, u);
+    const uint32_t z = dirty_zipf_post(t.J, ep.zc, pre, t.zeta, t.den, u);
     const uint32_t room = n - 1 - ra;
     const uint32_t rb_back = ra >= z ? ra - z : 0u;                                        // saturating_sub
     const uint32_t rb_fwd = z < room ? ra + z : n - 1;                                     // min(ra + z, n - 1)
@@ -236,6 +249,7 @@ struct SgdArgs {
     uint32_t chunk_updates;
     unsigned long long* work_ctr;
     uint64_t iter_cap;           // watchdog: a warp that loops more often than this sets counters[2] and stops
+    uint32_t zeta_smem;          // experiment: zeta-table entries (per theta) staged in shared memory; 0 = none
 };
 
 // 1D update of one warp's terms (sgd.rs:512-576), optionally merging lanes that hit the same node.
@@ -342,6 +356,16 @@ sgd_kernel(const SgdArgs a) {
     pl.blk = tables ? s_blk : nullptr;
     pl.shift = a.g.blk_shift;
     pl.P = a.g.P;
+    pl.zs = nullptr; pl.zs_n = 0;
+    if (a.zeta_smem) {
+        // after the path tables, 16-byte aligned
+        const size_t off = ((size_t)n_fs * 8 + (tables ? (size_t)BLK_TABLE * 2 : 0) + 15) & ~(size_t)15;
+        double2* s_z = reinterpret_cast<double2*>(smem_raw + off);
+        const uint32_t n = a.zeta_smem < a.g.zlen ? a.zeta_smem : a.g.zlen;
+        for (uint32_t k = threadIdx.x; k < 2 * n; k += blockDim.x) s_z[k] = a.g.zetas[(size_t)(k / n) * a.g.zlen + (k % n)];
+        __syncthreads();
+        pl.zs = s_z; pl.zs_n = n;
+    }
 
     const unsigned warp_mask = __activemask();
     const int lane = threadIdx.x & 31;

@@ -22,7 +22,9 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <atomic>
 #include <cstring>
+#include <memory>
 #include <string>
 #include <thread>
 #include <vector>
@@ -88,6 +90,21 @@ static void h_zetas(const gfs_sgd_params& p, uint64_t max_path_steps, std::vecto
 }
 
 
+// What the kernels read: for each of the run's two thetas (params.theta while warm, 0.001 while cooling, sgd.rs:394)
+// a table of {zetas[k], 1 - zeta2theta/zetas[k]} — the second member is the denominator of DirtyZipfian's eta
+// (sgd.rs:133-134), computed here with the same two IEEE operations the reference performs per sample.
+static void h_zeta_tables(const gfs_sgd_params& p, uint64_t max_path_steps, std::vector<double2>& out, uint32_t& zlen) {
+    std::vector<double> z;
+    h_zetas(p, max_path_steps, z);
+    zlen = (uint32_t)z.size();
+    out.resize(2 * z.size());
+    const double thetas[2] = {p.theta, 0.001};
+    for (int t = 0; t < 2; ++t) {
+        const double z2 = 1.0 + h_fast_precise_pow(0.5, thetas[t]);
+        for (size_t k = 0; k < z.size(); ++k) out[t * z.size() + k] = make_double2(z[k], 1.0 - z2 / z[k]);
+    }
+}
+
 static void h_epochs(const gfs_sgd_params& p, std::vector<EpochDesc>& out) {
     std::vector<double> etas;
     h_schedule(p, etas);
@@ -97,6 +114,7 @@ static void h_epochs(const gfs_sgd_params& p, std::vector<EpochDesc>& out) {
         EpochDesc d{};
         d.eta = etas[e];
         d.cooling = e > first_cooling ? 1u : 0u;                    // strict (sgd.rs:393)
+        d.ztab = d.cooling;
         const double theta = d.cooling ? 0.001 : p.theta;           // sgd.rs:394
         d.zc.theta = theta;
         d.zc.one_minus_theta = 1.0 - theta;
@@ -162,17 +180,57 @@ extern "C" const char* gfs_device_info(void) {
 static int radix_sort_pairs(uint64_t*& k0, uint64_t*& k1, uint32_t*& v0, uint32_t*& v1, uint32_t* hist, uint64_t n, int passes,
                             cudaStream_t st, uint64_t* launches);
 
-// Copies `bytes` with several host threads (pageable source -> pinned bounce buffer): one thread tops out
-// well below what a PCIe 5 x16 link drains.
-static void parallel_memcpy(void* dst, const void* src, size_t bytes, int threads) {
-    if (threads <= 1 || bytes < (8u << 20)) { std::memcpy(dst, src, bytes); return; }
-    std::vector<std::thread> pool;
-    const size_t per = ((bytes + threads - 1) / threads + 4095) & ~(size_t)4095;
-    for (int t = 0; t < threads; ++t) {
-        const size_t lo = std::min(bytes, per * t), hi = std::min(bytes, per * (t + 1));
-        if (hi > lo) pool.emplace_back([=] { std::memcpy((char*)dst + lo, (const char*)src + lo, hi - lo); });
+// Host threads that copy a pageable source into a pinned bounce buffer, slice by slice: one thread tops out well
+// below what a PCIe 5 x16 link drains.  The workers live for one index build and spin (yielding) between copies,
+// which come a few hundred microseconds apart.
+struct CopyPool {
+    std::vector<std::thread> workers;
+    std::atomic<uint64_t> seq{0};
+    std::atomic<uint32_t> done{0};
+    std::atomic<bool> stop{false};
+    char* dst = nullptr; const char* src = nullptr; size_t len = 0;
+    int T = 1;
+    void slice(int t) const {
+        const size_t per = ((len + T - 1) / T + 4095) & ~(size_t)4095;
+        const size_t lo = std::min(len, per * t), hi = std::min(len, per * (t + 1));
+        if (hi > lo) std::memcpy(dst + lo, src + lo, hi - lo);
     }
-    for (auto& th : pool) th.join();
+    explicit CopyPool(int threads) : T(std::max(threads, 1)) {
+        for (int t = 1; t < T; ++t)
+            workers.emplace_back([this, t] {
+                uint64_t seen = 0;
+                for (;;) {
+                    uint64_t cur;
+                    while ((cur = seq.load(std::memory_order_acquire)) == seen) {
+                        if (stop.load(std::memory_order_relaxed)) return;
+                        std::this_thread::yield();
+                    }
+                    seen = cur;
+                    slice(t);
+                    done.fetch_add(1, std::memory_order_release);
+                }
+            });
+    }
+    void copy(void* d, const void* s, size_t n) {
+        dst = static_cast<char*>(d); src = static_cast<const char*>(s); len = n;
+        done.store(0, std::memory_order_relaxed);
+        seq.fetch_add(1, std::memory_order_release);
+        slice(0);
+        while (done.load(std::memory_order_acquire) != (uint32_t)(T - 1)) std::this_thread::yield();
+    }
+    ~CopyPool() {
+        stop.store(true);
+        for (auto& w : workers) w.join();
+    }
+};
+
+// GFASORT_BUILD_TRACE=1: phase times of the index build on stderr
+static thread_local double g_trace_last = 0.0;
+static void trace_mark(const char* what) {
+    if (g_trace_last == 0.0) return;
+    const double t = now_s();
+    std::fprintf(stderr, "[gfs_index_build]   %-26s +%.4f s\n", what, t - g_trace_last);
+    g_trace_last = t;
 }
 
 static int relabel_rewrite(gfs_index* ix, cudaStream_t st) {
@@ -181,6 +239,7 @@ static int relabel_rewrite(gfs_index* ix, cudaStream_t st) {
     ix->launches += ix->S ? 1 : 0;
     GFS_CUDA(cudaStreamSynchronize(st));
     GFS_CUDA(cudaGetLastError());
+    trace_mark("rl_rewrite + sync");
     return GFS_OK;
 }
 
@@ -188,8 +247,8 @@ static int relabel_rewrite(gfs_index* ix, cudaStream_t st) {
 static int index_relabel_given(gfs_index* ix, const uint32_t* given, cudaStream_t st) {
     if (ix->N == 0) return GFS_OK;
     const uint32_t N = (uint32_t)ix->N;
-    GFS_CUDA(cudaMalloc(&ix->d_new_of_old, (size_t)N * 4));
-    GFS_CUDA(cudaMalloc(&ix->d_old_of_new, (size_t)N * 4));
+    if (!ix->d_new_of_old) GFS_CUDA(cudaMalloc(&ix->d_new_of_old, (size_t)N * 4));
+    if (!ix->d_old_of_new) GFS_CUDA(cudaMalloc(&ix->d_old_of_new, (size_t)N * 4));
     GFS_CUDA(cudaMemcpyAsync(ix->d_new_of_old, given, (size_t)N * 4, cudaMemcpyHostToDevice, st));
     rl_invert<<<(N + 255) / 256, 256, 0, st>>>(ix->d_new_of_old, N, ix->d_old_of_new);
     ix->launches += 1;
@@ -198,24 +257,29 @@ static int index_relabel_given(gfs_index* ix, const uint32_t* given, cudaStream_
 
 // Relabel by order of first appearance: a stable radix sort of the N first-occurrence keys K1 left in the
 // node table (32-bit keys: 4 passes), never-visited nodes last.
-static int index_relabel_first_occ(gfs_index* ix, const NodeEnt* d_tbl, cudaStream_t st) {
+// sort scratch of the relabelling for N nodes: k0[N] u64 | k1[N] u64 | v1[N] u32 | hist[256 * n_blocks] u32
+static uint64_t relabel_scratch_bytes(uint64_t N) {
+    const uint64_t n_blocks = (N + RS_TILE - 1) / RS_TILE;
+    auto up256 = [](uint64_t v) { return (v + 255) / 256 * 256; };
+    return up256(N * 8) * 2 + up256(N * 4) + up256(256 * n_blocks * 4);
+}
+// ix->d_new_of_old / d_old_of_new are allocated by the caller; `scratch` holds relabel_scratch_bytes(N) bytes.
+static int index_relabel_first_occ(gfs_index* ix, const uint32_t* d_first_key, char* scratch, cudaStream_t st) {
     if (ix->N == 0) return GFS_OK;
     const uint32_t N = (uint32_t)ix->N;
-    GFS_CUDA(cudaMalloc(&ix->d_new_of_old, (size_t)N * 4));
-    GFS_CUDA(cudaMalloc(&ix->d_old_of_new, (size_t)N * 4));
-    {
-        DevBuf<uint64_t> b_k0, b_k1; DevBuf<uint32_t> b_v1, b_hist;
-        const uint32_t n_blocks = (uint32_t)(((uint64_t)N + RS_TILE - 1) / RS_TILE);
-        GFS_CUDA(b_k0.alloc(N)); GFS_CUDA(b_k1.alloc(N)); GFS_CUDA(b_v1.alloc(N)); GFS_CUDA(b_hist.alloc((size_t)256 * n_blocks));
-        uint64_t *k0 = b_k0.p, *k1 = b_k1.p; uint32_t *v0 = ix->d_old_of_new, *v1 = b_v1.p;
-        rl_keys<<<(N + 255) / 256, 256, 0, st>>>(d_tbl, N, k0, v0);
-        ix->launches += 1;
-        int rc = radix_sort_pairs(k0, k1, v0, v1, b_hist.p, N, 4, st, &ix->launches);     // even number of passes: result in v0
-        if (rc) return rc;
-        rl_invert<<<(N + 255) / 256, 256, 0, st>>>(ix->d_old_of_new, N, ix->d_new_of_old);
-        ix->launches += 1;
-        GFS_CUDA(cudaStreamSynchronize(st));        // the scratch buffers go out of scope
-    }
+    auto up256 = [](uint64_t v) { return (v + 255) / 256 * 256; };
+    uint64_t* k0 = reinterpret_cast<uint64_t*>(scratch);
+    uint64_t* k1 = reinterpret_cast<uint64_t*>(scratch + up256((uint64_t)N * 8));
+    uint32_t* v1 = reinterpret_cast<uint32_t*>(scratch + 2 * up256((uint64_t)N * 8));
+    uint32_t* hist = reinterpret_cast<uint32_t*>(scratch + 2 * up256((uint64_t)N * 8) + up256((uint64_t)N * 4));
+    uint32_t* v0 = ix->d_old_of_new;
+    rl_keys<<<(N + 255) / 256, 256, 0, st>>>(d_first_key, N, k0, v0);
+    ix->launches += 1;
+    int rc = radix_sort_pairs(k0, k1, v0, v1, hist, N, 4, st, &ix->launches);     // even number of passes: result in v0
+    if (rc) return rc;
+    rl_invert<<<(N + 255) / 256, 256, 0, st>>>(ix->d_old_of_new, N, ix->d_new_of_old);
+    ix->launches += 1;
+    trace_mark("relabel: sort enqueued");
     return relabel_rewrite(ix, st);
 }
 
@@ -245,6 +309,14 @@ static int build_shard_impl(const HT* step_handles, const uint64_t* path_first_s
     if (rc) return rc;
 
     const double t_begin = now_s();
+    const bool trace = env_long("GFASORT_BUILD_TRACE", 0) != 0;
+    double t_last = t_begin;
+    auto mark = [&](const char* what) {
+        if (!trace) return;
+        const double t = now_s();
+        std::fprintf(stderr, "[gfs_index_build] %-28s +%.4f s (at %.4f)\n", what, t - t_last, t - t_begin);
+        t_last = t;
+    };
     gfs_index* ix = new gfs_index();
     cudaGetDevice(&ix->device);
     const uint64_t s_begin = path_first_step[path_begin], s_end = path_first_step[path_end];
@@ -274,27 +346,44 @@ static int build_shard_impl(const HT* step_handles, const uint64_t* path_first_s
     const uint64_t n_chunks = (ix->S + CH - 1) / CH;
     const uint64_t tiles_total = (ix->S + K1_TILE - 1) / K1_TILE;
 
-    DevBuf<uint64_t> b_desc; DevBuf<unsigned int> b_ticket; DevBuf<uint32_t> b_node_len; DevBuf<NodeEnt> b_tbl;
-    DevBuf<HT> b_h[2];
     IX_CUDA(cudaMalloc(&ix->d_first_step, (ix->P + 1) * 8));
     IX_CUDA(cudaMalloc(&ix->d_path_len, std::max<uint64_t>(ix->P, 1) * 8));
-    IX_CUDA(cudaMalloc(&ix->d_recs, std::max<uint64_t>(ix->S, 1) * sizeof(StepRec)));
-    IX_CUDA(b_desc.alloc(tiles_total + 1));
-    IX_CUDA(b_ticket.alloc(2));
-    IX_CUDA(cudaMemsetAsync(b_ticket.p, 0, 2 * sizeof(unsigned int), s_k));
-    IX_CUDA(b_node_len.alloc(N));
-    IX_CUDA(b_tbl.alloc(N));
-    IX_CUDA(b_h[0].alloc(chunk_cap));
-    if (n_chunks > 1) IX_CUDA(b_h[1].alloc(chunk_cap));
-    IX_CUDA(cudaMemsetAsync(b_desc.p, 0, (tiles_total + 1) * 8, s_k));
-    IX_CUDA(cudaMemsetAsync(ix->d_path_len, 0, std::max<uint64_t>(ix->P, 1) * 8, s_k));
-    const double t_h2d0 = now_s();
-    IX_CUDA(cudaMemcpyAsync(ix->d_first_step, ix->h_first_step.data(), (ix->P + 1) * 8, cudaMemcpyHostToDevice, s_k));
-    if (N) {
-        IX_CUDA(cudaMemcpyAsync(b_node_len.p, node_len, N * 4, cudaMemcpyHostToDevice, s_k));
-        k1_init_table<<<(unsigned)((N + 255) / 256), 256, 0, s_k>>>(b_node_len.p, (uint32_t)N, b_tbl.p);
-        ix->launches += 1;
+    // records and staged handles are padded to whole tiles: K1 works without bounds checks (padding handles are all-ones,
+    // i.e. "missing node"; padding records are written and never read)
+    IX_CUDA(cudaMalloc(&ix->d_recs, std::max<uint64_t>(tiles_total * K1_TILE, 1) * sizeof(StepRec)));
+    // everything transient in ONE allocation: [descriptors | watchdog flag | node_len | visited bitmap | first keys | 2 handle buffers]
+    const uint64_t chunk_alloc = (chunk_cap + K1_TILE - 1) / K1_TILE * K1_TILE;
+    auto up256 = [](uint64_t v) { return (v + 255) / 256 * 256; };
+    const uint64_t o_desc = 0, o_flag = o_desc + up256((tiles_total + 1) * 8), o_len = o_flag + 256, o_vis = o_len + up256(N * 4 + 4),
+                   o_key = o_vis + up256((N / 32 + 1) * 4), o_h0 = o_key + up256(N * 4 + 4), o_h1 = o_h0 + up256(chunk_alloc * sizeof(HT)),
+                   k1_bytes = o_h1 + (n_chunks > 1 ? up256(chunk_alloc * sizeof(HT)) : 0),
+                   // the relabelling's sort scratch reuses the handle buffers (idle once K1 has drained)
+                   arena_bytes = std::max(k1_bytes, relabel_mode == 1 ? o_h0 + relabel_scratch_bytes(N) : 0);
+    // cudaMalloc / cudaFree calls are kept to a handful per build, all before the first copy: on this pool single
+    // calls sporadically stall for 0.5-1.7 s when issued between kernels (profiles/r2_index_build.md); the arena is
+    // handed to the index and freed with it
+    struct Arena { char* p = nullptr; } arena;
+    IX_CUDA(cudaMalloc(&ix->d_build_arena, std::max<uint64_t>(arena_bytes, 256)));
+    arena.p = static_cast<char*>(ix->d_build_arena);
+    if (relabel_mode != 0 && N) {
+        IX_CUDA(cudaMalloc(&ix->d_new_of_old, (size_t)N * 4));
+        IX_CUDA(cudaMalloc(&ix->d_old_of_new, (size_t)N * 4));
     }
+    uint64_t* d_desc = reinterpret_cast<uint64_t*>(arena.p + o_desc);
+    unsigned int* d_flag = reinterpret_cast<unsigned int*>(arena.p + o_flag);
+    uint32_t* d_node_len = reinterpret_cast<uint32_t*>(arena.p + o_len);
+    uint32_t* d_visited = reinterpret_cast<uint32_t*>(arena.p + o_vis);
+    uint32_t* d_first_key = reinterpret_cast<uint32_t*>(arena.p + o_key);
+    HT* d_h[2] = {reinterpret_cast<HT*>(arena.p + o_h0), reinterpret_cast<HT*>(arena.p + o_h1)};
+    IX_CUDA(cudaMemsetAsync(arena.p, 0, o_len, s_k));                                   // descriptors, flag
+    IX_CUDA(cudaMemsetAsync(d_visited, 0, o_key - o_vis, s_k));
+    IX_CUDA(cudaMemsetAsync(d_first_key, 0xff, o_h0 - o_key, s_k));                     // 0xffffffff = never visited
+    IX_CUDA(cudaMemsetAsync(ix->d_path_len, 0, std::max<uint64_t>(ix->P, 1) * 8, s_k));
+    mark("device allocations");
+    const double t_h2d0 = now_s();
+    ix->alloc_seconds = t_h2d0 - t_begin;
+    IX_CUDA(cudaMemcpyAsync(ix->d_first_step, ix->h_first_step.data(), (ix->P + 1) * 8, cudaMemcpyHostToDevice, s_k));
+    if (N) IX_CUDA(cudaMemcpyAsync(d_node_len, node_len, N * 4, cudaMemcpyHostToDevice, s_k));
 
     // is the caller's step array page-locked?  (cudaHostAlloc / cudaHostRegister memory: the copy engine reads it directly)
     bool src_pinned = false;
@@ -303,16 +392,21 @@ static int build_shard_impl(const HT* step_handles, const uint64_t* path_first_s
         if (cudaPointerGetAttributes(&attr, step_handles + s_begin) == cudaSuccess) src_pinned = attr.type == cudaMemoryTypeHost;
         else (void)cudaGetLastError();
     }
-    struct Pinned { void* p = nullptr; ~Pinned() { if (p) cudaFreeHost(p); } } pin[2];
+    // pageable source: NB bounce buffers of BB bytes (page-locking memory costs ~1 ms per MB, so they are small and
+    // decoupled from the device chunk: a chunk arrives as several sub-copies)
+    constexpr int NB = 4;
+    const size_t BB = (size_t)std::max<long>(1l << 20, env_long("GFASORT_BOUNCE_BYTES", 8l << 20));
+    struct Pinned { void* p = nullptr; ~Pinned() { if (p) cudaFreeHost(p); } } pin;
     const int copy_threads = (int)std::max<long>(1, env_long("GFASORT_COPY_THREADS", std::min<long>(8, std::max<long>(1, (long)std::thread::hardware_concurrency() / 2))));
-    if (ix->S && !src_pinned) {
-        IX_CUDA(cudaHostAlloc(&pin[0].p, chunk_cap * sizeof(HT), cudaHostAllocDefault));
-        if (n_chunks > 1) IX_CUDA(cudaHostAlloc(&pin[1].p, chunk_cap * sizeof(HT), cudaHostAllocDefault));
-    }
-    cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_k[2] = {nullptr, nullptr};
+    if (ix->S && !src_pinned) IX_CUDA(cudaHostAlloc(&pin.p, NB * BB, cudaHostAllocDefault));
+    std::unique_ptr<CopyPool> pool;
+    if (pin.p) pool.reset(new CopyPool(copy_threads));
+    mark("pinned bounce buffers");
+    cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_k[2] = {nullptr, nullptr}, ev_b[NB] = {};
     std::vector<cudaEvent_t> ev_t;      // kernel timing: one pair per chunk
     auto drop_events = [&]() {
         for (int b = 0; b < 2; ++b) { if (ev_h2d[b]) cudaEventDestroy(ev_h2d[b]); if (ev_k[b]) cudaEventDestroy(ev_k[b]); }
+        for (int b = 0; b < NB; ++b) if (ev_b[b]) cudaEventDestroy(ev_b[b]);
         for (cudaEvent_t e : ev_t) cudaEventDestroy(e);
     };
 #define IXE_CUDA(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { set_error(std::string(#call) + " failed: " + cudaGetErrorString(e__)); drop_events(); return fail(GFS_ERR_CUDA); } } while (0)
@@ -320,6 +414,8 @@ static int build_shard_impl(const HT* step_handles, const uint64_t* path_first_s
         IXE_CUDA(cudaEventCreateWithFlags(&ev_h2d[b], cudaEventDisableTiming));
         IXE_CUDA(cudaEventCreateWithFlags(&ev_k[b], cudaEventDisableTiming));
     }
+    if (pin.p) for (int b = 0; b < NB; ++b) IXE_CUDA(cudaEventCreateWithFlags(&ev_b[b], cudaEventDisableTiming));
+    uint64_t n_sub = 0;                 // bounce sub-copies issued so far (buffer n_sub % NB is next)
     for (uint64_t c = 0; c < n_chunks; ++c) {
         const int b = (int)(c & 1);
         const uint64_t c0 = c * CH, clen = std::min(CH, ix->S - c0);
@@ -327,49 +423,69 @@ static int build_shard_impl(const HT* step_handles, const uint64_t* path_first_s
         const HT* src = step_handles + s_begin + c0;
         if (c >= 2) IXE_CUDA(cudaStreamWaitEvent(s_copy, ev_k[b], 0));          // the kernel of chunk c-2 is done with this buffer
         if (src_pinned) {
-            IXE_CUDA(cudaMemcpyAsync(b_h[b].p, src, bytes, cudaMemcpyHostToDevice, s_copy));
+            IXE_CUDA(cudaMemcpyAsync(d_h[b], src, bytes, cudaMemcpyHostToDevice, s_copy));
         } else {
-            if (c >= 2) IXE_CUDA(cudaEventSynchronize(ev_h2d[b]));             // the DMA of chunk c-2 has drained this bounce buffer
-            parallel_memcpy(pin[b].p, src, bytes, copy_threads);
-            IXE_CUDA(cudaMemcpyAsync(b_h[b].p, pin[b].p, bytes, cudaMemcpyHostToDevice, s_copy));
+            for (size_t off = 0; off < bytes; off += BB, ++n_sub) {
+                const int k = (int)(n_sub % NB);
+                const size_t len = std::min(BB, bytes - off);
+                char* stage = static_cast<char*>(pin.p) + (size_t)k * BB;
+                if (n_sub >= NB) IXE_CUDA(cudaEventSynchronize(ev_b[k]));       // the DMA that last read this bounce buffer has finished
+                pool->copy(stage, reinterpret_cast<const char*>(src) + off, len);
+                IXE_CUDA(cudaMemcpyAsync(reinterpret_cast<char*>(d_h[b]) + off, stage, len, cudaMemcpyHostToDevice, s_copy));
+                IXE_CUDA(cudaEventRecord(ev_b[k], s_copy));
+            }
         }
+        const uint64_t cpad = (clen + K1_TILE - 1) / K1_TILE * K1_TILE;
+        if (cpad > clen) IXE_CUDA(cudaMemsetAsync(d_h[b] + clen, 0xff, (cpad - clen) * sizeof(HT), s_copy));   // the last tile's padding
         IXE_CUDA(cudaEventRecord(ev_h2d[b], s_copy));
         IXE_CUDA(cudaStreamWaitEvent(s_k, ev_h2d[b], 0));
-        IXE_CUDA(cudaMemsetAsync(b_ticket.p, 0, sizeof(unsigned int), s_k));
         cudaEvent_t t0 = nullptr, t1 = nullptr;
         IXE_CUDA(cudaEventCreate(&t0)); ev_t.push_back(t0);
         IXE_CUDA(cudaEventCreate(&t1)); ev_t.push_back(t1);
         IXE_CUDA(cudaEventRecord(t0, s_k));
         const unsigned n_tiles = (unsigned)((clen + K1_TILE - 1) / K1_TILE);
         if (first_occ)
-            k1_scan_write<HT, true><<<n_tiles, K1_THREADS, 0, s_k>>>(b_h[b].p, b_tbl.p, (uint32_t)N, ix->d_first_step, (uint32_t)ix->P, c0, clen,
-                                                                      b_desc.p, b_ticket.p, key_shift, ix->d_recs, ix->d_path_len);
+            k1_scan_write<HT, true><<<n_tiles, K1_BLOCK, 0, s_k>>>(d_h[b], d_node_len, d_visited, d_first_key, (uint32_t)N, ix->d_first_step,
+                                                                    (uint32_t)ix->P, c0, ix->S, d_desc, d_flag, key_shift, ix->d_recs, ix->d_path_len);
         else
-            k1_scan_write<HT, false><<<n_tiles, K1_THREADS, 0, s_k>>>(b_h[b].p, b_tbl.p, (uint32_t)N, ix->d_first_step, (uint32_t)ix->P, c0, clen,
-                                                                       b_desc.p, b_ticket.p, key_shift, ix->d_recs, ix->d_path_len);
+            k1_scan_write<HT, false><<<n_tiles, K1_BLOCK, 0, s_k>>>(d_h[b], d_node_len, d_visited, d_first_key, (uint32_t)N, ix->d_first_step,
+                                                                     (uint32_t)ix->P, c0, ix->S, d_desc, d_flag, key_shift, ix->d_recs, ix->d_path_len);
+        if (ix->P > 1) {
+            k1_fix_path_starts<<<(unsigned)(ix->P - 1), K1_THREADS, 0, s_k>>>(ix->d_first_step, (uint32_t)ix->P, c0, c0 + clen, ix->d_recs, ix->d_path_len);
+            ix->launches += 1;
+        }
         IXE_CUDA(cudaGetLastError());
         IXE_CUDA(cudaEventRecord(t1, s_k));
         IXE_CUDA(cudaEventRecord(ev_k[b], s_k));
         ix->launches += 1;
     }
+    mark("chunks enqueued");
     IXE_CUDA(cudaStreamSynchronize(s_k));
     IXE_CUDA(cudaGetLastError());
-    {
-        unsigned int tk[2] = {0, 0};
-        IXE_CUDA(cudaMemcpy(tk, b_ticket.p, sizeof tk, cudaMemcpyDeviceToHost));
-        if (tk[1]) { set_error("gfs_index_build: the scan's look-back watchdog tripped (a tile never published its prefix)"); drop_events(); return fail(GFS_ERR_CUDA); }
-    }
+    mark("copy + K1 drained");
     ix->h2d_seconds = now_s() - t_h2d0;          // wall time of the streamed copy + K1 (they overlap)
     for (size_t k = 0; k + 1 < ev_t.size(); k += 2) {
         float ms = 0;
         if (cudaEventElapsedTime(&ms, ev_t[k], ev_t[k + 1]) == cudaSuccess) ix->kernel_seconds += ms * 1e-3;
     }
     drop_events();
+    mark("events read and destroyed");
 #undef IXE_CUDA
-    b_h[0].release(); b_h[1].release(); b_desc.release(); b_ticket.release(); b_node_len.release();   // before relabelling allocates
-    if (relabel_mode == 1) rc = index_relabel_first_occ(ix, b_tbl.p, s_k);
+    // relabelling reads the watchdog flag with its own results (one blocking copy at the end instead of one here)
+    const double t_rl0 = now_s();
+    g_trace_last = trace ? t_rl0 : 0.0;
+    if (relabel_mode == 1) rc = index_relabel_first_occ(ix, d_first_key, arena.p + o_h0, s_k);
     else if (relabel_mode == 2) rc = index_relabel_given(ix, new_of_old, s_k);
     if (rc) return fail(rc);
+    ix->relabel_seconds = now_s() - t_rl0;
+    g_trace_last = 0.0;
+    mark("relabel");
+    {
+        unsigned int tk = 0;
+        IX_CUDA(cudaMemcpy(&tk, d_flag, sizeof tk, cudaMemcpyDeviceToHost));
+        if (tk) { set_error("gfs_index_build: the scan's look-back watchdog tripped (a tile never published its prefix)"); return fail(GFS_ERR_CUDA); }
+    }
+    mark("watchdog flag read");
     ix->build_seconds = now_s() - t_begin;
     *out = ix;
     return GFS_OK;
@@ -431,6 +547,8 @@ static int build_multi_impl(const HT* step_handles, const uint64_t* path_first_s
         mix->launches += mix->shards[g]->launches;
         mix->kernel_seconds = std::max(mix->kernel_seconds, mix->shards[g]->kernel_seconds);
         mix->h2d_seconds = std::max(mix->h2d_seconds, mix->shards[g]->h2d_seconds);
+        mix->alloc_seconds = std::max(mix->alloc_seconds, mix->shards[g]->alloc_seconds);
+        mix->relabel_seconds = std::max(mix->relabel_seconds, mix->shards[g]->relabel_seconds);
     }
     mix->build_seconds = now_s() - t0;
     *out = mix;
@@ -468,6 +586,18 @@ extern "C" int gfs_index_build32(const uint32_t* step_handles, const uint64_t* p
     return index_build_env<uint32_t>(step_handles, path_first_step, node_len, S, P, N, out);
 }
 
+// Page-locked host memory for the flattened step array: the copy engine reads it directly, so a host that flattens
+// its paths straight into such a buffer skips the bounce-buffer staging a pageable array needs.
+extern "C" int gfs_host_alloc(uint64_t bytes, void** out) {
+    if (!out) { set_error("gfs_host_alloc: out is null"); return GFS_ERR_INVALID; }
+    *out = nullptr;
+    int rc = select_device(-1);
+    if (rc) return rc;
+    GFS_CUDA(cudaHostAlloc(out, std::max<uint64_t>(bytes, 1), cudaHostAllocPortable));
+    return GFS_OK;
+}
+extern "C" void gfs_host_free(void* p) { if (p) cudaFreeHost(p); }
+
 extern "C" int gfs_index_apply_relabel(gfs_index* ix, const uint32_t* new_of_old) {
     if (!ix || !new_of_old) { set_error("gfs_index_apply_relabel: null argument"); return GFS_ERR_INVALID; }
     if (!ix->shards.empty()) { set_error("gfs_index_apply_relabel: not for a multi-GPU index (its shards already share one order)"); return GFS_ERR_INVALID; }
@@ -493,7 +623,7 @@ extern "C" void gfs_index_free(gfs_index* ix) {
     if (ix->shards.empty()) {
         cudaSetDevice(ix->device);
         cudaFree(ix->d_recs); cudaFree(ix->d_first_step); cudaFree(ix->d_path_len);
-        cudaFree(ix->d_new_of_old); cudaFree(ix->d_old_of_new);
+        cudaFree(ix->d_new_of_old); cudaFree(ix->d_old_of_new); cudaFree(ix->d_build_arena);
     }
     delete ix;
 }
@@ -508,11 +638,13 @@ extern "C" int gfs_index_dims(const gfs_index* ix, uint64_t* S, uint64_t* P, uin
 }
 
 extern "C" int gfs_index_build_info(const gfs_index* ix, double* build_seconds, double* copy_seconds, double* kernel_seconds,
-                                    uint64_t* launches, uint32_t* n_devices) {
+                                    double* alloc_seconds, double* relabel_seconds, uint64_t* launches, uint32_t* n_devices) {
     if (!ix) { set_error("gfs_index_build_info: null index"); return GFS_ERR_INVALID; }
     if (build_seconds) *build_seconds = ix->build_seconds;
     if (copy_seconds) *copy_seconds = ix->h2d_seconds;
     if (kernel_seconds) *kernel_seconds = ix->kernel_seconds;
+    if (alloc_seconds) *alloc_seconds = ix->alloc_seconds;
+    if (relabel_seconds) *relabel_seconds = ix->relabel_seconds;
     if (launches) *launches = ix->launches;
     if (n_devices) *n_devices = ix->shards.empty() ? 1u : (uint32_t)ix->shards.size();
     return GFS_OK;
@@ -600,7 +732,7 @@ static sgd_kernel_fn pick_kernel(uint32_t dims, bool f64, bool agg, int inflight
     return inflight >= 2 ? pick_kernel_k<2>(dims, f64, agg, DS) : pick_kernel_k<1>(dims, f64, agg, DS);
 }
 
-static KernelGraph make_kgraph(const gfs_index* ix, const gfs_sgd_params& p, const double* d_zetas, uint32_t zlen) {
+static KernelGraph make_kgraph(const gfs_index* ix, const gfs_sgd_params& p, const double2* d_zetas, uint32_t zlen) {
     KernelGraph g{};
     g.recs = ix->d_recs; g.first_step = ix->d_first_step; g.zetas = d_zetas;
     g.S = ix->S; g.P = (uint32_t)ix->P; g.N = (uint32_t)ix->N; g.zlen = zlen;
@@ -627,8 +759,10 @@ extern "C" void gfs_sgd_session_destroy(gfs_sgd_session* s) {
     if (s->own_pos) cudaFree(s->d_pos);
     cudaFree(s->d_zetas); cudaFree(s->d_epochs); cudaFree(s->d_attempts); cudaFree(s->d_counters); cudaFree(s->d_stage);
     cudaFree(s->d_work); cudaFree(s->d_saved);
-    if (s->ev0) cudaEventDestroy(s->ev0);
-    if (s->ev1) cudaEventDestroy(s->ev1);
+    for (int k = 0; k < gfs_sgd_session::EV_RING; ++k) {
+        if (s->ev0[k]) cudaEventDestroy(s->ev0[k]);
+        if (s->ev1[k]) cudaEventDestroy(s->ev1[k]);
+    }
     if (s->own_stream && s->stream) cudaStreamDestroy(s->stream);
     delete s;
 }
@@ -667,8 +801,10 @@ extern "C" int gfs_sgd_session_create(const gfs_index* ix, const gfs_sgd_params*
 
     if (cfg && cfg->stream) { s->stream = (cudaStream_t)cfg->stream; s->own_stream = false; }
     else { SS_CUDA(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking)); s->own_stream = true; }
-    SS_CUDA(cudaEventCreate(&s->ev0));
-    SS_CUDA(cudaEventCreate(&s->ev1));
+    for (int k = 0; k < gfs_sgd_session::EV_RING; ++k) {
+        SS_CUDA(cudaEventCreate(&s->ev0[k]));
+        SS_CUDA(cudaEventCreate(&s->ev1[k]));
+    }
 
     // terms in flight per thread: 2 for real runs; 1 (strictly sequential per thread, like one reference
     // worker) when the caller asks for a handful of threads, which is what the bit-exact tests do
@@ -681,17 +817,19 @@ extern "C" int gfs_sgd_session_create(const gfs_index* ix, const gfs_sgd_params*
 
     // schedule, zeta table
     std::vector<EpochDesc> epochs; h_epochs(*params, epochs);
-    std::vector<double> zetas; h_zetas(*params, ix->max_path_steps, zetas);
-    s->n_epochs = (uint32_t)epochs.size(); s->zlen = (uint32_t)zetas.size();
+    std::vector<double2> zetas; h_zeta_tables(*params, ix->max_path_steps, zetas, s->zlen);
+    s->n_epochs = (uint32_t)epochs.size();
     SS_CUDA(cudaMalloc(&s->d_epochs, epochs.size() * sizeof(EpochDesc)));
-    SS_CUDA(cudaMalloc(&s->d_zetas, std::max<size_t>(zetas.size(), 1) * 8));
+    SS_CUDA(cudaMalloc(&s->d_zetas, std::max<size_t>(zetas.size(), 1) * sizeof(double2)));
     SS_CUDA(cudaMemcpyAsync(s->d_epochs, epochs.data(), epochs.size() * sizeof(EpochDesc), cudaMemcpyHostToDevice, s->stream));
-    SS_CUDA(cudaMemcpyAsync(s->d_zetas, zetas.data(), zetas.size() * 8, cudaMemcpyHostToDevice, s->stream));
+    SS_CUDA(cudaMemcpyAsync(s->d_zetas, zetas.data(), zetas.size() * sizeof(double2), cudaMemcpyHostToDevice, s->stream));
     SS_CUDA(cudaStreamSynchronize(s->stream));   // host vectors go out of scope
 
     // launch shape: persistent, every block co-resident
     const uint32_t n_fs = (ix->P + 1 <= SMEM_FS_MAX) ? (uint32_t)ix->P + 1 : 0;
     s->smem_bytes = n_fs ? (size_t)n_fs * 8 + (size_t)BLK_TABLE * 2 : 0;
+    s->zeta_smem = (uint32_t)std::min<long>(std::max<long>(env_long("GFASORT_ZETA_SMEM", 0), 0), 6000);      // experiment; default off
+    if (s->zeta_smem) s->smem_bytes = ((s->smem_bytes + 15) & ~(size_t)15) + (size_t)2 * std::min<uint32_t>(s->zeta_smem, s->zlen) * sizeof(double2);
     SS_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_bytes));
     int per_sm = 0, sms = 0;
     SS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, SGD_BLOCK, s->smem_bytes));
@@ -734,7 +872,12 @@ extern "C" int gfs_sgd_session_create(const gfs_index* ix, const gfs_sgd_params*
         if (ws + 32 > s->samp_len) ws = 0;
         s->window_steps = ws;
         s->chunk_updates = (uint32_t)std::max<long>(1, env_long("GFASORT_CHUNK", 256));
-        s->coherent = env_long("GFASORT_COHERENT", 1) != 0;
+        {   // GFASORT_COHERENT: 0 = off, 1 = default group (32 lanes), else the group size rounded down to a power of two <= 32
+            long c = env_long("GFASORT_COHERENT", 1);
+            uint32_t g = c <= 0 ? 0u : (c == 1 ? 32u : (uint32_t)std::min<long>(c, 32));
+            while (g & (g - 1)) g &= g - 1;
+            s->coherent = g < 2 ? 0u : g;
+        }
         SS_CUDA(cudaMalloc(&s->d_work, 8));
     }
 
@@ -766,16 +909,18 @@ extern "C" int gfs_sgd_session_upload(gfs_sgd_session* s, const double* position
     return GFS_OK;
 }
 
-static int session_flush_events(gfs_sgd_session* s) {
-    if (s->ev_pending) {
-        GFS_CUDA(cudaEventSynchronize(s->ev1));
+// reads (blocking) the oldest `n` recorded event pairs into kernel_ms
+static int session_read_events(gfs_sgd_session* s, uint32_t n) {
+    for (; n > 0 && s->ev_tail != s->ev_head; --n, ++s->ev_tail) {
+        const uint32_t k = s->ev_tail % gfs_sgd_session::EV_RING;
+        GFS_CUDA(cudaEventSynchronize(s->ev1[k]));
         float ms = 0;
-        GFS_CUDA(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
+        GFS_CUDA(cudaEventElapsedTime(&ms, s->ev0[k], s->ev1[k]));
         s->kernel_ms += ms;
-        s->ev_pending = false;
     }
     return GFS_OK;
 }
+static int session_flush_events(gfs_sgd_session* s) { return session_read_events(s, s->ev_head - s->ev_tail); }
 
 extern "C" int gfs_sgd_session_download(gfs_sgd_session* s, double* positions) {
     if (!s || !positions) { set_error("gfs_sgd_session_download: null argument"); return GFS_ERR_INVALID; }
@@ -810,14 +955,16 @@ extern "C" int gfs_sgd_session_run(gfs_sgd_session* s, uint64_t epoch_begin, uin
     }
     if (epoch_begin == epoch_end) return GFS_OK;
     GFS_CUDA(cudaSetDevice(s->device));
-    int rc = session_flush_events(s);
-    if (rc) return rc;
+    if (s->ev_head - s->ev_tail == gfs_sgd_session::EV_RING) {       // ring full: read the oldest pair (long finished, normally)
+        int rc = session_read_events(s, 1);
+        if (rc) return rc;
+    }
     uint32_t DS;
     sgd_kernel_fn fn = pick_kernel(s->dims, s->f64, s->aggregate, s->inflight, DS);
     SgdArgs a{};
     a.g = make_kgraph(s->ix, s->params, s->d_zetas, s->zlen);
     a.g.samp_base = s->samp_base; a.g.samp_len = s->samp_len;
-    a.g.coherent = (s->window_steps > 0 && s->coherent) ? 1u : 0u;
+    a.g.coherent = s->window_steps > 0 ? s->coherent : 0u;
     a.epochs = s->d_epochs;
     a.epoch_begin = (uint32_t)epoch_begin; a.epoch_end = (uint32_t)epoch_end;
     a.slice = slice; a.n_slices = n_slices;
@@ -827,6 +974,7 @@ extern "C" int gfs_sgd_session_run(gfs_sgd_session* s, uint64_t epoch_begin, uin
     a.positions = s->d_pos;
     a.window_steps = s->window_steps; a.chunk_updates = s->chunk_updates;
     a.work_ctr = s->d_work;
+    a.zeta_smem = s->zeta_smem;
     {
         // generous bound on loop iterations per warp: 64x its fair share of the launch's attempts + slack
         const uint64_t m = s->params.min_term_updates / n_slices + 1;
@@ -835,10 +983,11 @@ extern "C" int gfs_sgd_session_run(gfs_sgd_session* s, uint64_t epoch_begin, uin
     }
     GFS_CUDA(cudaMemsetAsync(s->d_work, 0, 8, s->stream));
     void* kargs[] = {(void*)&a};
-    GFS_CUDA(cudaEventRecord(s->ev0, s->stream));
+    const uint32_t ek = s->ev_head % gfs_sgd_session::EV_RING;
+    GFS_CUDA(cudaEventRecord(s->ev0[ek], s->stream));
     GFS_CUDA(cudaLaunchCooperativeKernel((const void*)fn, dim3(s->grid), dim3(s->block), kargs, s->smem_bytes, s->stream));
-    GFS_CUDA(cudaEventRecord(s->ev1, s->stream));
-    s->ev_pending = true;
+    GFS_CUDA(cudaEventRecord(s->ev1[ek], s->stream));
+    s->ev_head += 1;
     s->launches += 1;
     return GFS_OK;
 }
@@ -892,7 +1041,7 @@ extern "C" int gfs_sgd_session_stats(gfs_sgd_session* s, gfs_stats* st) {
     st->kernel_seconds = s->kernel_ms * 1e-3;
     st->h2d_seconds = s->h2d_s; st->d2h_seconds = s->d2h_s;
     st->grid = s->grid; st->block = s->block; st->coord_bytes = s->f64 ? 8 : 4;
-    st->n_devices = 1; st->window_steps = s->window_steps; st->coherent = (s->window_steps > 0 && s->coherent) ? 1u : 0u;
+    st->n_devices = 1; st->window_steps = s->window_steps; st->coherent = s->window_steps > 0 ? s->coherent : 0u;
     st->syncs_per_epoch = 0;
     return GFS_OK;
 }
@@ -1056,12 +1205,12 @@ extern "C" int gfs_debug_trace_terms(const gfs_index* ix, const gfs_sgd_params* 
     if (!ix || epoch > params->iter_max) { set_error("gfs_debug_trace_terms: bad argument"); return GFS_ERR_INVALID; }
     GFS_CUDA(cudaSetDevice(ix->device));
     std::vector<EpochDesc> epochs; h_epochs(*params, epochs);
-    std::vector<double> zetas; h_zetas(*params, ix->max_path_steps, zetas);
-    DevBuf<EpochDesc> de; DevBuf<double> dz, dd; DevBuf<uint8_t> dv, df; DevBuf<uint64_t> da, db;
+    std::vector<double2> zetas; uint32_t zlen = 0; h_zeta_tables(*params, ix->max_path_steps, zetas, zlen);
+    DevBuf<EpochDesc> de; DevBuf<double2> dz; DevBuf<double> dd; DevBuf<uint8_t> dv, df; DevBuf<uint64_t> da, db;
     GFS_CUDA(de.alloc(epochs.size())); GFS_CUDA(dz.alloc(zetas.size()));
     GFS_CUDA(de.up(epochs.data(), epochs.size())); GFS_CUDA(dz.up(zetas.data(), zetas.size()));
     GFS_CUDA(dv.alloc(count)); GFS_CUDA(df.alloc(count)); GFS_CUDA(da.alloc(count)); GFS_CUDA(db.alloc(count)); GFS_CUDA(dd.alloc(count));
-    KernelGraph g = make_kgraph(ix, *params, dz.p, (uint32_t)zetas.size());
+    KernelGraph g = make_kgraph(ix, *params, dz.p, zlen);
     const unsigned grid = (unsigned)((count + 255) / 256);
     if (nd) dbg_trace<true><<<grid, 256>>>(g, de.p, (uint32_t)epoch, (uint32_t)params->seed, (uint32_t)(params->seed >> 32), tid, attempt0, count, dv.p, da.p, db.p, df.p, dd.p);
     else dbg_trace<false><<<grid, 256>>>(g, de.p, (uint32_t)epoch, (uint32_t)params->seed, (uint32_t)(params->seed >> 32), tid, attempt0, count, dv.p, da.p, db.p, df.p, dd.p);

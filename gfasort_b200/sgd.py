@@ -103,9 +103,10 @@ class PathIndex:
 
     def build_info(self) -> dict:
         """Wall / copy / K1-kernel seconds, launches and devices of the build (gfs_index_build_info)."""
-        b, c, k, n, d = C.c_double(), C.c_double(), C.c_double(), C.c_uint64(), C.c_uint32()
-        check(lib().gfs_index_build_info(self._h, C.byref(b), C.byref(c), C.byref(k), C.byref(n), C.byref(d)))
-        return {"build_seconds": b.value, "copy_seconds": c.value, "kernel_seconds": k.value, "launches": n.value, "devices": d.value}
+        b, c, k, al, rl, n, d = C.c_double(), C.c_double(), C.c_double(), C.c_double(), C.c_double(), C.c_uint64(), C.c_uint32()
+        check(lib().gfs_index_build_info(self._h, C.byref(b), C.byref(c), C.byref(k), C.byref(al), C.byref(rl), C.byref(n), C.byref(d)))
+        return {"build_seconds": b.value, "copy_seconds": c.value, "kernel_seconds": k.value, "alloc_seconds": al.value,
+                "relabel_seconds": rl.value, "launches": n.value, "devices": d.value}
 
     def relabel_permutation(self) -> np.ndarray:
         """new_of_old[N]: the library's internal node order (identity when relabelling is off)."""
@@ -455,3 +456,27 @@ def layout_stress(graph, coords: np.ndarray, dims: int, sample_count: int, path_
 def sort_stress(graph, x: np.ndarray, sample_count: int, path_index: PathIndex | None = None, seed: int = 12345):
     """Sampled stress of a 1D sort (positions x[N])."""
     return layout_stress(graph, x, 1, sample_count, path_index, seed, layout_order=False)
+
+
+class PinnedArray:
+    """A numpy view of page-locked host memory from the library (gfs_host_alloc): the flatten target a host uses when
+    it wants the index build to run at PCIe rate.  Keep the object alive while the view is in use."""
+
+    def __init__(self, n: int, dtype):
+        self._p = C.c_void_p()
+        dt = np.dtype(dtype)
+        check(lib().gfs_host_alloc(max(n, 1) * dt.itemsize, C.byref(self._p)))
+        buf = (C.c_char * (max(n, 1) * dt.itemsize)).from_address(self._p.value)
+        self.array = np.frombuffer(buf, dtype=dt, count=n)
+
+    def close(self):
+        if self._p:
+            self.array = None
+            lib().gfs_host_free(self._p)
+            self._p = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

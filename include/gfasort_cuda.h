@@ -70,8 +70,8 @@ typedef struct gfs_sgd_params {
  * GFASORT_RELABEL (0/1 internal first-appearance node order, default 1),
  * GFASORT_WINDOW (sampling window in steps: 0 = every step ~ U[0,S) exactly like the reference,
  * -1 = auto: 2^20 for graphs whose records exceed 64 MB, else 0), GFASORT_CHUNK (updates per claimed
- * chunk, default 256), GFASORT_COHERENT (0/1 warps sample 32 consecutive steps in window mode,
- * default 1), GFASORT_INFLIGHT (terms in flight per thread and pipeline stage, 1 or 2),
+ * chunk, default 256), GFASORT_COHERENT (0 = off, 1 = default: whole warps sample 32 consecutive steps in
+ * window mode, 2..32 = group size), GFASORT_INFLIGHT (terms in flight per thread and pipeline stage, 1 or 2),
  * GFASORT_INDEX_CHUNK (steps per host->device chunk of the index build).  DESIGN.md §4. */
 typedef struct gfs_launch_cfg {
     int32_t device;            /* CUDA device ordinal; -1 = current */
@@ -103,7 +103,7 @@ typedef struct gfs_stats {
     uint32_t n_devices;        /* GPUs the call ran on (GFASORT_GPUS) */
     uint64_t window_steps;     /* sampling schedule used: 0 = every step ~ U[0,S) (the reference's), else the
                                   sliding window's length in steps */
-    uint32_t coherent;         /* 1 = warps sampled 32 consecutive steps (window mode only) */
+    uint32_t coherent;         /* lanes per group that sampled consecutive steps (window mode only; 0 = none, 32 = whole warps) */
     uint32_t syncs_per_epoch;  /* replica reconciles per epoch (n_devices > 1) */
 } gfs_stats;
 
@@ -130,10 +130,16 @@ int gfs_index_build32(const uint32_t* step_handles, const uint64_t* path_first_s
  * The step array is streamed in chunks (GFASORT_INDEX_CHUNK steps, default 2^24) with the copy of chunk c+1 under
  * the kernel of chunk c; a pageable source goes through pinned bounce buffers filled by GFASORT_COPY_THREADS
  * host threads. */
+/* Page-locked host memory for the step array (cudaHostAlloc, portable across devices): flattening Vec<Handle> straight
+ * into it lets the copy engine stream it at PCIe rate; a pageable array is staged through bounce buffers by host threads
+ * (config 3, 32-bit handles, B200: 0.08 s vs 0.25 s for the whole index build).  Optional. */
+int gfs_host_alloc(uint64_t bytes, void** out);
+void gfs_host_free(void* p);
 /* How the last build went: wall seconds of the whole call, of the streamed copy + K1 phase, K1 kernel seconds
- * (CUDA events; max over shards), kernels launched, devices used.  Any pointer may be NULL. */
+ * (CUDA events; max over shards), of the allocations before and the relabelling after; kernels launched, devices used.
+ * Any pointer may be NULL. */
 int gfs_index_build_info(const gfs_index* ix, double* build_seconds, double* copy_seconds, double* kernel_seconds,
-                         uint64_t* launches, uint32_t* n_devices);
+                         double* alloc_seconds, double* relabel_seconds, uint64_t* launches, uint32_t* n_devices);
 /* As gfs_index_build, on `device` and on a sub-range of paths [path_begin, path_end): the shard one GPU of a
  * multi-GPU run owns.  step_handles/path_first_step still describe the whole graph. */
 int gfs_index_build_shard(const uint64_t* step_handles, const uint64_t* path_first_step, const uint32_t* node_len,

@@ -279,3 +279,59 @@ def test_oracle_matches_committed_golden_vectors(oracle):
         assert got["traces"][k] == v, k
     # the hand-derived known answers and the golden file agree where they overlap
     assert want["index"]["simple"]["path_length"] == [50] and want["index"]["lil"]["path_length"] == [50, 50, 50]
+
+
+# ---- a second, independent restatement (tests/second_oracle.py) cross-checks the C++ oracle -----------------
+@pytest.mark.parametrize("name,iter_max,updates,seed", [("simple", None, None, 9399220), ("lil", None, None, 9399220),
+                                                        ("lil", 20, 200, 7), ("DRB1-3123", 3, 2500, 9399220),
+                                                        ("DRB1-3123", 6, 1500, 12345)])
+def test_second_restatement_agrees_bit_for_bit(name, iter_max, updates, seed, oracle):
+    """Whole single-thread xoshiro runs with exact-count epochs: the pure-Python restatement written from the
+    reference source and SURVEY.md Appendix A ends with bit-identical positions to the C++ oracle — warm and cooling
+    epochs, Zipf and uniform partners, both fast paths of the sampler, the quantised zeta index (DRB1 paths have up to
+    3100 steps), a fully reverse path, saturating rank arithmetic.  DRB1 is run on a shortened schedule (10k / 10.5k
+    applied updates) to keep pure Python within seconds."""
+    import second_oracle as so
+    g = oracle.parse_gfa(os.path.join(DATA, f"{name}.gfa"))
+    p = oracle.params_from_graph(g, nthreads=1)
+    p.seed = seed
+    if iter_max is not None:
+        p.iter_max, p.min_term_updates = iter_max, updates
+    x_cpp, st, rc = oracle.path_linear_sgd(g, p, mode=oracle.MODE_EXACT, draw=oracle.DRAW_XOSHIRO)
+    assert rc == 0 and st.applied == (p.iter_max + 1) * p.min_term_updates
+    x_py = np.array(so.path_linear_sgd_single_thread(g, p))
+    assert len(x_py) == len(x_cpp)
+    assert not np.array_equal(x_cpp, oracle.init_x(g))                      # something moved
+    assert np.array_equal(x_py.view(np.uint64), x_cpp.view(np.uint64)), \
+        f"max |diff| = {np.abs(x_py - x_cpp).max()} at {int(np.abs(x_py - x_cpp).argmax())}"
+
+
+def test_second_restatement_scalar_helpers(ka):
+    """... and its helpers reproduce the hand-derived / published known answers on their own (no C++ oracle involved)."""
+    import second_oracle as so
+    for row in ka["fast_precise_pow_bits"]:
+        assert _bits(so.fast_precise_pow(row["a"], row["b"])) == int(row["bits"], 16)
+    z = so.zeta_table(200, 100, 100, 0.99)
+    for k, v in ka["zetas_theta_0.99"].items():
+        assert z[int(k)] == v
+    e = ka["etas_default"]
+    etas = so.schedule(1.0 / e["eta_max"], 1.0, e["iter_max"], 0, e["eps"])
+    assert len(etas) == e["len"]
+    for k, v in e["values"].items():
+        assert abs(etas[int(k)] - v) <= 1e-12 * v
+    row = ka["xoshiro256plus_state_1_2_3_4"]
+    r = so.Xoshiro256Plus(0)
+    r.s = list(row["state"])
+    assert [r.next_u64() for _ in row["out"]] == row["out"]
+    for row in ka["splitmix64"]:
+        r = so.Xoshiro256Plus(row["seed"])
+        assert r.s == row["out"][:4]
+
+    class FixedU:                                   # DirtyZipfian at u = k/16 (SURVEY.md §8c table)
+        def __init__(self, u): self.u = u
+        def f64(self): return self.u
+    for theta, want in ka["zipf_n100_u_k16"].items():
+        th = float(theta)
+        zeta = z[100]
+        got = [so.dirty_zipf(FixedU(k / 16.0), 1, 100, th, zeta, 1.0 + so.fast_precise_pow(0.5, th)) for k in range(16)]
+        assert got == want
