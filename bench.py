@@ -177,6 +177,8 @@ def workload_config(wl, total_steps, world, syncs, reconcile):
     nodes, paths, dims, desc = wl
     iter_max = 100 if dims == 0 else 30
     M = total_steps if dims == 0 else 10 * total_steps
+    if not syncs:                       # the library's default (gfs_default_syncs_per_epoch): one reconcile per S applied updates
+        syncs = min(max((M + total_steps // 2) // max(total_steps, 1), 1), 64)
     return {"workload": desc, "nodes": nodes, "paths": paths, "total_steps": int(total_steps), "dims": dims,
             "updates_per_step": int(M), "iter_max": iter_max,
             "step": "one epoch of the eta schedule (min_term_updates applied updates); step k of K runs epoch "
@@ -311,24 +313,35 @@ def measure_workload(a, wl, name, rank, world, local, dev, K, W, with_cpu, e2e_e
     x0 = initial_positions(node_len, dims)
     sampler = {"window": os.environ.get("GFASORT_WINDOW", "auto"), "chunk": os.environ.get("GFASORT_CHUNK", "256"),
                "coherent": os.environ.get("GFASORT_COHERENT", "1"), "relabel": os.environ.get("GFASORT_RELABEL", "1")}
-    syncs = a.syncs if world > 1 else 1
+    syncs = a.syncs if world > 1 else 1          # 0 = the library's default (one reconcile per S applied updates: 1 for Y, 10 for L)
+
+    phases = {}
 
     def build_run(iter_max=None):
+        t0 = time.perf_counter()
         ix = multi.build_shard_index(handles, sg.path_first, node_len, device=local, rank=rank, world=world)
+        t1 = time.perf_counter()
         max_bp = int(ix.path_lengths().max()) if sg.P else 0
         if world > 1:
             t = torch.tensor([max_bp], dtype=torch.int64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             max_bp = int(t.item())
         params = derive_params(G, dims, counts, max_bp, iter_max)
+        t2 = time.perf_counter()
         run = multi.ReplicaRun(ix, nodes, shard, S, params, dims=dims, device=local, syncs_per_epoch=syncs, mode=a.reconcile)
+        t3 = time.perf_counter()
+        phases.update(index=t1 - t0, params=t2 - t1, replica=t3 - t2)
         return ix, params, run
+
+    def syncs_of(run):
+        return run.syncs if world > 1 else 1
 
     # ---- device-resident measurement -------------------------------------------------------------
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
     ix, params, run = build_run()
+    syncs = syncs_of(run)
     binfo = ix.build_info()
     run.upload(x0)
     n_epochs = params.iter_max + 1
@@ -426,7 +439,7 @@ def measure_workload(a, wl, name, rank, world, local, dev, K, W, with_cpu, e2e_e
                 check(lib().gfs_sgd_nd(ix.handle, C.byref(cp), dims, xf.ctypes.data_as(f64p), C.byref(stats_e)))
             t3 = time.perf_counter()
             dt = t3 - t0                                   # params derivation + x0 copy stay inside: the host does them too
-            phases = f"gfs_index_build{a.handles if a.handles == 32 else ''} {t1-t0:.3f}s, params + x0 copy {t2-t1:.3f}s, gfs_sgd_{'1d' if dims == 0 else 'nd'} {t3-t2:.3f}s"
+            phases_s = f"gfs_index_build{a.handles if a.handles == 32 else ''} {t1-t0:.3f}s, params + x0 copy {t2-t1:.3f}s, gfs_sgd_{'1d' if dims == 0 else 'nd'} {t3-t2:.3f}s"
             e2e_binfo = ix.build_info()
         else:
             ix, p2, run = build_run(e_iter)               # H2D: step handles, first_step, node lengths
@@ -439,10 +452,11 @@ def measure_workload(a, wl, name, rank, world, local, dev, K, W, with_cpu, e2e_e
             t3 = time.perf_counter()
             barrier()
             dt = time.perf_counter() - t0
-            phases = f"index build + replica {t1-t0:.3f}s, upload {t2-t1:.3f}s, {p2.iter_max+1} epochs + download {t3-t2:.3f}s"
+            phases_s = (f"index build (K1 + shared node order) {phases['index']:.3f}s, params {phases['params']:.3f}s, replica create + connect "
+                        f"{phases['replica']:.3f}s, upload {t2-t1:.3f}s, {p2.iter_max+1} epochs + download {t3-t2:.3f}s")
             e2e_binfo = ix.build_info()
         if rank == 0:
-            log(f"[bench] e2e phases: {phases}")
+            log(f"[bench] e2e phases: {phases_s}")
         t = torch.tensor([dt], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -555,7 +569,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=os.environ.get("GFASORT_BENCH_WORKLOAD", "y10m"), choices=sorted(WORKLOADS))
     ap.add_argument("--seed", type=int, default=42)
-    ap.add_argument("--syncs", type=int, default=int(os.environ.get("GFASORT_SYNCS", "1")), help="replica reconciles per epoch (N > 1)")
+    ap.add_argument("--syncs", type=int, default=int(os.environ.get("GFASORT_SYNCS", "0")),
+                    help="replica reconciles per epoch (N > 1); 0 = the library's default: one per S applied updates (1 for Y, 10 for L)")
     ap.add_argument("--reconcile", default=os.environ.get("GFASORT_RECONCILE", "p2p"), choices=["p2p", "tavg", "avg", "delta"],
                     help="p2p: one peer-memory kernel per rank behind the C ABI (default); tavg/avg/delta: NCCL all-reduce driven from torch")
     ap.add_argument("--e2e-epochs", type=int, default=-1, help="-1 = the full schedule, 0 = skip the e2e leg")

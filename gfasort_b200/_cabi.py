@@ -151,6 +151,7 @@ SIGNATURES = {
     "gfs_p2p_region_check": (C.c_int, [C.c_void_p]),
     "gfs_p2p_region_free": (None, [C.c_void_p]),
     "gfs_shard_plan_make": (C.c_int, [u64p, C.c_uint64, C.c_uint32, C.c_uint32, C.POINTER(ShardPlan)]),
+    "gfs_default_syncs_per_epoch": (C.c_uint32, [C.c_uint64, C.c_uint64]),
     "gfs_shard_epoch_quota": (C.c_uint64, [C.c_uint64, C.POINTER(ShardPlan), C.c_uint64]),
     "gfs_replica_create": (C.c_int, [C.c_void_p, C.POINTER(SgdParams), C.c_uint32, C.POINTER(LaunchCfg), C.POINTER(ShardPlan),
                                      C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p)]),

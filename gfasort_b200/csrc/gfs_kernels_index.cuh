@@ -101,7 +101,7 @@ template <typename HT> __device__ __forceinline__ uint64_t k1_node_of(uint64_t h
 // handles: this chunk's steps, PADDED to a whole number of tiles with all-ones handles (node >= N: length 0);
 // recs is padded likewise (records past the last step are written and never read).
 // chunk_begin (a multiple of K1_TILE): index-local step of handles[0];  S: steps in the index.
-// flags[0]: look-back watchdog.
+// flags[0]: look-back watchdog; flags[1]: skip the look-back (timing experiment).
 constexpr int K1_BLOCK = K1_THREADS + 32;
 template <typename HT, bool FIRST_OCC>
 __global__ void __launch_bounds__(K1_BLOCK, 4)
@@ -131,7 +131,7 @@ k1_scan_write(const HT* __restrict__ handles, const uint32_t* __restrict__ node_
         // round trips separate a tile from the inclusive front — with hundreds of tiles in flight that chain, not
         // bandwidth, is what bounds a chained scan (32 per round capped this kernel at ~27 tiles/us).
         uint64_t T = 0;
-        if (!start_first) {
+        if (!start_first && !flags[1]) {                        // flags[1]: timing experiment only (GFASORT_K1_NO_LOOKBACK: wrong offsets)
             int64_t look = (int64_t)gtile - 1;
             bool found = false;
             while (!found) {

@@ -375,7 +375,12 @@ static int build_shard_impl(const HT* step_handles, const uint64_t* path_first_s
     uint32_t* d_visited = reinterpret_cast<uint32_t*>(arena.p + o_vis);
     uint32_t* d_first_key = reinterpret_cast<uint32_t*>(arena.p + o_key);
     HT* d_h[2] = {reinterpret_cast<HT*>(arena.p + o_h0), reinterpret_cast<HT*>(arena.p + o_h1)};
-    IX_CUDA(cudaMemsetAsync(arena.p, 0, o_len, s_k));                                   // descriptors, flag
+    IX_CUDA(cudaMemsetAsync(arena.p, 0, o_len, s_k));                                   // descriptors, flags
+    if (env_long("GFASORT_K1_NO_LOOKBACK", 0)) {                                        // timing experiment: offsets are WRONG
+        const unsigned int one = 1;
+        IX_CUDA(cudaMemcpyAsync(d_flag + 1, &one, sizeof one, cudaMemcpyHostToDevice, s_k));
+        IX_CUDA(cudaStreamSynchronize(s_k));
+    }
     IX_CUDA(cudaMemsetAsync(d_visited, 0, o_key - o_vis, s_k));
     IX_CUDA(cudaMemsetAsync(d_first_key, 0xff, o_h0 - o_key, s_k));                     // 0xffffffff = never visited
     IX_CUDA(cudaMemsetAsync(ix->d_path_len, 0, std::max<uint64_t>(ix->P, 1) * 8, s_k));

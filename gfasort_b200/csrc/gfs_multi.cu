@@ -18,6 +18,7 @@
 #include <algorithm>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "gfs_internal.h"
@@ -43,6 +44,16 @@ extern "C" int gfs_shard_plan_make(const uint64_t* path_first_step, uint64_t P, 
     out->path_begin = pb; out->path_end = pe;
     out->first_step = fs[pb];
     return GFS_OK;
+}
+
+// Reconciles per epoch when the caller does not say (syncs_per_epoch = 0): one per S applied updates of the whole run,
+// S = the graph's step count — once per epoch for `Y` (min_term_updates = S, ygs.rs:60-70), ten times for `L`
+// (min_term_updates = 10 S, sgd.rs:736-745).  Replicas that run 10 S updates apart drift: the 2D layout of config 4 on
+// 8 GPUs ended at 6.7x the one-GPU stress with one reconcile per epoch (profiles/r2_bench.md).
+extern "C" uint32_t gfs_default_syncs_per_epoch(uint64_t min_term_updates, uint64_t total_steps) {
+    if (total_steps == 0) return 1;
+    const uint64_t k = (min_term_updates + total_steps / 2) / total_steps;
+    return (uint32_t)std::min<uint64_t>(std::max<uint64_t>(k, 1), 64);
 }
 
 extern "C" uint64_t gfs_shard_epoch_quota(uint64_t min_term_updates, const gfs_shard_plan* plan, uint64_t total_steps) {
@@ -80,7 +91,8 @@ extern "C" int gfs_replica_create(const gfs_index* shard, const gfs_sgd_params* 
     if (plan->sample_end < plan->sample_begin || plan->sample_begin < plan->first_step ||
         plan->sample_end - plan->first_step > shard->S) { set_error("gfs_replica_create: the plan's step slice is outside the shard"); return GFS_ERR_INVALID; }
     gfs_replica* r = new gfs_replica();
-    r->rank = rank; r->world = world; r->syncs = std::max(1u, syncs_per_epoch);
+    r->rank = rank; r->world = world;
+    r->syncs = syncs_per_epoch ? syncs_per_epoch : gfs_default_syncs_per_epoch(params->min_term_updates, total_steps);
     auto fail = [&](int code) { gfs_replica_destroy(r); return code; };
     const int f64 = dims == 0 ? 1 : (cfg && cfg->layout_f64 >= 0 ? cfg->layout_f64 : (int)env_long("GFASORT_LAYOUT_F64", 0));
     const uint64_t n_elems = dims == 0 ? shard->N : shard->N * 2 * coord_stride(dims);
@@ -193,14 +205,28 @@ int gfs_multi_run_whole(const gfs_index* ix, const gfs_sgd_params* params, const
     const uint32_t G = (uint32_t)ix->shards.size();
     if (!params) { set_error("params is null"); return GFS_ERR_INVALID; }
     if (!ix->any_multi_step) { set_error("no paths with multiple steps found"); return GFS_ERR_NO_VALID_PATH; }
-    const uint32_t syncs = (uint32_t)std::max<long>(1, env_long("GFASORT_SYNCS", 1));
+    const uint32_t syncs = (uint32_t)std::max<long>(0, env_long("GFASORT_SYNCS", 0));       // 0 = gfs_default_syncs_per_epoch
     std::vector<gfs_replica*> reps(G, nullptr);
     auto cleanup = [&]() { for (gfs_replica* r : reps) gfs_replica_destroy(r); };
-    int rc = GFS_OK;
-    for (uint32_t g = 0; g < G && !rc; ++g)
-        rc = gfs_replica_create(ix->shards[g], params, dims, cfg, &ix->plans[g], ix->S, g, G, syncs, &reps[g]);
+    // per-device setup runs on one host thread per device (allocations, table uploads, the 80 MB position upload):
+    // done one after the other it costs more than the whole schedule at 8 GPUs
+    std::vector<int> rcs(G, GFS_OK);
+    std::vector<std::string> errs(G);
+    auto on_all = [&](auto fn) {
+        std::vector<std::thread> pool;
+        for (uint32_t g = 0; g < G; ++g)
+            pool.emplace_back([&, g] {
+                rcs[g] = fn(g);
+                if (rcs[g]) errs[g] = gfs_last_error();
+            });
+        for (auto& th : pool) th.join();
+        for (uint32_t g = 0; g < G; ++g)
+            if (rcs[g]) { set_error("device " + std::to_string(g) + ": " + errs[g]); return rcs[g]; }
+        return (int)GFS_OK;
+    };
+    int rc = on_all([&](uint32_t g) { return gfs_replica_create(ix->shards[g], params, dims, cfg, &ix->plans[g], ix->S, g, G, syncs, &reps[g]); });
     if (!rc) rc = gfs_replica_connect_local(reps.data(), G);
-    for (uint32_t g = 0; g < G && !rc; ++g) rc = gfs_replica_upload(reps[g], pos_inout);
+    if (!rc) rc = on_all([&](uint32_t g) { return gfs_replica_upload(reps[g], pos_inout); });
     // one epoch at a time over all devices: no device's queue runs far ahead of a peer it will wait for
     const uint64_t n_epochs = params->iter_max + 1;
     for (uint64_t e = 0; e < n_epochs && !rc; ++e)
@@ -218,7 +244,7 @@ int gfs_multi_run_whole(const gfs_index* ix, const gfs_sgd_params* params, const
         tot.epochs = st.epochs; tot.grid = st.grid; tot.block = st.block; tot.coord_bytes = st.coord_bytes;
         tot.window_steps = st.window_steps; tot.coherent = st.coherent;
     }
-    tot.n_devices = G; tot.syncs_per_epoch = syncs;
+    tot.n_devices = G; tot.syncs_per_epoch = reps[0] ? reps[0]->syncs : syncs;
     tot.total_seconds = now_s() - t0;
     if (!rc && stats) *stats = tot;
     cleanup();

@@ -238,14 +238,16 @@ class ReplicaRun:
     """
 
     def __init__(self, index, n_nodes: int, shard: Shard, total_steps: int, params, dims: int = 0,
-                 device: int = 0, syncs_per_epoch: int = 1, mode: str = "p2p", group=None,
+                 device: int = 0, syncs_per_epoch: int = 0, mode: str = "p2p", group=None,
                  layout_f64: bool = False):
         import ctypes as C
 
         import torch
 
         from ._cabi import LaunchCfg, check, lib
-        self.shard, self.mode, self.group, self.syncs = shard, mode, group, max(1, int(syncs_per_epoch))
+        # syncs_per_epoch = 0: the library's default, one reconcile per total_steps applied updates (1 for Y, 10 for L)
+        syncs = int(syncs_per_epoch) if syncs_per_epoch else int(lib().gfs_default_syncs_per_epoch(params.min_term_updates, total_steps))
+        self.shard, self.mode, self.group, self.syncs = shard, mode, group, max(1, syncs)
         self.dims, self.device = dims, device
         self.index = index
         self.N = int(n_nodes)

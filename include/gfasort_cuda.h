@@ -126,7 +126,8 @@ int gfs_index_build32(const uint32_t* step_handles, const uint64_t* path_first_s
  * gfs_index_build32 build one shard per device 0..G-1 (concurrently, each device pulling its own steps), with one
  * node order for all shards, and gfs_sgd_1d / gfs_sgd_nd / gfs_sgd_sort_1d / gfs_stress / gfs_index_export on the
  * returned index drive all G GPUs from this one process: replicated positions, terms sharded by step slice,
- * replicas reconciled GFASORT_SYNCS (default 1) times per epoch over NVLink peer memory.
+ * replicas reconciled GFASORT_SYNCS times per epoch (default: once per S applied updates, gfs_default_syncs_per_epoch)
+ * over NVLink peer memory.
  * The step array is streamed in chunks (GFASORT_INDEX_CHUNK steps, default 2^24) with the copy of chunk c+1 under
  * the kernel of chunk c; a pageable source goes through pinned bounce buffers filled by GFASORT_COPY_THREADS
  * host threads. */
@@ -344,6 +345,9 @@ typedef struct gfs_shard_plan {
 } gfs_shard_plan;
 int gfs_shard_plan_make(const uint64_t* path_first_step /*P+1*/, uint64_t P, uint32_t rank, uint32_t world, gfs_shard_plan* out);
 uint64_t gfs_shard_epoch_quota(uint64_t min_term_updates, const gfs_shard_plan* plan, uint64_t total_steps);
+/* Reconciles per epoch used when a caller passes syncs_per_epoch = 0 (and by GFASORT_GPUS runs unless GFASORT_SYNCS says
+ * otherwise): one per total_steps applied updates of the whole run — 1 for `Y` (min_term_updates = S), 10 for `L` (10 S). */
+uint32_t gfs_default_syncs_per_epoch(uint64_t min_term_updates, uint64_t total_steps);
 /* One rank: a session on `shard` (built for plan->path_begin..path_end) whose positions live in a peer region.
  * `params` are the WHOLE run's (the quota is derived here); cfg may be NULL (total_threads, aggregate, layout_f64 are
  * honoured).  One process per GPU: create, exchange gfs_replica_ipc_handle blobs (GFS_P2P_HANDLE_BYTES each, rank
@@ -351,7 +355,7 @@ uint64_t gfs_shard_epoch_quota(uint64_t min_term_updates, const gfs_shard_plan* 
 typedef struct gfs_replica gfs_replica;
 int gfs_replica_create(const gfs_index* shard, const gfs_sgd_params* params, uint32_t dims, const gfs_launch_cfg* cfg,
                        const gfs_shard_plan* plan, uint64_t total_steps, uint32_t rank, uint32_t world,
-                       uint32_t syncs_per_epoch, gfs_replica** out);
+                       uint32_t syncs_per_epoch /*0 = gfs_default_syncs_per_epoch*/, gfs_replica** out);
 int gfs_replica_ipc_handle(gfs_replica* r, uint8_t* blob /*GFS_P2P_HANDLE_BYTES*/);
 int gfs_replica_connect_ipc(gfs_replica* r, const uint8_t* blobs /*world x GFS_P2P_HANDLE_BYTES*/, uint32_t world, uint32_t rank);
 int gfs_replica_connect_local(gfs_replica* const* replicas /*world, rank order, distinct devices*/, uint32_t world);
