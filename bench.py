@@ -348,6 +348,7 @@ def measure_workload(a, wl, name, rank, world, local, dev, K, W, with_cpu, e2e_e
     M = params.min_term_updates
     for k in range(W):
         run.run_epoch(epoch_of_step(k, max(W, 1), n_epochs))
+    run.flush()
     barrier()
     st0 = run.stats()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -358,6 +359,7 @@ def measure_workload(a, wl, name, rank, world, local, dev, K, W, with_cpu, e2e_e
         ev0.record()
     for k in range(K):
         run.run_epoch(epoch_of_step(k, K, n_epochs))
+    run.flush()                          # the last overlapped reconcile belongs to the timed region
     with torch.cuda.stream(run.stream):
         ev1.record()
     barrier()
@@ -505,7 +507,8 @@ def measure_workload(a, wl, name, rank, world, local, dev, K, W, with_cpu, e2e_e
             "vs_baseline": None, "dtype": "f64" if dims == 0 else "f32", "data": "synthetic",
             "config": cfg,
             "launch": {"sampler": sampler, "grid": grid, "block": block, "window_steps": window_steps, "coherent": coherent,
-                       "reconcile": a.reconcile if world > 1 else None, "syncs_per_epoch": syncs},
+                       "reconcile": a.reconcile if world > 1 else None, "syncs_per_epoch": syncs,
+                       "overlapped_reconcile": (os.environ.get("GFASORT_OVERLAP", "1") != "0") if (world > 1 and a.reconcile == "p2p") else None},
             "clocks": clk, "e2e": e2e, "gpu_launches": int(launches_per_rank * world),
             "attempts_per_update": float(attempts.item()) / total_applied,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

@@ -148,6 +148,10 @@ SIGNATURES = {
     "gfs_p2p_region_snapshot": (C.c_int, [C.c_void_p, C.c_void_p]),
     "gfs_p2p_reconcile": (C.c_int, [C.c_void_p, C.c_void_p]),
     "gfs_p2p_reconcile_local": (C.c_int, [C.POINTER(C.c_void_p), C.c_uint32, C.c_void_p]),
+    "gfs_p2p_region_snap_ptr": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "gfs_p2p_region_snapshot_x": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "gfs_p2p_reconcile_async": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "gfs_p2p_reconcile_async_local": (C.c_int, [C.POINTER(C.c_void_p), C.c_uint32, C.c_void_p]),
     "gfs_p2p_region_check": (C.c_int, [C.c_void_p]),
     "gfs_p2p_region_free": (None, [C.c_void_p]),
     "gfs_shard_plan_make": (C.c_int, [u64p, C.c_uint64, C.c_uint32, C.c_uint32, C.POINTER(ShardPlan)]),
@@ -160,6 +164,7 @@ SIGNATURES = {
     "gfs_replica_connect_local": (C.c_int, [C.POINTER(C.c_void_p), C.c_uint32]),
     "gfs_replica_upload": (C.c_int, [C.c_void_p, f64p]),
     "gfs_replica_run": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64]),
+    "gfs_replica_flush": (C.c_int, [C.c_void_p]),
     "gfs_replica_sync": (C.c_int, [C.c_void_p]),
     "gfs_replica_download": (C.c_int, [C.c_void_p, f64p]),
     "gfs_replica_stats": (C.c_int, [C.c_void_p, C.POINTER(Stats)]),
@@ -167,6 +172,7 @@ SIGNATURES = {
     "gfs_replica_destroy": (None, [C.c_void_p]),
     "gfs_debug_schedule": (C.c_int, [C.POINTER(SgdParams), f64p]),
     "gfs_debug_zetas": (C.c_int, [C.c_void_p, C.POINTER(SgdParams), f64p, C.c_uint64, u64p]),
+    "gfs_debug_zetas_host": (C.c_int, [C.POINTER(SgdParams), C.c_uint64, f64p, C.c_uint64, u64p]),
 }
 
 _lib = None

@@ -7,6 +7,7 @@
 #include <chrono>
 #include <cstdint>
 #include <cstdlib>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -73,6 +74,10 @@ struct gfs_index {
     uint32_t* d_new_of_old = nullptr;   // N, null when not relabelled
     uint32_t* d_old_of_new = nullptr;   // N
     void* d_build_arena = nullptr;      // the build's transient device memory, released with the index
+    // the zeta table of the last (theta, space, space_max, q) asked for: every session of a run needs the same one
+    mutable std::mutex zeta_mu;
+    mutable std::vector<double> zeta_cache;
+    mutable double zeta_key[4] = {0, 0, 0, 0};
     std::vector<uint64_t> h_first_step;
     double build_seconds = 0, h2d_seconds = 0, kernel_seconds = 0, alloc_seconds = 0, relabel_seconds = 0;
     uint64_t launches = 0;

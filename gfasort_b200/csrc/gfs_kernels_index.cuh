@@ -25,11 +25,19 @@ constexpr int K1_THREADS = 256;
 constexpr int K1_ITEMS = 8;
 constexpr int K1_TILE = K1_THREADS * K1_ITEMS;
 
-// What the kernel gathers per step is node_len[node] alone (4 bytes: the 40 MB table of config 3 stays L2-resident
-// next to the streamed handles and records).  First occurrences use two more arrays: a bitmap of visited nodes (1 bit
-// per node, 1.25 MB at config 3 — read per step, cached) and first_key[node] = (step index >> key_shift) of the first
-// step that visits the node, 0xffffffff = never visited (atomicMin, touched only while a node's bit is still clear,
-// i.e. almost only during the first path).
+// What the kernel gathers per step is ONE 4-byte word per node: bits 0..30 = node length, bit 31 = "visited" (the
+// 40 MB table of config 3 stays L2-resident next to the streamed handles and records; the kernel is bound by L2 sector
+// throughput — every random gather costs a whole 32-byte sector — so one gather per step, not two).  First
+// occurrences: first_key[node] = (step index >> key_shift) of the first step that visits the node, 0xffffffff = never
+// visited — an atomicMin issued only while the node's visited bit is still clear, i.e. almost only during the first path.
+constexpr uint32_t K1_VISITED = 0x80000000u;
+__global__ void k1_init_table(const uint32_t* __restrict__ node_len, uint32_t N, uint32_t* __restrict__ tbl, unsigned int* __restrict__ flags) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const uint32_t l = node_len[i];
+    if (l & K1_VISITED) atomicExch(flags + 2, 1u);           // a node of >= 2^31 bp: not representable next to the flag
+    tbl[i] = l & ~K1_VISITED;
+}
 
 constexpr uint64_t K1_ST_AGG = 1ull << 62;      // descriptor holds the tile's sum; the tile has no path start
 constexpr uint64_t K1_ST_INCL = 2ull << 62;     // descriptor holds the offset, in its path, of the step after the tile
@@ -101,11 +109,11 @@ template <typename HT> __device__ __forceinline__ uint64_t k1_node_of(uint64_t h
 // handles: this chunk's steps, PADDED to a whole number of tiles with all-ones handles (node >= N: length 0);
 // recs is padded likewise (records past the last step are written and never read).
 // chunk_begin (a multiple of K1_TILE): index-local step of handles[0];  S: steps in the index.
-// flags[0]: look-back watchdog; flags[1]: skip the look-back (timing experiment).
+// flags[0]: look-back watchdog; flags[1]: skip the look-back (timing experiment); flags[2]: a node length >= 2^31.
 constexpr int K1_BLOCK = K1_THREADS + 32;
 template <typename HT, bool FIRST_OCC>
 __global__ void __launch_bounds__(K1_BLOCK, 4)
-k1_scan_write(const HT* __restrict__ handles, const uint32_t* __restrict__ node_len, uint32_t* __restrict__ visited,
+k1_scan_write(const HT* __restrict__ handles, uint32_t* __restrict__ node_tbl,
               uint32_t* __restrict__ first_key, uint32_t N, const uint64_t* __restrict__ first_step,
               uint32_t P, uint64_t chunk_begin, uint64_t S, uint64_t* __restrict__ desc, unsigned int* __restrict__ flags,
               uint32_t key_shift, StepRec* __restrict__ recs, uint64_t* __restrict__ path_len) {
@@ -175,15 +183,13 @@ k1_scan_write(const HT* __restrict__ handles, const uint32_t* __restrict__ node_
     const uint64_t my_first = g_first + (uint64_t)threadIdx.x * K1_ITEMS;      // this thread's first step
     uint64_t hh[K1_ITEMS];
     K1Load<HT>::load(handles + (my_first - chunk_begin), hh);
-    uint32_t len[K1_ITEMS], vis[K1_ITEMS];
+    uint32_t len[K1_ITEMS];
 #pragma unroll
     for (int k = 0; k < K1_ITEMS; ++k) {                            // all gathers in flight before the first use
         const uint64_t node = k1_node_of<HT>(hh[k]);
-        len[k] = 0; vis[k] = ~0u;
-        if (node < N) {
-            len[k] = __ldg(node_len + node);                        // missing node => +0 (src/sgd.rs:52-54)
-            if (FIRST_OCC) vis[k] = visited[node >> 5];             // plain load: a stale clear bit only costs a redundant atomicMin
-        }
+        len[k] = K1_VISITED;                                        // missing node => +0 (src/sgd.rs:52-54), nothing to mark
+        // L2 load (the visited bits change during the launch; a stale clear bit only costs a redundant atomicMin)
+        if (node < N) asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(len[k]) : "l"(node_tbl + node));
     }
     uint32_t nr[K1_ITEMS];
     uint64_t loc[K1_ITEMS];
@@ -192,12 +198,13 @@ k1_scan_write(const HT* __restrict__ handles, const uint32_t* __restrict__ node_
     for (int k = 0; k < K1_ITEMS; ++k) {
         const uint64_t node = k1_node_of<HT>(hh[k]);
         nr[k] = (uint32_t)(((node < N ? node : N) << 1) | (hh[k] & 1));
-        loc[k] = tsum;
-        tsum += len[k];
-        if (FIRST_OCC && node < N && !((vis[k] >> (node & 31)) & 1u)) {
-            atomicOr(visited + (node >> 5), 1u << (node & 31));
+        if (FIRST_OCC && !(len[k] & K1_VISITED)) {
+            atomicOr(node_tbl + node, K1_VISITED);
             atomicMin(first_key + node, (uint32_t)((my_first + k) >> key_shift));
         }
+        len[k] &= ~K1_VISITED;
+        loc[k] = tsum;
+        tsum += len[k];
     }
     uint64_t inc = tsum;
 #pragma unroll

@@ -71,6 +71,10 @@ static void h_schedule(const gfs_sgd_params& p, std::vector<double>& etas) {   /
 // src/sgd.rs:311-331.  The serial summation order is kept (it defines the values); the loop stops
 // at the largest jump_space any path can produce (max_path_steps), since entries beyond it are
 // unreachable (jump_space = min(space, rank) <= max_path_steps - 1, src/sgd.rs:462,477).
+// The reference's loop is one dependent chain of `space` iterations (3e8 at config 3; 1e7 even after the cap).
+// Only the ADDITIONS depend on one another: the terms fpp(1/i, theta) are computed block by block on several host
+// threads, then added up in the reference's order by one — same operations, same order, same bits, a few
+// milliseconds instead of 0.1 s (config 3) / 1 s (config 5) per session.
 static void h_zetas(const gfs_sgd_params& p, uint64_t max_path_steps, std::vector<double>& z) {
     const uint64_t sm = p.space_max, q = p.space_quantization_step ? p.space_quantization_step : 1;
     const uint64_t full = ((p.space <= sm) ? p.space : sm + (p.space - sm) / q + 1) + 1;
@@ -78,24 +82,50 @@ static void h_zetas(const gfs_sgd_params& p, uint64_t max_path_steps, std::vecto
     const uint64_t reach_idx = reach > sm ? sm + (reach - sm) / q + 1 : reach;
     const uint64_t n = std::min(full, reach_idx + 2);
     z.assign(n, 0.0);
+    constexpr uint64_t BLK = 1u << 16;
+    const int T = (int)std::max<long>(1, std::min<long>(8, (long)std::thread::hardware_concurrency()));
+    const double theta = p.theta;
+    std::vector<double> terms((size_t)std::min<uint64_t>(reach, BLK * T));
     double acc = 0.0;
-    for (uint64_t i = 1; i <= reach; ++i) {
-        acc += h_fast_precise_pow(1.0 / (double)i, p.theta);
-        if (i <= sm) { if (i < n) z[i] = acc; }
-        if (i >= sm && (i - sm) % q == 0) {
-            uint64_t idx = sm + 1 + (i - sm) / q;
-            if (idx < n) z[idx] = acc;
+    for (uint64_t i0 = 1; i0 <= reach; i0 += BLK * T) {
+        const uint64_t cnt = std::min<uint64_t>(BLK * T, reach - i0 + 1);
+        auto fill = [&](uint64_t lo, uint64_t hi) { for (uint64_t k = lo; k < hi; ++k) terms[k] = h_fast_precise_pow(1.0 / (double)(i0 + k), theta); };
+        if (cnt < BLK || T == 1) fill(0, cnt);
+        else {
+            std::vector<std::thread> pool;
+            const uint64_t per = (cnt + T - 1) / T;
+            for (int t = 0; t < T; ++t) { const uint64_t lo = std::min(cnt, per * t), hi = std::min(cnt, per * (t + 1)); if (hi > lo) pool.emplace_back(fill, lo, hi); }
+            for (auto& th : pool) th.join();
+        }
+        for (uint64_t k = 0; k < cnt; ++k) {
+            const uint64_t i = i0 + k;
+            acc += terms[k];
+            if (i <= sm) { if (i < n) z[i] = acc; }
+            if (i >= sm && (i - sm) % q == 0) {
+                const uint64_t idx = sm + 1 + (i - sm) / q;
+                if (idx < n) z[idx] = acc;
+            }
         }
     }
 }
 
-
 // What the kernels read: for each of the run's two thetas (params.theta while warm, 0.001 while cooling, sgd.rs:394)
 // a table of {zetas[k], 1 - zeta2theta/zetas[k]} — the second member is the denominator of DirtyZipfian's eta
 // (sgd.rs:133-134), computed here with the same two IEEE operations the reference performs per sample.
-static void h_zeta_tables(const gfs_sgd_params& p, uint64_t max_path_steps, std::vector<double2>& out, uint32_t& zlen) {
+static void h_zeta_tables(const gfs_sgd_params& p, uint64_t max_path_steps, std::vector<double2>& out, uint32_t& zlen,
+                          const gfs_index* cache_in = nullptr) {
     std::vector<double> z;
-    h_zetas(p, max_path_steps, z);
+    if (cache_in) {
+        std::lock_guard<std::mutex> lk(cache_in->zeta_mu);
+        const double key[4] = {p.theta, (double)p.space, (double)p.space_max, (double)p.space_quantization_step};
+        if (cache_in->zeta_cache.empty() || std::memcmp(key, cache_in->zeta_key, sizeof key) != 0) {
+            h_zetas(p, max_path_steps, cache_in->zeta_cache);
+            std::memcpy(cache_in->zeta_key, key, sizeof key);
+        }
+        z = cache_in->zeta_cache;
+    } else {
+        h_zetas(p, max_path_steps, z);
+    }
     zlen = (uint32_t)z.size();
     out.resize(2 * z.size());
     const double thetas[2] = {p.theta, 0.001};
@@ -351,11 +381,11 @@ static int build_shard_impl(const HT* step_handles, const uint64_t* path_first_s
     // records and staged handles are padded to whole tiles: K1 works without bounds checks (padding handles are all-ones,
     // i.e. "missing node"; padding records are written and never read)
     IX_CUDA(cudaMalloc(&ix->d_recs, std::max<uint64_t>(tiles_total * K1_TILE, 1) * sizeof(StepRec)));
-    // everything transient in ONE allocation: [descriptors | watchdog flag | node_len | visited bitmap | first keys | 2 handle buffers]
+    // everything transient in ONE allocation: [descriptors | flags | node table (length + visited bit) | node_len staging | first keys | 2 handle buffers]
     const uint64_t chunk_alloc = (chunk_cap + K1_TILE - 1) / K1_TILE * K1_TILE;
     auto up256 = [](uint64_t v) { return (v + 255) / 256 * 256; };
     const uint64_t o_desc = 0, o_flag = o_desc + up256((tiles_total + 1) * 8), o_len = o_flag + 256, o_vis = o_len + up256(N * 4 + 4),
-                   o_key = o_vis + up256((N / 32 + 1) * 4), o_h0 = o_key + up256(N * 4 + 4), o_h1 = o_h0 + up256(chunk_alloc * sizeof(HT)),
+                   o_key = o_vis + up256(N * 4 + 4), o_h0 = o_key + up256(N * 4 + 4), o_h1 = o_h0 + up256(chunk_alloc * sizeof(HT)),
                    k1_bytes = o_h1 + (n_chunks > 1 ? up256(chunk_alloc * sizeof(HT)) : 0),
                    // the relabelling's sort scratch reuses the handle buffers (idle once K1 has drained)
                    arena_bytes = std::max(k1_bytes, relabel_mode == 1 ? o_h0 + relabel_scratch_bytes(N) : 0);
@@ -371,8 +401,8 @@ static int build_shard_impl(const HT* step_handles, const uint64_t* path_first_s
     }
     uint64_t* d_desc = reinterpret_cast<uint64_t*>(arena.p + o_desc);
     unsigned int* d_flag = reinterpret_cast<unsigned int*>(arena.p + o_flag);
-    uint32_t* d_node_len = reinterpret_cast<uint32_t*>(arena.p + o_len);
-    uint32_t* d_visited = reinterpret_cast<uint32_t*>(arena.p + o_vis);
+    uint32_t* d_node_tbl = reinterpret_cast<uint32_t*>(arena.p + o_len);
+    uint32_t* d_node_len = reinterpret_cast<uint32_t*>(arena.p + o_vis);       // staging of the caller's node_len
     uint32_t* d_first_key = reinterpret_cast<uint32_t*>(arena.p + o_key);
     HT* d_h[2] = {reinterpret_cast<HT*>(arena.p + o_h0), reinterpret_cast<HT*>(arena.p + o_h1)};
     IX_CUDA(cudaMemsetAsync(arena.p, 0, o_len, s_k));                                   // descriptors, flags
@@ -381,14 +411,17 @@ static int build_shard_impl(const HT* step_handles, const uint64_t* path_first_s
         IX_CUDA(cudaMemcpyAsync(d_flag + 1, &one, sizeof one, cudaMemcpyHostToDevice, s_k));
         IX_CUDA(cudaStreamSynchronize(s_k));
     }
-    IX_CUDA(cudaMemsetAsync(d_visited, 0, o_key - o_vis, s_k));
     IX_CUDA(cudaMemsetAsync(d_first_key, 0xff, o_h0 - o_key, s_k));                     // 0xffffffff = never visited
     IX_CUDA(cudaMemsetAsync(ix->d_path_len, 0, std::max<uint64_t>(ix->P, 1) * 8, s_k));
     mark("device allocations");
     const double t_h2d0 = now_s();
     ix->alloc_seconds = t_h2d0 - t_begin;
     IX_CUDA(cudaMemcpyAsync(ix->d_first_step, ix->h_first_step.data(), (ix->P + 1) * 8, cudaMemcpyHostToDevice, s_k));
-    if (N) IX_CUDA(cudaMemcpyAsync(d_node_len, node_len, N * 4, cudaMemcpyHostToDevice, s_k));
+    if (N) {
+        IX_CUDA(cudaMemcpyAsync(d_node_len, node_len, N * 4, cudaMemcpyHostToDevice, s_k));
+        k1_init_table<<<(unsigned)((N + 255) / 256), 256, 0, s_k>>>(d_node_len, (uint32_t)N, d_node_tbl, d_flag);
+        ix->launches += 1;
+    }
 
     // is the caller's step array page-locked?  (cudaHostAlloc / cudaHostRegister memory: the copy engine reads it directly)
     bool src_pinned = false;
@@ -450,10 +483,10 @@ static int build_shard_impl(const HT* step_handles, const uint64_t* path_first_s
         IXE_CUDA(cudaEventRecord(t0, s_k));
         const unsigned n_tiles = (unsigned)((clen + K1_TILE - 1) / K1_TILE);
         if (first_occ)
-            k1_scan_write<HT, true><<<n_tiles, K1_BLOCK, 0, s_k>>>(d_h[b], d_node_len, d_visited, d_first_key, (uint32_t)N, ix->d_first_step,
+            k1_scan_write<HT, true><<<n_tiles, K1_BLOCK, 0, s_k>>>(d_h[b], d_node_tbl, d_first_key, (uint32_t)N, ix->d_first_step,
                                                                     (uint32_t)ix->P, c0, ix->S, d_desc, d_flag, key_shift, ix->d_recs, ix->d_path_len);
         else
-            k1_scan_write<HT, false><<<n_tiles, K1_BLOCK, 0, s_k>>>(d_h[b], d_node_len, d_visited, d_first_key, (uint32_t)N, ix->d_first_step,
+            k1_scan_write<HT, false><<<n_tiles, K1_BLOCK, 0, s_k>>>(d_h[b], d_node_tbl, d_first_key, (uint32_t)N, ix->d_first_step,
                                                                      (uint32_t)ix->P, c0, ix->S, d_desc, d_flag, key_shift, ix->d_recs, ix->d_path_len);
         if (ix->P > 1) {
             k1_fix_path_starts<<<(unsigned)(ix->P - 1), K1_THREADS, 0, s_k>>>(ix->d_first_step, (uint32_t)ix->P, c0, c0 + clen, ix->d_recs, ix->d_path_len);
@@ -486,9 +519,10 @@ static int build_shard_impl(const HT* step_handles, const uint64_t* path_first_s
     g_trace_last = 0.0;
     mark("relabel");
     {
-        unsigned int tk = 0;
-        IX_CUDA(cudaMemcpy(&tk, d_flag, sizeof tk, cudaMemcpyDeviceToHost));
-        if (tk) { set_error("gfs_index_build: the scan's look-back watchdog tripped (a tile never published its prefix)"); return fail(GFS_ERR_CUDA); }
+        unsigned int tk[3] = {0, 0, 0};
+        IX_CUDA(cudaMemcpy(tk, d_flag, sizeof tk, cudaMemcpyDeviceToHost));
+        if (tk[0]) { set_error("gfs_index_build: the scan's look-back watchdog tripped (a tile never published its prefix)"); return fail(GFS_ERR_CUDA); }
+        if (tk[2]) { set_error("gfs_index_build: a node is 2^31 bp or longer"); return fail(GFS_ERR_INVALID); }
     }
     mark("watchdog flag read");
     ix->build_seconds = now_s() - t_begin;
@@ -822,7 +856,7 @@ extern "C" int gfs_sgd_session_create(const gfs_index* ix, const gfs_sgd_params*
 
     // schedule, zeta table
     std::vector<EpochDesc> epochs; h_epochs(*params, epochs);
-    std::vector<double2> zetas; h_zeta_tables(*params, ix->max_path_steps, zetas, s->zlen);
+    std::vector<double2> zetas; h_zeta_tables(*params, ix->max_path_steps, zetas, s->zlen, ix);
     s->n_epochs = (uint32_t)epochs.size();
     SS_CUDA(cudaMalloc(&s->d_epochs, epochs.size() * sizeof(EpochDesc)));
     SS_CUDA(cudaMalloc(&s->d_zetas, std::max<size_t>(zetas.size(), 1) * sizeof(double2)));
@@ -1193,6 +1227,14 @@ extern "C" int gfs_debug_schedule(const gfs_sgd_params* params, double* etas) {
     int rc = validate_params(params); if (rc) return rc;
     std::vector<double> e; h_schedule(*params, e);
     std::memcpy(etas, e.data(), e.size() * 8);
+    return GFS_OK;
+}
+// Host-only twin of gfs_debug_zetas (no index, no device): the table for a graph whose longest path has max_path_steps steps.
+extern "C" int gfs_debug_zetas_host(const gfs_sgd_params* params, uint64_t max_path_steps, double* zetas, uint64_t cap, uint64_t* n) {
+    int rc = validate_params(params); if (rc) return rc;
+    std::vector<double> z; h_zetas(*params, max_path_steps, z);
+    if (n) *n = z.size();
+    if (zetas) std::memcpy(zetas, z.data(), std::min<uint64_t>(cap, z.size()) * 8);
     return GFS_OK;
 }
 extern "C" int gfs_debug_zetas(const gfs_index* ix, const gfs_sgd_params* params, double* zetas, uint64_t cap, uint64_t* n) {

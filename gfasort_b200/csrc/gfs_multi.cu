@@ -71,10 +71,19 @@ struct gfs_replica {
     uint32_t rank = 0, world = 1, syncs = 1;
     uint64_t reconciles = 0;
     uint64_t n_epochs = 0;
+    // overlapped reconcile (GFASORT_OVERLAP, gfs_p2p.cu): the exchange runs on `side` over a snapshot while the next
+    // SGD slice runs on the session's stream
+    bool overlap = false, rc_pending = false;
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev_snap = nullptr, ev_rc = nullptr;
 };
 
 extern "C" void gfs_replica_destroy(gfs_replica* r) {
     if (!r) return;
+    if (r->s) cudaSetDevice(r->s->device);
+    if (r->side) { cudaStreamSynchronize(r->side); cudaStreamDestroy(r->side); }
+    if (r->ev_snap) cudaEventDestroy(r->ev_snap);
+    if (r->ev_rc) cudaEventDestroy(r->ev_rc);
     if (r->s) gfs_sgd_session_destroy(r->s);
     if (r->region) gfs_p2p_region_free(r->region);
     delete r;
@@ -115,6 +124,13 @@ extern "C" int gfs_replica_create(const gfs_index* shard, const gfs_sgd_params* 
     rc = gfs_sgd_session_create(shard, &p, dims, &c, &r->s);
     if (rc) return fail(rc);
     r->n_epochs = params->iter_max + 1;
+    r->overlap = world > 1 && env_long("GFASORT_OVERLAP", 1) != 0;
+    if (r->overlap) {
+        cudaError_t e = cudaStreamCreateWithFlags(&r->side, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&r->ev_snap, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&r->ev_rc, cudaEventDisableTiming);
+        if (e != cudaSuccess) { set_error(std::string("gfs_replica_create: ") + cudaGetErrorString(e)); return fail(GFS_ERR_CUDA); }
+    }
     *out = r;
     return GFS_OK;
 }
@@ -153,27 +169,59 @@ extern "C" int gfs_replica_upload(gfs_replica* r, const double* positions) {
     return rc;
 }
 
+// the session's stream waits (on the device) for the reconcile still in flight on the side stream
+static int replica_join_reconcile(gfs_replica* r) {
+    if (r->rc_pending) {
+        GFS_CUDA(cudaStreamWaitEvent(r->s->stream, r->ev_rc, 0));
+        r->rc_pending = false;
+    }
+    return GFS_OK;
+}
+
 // Asynchronous: epochs [epoch_begin, epoch_end) of this rank's share, `syncs` slices per epoch, replicas reconciled
 // after every slice.  Every rank must enqueue the same epochs in the same order.
+// Overlapped (default, GFASORT_OVERLAP=0 turns it off): after a slice the replica is copied to a snapshot and the next
+// slice starts at once; the exchange over the snapshots runs beside it on a second stream and adds its corrections to the
+// live replicas (gfs_p2p.cu, rc_p2p_async).  The next snapshot waits for it.
 extern "C" int gfs_replica_run(gfs_replica* r, uint64_t epoch_begin, uint64_t epoch_end) {
     if (!r) { set_error("gfs_replica_run: null replica"); return GFS_ERR_INVALID; }
     for (uint64_t e = epoch_begin; e < epoch_end; ++e)
         for (uint32_t k = 0; k < r->syncs; ++k) {
             int rc = gfs_sgd_session_run(r->s, e, e + 1, k, r->syncs);
             if (rc) return rc;
-            if (r->world > 1) {
+            if (r->world <= 1) continue;
+            if (r->overlap) {
+                rc = replica_join_reconcile(r);                                       // the previous round's corrections are in
+                if (!rc) rc = gfs_p2p_region_snapshot_x(r->region, r->s->stream);
+                if (rc) return rc;
+                GFS_CUDA(cudaEventRecord(r->ev_snap, r->s->stream));
+                GFS_CUDA(cudaStreamWaitEvent(r->side, r->ev_snap, 0));
+                rc = gfs_p2p_reconcile_async(r->region, r->side);
+                if (rc) return rc;
+                GFS_CUDA(cudaEventRecord(r->ev_rc, r->side));
+                r->rc_pending = true;
+            } else {
                 rc = gfs_p2p_reconcile(r->region, r->s->stream);
                 if (rc) return rc;
-                r->reconciles += 1;
             }
+            r->reconciles += 1;
         }
     return GFS_OK;
+}
+
+// Asynchronous: makes the session's stream wait for the last overlapped reconcile (call it before timing events or before
+// reading the replica on that stream).
+extern "C" int gfs_replica_flush(gfs_replica* r) {
+    if (!r) { set_error("gfs_replica_flush: null replica"); return GFS_ERR_INVALID; }
+    GFS_CUDA(cudaSetDevice(r->s->device));
+    return replica_join_reconcile(r);
 }
 
 // Blocking: waits for everything enqueued; a reconcile barrier that timed out on ANY rank is an error here.
 extern "C" int gfs_replica_sync(gfs_replica* r) {
     if (!r) { set_error("gfs_replica_sync: null replica"); return GFS_ERR_INVALID; }
-    int rc = gfs_sgd_session_sync(r->s);
+    int rc = gfs_replica_flush(r);
+    if (!rc) rc = gfs_sgd_session_sync(r->s);
     if (!rc) rc = gfs_p2p_region_check(r->region);
     return rc;
 }

@@ -24,6 +24,16 @@
 // replicas are in an undefined state (other blocks may already have scattered); the contract is "an error, never a
 // hang and never a silently wrong result", not "untouched replicas".
 //
+// OVERLAPPED form (rc_p2p_async; gfs_p2p_reconcile_async): the same rule without stopping the SGD.  After an SGD slice the
+// rank copies its replica into a snapshot x_snap (local, 30 us) and starts the next slice at once; on a second stream a
+// small kernel (128 threads per block, <= 32 registers: it fits next to the three resident SGD blocks of every SM) meets
+// its peers at the same barriers, forms the new common base B' = x_sync + moved-replica mean of (x_snap_g - x_sync) for
+// its slice, and for EVERY rank g — its own included — adds (B' - x_snap_g) to the live replica with red.add (over NVLink
+// for the peers) and stores B' into that rank's x_sync.  The live replica is then B' + whatever the rank has done since
+// its snapshot: peers' contributions arrive a fraction of an epoch late instead of stopping everybody for the exchange.
+// "Moved" is |x_snap - x_sync| above a few ulps, because x + (B' - x) is B' only up to rounding.  The next snapshot waits
+// (stream event) until this kernel — whose end barrier says every peer's corrections have landed — has finished.
+//
 // One device, several replicas (tests): kernels that wait on one another must not be separate launches on one GPU
 // (nothing guarantees they run at the same time), so gfs_p2p_reconcile_local runs all ranks as ONE cooperative
 // launch in which block group g plays rank g.
@@ -53,6 +63,8 @@ struct P2pArgs {
     void* x[P2P_MAX_RANKS];                  // replicas, by rank (own entry = local pointer)
     uint32_t* flags[P2P_MAX_RANKS];          // [phase 0/1][block][source rank]
     unsigned long long* err[P2P_MAX_RANKS];  // every rank's error word
+    void* snap[P2P_MAX_RANKS];               // overlapped form: every rank's snapshot x_snap
+    void* xs_all[P2P_MAX_RANKS];             // overlapped form: every rank's x_sync
     void* xs;                                // local x_sync
     uint64_t nvec;                           // 16-byte vectors per replica (arrays are padded to 256 B)
     uint64_t spin_cap;
@@ -219,6 +231,68 @@ __global__ void __launch_bounds__(P2P_THREADS) rc_p2p_emulated(const P2pEmuArgs 
     rc_p2p_body<T>(e.r[blockIdx.x / blocks], blockIdx.x % blocks);
 }
 
+// ---- overlapped form -------------------------------------------------------------------------------------------
+constexpr uint32_t P2P_ASYNC_THREADS = 128;
+template <typename T> __device__ __forceinline__ bool moved_beyond_rounding(T v, T s);
+template <> __device__ __forceinline__ bool moved_beyond_rounding<double>(double v, double s) {
+    return fabs(v - s) > fabs(s) * 1.8e-15 + 1e-300;             // 8 ulps: x + (B' - x) returns to B' only up to rounding
+}
+template <> __device__ __forceinline__ bool moved_beyond_rounding<float>(float v, float s) {
+    return fabsf(v - s) > fabsf(s) * 1e-6f + 1e-37f;
+}
+template <typename T> __device__ __forceinline__ void red_add(T* p, T v);
+template <> __device__ __forceinline__ void red_add<double>(double* p, double v) {
+    asm volatile("red.relaxed.sys.global.add.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+template <> __device__ __forceinline__ void red_add<float>(float* p, float v) {
+    asm volatile("red.relaxed.sys.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+
+template <typename T>
+__device__ void rc_p2p_async_body(const P2pArgs& a, uint32_t b) {
+    using V = V16<T>;
+    __shared__ int s_dead;
+    if (threadIdx.x == 0) s_dead = ld_relaxed_sys_u64(a.err[a.rank]) != 0;
+    __syncthreads();
+    if (s_dead) return;
+    if (!p2p_barrier<0>(a, b)) { p2p_raise(a); return; }          // every rank's snapshot of this round is complete
+    const uint64_t lo = slice_begin(a.nvec, a.world, a.rank), hi = slice_begin(a.nvec, a.world, a.rank + 1);
+    const uint64_t stride = (uint64_t)a.blocks * blockDim.x;
+    for (uint64_t i = lo + (uint64_t)b * blockDim.x + threadIdx.x; i < hi; i += stride) {
+        const V s = *reinterpret_cast<const V*>(static_cast<const char*>(a.xs) + i * 16);
+        double sum[V::N]; uint32_t moved[V::N]; T only[V::N];
+#pragma unroll
+        for (int k = 0; k < V::N; ++k) { sum[k] = 0.0; moved[k] = 0; only[k] = s.v[k]; }
+        for (uint32_t g = 0; g < a.world; ++g) {
+            const V v = V::ld_sys(static_cast<const char*>(a.snap[g]) + i * 16);
+#pragma unroll
+            for (int k = 0; k < V::N; ++k)
+                if (moved_beyond_rounding<T>(v.v[k], s.v[k])) { sum[k] += (double)v.v[k] - (double)s.v[k]; ++moved[k]; only[k] = v.v[k]; }
+        }
+        V nv;
+#pragma unroll
+        for (int k = 0; k < V::N; ++k) nv.v[k] = moved[k] <= 1 ? only[k] : (T)((double)s.v[k] + sum[k] / (double)moved[k]);
+        for (uint32_t g = 0; g < a.world; ++g) {
+            const V v = V::ld_sys(static_cast<const char*>(a.snap[g]) + i * 16);
+            T* xg = reinterpret_cast<T*>(static_cast<char*>(a.x[g]) + i * 16);
+#pragma unroll
+            for (int k = 0; k < V::N; ++k) {
+                const T d = (T)((double)nv.v[k] - (double)v.v[k]);
+                if (d != T(0)) red_add<T>(xg + k, d);             // the rank keeps what it did since its snapshot
+            }
+            V::st(static_cast<char*>(a.xs_all[g]) + i * 16, nv);
+        }
+    }
+    if (!p2p_barrier<1>(a, b)) { p2p_raise(a); return; }          // every peer's corrections to MY replica have landed
+}
+template <typename T>
+__global__ void __launch_bounds__(P2P_ASYNC_THREADS, 16) rc_p2p_async(const P2pArgs a) { rc_p2p_async_body<T>(a, blockIdx.x); }
+template <typename T>
+__global__ void __launch_bounds__(P2P_ASYNC_THREADS, 16) rc_p2p_async_emulated(const P2pEmuArgs e) {
+    const uint32_t blocks = e.r[0].blocks;
+    rc_p2p_async_body<T>(e.r[blockIdx.x / blocks], blockIdx.x % blocks);
+}
+
 uint64_t align_up(uint64_t v) { return (v + P2P_ALIGN - 1) / P2P_ALIGN * P2P_ALIGN; }
 
 }  // namespace
@@ -228,7 +302,7 @@ struct gfs_p2p_region {
     uint64_t n = 0;
     uint32_t elem_bytes = 8;
     uint32_t rank = 0, world = 1, blocks = 1, tag = 0;
-    size_t off_xs = 0, off_flags = 0, off_err = 0, bytes = 0;
+    size_t off_xs = 0, off_snap = 0, off_flags = 0, off_err = 0, bytes = 0;
     char* base = nullptr;                               // this rank's allocation
     char* peer_base[P2P_MAX_RANKS] = {};                // every rank's allocation as mapped here
     bool ipc_opened[P2P_MAX_RANKS] = {};
@@ -268,7 +342,8 @@ extern "C" int gfs_p2p_region_create(int32_t device, uint64_t n, uint32_t elem_b
     r->spin_cap = cap && *cap ? std::strtoull(cap, nullptr, 10) : (1ull << 24);   // x >= 64 ns: seconds, not forever
     const uint64_t arr = align_up(std::max<uint64_t>(n, 1) * elem_bytes);  // padded: the kernel works on whole 16-byte vectors
     r->off_xs = arr;
-    r->off_flags = 2 * arr;
+    r->off_snap = 2 * arr;
+    r->off_flags = 3 * arr;
     r->off_err = r->off_flags + align_up((uint64_t)2 * P2P_MAX_BLOCKS * P2P_MAX_RANKS * 4);
     r->bytes = r->off_err + P2P_ALIGN;
     cudaError_t e = cudaMalloc(&r->base, r->bytes);
@@ -280,6 +355,11 @@ extern "C" int gfs_p2p_region_create(int32_t device, uint64_t n, uint32_t elem_b
     return GFS_OK;
 }
 
+extern "C" int gfs_p2p_region_snap_ptr(gfs_p2p_region* r, void** x_snap) {
+    if (!r || !x_snap) { gfs::set_error("gfs_p2p_region_snap_ptr: null argument"); return GFS_ERR_INVALID; }
+    *x_snap = r->base + r->off_snap;
+    return GFS_OK;
+}
 extern "C" int gfs_p2p_region_ptrs(gfs_p2p_region* r, void** x, void** x_sync, uint64_t* region_bytes) {
     if (!r) { gfs::set_error("gfs_p2p_region_ptrs: null region"); return GFS_ERR_INVALID; }
     if (x) *x = r->base;
@@ -388,6 +468,8 @@ static P2pArgs make_args(gfs_p2p_region* r, uint32_t blocks) {
     P2pArgs a{};
     for (uint32_t g = 0; g < r->world; ++g) {
         a.x[g] = r->peer_base[g];
+        a.snap[g] = r->peer_base[g] + r->off_snap;
+        a.xs_all[g] = r->peer_base[g] + r->off_xs;
         a.flags[g] = reinterpret_cast<uint32_t*>(r->peer_base[g] + r->off_flags);
         a.err[g] = reinterpret_cast<unsigned long long*>(r->peer_base[g] + r->off_err);
     }
@@ -414,9 +496,37 @@ extern "C" int gfs_p2p_reconcile(gfs_p2p_region* r, void* stream) {
     return GFS_OK;
 }
 
+// Overlapped form, step 1 (asynchronous on `stream`, the stream the SGD runs on): x_snap <- x.
+extern "C" int gfs_p2p_region_snapshot_x(gfs_p2p_region* r, void* stream) {
+    if (!r) { gfs::set_error("gfs_p2p_region_snapshot_x: null region"); return GFS_ERR_INVALID; }
+    P2P_CUDA(cudaSetDevice(r->device));
+    P2P_CUDA(cudaMemcpyAsync(r->base + r->off_snap, r->base, r->n * r->elem_bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return GFS_OK;
+}
+// Overlapped form, step 2 (asynchronous on `stream`, a SECOND stream that waits for the snapshot): the exchange over the
+// snapshots; corrections are added to the live replicas while their owners go on sampling.
+extern "C" int gfs_p2p_reconcile_async(gfs_p2p_region* r, void* stream) {
+    if (!r) { gfs::set_error("gfs_p2p_reconcile_async: null region"); return GFS_ERR_INVALID; }
+    if (!r->connected) { gfs::set_error("gfs_p2p_reconcile_async: region is not connected to its peers"); return GFS_ERR_INVALID; }
+    P2P_CUDA(cudaSetDevice(r->device));
+    const P2pArgs a = make_args(r, r->blocks);
+    if (r->elem_bytes == 8) rc_p2p_async<double><<<r->blocks, P2P_ASYNC_THREADS, 0, (cudaStream_t)stream>>>(a);
+    else rc_p2p_async<float><<<r->blocks, P2P_ASYNC_THREADS, 0, (cudaStream_t)stream>>>(a);
+    P2P_CUDA(cudaGetLastError());
+    return GFS_OK;
+}
+
 // All `world` replicas live on ONE device and were connected with gfs_p2p_region_connect_local: one cooperative
 // launch in which block group g plays rank g (same barriers, same partition, same arithmetic as G ranks on G GPUs).
+static int reconcile_local(gfs_p2p_region* const* regions, uint32_t world, void* stream, bool overlapped);
 extern "C" int gfs_p2p_reconcile_local(gfs_p2p_region* const* regions, uint32_t world, void* stream) {
+    return reconcile_local(regions, world, stream, false);
+}
+// the overlapped form's kernel for replicas that share one device (tests of its arithmetic): x_snap must have been taken
+extern "C" int gfs_p2p_reconcile_async_local(gfs_p2p_region* const* regions, uint32_t world, void* stream) {
+    return reconcile_local(regions, world, stream, true);
+}
+static int reconcile_local(gfs_p2p_region* const* regions, uint32_t world, void* stream, bool overlapped) {
     if (!regions || world == 0 || world > P2P_EMU_MAX) { gfs::set_error("gfs_p2p_reconcile_local: 1..4 regions"); return GFS_ERR_INVALID; }
     for (uint32_t g = 0; g < world; ++g) {
         if (!regions[g] || !regions[g]->connected || regions[g]->world != world || regions[g]->rank != g ||
@@ -427,16 +537,18 @@ extern "C" int gfs_p2p_reconcile_local(gfs_p2p_region* const* regions, uint32_t 
     }
     P2P_CUDA(cudaSetDevice(regions[0]->device));
     const bool f64 = regions[0]->elem_bytes == 8;
-    const void* fn = f64 ? (const void*)rc_p2p_emulated<double> : (const void*)rc_p2p_emulated<float>;
+    const void* fn = overlapped ? (f64 ? (const void*)rc_p2p_async_emulated<double> : (const void*)rc_p2p_async_emulated<float>)
+                                : (f64 ? (const void*)rc_p2p_emulated<double> : (const void*)rc_p2p_emulated<float>);
+    const uint32_t threads = overlapped ? P2P_ASYNC_THREADS : P2P_THREADS;
     int per_sm = 0, sms = 0;
-    P2P_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, P2P_THREADS, 0));
+    P2P_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, threads, 0));
     P2P_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, regions[0]->device));
     const uint32_t blocks = std::min<uint32_t>(regions[0]->blocks, (uint32_t)(per_sm * sms) / world);
     if (blocks == 0) { gfs::set_error("gfs_p2p_reconcile_local: the device cannot hold all ranks at once"); return GFS_ERR_INVALID; }
     P2pEmuArgs e{};
     for (uint32_t g = 0; g < world; ++g) e.r[g] = make_args(regions[g], blocks);
     void* kargs[] = {(void*)&e};
-    P2P_CUDA(cudaLaunchCooperativeKernel(fn, dim3(blocks * world), dim3(P2P_THREADS), kargs, 0, (cudaStream_t)stream));
+    P2P_CUDA(cudaLaunchCooperativeKernel(fn, dim3(blocks * world), dim3(threads), kargs, 0, (cudaStream_t)stream));
     return GFS_OK;
 }
 

@@ -149,6 +149,9 @@ class PeerRegion:
         dev = f"cuda:{device}"
         self.x = torch.as_tensor(_DeviceArray(self.x_ptr, self.n, ts), device=dev)
         self.x_sync = torch.as_tensor(_DeviceArray(self.x_sync_ptr, self.n, ts), device=dev)
+        psn = C.c_void_p()
+        check(lib().gfs_p2p_region_snap_ptr(self._h, C.byref(psn)))
+        self.x_snap = torch.as_tensor(_DeviceArray(psn.value, self.n, ts), device=dev)     # the overlapped form's snapshot
         if self.n and (self.x.data_ptr() != self.x_ptr or self.x_sync.data_ptr() != self.x_sync_ptr):
             raise RuntimeError("PeerRegion: torch copied the region instead of viewing it")
 
@@ -192,6 +195,16 @@ class PeerRegion:
         arr = (C.c_void_p * len(regions))(*[r._h for r in regions])
         check(lib().gfs_p2p_reconcile_local(arr, len(regions), stream_ptr))
 
+    @staticmethod
+    def reconcile_async_local(regions: list, stream_ptr: int) -> None:
+        """The overlapped form's kernel (exchange over the snapshots, corrections added to the live replicas) for
+        replicas that share ONE device, as one cooperative launch (tests)."""
+        import ctypes as C
+
+        from ._cabi import check, lib
+        arr = (C.c_void_p * len(regions))(*[r._h for r in regions])
+        check(lib().gfs_p2p_reconcile_async_local(arr, len(regions), stream_ptr))
+
     def check(self) -> None:
         from ._cabi import check, lib
         check(lib().gfs_p2p_region_check(self._h))
@@ -199,7 +212,7 @@ class PeerRegion:
     def close(self) -> None:
         from ._cabi import lib
         if self._h:
-            self.x = self.x_sync = None
+            self.x = self.x_sync = self.x_snap = None
             lib().gfs_p2p_region_free(self._h)
             self._h = None
 
@@ -347,6 +360,12 @@ class ReplicaRun:
                 check(lib().gfs_sgd_session_run(self._h, epoch, epoch + 1, k, self.syncs))
                 if self.shard.world > 1:
                     reconcile(self.x, self.x_sync, self.mode, self.group, self.scratch)
+
+    def flush(self):
+        """Asynchronous: self.stream waits for the last overlapped reconcile (before a timing event on that stream)."""
+        from ._cabi import check, lib
+        if self._rep is not None:
+            check(lib().gfs_replica_flush(self._rep))
 
     def stats(self) -> dict:
         import ctypes as C

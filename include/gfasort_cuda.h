@@ -328,6 +328,14 @@ int gfs_p2p_reconcile(gfs_p2p_region* r, void* stream);
 /* Replicas that share ONE device (tests): all `world` (<= 4) ranks as one cooperative launch, block group g playing
  * rank g — kernels of one GPU that wait on one another must not be separate launches. */
 int gfs_p2p_reconcile_local(gfs_p2p_region* const* regions /*world, rank order, one device*/, uint32_t world, void* stream);
+/* Overlapped form (what gfs_replica_run uses by default): gfs_p2p_region_snapshot_x copies the replica into the region's
+ * snapshot on the SGD's stream; gfs_p2p_reconcile_async, on a second stream that waits for that copy, exchanges the
+ * SNAPSHOTS and adds (new common base - own snapshot) to every rank's live replica with red.add, so the next SGD slice runs
+ * during the exchange; the next snapshot must wait for it.  The _local form is the same kernel for replicas sharing a device. */
+int gfs_p2p_region_snap_ptr(gfs_p2p_region* r, void** x_snap);
+int gfs_p2p_region_snapshot_x(gfs_p2p_region* r, void* stream);
+int gfs_p2p_reconcile_async(gfs_p2p_region* r, void* stream);
+int gfs_p2p_reconcile_async_local(gfs_p2p_region* const* regions, uint32_t world, void* stream);
 /* Blocking: GFS_ERR_CUDA if a barrier of an earlier reconcile timed out on ANY rank (a rank missing, kernels not
  * co-resident).  After a timeout the replicas are undefined and every later reconcile returns at once: the run failed. */
 int gfs_p2p_region_check(gfs_p2p_region* r);
@@ -362,6 +370,9 @@ int gfs_replica_connect_local(gfs_replica* const* replicas /*world, rank order, 
 int gfs_replica_upload(gfs_replica* r, const double* positions);            /* every rank uploads the same positions */
 /* Asynchronous: epochs [epoch_begin, epoch_end), syncs_per_epoch (SGD slice, reconcile) pairs each. */
 int gfs_replica_run(gfs_replica* r, uint64_t epoch_begin, uint64_t epoch_end);
+/* Asynchronous: the rank's stream waits for its last overlapped reconcile (before timing events / reads on that stream).
+ * GFASORT_OVERLAP=0 selects the stop-the-world reconcile instead (one kernel on the rank's stream after every slice). */
+int gfs_replica_flush(gfs_replica* r);
 int gfs_replica_sync(gfs_replica* r);                                        /* blocking; reports reconcile time-outs */
 int gfs_replica_download(gfs_replica* r, double* positions);
 int gfs_replica_stats(gfs_replica* r, gfs_stats* stats);                     /* this rank's share; synchronises first */
@@ -406,6 +417,8 @@ int gfs_debug_trace_terms(const gfs_index* ix, const gfs_sgd_params* params, int
 /* Host-computed schedule and zeta table the kernels use (etas: iter_max+1; zetas: *n entries). */
 int gfs_debug_schedule(const gfs_sgd_params* params, double* etas);
 int gfs_debug_zetas(const gfs_index* ix, const gfs_sgd_params* params, double* zetas, uint64_t cap, uint64_t* n);
+/* the same table without an index or a device (host arithmetic only): for a longest path of max_path_steps steps */
+int gfs_debug_zetas_host(const gfs_sgd_params* params, uint64_t max_path_steps, double* zetas, uint64_t cap, uint64_t* n);
 
 #ifdef __cplusplus
 }

@@ -170,3 +170,24 @@ def test_synth_graph_shape_and_determinism(gfs):
     assert np.array_equal(r.step_handles, a.step_handles[lo:hi])
     from gfasort_b200.synth import synth_path_counts
     assert np.array_equal(synth_path_counts(20_000, 6, 42), counts)
+
+
+@pytest.mark.parametrize("space,max_steps,theta,space_max", [(50, 10, 0.99, 100), (15931, 3100, 0.99, 100), (3100, 3100, 0.99, 1000),
+                                                              (27624835, 1_000_000, 0.99, 100), (400_000, 400_000, 0.001, 100)])
+def test_host_zeta_table_matches_oracle_bit_for_bit(space, max_steps, theta, space_max, gfs, oracle):
+    """The library's zeta table (terms computed block-wise on several threads, added up in the reference's serial order,
+    truncated at the reachable index) against the oracle's plain serial loop (src/sgd.rs:311-331): identical bits."""
+    import time
+    from gfasort_b200._cabi import check, f64p, lib, u64p
+    p = gfs.PathSGDParams(iter_max=100, min_term_updates=1, eta_max=1.0, theta=theta, space=space, space_max=space_max,
+                          space_quantization_step=100)
+    cp = p.c()
+    n = C.c_uint64()
+    check(lib().gfs_debug_zetas_host(C.byref(cp), max_steps, None, 0, C.byref(n)))
+    got = np.zeros(n.value)
+    t0 = time.perf_counter()
+    check(lib().gfs_debug_zetas_host(C.byref(cp), max_steps, got.ctypes.data_as(f64p), n.value, C.byref(n)))
+    dt = time.perf_counter() - t0
+    want = oracle.zetas(space, space_max, 100, theta, iter_cap=min(space, max_steps), size=n.value)
+    assert np.array_equal(got.view(np.uint64), want.view(np.uint64)), f"first difference at {int(np.nonzero(got != want)[0][0])}"
+    assert dt < 2.0

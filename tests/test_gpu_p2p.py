@@ -198,3 +198,49 @@ def test_one_call_multi_gpu_through_the_cabi(dims, gfs, monkeypatch):
         print(f"2D stress one GPU {sa[1]:.5e} vs GFASORT_GPUS=2 {sb[1]:.5e}")
         assert sb[1] <= sa[1] * 1.10
     ix1.close(); ix2.close()
+
+
+@pytest.mark.parametrize("dtype,G,n", [("float64", 2, 100_003), ("float64", 4, 300_001), ("float32", 3, 65_537)])
+def test_p2p_overlapped_reconcile_arithmetic(dtype, G, n, gfs, monkeypatch):
+    """The overlapped form (rc_p2p_async) on one device, all ranks in one cooperative launch: the exchange works on the
+    SNAPSHOTS, every live replica receives (new base - its own snapshot) on top of whatever it did since the snapshot,
+    every x_sync becomes the new base."""
+    import torch
+    from gfasort_b200.multi import PeerRegion
+    monkeypatch.setenv("GFASORT_P2P_SPIN_CAP", str(1 << 21))
+    f64 = dtype == "float64"
+    regions = [PeerRegion(0, n, f64, max_blocks=8) for _ in range(G)]
+    try:
+        PeerRegion.connect_local(regions)
+        stream = torch.cuda.Stream(device=0)
+        rng = np.random.default_rng(9)
+        base = (rng.standard_normal(n) * 1e6).astype(dtype)
+        for rnd in range(2):
+            snaps, lives = [], []
+            for g, r in enumerate(regions):
+                mask = rng.random(n) < (0.6 if rnd == 0 else 0.05)
+                snap = base.copy()
+                snap[mask] += (rng.standard_normal(int(mask.sum())) * 100).astype(dtype)
+                since = np.zeros(n, dtype=dtype)                     # what the rank did after taking its snapshot
+                m2 = rng.random(n) < 0.3
+                since[m2] = (rng.standard_normal(int(m2.sum())) * 10).astype(dtype)
+                live = (snap + since).astype(dtype)
+                snaps.append(snap); lives.append(live)
+                r.x_sync.copy_(torch.from_numpy(base)); r.x_snap.copy_(torch.from_numpy(snap)); r.x.copy_(torch.from_numpy(live))
+            torch.cuda.synchronize()
+            PeerRegion.reconcile_async_local(regions, stream.cuda_stream)
+            torch.cuda.synchronize()
+            for r in regions:
+                r.check()
+            want_base = _expected(base, snaps)
+            tol = 1e-8 if f64 else 0.5
+            for g, r in enumerate(regions):
+                assert np.allclose(r.x_sync.cpu().numpy(), want_base, rtol=0, atol=tol), "x_sync is not the new common base"
+                want_live = lives[g].astype(np.float64) + (want_base.astype(np.float64) - snaps[g].astype(np.float64))
+                assert np.allclose(r.x.cpu().numpy().astype(np.float64), want_live, rtol=0, atol=tol * 4), "live replica: wrong correction"
+            for r in regions[1:]:
+                assert np.array_equal(r.x_sync.cpu().numpy(), regions[0].x_sync.cpu().numpy()), "bases differ between ranks"
+            base = regions[0].x_sync.cpu().numpy()
+    finally:
+        for r in regions:
+            r.close()

@@ -1,24 +1,18 @@
 set -x
 cd $GRAFT_REPO_ROOT
-cap() {   # cap <name> <kernel regex> <skip> <count> <updates per launch> <cmd...>
-  name=$1; rx=$2; skip=$3; cnt=$4; upd=$5; shift 5
-  timeout 900 "$@" > gpurun_out/plain_${name}.log 2>&1 && cat gpurun_out/plain_${name}.log | tail -3 &&
-  timeout 1500 ncu --set full --clock-control none --import-source on -k regex:$rx -s $skip -c $cnt -o gpurun_out/prof_${name} "$@" > gpurun_out/ncu_${name}.log 2>&1
-  tail -1 gpurun_out/ncu_${name}.log
-  python tools/ncu_summary.py gpurun_out/prof_${name}.ncu-rep --updates $upd --top 25 > gpurun_out/summary_${name}.md 2> gpurun_out/summary_${name}.err
-  rm -f gpurun_out/prof_${name}.ncu-rep
-}
-# 1. K1: how much of its time is the look-back chain?  (offsets are wrong with the flag: timing only)
-timeout 200 python tools/index_probe.py --reps 2 --modes pinned32 > gpurun_out/k1_lookback_on_r2i.log 2>&1; grep -o "K1 [0-9.]* ms" gpurun_out/k1_lookback_on_r2i.log
-GFASORT_K1_NO_LOOKBACK=1 timeout 200 python tools/index_probe.py --reps 2 --modes pinned32 > gpurun_out/k1_lookback_off_r2i.log 2>&1; grep -o "K1 [0-9.]* ms" gpurun_out/k1_lookback_off_r2i.log
-# 2. the whole GPU suite
-timeout 1800 python -m pytest tests -m gpu -x -q -s > gpurun_out/pytest_r2i.log 2>&1; tail -3 gpurun_out/pytest_r2i.log; grep -E "stress" gpurun_out/pytest_r2i.log | cut -c1-330
-# 3. the default bench line, every leg on
-( time timeout 1200 python bench.py > gpurun_out/bench_r2i.log 2> gpurun_out/bench_r2i.err ) 2>&1 | grep real; tail -4 gpurun_out/bench_r2i.err; cut -c1-400 gpurun_out/bench_r2i.log
-( time timeout 600 python bench.py --impl reference --steps 5 --warmup 2 > gpurun_out/bench_ref_r2i.log 2> gpurun_out/bench_ref_r2i.err ) 2>&1 | grep real; cut -c1-300 gpurun_out/bench_ref_r2i.log
-# 4. whole-epoch captures (the launches the bench times): traffic.json
-cap r2i_y10m_epoch sgd_kernel 1 2 833491505 python tools/ncu_target.py --workload y10m --slices 1 --launches 2
-cap r2i_l10m_slice10 sgd_kernel 1 2 833491505 python tools/ncu_target.py --workload l10m --slices 10 --launches 2
-timeout 300 python bench.py --steps 6 --warmup 3 --no-cpu --e2e-epochs 0 --also 0 > gpurun_out/plain_launches_r2i.log 2>&1 &&
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_r2i.csv python bench.py --steps 6 --warmup 3 --no-cpu --e2e-epochs 0 --also 0 > gpurun_out/ncu_launches_r2i.log 2>&1
-du -sh gpurun_out
+timeout 600 python -m pytest tests -m gpu -x -q -s -k "p2p or multi_gpu or replica" > gpurun_out/pytest_r2l_n2.log 2>&1; tail -4 gpurun_out/pytest_r2l_n2.log; grep "stress one GPU" gpurun_out/pytest_r2l_n2.log
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 10 --warmup 3 > gpurun_out/bench_r2l_n2_overlap.log 2> gpurun_out/bench_r2l_n2_overlap.err; grep "e2e phases" gpurun_out/bench_r2l_n2_overlap.err | cut -c1-250
+GFASORT_OVERLAP=0 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus 2 --steps 10 --warmup 3 --also 0 > gpurun_out/bench_r2l_n2_sync.log 2> gpurun_out/bench_r2l_n2_sync.err; grep "e2e phases" gpurun_out/bench_r2l_n2_sync.err | cut -c1-250
+python - <<'PY'
+import json
+for f in ["bench_r2l_n2_overlap.log", "bench_r2l_n2_sync.log"]:
+    try:
+        d = json.loads(open("gpurun_out/" + f).read().strip().splitlines()[-1])
+    except Exception as e:
+        print(f, "no line", e); continue
+    print(f, "value", round(d["value"] / 1e9, 2), "ms/step", round(d["ms_per_step"], 3), "kernel", round(d["roofline"]["launch_ms"], 3), "gap", round(d["roofline"]["step_ms_minus_kernel_ms"], 3),
+          "e2e", round(d["e2e"]["seconds"], 3), "stress", d["e2e"]["stress_mean_abs_rel"], d["e2e"]["stress_rms_rel"])
+    for a in d["also"]:
+        print("   also", a.get("workload"), round(a["value"] / 1e9, 2) if "value" in a else a, a.get("ms_per_step"), a["e2e"]["stress_mean_abs_rel"] if "e2e" in a else None)
+PY
+tail -3 gpurun_out/bench_r2l_n2_overlap.err

@@ -42,7 +42,10 @@ st = Stats()
 for name, e in (("warm", 1), ("cool", first_cool + 1)):
     check(lib().gfs_sgd_session_stats(h, C.byref(st))); k0, a0 = st.kernel_seconds, st.applied_updates
     for k in range(a.launches):
-        check(lib().gfs_sgd_session_run(h, e, e + 1, k, a.slices))
+        if a.slices == 1:
+            check(lib().gfs_sgd_session_run(h, e + k, e + k + 1, 0, 1))       # whole epochs: consecutive epochs
+        else:
+            check(lib().gfs_sgd_session_run(h, e, e + 1, k, a.slices))
     check(lib().gfs_sgd_session_stats(h, C.byref(st)))
     print(f"{name}: {a.launches} launches of {(st.applied_updates-a0)//a.launches} updates: {(st.applied_updates-a0)/(st.kernel_seconds-k0)/1e9:.2f} G upd/s", flush=True)
 lib().gfs_sgd_session_destroy(h)
