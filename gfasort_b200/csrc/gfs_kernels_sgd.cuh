@@ -421,10 +421,15 @@ sgd_kernel(const SgdArgs a) {
     // samples from the window starting at cc * samp_len / chunks_per_epoch.  Claiming in order keeps all
     // warps on neighbouring chunks (a static assignment lets them drift apart by SM speed), so the windows
     // in use at any moment cover about n_warps * C * samp_len / m + window_steps consecutive steps.
-    const uint64_t m_sweep = ep.updates / a.n_slices + (a.slice < ep.updates % a.n_slices ? 1 : 0);
-    const uint64_t cpe = sweep ? (m_sweep + C - 1) / C : 1;                           // chunks per epoch
+    // A sliced epoch (n_slices > 1: one launch per reconcile interval) is ONE sweep cut into n_slices consecutive pieces:
+    // slice k runs the epoch's chunks [cpe_all k / n, cpe_all (k+1) / n), so the window positions of the slices follow one
+    // another exactly as in a whole-epoch launch (restarting the sweep in every slice costs 6-7 % in L2 locality).
+    const uint64_t m_sweep = ep.updates;                                             // the whole epoch's updates
+    const uint64_t cpe_all = sweep ? (m_sweep + C - 1) / C : 1;                       // chunks per (whole) epoch
+    const uint64_t c_first = cpe_all * a.slice / a.n_slices;                          // this slice's chunks of every epoch
+    const uint64_t cpe = cpe_all * (a.slice + 1) / a.n_slices - c_first;
     const uint64_t total_chunks = cpe * (uint64_t)(a.epoch_end - a.epoch_begin);
-    const double steps_per_chunk = (double)a.g.samp_len / (double)cpe;
+    const double steps_per_chunk = (double)a.g.samp_len / (double)cpe_all;
     uint64_t c_lo = 0;                        // first chunk of epoch e_cur
     bool first_claim = true;
     auto claim = [&]() -> bool {
@@ -434,7 +439,7 @@ sgd_kernel(const SgdArgs a) {
             c = __shfl_sync(warp_mask, c, leader);
             if (c >= total_chunks) return false;
             while (c >= c_lo + cpe) { c_lo += cpe; ++e_cur; ep = a.epochs[e_cur]; }       // claims only move forward
-            const uint64_t cc = c - c_lo;
+            const uint64_t cc = c_first + (c - c_lo);                                     // chunk index within the whole epoch
             const uint64_t left = m_sweep - cc * C;
             const uint32_t n_upd = left < C ? (uint32_t)left : C;
             target += n_lanes == 32 ? (n_upd >> 5) + (lane_rank < (n_upd & 31u) ? 1u : 0u)

@@ -124,7 +124,13 @@ extern "C" int gfs_replica_create(const gfs_index* shard, const gfs_sgd_params* 
     rc = gfs_sgd_session_create(shard, &p, dims, &c, &r->s);
     if (rc) return fail(rc);
     r->n_epochs = params->iter_max + 1;
-    r->overlap = world > 1 && env_long("GFASORT_OVERLAP", 1) != 0;
+    {   // GFASORT_OVERLAP: 0 = stop-the-world reconcile, 2 = always overlapped, 1 (default) = overlapped when a slice is long
+        // enough to hide the exchange (>= 32M updates per rank and slice, about 1 ms: the overlapped kernel is small and
+        // slow by design, and on a small graph it would take longer than the SGD slice it runs beside)
+        const long ov = env_long("GFASORT_OVERLAP", 1);
+        const uint64_t per_slice = p.min_term_updates / std::max(1u, r->syncs);
+        r->overlap = world > 1 && (ov >= 2 || (ov == 1 && per_slice >= (uint64_t)env_long("GFASORT_OVERLAP_MIN_UPDATES", 32l << 20)));
+    }
     if (r->overlap) {
         cudaError_t e = cudaStreamCreateWithFlags(&r->side, cudaStreamNonBlocking);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&r->ev_snap, cudaEventDisableTiming);

@@ -14,10 +14,14 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
-def _expected(xs, xr):
-    """x_sync + sum of displacements / #replicas that moved the element; exact when at most one moved it."""
+def _expected(xs, xr, rel_thr=0.0):
+    """x_sync + sum of displacements / #replicas that moved the element; exact when at most one moved it.
+    rel_thr: the overlapped form calls an element moved when |x - x_sync| > rel_thr * |x_sync| (2.5 ulps)."""
     d = np.stack([x.astype(np.float64) - xs.astype(np.float64) for x in xr])
-    moved = np.stack([x != xs for x in xr])
+    if rel_thr:
+        moved = np.stack([np.abs(x.astype(np.float64) - xs.astype(np.float64)) > np.abs(xs.astype(np.float64)) * rel_thr for x in xr])
+    else:
+        moved = np.stack([x != xs for x in xr])
     cnt = moved.sum(0)
     mean = xs.astype(np.float64) + (d * moved).sum(0) / np.maximum(cnt, 1)
     out = mean.astype(xs.dtype)
@@ -190,13 +194,18 @@ def test_one_call_multi_gpu_through_the_cabi(dims, gfs, monkeypatch):
         print(f"1D stress one GPU {sa[1]:.5e} vs GFASORT_GPUS=2 {sb[1]:.5e}")
         assert sb[1] <= sa[1] * 1.02          # measured on 2 B200s: 2.724e-4 vs 2.822e-4 (the replicated run ends slightly lower)
     else:
+        from dataclasses import replace
         p = gfs.LayoutSGDParams(dimensions=2, iter_max=30, min_term_updates=10 * int(counts.sum()),
                                 eta_max=float(int(counts.max()) ** 2), space=int(counts.max()), space_max=1000)
-        la = gfs.path_linear_sgd_layout(graph, p, ix1)
-        lb = gfs.path_linear_sgd_layout(graph, p, ix2, coords0=gfs.initial_layout(graph, 2, p.seed))
-        sa, sb = gfs.layout_stress(graph, la.coords, 2, 500_000, ix1), gfs.layout_stress(graph, lb.coords, 2, 500_000, ix2)
-        print(f"2D stress one GPU {sa[1]:.5e} vs GFASORT_GPUS=2 {sb[1]:.5e}")
-        assert sb[1] <= sa[1] * 1.10
+        c0 = gfs.initial_layout(graph, 2, p.seed)
+        one, two = [], []
+        for k in range(3):              # a 31-epoch 2D layout of this size moves +-15 % from run to run: medians of 3 seeds
+            q = replace(p, seed=p.seed + 1000 * k)
+            one.append(gfs.layout_stress(graph, gfs.path_linear_sgd_layout(graph, q, ix1, coords0=c0).coords, 2, 500_000, ix1)[1])
+            two.append(gfs.layout_stress(graph, gfs.path_linear_sgd_layout(graph, q, ix2, coords0=c0).coords, 2, 500_000, ix2)[1])
+        a1, a2 = float(np.median(one)), float(np.median(two))
+        print(f"2D stress, medians of 3: one GPU {a1:.5e} {one} vs GFASORT_GPUS=2 {a2:.5e} {two}")
+        assert a2 <= a1 * 1.15
     ix1.close(); ix2.close()
 
 
@@ -232,7 +241,7 @@ def test_p2p_overlapped_reconcile_arithmetic(dtype, G, n, gfs, monkeypatch):
             torch.cuda.synchronize()
             for r in regions:
                 r.check()
-            want_base = _expected(base, snaps)
+            want_base = _expected(base, snaps, 5.6e-16 if f64 else 3e-7)
             tol = 1e-8 if f64 else 0.5
             for g, r in enumerate(regions):
                 assert np.allclose(r.x_sync.cpu().numpy(), want_base, rtol=0, atol=tol), "x_sync is not the new common base"

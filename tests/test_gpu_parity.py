@@ -532,7 +532,7 @@ def test_sgd_nd_stress_parity_drb1(dims, f64, gfs, oracle):
 # ------------------------------------------------------------------------------------------------
 def _oracle_fixture():
     """tests/golden/oracle_stress.json: stress reached by the oracle (all host cores, exact budget) on the named
-    graphs, on the same Philox sample gfs_stress uses — made by tools/oracle_config3.py (commands inside)."""
+    graphs, on the same Philox sample gfs_stress uses — made by tools/oracle_runs.py (commands inside)."""
     import json
     from conftest import GOLDEN
     path = os.path.join(GOLDEN, "oracle_stress.json")
@@ -615,7 +615,7 @@ def test_default_schedule_config2_vs_oracle(gfs, oracle):
                           space=int(ix.path_lengths().max()), space_max=100)
     fx = _oracle_fixture().get("config2_1M_32")
     if fx is None:
-        pytest.skip("tests/golden/oracle_stress.json has no config2_1M_32 entry (make it with tools/oracle_config3.py)")
+        pytest.skip("tests/golden/oracle_stress.json has no config2_1M_32 entry (make it with tools/oracle_runs.py)")
     assert fx["steps"] == s.S and fx["params"]["min_term_updates"] == p.min_term_updates and fx["params"]["space"] == p.space
     seeds = [r["sgd_seed"] for r in fx["runs"]]
     samples = fx["stress_sample"]["samples"]
