@@ -508,8 +508,9 @@ def measure_workload(a, wl, name, rank, world, local, dev, K, W, with_cpu, e2e_e
             "config": cfg,
             "launch": {"sampler": sampler, "grid": grid, "block": block, "window_steps": window_steps, "coherent": coherent,
                        "reconcile": a.reconcile if world > 1 else None, "syncs_per_epoch": syncs,
-                       "overlapped_reconcile": ("auto (on when a slice is >= 32M updates per rank)" if os.environ.get("GFASORT_OVERLAP", "1") == "1"
-                                                else os.environ.get("GFASORT_OVERLAP")) if (world > 1 and a.reconcile == "p2p") else None},
+                       "overlapped_reconcile": {"0": "off (stop-the-world exchange; the default)", "1": "when the exchange is short against a slice",
+                                                "2": "always", "3": "overlapped arithmetic, joined at once"}.get(os.environ.get("GFASORT_OVERLAP", "0"))
+                                               if (world > 1 and a.reconcile == "p2p") else None},
             "clocks": clk, "e2e": e2e, "gpu_launches": int(launches_per_rank * world),
             "attempts_per_update": float(attempts.item()) / total_applied,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

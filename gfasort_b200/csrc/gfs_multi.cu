@@ -74,8 +74,10 @@ struct gfs_replica {
     // overlapped reconcile (GFASORT_OVERLAP, gfs_p2p.cu): the exchange runs on `side` over a snapshot while the next
     // SGD slice runs on the session's stream
     bool overlap = false, rc_pending = false;
+    bool join_at_once = false;                 // GFASORT_OVERLAP=3: the overlapped arithmetic without the overlap (an A/B switch)
     cudaStream_t side = nullptr;
     cudaEvent_t ev_snap = nullptr, ev_rc = nullptr;
+    std::vector<cudaEvent_t> trace;            // GFASORT_RC_TRACE=1: (start, end) of every overlapped exchange on `side`
 };
 
 extern "C" void gfs_replica_destroy(gfs_replica* r) {
@@ -84,6 +86,7 @@ extern "C" void gfs_replica_destroy(gfs_replica* r) {
     if (r->side) { cudaStreamSynchronize(r->side); cudaStreamDestroy(r->side); }
     if (r->ev_snap) cudaEventDestroy(r->ev_snap);
     if (r->ev_rc) cudaEventDestroy(r->ev_rc);
+    for (cudaEvent_t e : r->trace) cudaEventDestroy(e);
     if (r->s) gfs_sgd_session_destroy(r->s);
     if (r->region) gfs_p2p_region_free(r->region);
     delete r;
@@ -124,15 +127,25 @@ extern "C" int gfs_replica_create(const gfs_index* shard, const gfs_sgd_params* 
     rc = gfs_sgd_session_create(shard, &p, dims, &c, &r->s);
     if (rc) return fail(rc);
     r->n_epochs = params->iter_max + 1;
-    {   // GFASORT_OVERLAP: 0 = stop-the-world reconcile, 2 = always overlapped, 1 (default) = overlapped when a slice is long
-        // enough to hide the exchange (>= 32M updates per rank and slice, about 1 ms: the overlapped kernel is small and
-        // slow by design, and on a small graph it would take longer than the SGD slice it runs beside)
-        const long ov = env_long("GFASORT_OVERLAP", 1);
+    {   // GFASORT_OVERLAP: 0 (default) = stop-the-world reconcile; 1 = overlapped when the exchange is short against the SGD
+        // slice it runs beside (>= GFASORT_OVERLAP_MIN_RATIO, default 40, updates per rank and slice for every 16-byte
+        // vector of the replica); 2 = always overlapped; 3 = the overlapped arithmetic, joined at once (A/B switch).
+        // Why it is off by default (profiles/r2_experiments.md §7): corrections that arrive late are applied on top of what
+        // the replica has meanwhile done about the same deviation by itself; with the capped step size (mu = 1) of most of
+        // the schedule that double correction does not decay.  Measured on config 3: exchange done within ~10-20 % of the
+        // slice (2 and 4 GPUs) -> same stress, +1 %; ~half of the slice (8 GPUs) -> +16 % stress; a whole slice late -> x2.
+        const long ov = env_long("GFASORT_OVERLAP", 0);
         const uint64_t per_slice = p.min_term_updates / std::max(1u, r->syncs);
-        r->overlap = world > 1 && (ov >= 2 || (ov == 1 && per_slice >= (uint64_t)env_long("GFASORT_OVERLAP_MIN_UPDATES", 32l << 20)));
+        const uint64_t nvec = (n_elems * (f64 ? 8 : 4) + 15) / 16;
+        r->overlap = world > 1 && (ov >= 2 || (ov == 1 && per_slice >= (uint64_t)env_long("GFASORT_OVERLAP_MIN_RATIO", 40) * nvec));
+        r->join_at_once = ov == 3;
     }
     if (r->overlap) {
-        cudaError_t e = cudaStreamCreateWithFlags(&r->side, cudaStreamNonBlocking);
+        // highest priority: the exchange's few blocks must become resident the moment an SM has room, not behind the
+        // next SGD launch's 444 blocks
+        int pr_lo = 0, pr_hi = 0;
+        cudaDeviceGetStreamPriorityRange(&pr_lo, &pr_hi);
+        cudaError_t e = cudaStreamCreateWithPriority(&r->side, cudaStreamNonBlocking, env_long("GFASORT_RC_PRIORITY", 1) ? pr_hi : pr_lo);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&r->ev_snap, cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&r->ev_rc, cudaEventDisableTiming);
         if (e != cudaSuccess) { set_error(std::string("gfs_replica_create: ") + cudaGetErrorString(e)); return fail(GFS_ERR_CUDA); }
@@ -186,9 +199,9 @@ static int replica_join_reconcile(gfs_replica* r) {
 
 // Asynchronous: epochs [epoch_begin, epoch_end) of this rank's share, `syncs` slices per epoch, replicas reconciled
 // after every slice.  Every rank must enqueue the same epochs in the same order.
-// Overlapped (default, GFASORT_OVERLAP=0 turns it off): after a slice the replica is copied to a snapshot and the next
-// slice starts at once; the exchange over the snapshots runs beside it on a second stream and adds its corrections to the
-// live replicas (gfs_p2p.cu, rc_p2p_async).  The next snapshot waits for it.
+// Overlapped (GFASORT_OVERLAP=1/2; off by default, see gfs_replica_create): after a slice the replica is copied to a
+// snapshot and the next slice starts at once; the exchange over the snapshots runs beside it on a second stream and adds
+// its corrections to the live replicas (gfs_p2p.cu, rc_p2p_async).  The next snapshot waits for it.
 extern "C" int gfs_replica_run(gfs_replica* r, uint64_t epoch_begin, uint64_t epoch_end) {
     if (!r) { set_error("gfs_replica_run: null replica"); return GFS_ERR_INVALID; }
     for (uint64_t e = epoch_begin; e < epoch_end; ++e)
@@ -202,10 +215,19 @@ extern "C" int gfs_replica_run(gfs_replica* r, uint64_t epoch_begin, uint64_t ep
                 if (rc) return rc;
                 GFS_CUDA(cudaEventRecord(r->ev_snap, r->s->stream));
                 GFS_CUDA(cudaStreamWaitEvent(r->side, r->ev_snap, 0));
+                const bool trace = env_long("GFASORT_RC_TRACE", 0) != 0 && r->trace.size() < 4096;
+                if (trace) {
+                    cudaEvent_t t0, t1;
+                    GFS_CUDA(cudaEventCreate(&t0)); GFS_CUDA(cudaEventCreate(&t1));
+                    r->trace.push_back(t0); r->trace.push_back(t1);
+                    GFS_CUDA(cudaEventRecord(t0, r->side));
+                }
                 rc = gfs_p2p_reconcile_async(r->region, r->side);
                 if (rc) return rc;
+                if (trace) GFS_CUDA(cudaEventRecord(r->trace.back(), r->side));
                 GFS_CUDA(cudaEventRecord(r->ev_rc, r->side));
                 r->rc_pending = true;
+                if (r->join_at_once) { rc = replica_join_reconcile(r); if (rc) return rc; }
             } else {
                 rc = gfs_p2p_reconcile(r->region, r->s->stream);
                 if (rc) return rc;
@@ -229,6 +251,18 @@ extern "C" int gfs_replica_sync(gfs_replica* r) {
     int rc = gfs_replica_flush(r);
     if (!rc) rc = gfs_sgd_session_sync(r->s);
     if (!rc) rc = gfs_p2p_region_check(r->region);
+    if (!rc && !r->trace.empty()) {             // GFASORT_RC_TRACE: barrier wait + exchange, as the side stream saw them
+        double sum = 0, mx = 0;
+        const size_t n = r->trace.size() / 2;
+        for (size_t k = 0; k < n; ++k) {
+            float ms = 0;
+            if (cudaEventElapsedTime(&ms, r->trace[2 * k], r->trace[2 * k + 1]) == cudaSuccess) { sum += ms; mx = std::max<double>(mx, ms); }
+        }
+        std::fprintf(stderr, "[gfasort rc trace] rank %u of %u: %zu overlapped exchanges, mean %.3f ms, max %.3f ms (barrier wait included)\n",
+                     r->rank, r->world, n, sum / (double)n, mx);
+        for (cudaEvent_t e : r->trace) cudaEventDestroy(e);
+        r->trace.clear();
+    }
     return rc;
 }
 extern "C" int gfs_replica_download(gfs_replica* r, double* positions) {

@@ -26,7 +26,8 @@
 //
 // OVERLAPPED form (rc_p2p_async; gfs_p2p_reconcile_async): the same rule without stopping the SGD.  After an SGD slice the
 // rank copies its replica into a snapshot x_snap (local, 30 us) and starts the next slice at once; on a second stream a
-// small kernel (128 threads per block, <= 32 registers: it fits next to the three resident SGD blocks of every SM) meets
+// small kernel (128 threads per block, <= 32 registers: one warp of 1024 registers per SM sub-partition, which is exactly
+// what the three resident SGD blocks leave free there — 64 threads x 64 registers is the same total and does NOT fit) meets
 // its peers at the same barriers, forms the new common base B' = x_sync + moved-replica mean of (x_snap_g - x_sync) for
 // its slice, and for EVERY rank g — its own included — adds (B' - x_snap_g) to the live replica with red.add (over NVLink
 // for the peers) and stores B' into that rank's x_sync.  The live replica is then B' + whatever the rank has done since
@@ -57,7 +58,7 @@ constexpr uint32_t P2P_MAX_RANKS = GFS_P2P_MAX_RANKS;
 constexpr uint32_t P2P_MAX_BLOCKS = 256;
 constexpr uint32_t P2P_THREADS = 512;
 constexpr uint64_t P2P_ALIGN = 256;
-constexpr uint32_t P2P_EMU_MAX = 4;         // ranks one emulated launch can hold (kernel parameter space)
+constexpr uint32_t P2P_EMU_MAX = 8;         // ranks one emulated launch can hold (kernel parameter space: 8 x 360 B)
 
 struct P2pArgs {
     void* x[P2P_MAX_RANKS];                  // replicas, by rank (own entry = local pointer)
@@ -248,7 +249,10 @@ template <> __device__ __forceinline__ void red_add<float>(float* p, float v) {
     asm volatile("red.relaxed.sys.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
 }
 
-template <typename T>
+// G > 0: the world size is a compile-time constant — all G snapshots of a vector are loaded at once (G loads in flight
+// per thread over NVLink) and stay in registers for the second half, so every snapshot crosses the link ONCE.
+// G == 0: any world size, two sequential passes over the snapshots.
+template <typename T, int G>
 __device__ void rc_p2p_async_body(const P2pArgs& a, uint32_t b) {
     using V = V16<T>;
     __shared__ int s_dead;
@@ -263,34 +267,68 @@ __device__ void rc_p2p_async_body(const P2pArgs& a, uint32_t b) {
         double sum[V::N]; uint32_t moved[V::N]; T only[V::N];
 #pragma unroll
         for (int k = 0; k < V::N; ++k) { sum[k] = 0.0; moved[k] = 0; only[k] = s.v[k]; }
-        for (uint32_t g = 0; g < a.world; ++g) {
-            const V v = V::ld_sys(static_cast<const char*>(a.snap[g]) + i * 16);
+        if constexpr (G > 0) {
+            V v[G];
 #pragma unroll
-            for (int k = 0; k < V::N; ++k)
-                if (moved_beyond_rounding<T>(v.v[k], s.v[k])) { sum[k] += (double)v.v[k] - (double)s.v[k]; ++moved[k]; only[k] = v.v[k]; }
-        }
-        V nv;
+            for (int g = 0; g < G; ++g) v[g] = V::ld_sys(static_cast<const char*>(a.snap[g]) + i * 16);
 #pragma unroll
-        for (int k = 0; k < V::N; ++k) nv.v[k] = moved[k] <= 1 ? only[k] : (T)((double)s.v[k] + sum[k] / (double)moved[k]);
-        for (uint32_t g = 0; g < a.world; ++g) {
-            const V v = V::ld_sys(static_cast<const char*>(a.snap[g]) + i * 16);
-            T* xg = reinterpret_cast<T*>(static_cast<char*>(a.x[g]) + i * 16);
+            for (int g = 0; g < G; ++g)
 #pragma unroll
-            for (int k = 0; k < V::N; ++k) {
-                const T d = (T)((double)nv.v[k] - (double)v.v[k]);
-                if (d != T(0)) red_add<T>(xg + k, d);             // the rank keeps what it did since its snapshot
+                for (int k = 0; k < V::N; ++k)
+                    if (moved_beyond_rounding<T>(v[g].v[k], s.v[k])) { sum[k] += (double)v[g].v[k] - (double)s.v[k]; ++moved[k]; only[k] = v[g].v[k]; }
+            V nv;
+#pragma unroll
+            for (int k = 0; k < V::N; ++k) nv.v[k] = moved[k] <= 1 ? only[k] : (T)((double)s.v[k] + sum[k] / (double)moved[k]);
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+                T* xg = reinterpret_cast<T*>(static_cast<char*>(a.x[g]) + i * 16);
+#pragma unroll
+                for (int k = 0; k < V::N; ++k) {
+                    const T d = (T)((double)nv.v[k] - (double)v[g].v[k]);
+                    if (d != T(0)) red_add<T>(xg + k, d);         // the rank keeps what it did since its snapshot
+                }
+                V::st(static_cast<char*>(a.xs_all[g]) + i * 16, nv);
             }
-            V::st(static_cast<char*>(a.xs_all[g]) + i * 16, nv);
+        } else {
+            for (uint32_t g = 0; g < a.world; ++g) {
+                const V v = V::ld_sys(static_cast<const char*>(a.snap[g]) + i * 16);
+#pragma unroll
+                for (int k = 0; k < V::N; ++k)
+                    if (moved_beyond_rounding<T>(v.v[k], s.v[k])) { sum[k] += (double)v.v[k] - (double)s.v[k]; ++moved[k]; only[k] = v.v[k]; }
+            }
+            V nv;
+#pragma unroll
+            for (int k = 0; k < V::N; ++k) nv.v[k] = moved[k] <= 1 ? only[k] : (T)((double)s.v[k] + sum[k] / (double)moved[k]);
+            for (uint32_t g = 0; g < a.world; ++g) {
+                const V v = V::ld_sys(static_cast<const char*>(a.snap[g]) + i * 16);
+                T* xg = reinterpret_cast<T*>(static_cast<char*>(a.x[g]) + i * 16);
+#pragma unroll
+                for (int k = 0; k < V::N; ++k) {
+                    const T d = (T)((double)nv.v[k] - (double)v.v[k]);
+                    if (d != T(0)) red_add<T>(xg + k, d);
+                }
+                V::st(static_cast<char*>(a.xs_all[g]) + i * 16, nv);
+            }
         }
     }
     if (!p2p_barrier<1>(a, b)) { p2p_raise(a); return; }          // every peer's corrections to MY replica have landed
 }
-template <typename T>
-__global__ void __launch_bounds__(P2P_ASYNC_THREADS, 16) rc_p2p_async(const P2pArgs a) { rc_p2p_async_body<T>(a, blockIdx.x); }
-template <typename T>
+// 4 warps x 32 x 32 registers: each SM sub-partition has 1024 registers left beside three resident SGD blocks (24 warps x
+// 80 registers = 15360 of its 16384).  Measured: a 64-thread x 64-register block never became resident next to the SGD.
+template <typename T, int G>
+__global__ void __launch_bounds__(P2P_ASYNC_THREADS, 16) rc_p2p_async(const P2pArgs a) { rc_p2p_async_body<T, G>(a, blockIdx.x); }
+template <typename T, int G>
 __global__ void __launch_bounds__(P2P_ASYNC_THREADS, 16) rc_p2p_async_emulated(const P2pEmuArgs e) {
     const uint32_t blocks = e.r[0].blocks;
-    rc_p2p_async_body<T>(e.r[blockIdx.x / blocks], blockIdx.x % blocks);
+    rc_p2p_async_body<T, G>(e.r[blockIdx.x / blocks], blockIdx.x % blocks);
+}
+template <typename T> const void* async_kernel(uint32_t world, bool emulated) {
+    switch (world) {
+        case 2: return emulated ? (const void*)rc_p2p_async_emulated<T, 2> : (const void*)rc_p2p_async<T, 2>;
+        case 4: return emulated ? (const void*)rc_p2p_async_emulated<T, 4> : (const void*)rc_p2p_async<T, 4>;
+        case 8: return emulated ? (const void*)rc_p2p_async_emulated<T, 8> : (const void*)rc_p2p_async<T, 8>;
+        default: return emulated ? (const void*)rc_p2p_async_emulated<T, 0> : (const void*)rc_p2p_async<T, 0>;
+    }
 }
 
 uint64_t align_up(uint64_t v) { return (v + P2P_ALIGN - 1) / P2P_ALIGN * P2P_ALIGN; }
@@ -509,10 +547,10 @@ extern "C" int gfs_p2p_reconcile_async(gfs_p2p_region* r, void* stream) {
     if (!r) { gfs::set_error("gfs_p2p_reconcile_async: null region"); return GFS_ERR_INVALID; }
     if (!r->connected) { gfs::set_error("gfs_p2p_reconcile_async: region is not connected to its peers"); return GFS_ERR_INVALID; }
     P2P_CUDA(cudaSetDevice(r->device));
-    const P2pArgs a = make_args(r, r->blocks);
-    if (r->elem_bytes == 8) rc_p2p_async<double><<<r->blocks, P2P_ASYNC_THREADS, 0, (cudaStream_t)stream>>>(a);
-    else rc_p2p_async<float><<<r->blocks, P2P_ASYNC_THREADS, 0, (cudaStream_t)stream>>>(a);
-    P2P_CUDA(cudaGetLastError());
+    P2pArgs a = make_args(r, r->blocks);
+    const void* fn = r->elem_bytes == 8 ? async_kernel<double>(r->world, false) : async_kernel<float>(r->world, false);
+    void* kargs[] = {(void*)&a};
+    P2P_CUDA(cudaLaunchKernel(fn, dim3(r->blocks), dim3(P2P_ASYNC_THREADS), kargs, 0, (cudaStream_t)stream));
     return GFS_OK;
 }
 
@@ -527,7 +565,7 @@ extern "C" int gfs_p2p_reconcile_async_local(gfs_p2p_region* const* regions, uin
     return reconcile_local(regions, world, stream, true);
 }
 static int reconcile_local(gfs_p2p_region* const* regions, uint32_t world, void* stream, bool overlapped) {
-    if (!regions || world == 0 || world > P2P_EMU_MAX) { gfs::set_error("gfs_p2p_reconcile_local: 1..4 regions"); return GFS_ERR_INVALID; }
+    if (!regions || world == 0 || world > P2P_EMU_MAX) { gfs::set_error("gfs_p2p_reconcile_local: 1..8 regions"); return GFS_ERR_INVALID; }
     for (uint32_t g = 0; g < world; ++g) {
         if (!regions[g] || !regions[g]->connected || regions[g]->world != world || regions[g]->rank != g ||
             regions[g]->device != regions[0]->device) {
@@ -537,7 +575,7 @@ static int reconcile_local(gfs_p2p_region* const* regions, uint32_t world, void*
     }
     P2P_CUDA(cudaSetDevice(regions[0]->device));
     const bool f64 = regions[0]->elem_bytes == 8;
-    const void* fn = overlapped ? (f64 ? (const void*)rc_p2p_async_emulated<double> : (const void*)rc_p2p_async_emulated<float>)
+    const void* fn = overlapped ? (f64 ? async_kernel<double>(world, true) : async_kernel<float>(world, true))
                                 : (f64 ? (const void*)rc_p2p_emulated<double> : (const void*)rc_p2p_emulated<float>);
     const uint32_t threads = overlapped ? P2P_ASYNC_THREADS : P2P_THREADS;
     int per_sm = 0, sms = 0;

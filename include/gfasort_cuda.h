@@ -325,7 +325,7 @@ int gfs_p2p_region_snapshot(gfs_p2p_region* r, void* stream);
 /* Asynchronous on `stream`: x <- x_sync + (sum of the replicas' displacements) / (#replicas that moved the element)
  * on every replica, then x_sync <- x.  Every rank calls it once per reconcile, in the same order. */
 int gfs_p2p_reconcile(gfs_p2p_region* r, void* stream);
-/* Replicas that share ONE device (tests): all `world` (<= 4) ranks as one cooperative launch, block group g playing
+/* Replicas that share ONE device (tests): all `world` (<= 8) ranks as one cooperative launch, block group g playing
  * rank g — kernels of one GPU that wait on one another must not be separate launches. */
 int gfs_p2p_reconcile_local(gfs_p2p_region* const* regions /*world, rank order, one device*/, uint32_t world, void* stream);
 /* Overlapped form (what gfs_replica_run uses by default): gfs_p2p_region_snapshot_x copies the replica into the region's

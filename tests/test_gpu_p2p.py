@@ -199,17 +199,18 @@ def test_one_call_multi_gpu_through_the_cabi(dims, gfs, monkeypatch):
                                 eta_max=float(int(counts.max()) ** 2), space=int(counts.max()), space_max=1000)
         c0 = gfs.initial_layout(graph, 2, p.seed)
         one, two = [], []
-        for k in range(3):              # a 31-epoch 2D layout of this size moves +-15 % from run to run: medians of 3 seeds
+        for k in range(9):              # a 31-epoch 2D layout of this size moves +-30 % from run to run: medians of 9 seeds
             q = replace(p, seed=p.seed + 1000 * k)
             one.append(gfs.layout_stress(graph, gfs.path_linear_sgd_layout(graph, q, ix1, coords0=c0).coords, 2, 500_000, ix1)[1])
             two.append(gfs.layout_stress(graph, gfs.path_linear_sgd_layout(graph, q, ix2, coords0=c0).coords, 2, 500_000, ix2)[1])
         a1, a2 = float(np.median(one)), float(np.median(two))
-        print(f"2D stress, medians of 3: one GPU {a1:.5e} {one} vs GFASORT_GPUS=2 {a2:.5e} {two}")
+        print(f"2D stress, medians of 9: one GPU {a1:.5e} {one} vs GFASORT_GPUS=2 {a2:.5e} {two}")
         assert a2 <= a1 * 1.15
     ix1.close(); ix2.close()
 
 
-@pytest.mark.parametrize("dtype,G,n", [("float64", 2, 100_003), ("float64", 4, 300_001), ("float32", 3, 65_537)])
+@pytest.mark.parametrize("dtype,G,n", [("float64", 2, 100_003), ("float64", 4, 300_001), ("float32", 3, 65_537), ("float64", 8, 200_003),
+                                       ("float32", 8, 70_001), ("float32", 4, 50_001), ("float32", 2, 33_333), ("float64", 5, 40_001)])
 def test_p2p_overlapped_reconcile_arithmetic(dtype, G, n, gfs, monkeypatch):
     """The overlapped form (rc_p2p_async) on one device, all ranks in one cooperative launch: the exchange works on the
     SNAPSHOTS, every live replica receives (new base - its own snapshot) on top of whatever it did since the snapshot,
