@@ -8,12 +8,14 @@
 //   reduce+scatter  rank r owns the 16-byte vectors [nvec r/G, nvec (r+1)/G): for each it loads the G replicas' values
 //                   (G-1 of them over NVLink: one 16-byte load per peer, all G issued before the first use), forms
 //                   x_sync + sum of displacements / #replicas that moved the element (the "moved-replica mean" of
-//                   DESIGN.md §6, in f64) and stores the result into all G replicas (16-byte stores);
-//   end barrier     all of this rank's peer stores are visible (fence.sys + release) before any peer goes on;
-//   refresh         x_sync <- x over the whole local replica (local HBM traffic only).
+//                   DESIGN.md §6, in f64) and stores the result into all G replicas (16-byte stores) and into its OWN
+//                   x_sync — the base of a slice is only ever read by the slice's owner, so x_sync is kept per slice
+//                   by its owner and there is no refresh pass over the whole replica (until round 2's last change
+//                   there was one: 160 MB of local traffic per reconcile);
+//   end barrier     all of this rank's peer stores are visible (fence.sys + release) before any peer goes on.
 //
 // Per rank and reconcile: n(G-1)/G elements read and n(G-1)/G written over NVLink — the volume of a ring all-reduce —
-// in one launch, no staging buffer, 3 local passes instead of the 7 of pack + NCCL all-reduce + apply.
+// in one launch, no staging buffer, local traffic 3n/G reads + 2n/G writes.
 //
 // Barrier flags live in the region itself, one u32 per (phase, block, source rank), written by the source with
 // st.release.sys and polled by the owner with ld.acquire.sys; tags increase by one per reconcile, so no reset is
@@ -30,7 +32,7 @@
 // what the three resident SGD blocks leave free there — 64 threads x 64 registers is the same total and does NOT fit) meets
 // its peers at the same barriers, forms the new common base B' = x_sync + moved-replica mean of (x_snap_g - x_sync) for
 // its slice, and for EVERY rank g — its own included — adds (B' - x_snap_g) to the live replica with red.add (over NVLink
-// for the peers) and stores B' into that rank's x_sync.  The live replica is then B' + whatever the rank has done since
+// for the peers) and stores B' into its own x_sync.  The live replica is then B' + whatever the rank has done since
 // its snapshot: peers' contributions arrive a fraction of an epoch late instead of stopping everybody for the exchange.
 // "Moved" is |x_snap - x_sync| above 2.5 ulps, because x + (B' - x) is B' only up to one rounding.  The next snapshot waits
 // (stream event) until this kernel — whose end barrier says every peer's corrections have landed — has finished.
@@ -65,7 +67,6 @@ struct P2pArgs {
     uint32_t* flags[P2P_MAX_RANKS];          // [phase 0/1][block][source rank]
     unsigned long long* err[P2P_MAX_RANKS];  // every rank's error word
     void* snap[P2P_MAX_RANKS];               // overlapped form: every rank's snapshot x_snap
-    void* xs_all[P2P_MAX_RANKS];             // overlapped form: every rank's x_sync
     void* xs;                                // local x_sync
     uint64_t nvec;                           // 16-byte vectors per replica (arrays are padded to 256 B)
     uint64_t spin_cap;
@@ -149,7 +150,7 @@ __device__ void p2p_raise(const P2pArgs& a) {
 template <typename T, int W>
 __device__ __forceinline__ void reduce_scatter_vec(const P2pArgs& a, uint64_t i) {
     using V = V16<T>;
-    const V s = *reinterpret_cast<const V*>(static_cast<const char*>(a.xs) + i * 16);   // identical on every replica
+    const V s = *reinterpret_cast<const V*>(static_cast<const char*>(a.xs) + i * 16);   // the base, kept by the slice's owner
     V nv;
     if constexpr (W > 0) {
         V v[W];
@@ -179,6 +180,7 @@ __device__ __forceinline__ void reduce_scatter_vec(const P2pArgs& a, uint64_t i)
         for (int k = 0; k < V::N; ++k) nv.v[k] = moved[k] <= 1 ? only[k] : (T)((double)s.v[k] + sum[k] / (double)moved[k]);
         for (uint32_t g = 0; g < a.world; ++g) V::st(static_cast<char*>(a.x[g]) + i * 16, nv);
     }
+    *reinterpret_cast<V*>(static_cast<char*>(a.xs) + i * 16) = nv;       // the new base of this slice (only its owner ever reads it)
 }
 
 template <typename T>
@@ -198,27 +200,9 @@ __device__ void rc_p2p_body(const P2pArgs& a, uint32_t b) {
         case 8: for (uint64_t i = lo + first; i < hi; i += stride) reduce_scatter_vec<T, 8>(a, i); break;
         default: for (uint64_t i = lo + first; i < hi; i += stride) reduce_scatter_vec<T, 0>(a, i); break;
     }
+    // every peer's stores into MY replica have landed when this barrier opens.  There is no refresh pass: x_sync is only
+    // ever read by the owner of a slice, for that slice, and the owner stored the new base itself (reduce_scatter_vec)
     if (!p2p_barrier<1>(a, b)) { p2p_raise(a); return; }
-    // Refresh the local snapshot (local traffic only).  The barriers pair block b with block b of every peer, so
-    // this thread may only read what the SAME (block, thread) of rank g wrote: walk every rank's slice with the
-    // partition the data phase used.
-    // Four independent 16-byte loads in flight per thread: with one, 75 776 threads keep 1.2 MB in flight and the
-    // 160 MB of this pass take longer than the whole NVLink exchange.
-    const char* const x = static_cast<const char*>(a.x[a.rank]);
-    char* const xs = static_cast<char*>(a.xs);
-    for (uint32_t g = 0; g < a.world; ++g) {
-        const uint64_t glo = slice_begin(a.nvec, a.world, g), ghi = slice_begin(a.nvec, a.world, g + 1);
-        uint64_t i = glo + first;
-        for (; i + 3 * stride < ghi; i += 4 * stride) {
-            const V v0 = V::ld_sys(x + i * 16), v1 = V::ld_sys(x + (i + stride) * 16), v2 = V::ld_sys(x + (i + 2 * stride) * 16),
-                    v3 = V::ld_sys(x + (i + 3 * stride) * 16);
-            *reinterpret_cast<V*>(xs + i * 16) = v0;
-            *reinterpret_cast<V*>(xs + (i + stride) * 16) = v1;
-            *reinterpret_cast<V*>(xs + (i + 2 * stride) * 16) = v2;
-            *reinterpret_cast<V*>(xs + (i + 3 * stride) * 16) = v3;
-        }
-        for (; i < ghi; i += stride) *reinterpret_cast<V*>(xs + i * 16) = V::ld_sys(x + i * 16);
-    }
 }
 
 template <typename T>
@@ -287,8 +271,8 @@ __device__ void rc_p2p_async_body(const P2pArgs& a, uint32_t b) {
                     const T d = (T)((double)nv.v[k] - (double)v[g].v[k]);
                     if (d != T(0)) red_add<T>(xg + k, d);         // the rank keeps what it did since its snapshot
                 }
-                V::st(static_cast<char*>(a.xs_all[g]) + i * 16, nv);
             }
+            *reinterpret_cast<V*>(static_cast<char*>(a.xs) + i * 16) = nv;
         } else {
             for (uint32_t g = 0; g < a.world; ++g) {
                 const V v = V::ld_sys(static_cast<const char*>(a.snap[g]) + i * 16);
@@ -307,8 +291,8 @@ __device__ void rc_p2p_async_body(const P2pArgs& a, uint32_t b) {
                     const T d = (T)((double)nv.v[k] - (double)v.v[k]);
                     if (d != T(0)) red_add<T>(xg + k, d);
                 }
-                V::st(static_cast<char*>(a.xs_all[g]) + i * 16, nv);
             }
+            *reinterpret_cast<V*>(static_cast<char*>(a.xs) + i * 16) = nv;
         }
     }
     if (!p2p_barrier<1>(a, b)) { p2p_raise(a); return; }          // every peer's corrections to MY replica have landed
@@ -507,7 +491,6 @@ static P2pArgs make_args(gfs_p2p_region* r, uint32_t blocks) {
     for (uint32_t g = 0; g < r->world; ++g) {
         a.x[g] = r->peer_base[g];
         a.snap[g] = r->peer_base[g] + r->off_snap;
-        a.xs_all[g] = r->peer_base[g] + r->off_xs;
         a.flags[g] = reinterpret_cast<uint32_t*>(r->peer_base[g] + r->off_flags);
         a.err[g] = reinterpret_cast<unsigned long long*>(r->peer_base[g] + r->off_err);
     }

@@ -305,8 +305,9 @@ int gfs_reconcile_apply(void* x, void* x_sync, uint64_t n, uint32_t elem_bytes, 
  * The same exchange as pack -> all-reduce -> apply, as ONE kernel per rank over NVLink peer memory: every rank
  * maps every other rank's replica, reduces its 1/G slice of the elements across the G replicas and stores the
  * result into all of them, between two in-kernel barriers (flags in peer memory, bounded spins).
- * A region holds one rank's replica x[n], its snapshot x_sync[n] (elem_bytes = 8: f64 positions, 4: f32
- * coordinates) and the barrier flags in one allocation; give gfs_p2p_region_ptrs()'s x to the session as
+ * A region holds one rank's replica x[n], the common base x_sync[n] of the last reconcile (elem_bytes = 8: f64 positions,
+ * 4: f32 coordinates; after the first reconcile only the rank's OWN slice [n r/G, n (r+1)/G) of x_sync is kept up to
+ * date — nobody else ever reads it), a second snapshot for the overlapped form and the barrier flags in one allocation; give gfs_p2p_region_ptrs()'s x to the session as
  * gfs_launch_cfg.device_positions.  One process per GPU: exchange gfs_p2p_region_ipc_handle() blobs (all-gather)
  * and call gfs_p2p_region_connect_ipc; one process driving several GPUs (or several replicas on one GPU):
  * gfs_p2p_region_connect_local.  max_blocks = 0: one block per SM. */
@@ -323,12 +324,13 @@ int gfs_p2p_region_connect_local(gfs_p2p_region* const* regions /*world, rank or
  * with the region's x as gfs_launch_cfg.device_positions): all replicas start from equal snapshots. */
 int gfs_p2p_region_snapshot(gfs_p2p_region* r, void* stream);
 /* Asynchronous on `stream`: x <- x_sync + (sum of the replicas' displacements) / (#replicas that moved the element)
- * on every replica, then x_sync <- x.  Every rank calls it once per reconcile, in the same order. */
+ * on every replica; the owner of a slice stores the same value into its x_sync.  Every rank calls it once per
+ * reconcile, in the same order. */
 int gfs_p2p_reconcile(gfs_p2p_region* r, void* stream);
 /* Replicas that share ONE device (tests): all `world` (<= 8) ranks as one cooperative launch, block group g playing
  * rank g — kernels of one GPU that wait on one another must not be separate launches. */
 int gfs_p2p_reconcile_local(gfs_p2p_region* const* regions /*world, rank order, one device*/, uint32_t world, void* stream);
-/* Overlapped form (what gfs_replica_run uses by default): gfs_p2p_region_snapshot_x copies the replica into the region's
+/* Overlapped form (gfs_replica_run with GFASORT_OVERLAP=1/2; off by default): gfs_p2p_region_snapshot_x copies the replica into the region's
  * snapshot on the SGD's stream; gfs_p2p_reconcile_async, on a second stream that waits for that copy, exchanges the
  * SNAPSHOTS and adds (new common base - own snapshot) to every rank's live replica with red.add, so the next SGD slice runs
  * during the exchange; the next snapshot must wait for it.  The _local form is the same kernel for replicas sharing a device. */

@@ -32,8 +32,18 @@ def _expected(xs, xr, rel_thr=0.0):
     return out
 
 
+def _own_slice(n, elem_bytes, G, g):
+    """Element range of rank g's slice: the 16-byte vectors [nvec g/G, nvec (g+1)/G) of gfs_p2p.cu's slice_begin."""
+    per = 16 // elem_bytes
+    nvec = (n * elem_bytes + 15) // 16
+    q, rem = divmod(nvec, G)
+    lo = q * g + min(g, rem)
+    hi = q * (g + 1) + min(g + 1, rem)
+    return slice(min(lo * per, n), min(hi * per, n))
+
+
 @pytest.mark.parametrize("dtype,G,n", [("float64", 2, 100_003), ("float64", 4, 1_000_000), ("float32", 3, 65_537),
-                                       ("float32", 2, 1_000_001), ("float64", 1, 999)])
+                                       ("float32", 2, 1_000_001), ("float64", 1, 999), ("float64", 8, 123_457)])
 def test_p2p_reconcile_matches_moved_replica_mean(dtype, G, n, gfs, monkeypatch):
     import torch
     from gfasort_b200.multi import PeerRegion
@@ -65,7 +75,8 @@ def test_p2p_reconcile_matches_moved_replica_mean(dtype, G, n, gfs, monkeypatch)
             got = [r.x.cpu().numpy() for r in regions]
             for g in range(G):
                 assert np.array_equal(got[g], got[0]), "replicas differ after the reconcile"
-                assert np.array_equal(regions[g].x_sync.cpu().numpy(), got[g]), "x_sync not refreshed"
+                own = _own_slice(n, 8 if f64 else 4, G, g)          # the base of a slice is kept by its owner only
+                assert np.array_equal(regions[g].x_sync.cpu().numpy()[own], got[g][own]), "the owner's x_sync is not the new base"
             tol = 1e-9 if f64 else 1e-1
             assert np.allclose(got[0], want, rtol=0, atol=tol)
             one = np.stack([x != xs for x in xr]).sum(0) <= 1
@@ -218,7 +229,7 @@ def test_one_call_multi_gpu_through_the_cabi(dims, gfs, monkeypatch):
 def test_p2p_overlapped_reconcile_arithmetic(dtype, G, n, gfs, monkeypatch):
     """The overlapped form (rc_p2p_async) on one device, all ranks in one cooperative launch: the exchange works on the
     SNAPSHOTS, every live replica receives (new base - its own snapshot) on top of whatever it did since the snapshot,
-    every x_sync becomes the new base."""
+    and the owner of each slice stores the new base into its x_sync."""
     import torch
     from gfasort_b200.multi import PeerRegion
     monkeypatch.setenv("GFASORT_P2P_SPIN_CAP", str(1 << 21))
@@ -248,13 +259,15 @@ def test_p2p_overlapped_reconcile_arithmetic(dtype, G, n, gfs, monkeypatch):
                 r.check()
             want_base = _expected(base, snaps, 5.6e-16 if f64 else 3e-7)
             tol = 1e-8 if f64 else 0.5
+            new_base = base.copy()
             for g, r in enumerate(regions):
-                assert np.allclose(r.x_sync.cpu().numpy(), want_base, rtol=0, atol=tol), "x_sync is not the new common base"
+                own = _own_slice(n, 8 if f64 else 4, G, g)          # every rank keeps the base of its own slice
+                new_base[own] = r.x_sync.cpu().numpy()[own]
+            assert np.allclose(new_base, want_base, rtol=0, atol=tol), "the owners' x_sync slices are not the new common base"
+            for g, r in enumerate(regions):
                 want_live = lives[g].astype(np.float64) + (want_base.astype(np.float64) - snaps[g].astype(np.float64))
                 assert np.allclose(r.x.cpu().numpy().astype(np.float64), want_live, rtol=0, atol=tol * 4), "live replica: wrong correction"
-            for r in regions[1:]:
-                assert np.array_equal(r.x_sync.cpu().numpy(), regions[0].x_sync.cpu().numpy()), "bases differ between ranks"
-            base = regions[0].x_sync.cpu().numpy()
+            base = new_base
     finally:
         for r in regions:
             r.close()
