@@ -197,42 +197,48 @@ static int replica_join_reconcile(gfs_replica* r) {
     return GFS_OK;
 }
 
-// Asynchronous: epochs [epoch_begin, epoch_end) of this rank's share, `syncs` slices per epoch, replicas reconciled
-// after every slice.  Every rank must enqueue the same epochs in the same order.
+// Slice k of epoch e and the reconcile behind it (asynchronous).
 // Overlapped (GFASORT_OVERLAP=1/2; off by default, see gfs_replica_create): after a slice the replica is copied to a
 // snapshot and the next slice starts at once; the exchange over the snapshots runs beside it on a second stream and adds
 // its corrections to the live replicas (gfs_p2p.cu, rc_p2p_async).  The next snapshot waits for it.
+static int replica_run_slice(gfs_replica* r, uint64_t e, uint32_t k) {
+    int rc = gfs_sgd_session_run(r->s, e, e + 1, k, r->syncs);
+    if (rc) return rc;
+    if (r->world <= 1) return GFS_OK;
+    if (r->overlap) {
+        rc = replica_join_reconcile(r);                                       // the previous round's corrections are in
+        if (!rc) rc = gfs_p2p_region_snapshot_x(r->region, r->s->stream);
+        if (rc) return rc;
+        GFS_CUDA(cudaEventRecord(r->ev_snap, r->s->stream));
+        GFS_CUDA(cudaStreamWaitEvent(r->side, r->ev_snap, 0));
+        const bool trace = env_long("GFASORT_RC_TRACE", 0) != 0 && r->trace.size() < 4096;
+        if (trace) {
+            cudaEvent_t t0, t1;
+            GFS_CUDA(cudaEventCreate(&t0)); GFS_CUDA(cudaEventCreate(&t1));
+            r->trace.push_back(t0); r->trace.push_back(t1);
+            GFS_CUDA(cudaEventRecord(t0, r->side));
+        }
+        rc = gfs_p2p_reconcile_async(r->region, r->side);
+        if (rc) return rc;
+        if (trace) GFS_CUDA(cudaEventRecord(r->trace.back(), r->side));
+        GFS_CUDA(cudaEventRecord(r->ev_rc, r->side));
+        r->rc_pending = true;
+        if (r->join_at_once) { rc = replica_join_reconcile(r); if (rc) return rc; }
+    } else {
+        rc = gfs_p2p_reconcile(r->region, r->s->stream);
+        if (rc) return rc;
+    }
+    r->reconciles += 1;
+    return GFS_OK;
+}
+// Asynchronous: epochs [epoch_begin, epoch_end) of this rank's share, `syncs` slices per epoch, replicas reconciled
+// after every slice.  Every rank must enqueue the same epochs in the same order.
 extern "C" int gfs_replica_run(gfs_replica* r, uint64_t epoch_begin, uint64_t epoch_end) {
     if (!r) { set_error("gfs_replica_run: null replica"); return GFS_ERR_INVALID; }
     for (uint64_t e = epoch_begin; e < epoch_end; ++e)
         for (uint32_t k = 0; k < r->syncs; ++k) {
-            int rc = gfs_sgd_session_run(r->s, e, e + 1, k, r->syncs);
+            const int rc = replica_run_slice(r, e, k);
             if (rc) return rc;
-            if (r->world <= 1) continue;
-            if (r->overlap) {
-                rc = replica_join_reconcile(r);                                       // the previous round's corrections are in
-                if (!rc) rc = gfs_p2p_region_snapshot_x(r->region, r->s->stream);
-                if (rc) return rc;
-                GFS_CUDA(cudaEventRecord(r->ev_snap, r->s->stream));
-                GFS_CUDA(cudaStreamWaitEvent(r->side, r->ev_snap, 0));
-                const bool trace = env_long("GFASORT_RC_TRACE", 0) != 0 && r->trace.size() < 4096;
-                if (trace) {
-                    cudaEvent_t t0, t1;
-                    GFS_CUDA(cudaEventCreate(&t0)); GFS_CUDA(cudaEventCreate(&t1));
-                    r->trace.push_back(t0); r->trace.push_back(t1);
-                    GFS_CUDA(cudaEventRecord(t0, r->side));
-                }
-                rc = gfs_p2p_reconcile_async(r->region, r->side);
-                if (rc) return rc;
-                if (trace) GFS_CUDA(cudaEventRecord(r->trace.back(), r->side));
-                GFS_CUDA(cudaEventRecord(r->ev_rc, r->side));
-                r->rc_pending = true;
-                if (r->join_at_once) { rc = replica_join_reconcile(r); if (rc) return rc; }
-            } else {
-                rc = gfs_p2p_reconcile(r->region, r->s->stream);
-                if (rc) return rc;
-            }
-            r->reconciles += 1;
         }
     return GFS_OK;
 }
@@ -315,10 +321,15 @@ int gfs_multi_run_whole(const gfs_index* ix, const gfs_sgd_params* params, const
     int rc = on_all([&](uint32_t g) { return gfs_replica_create(ix->shards[g], params, dims, cfg, &ix->plans[g], ix->S, g, G, syncs, &reps[g]); });
     if (!rc) rc = gfs_replica_connect_local(reps.data(), G);
     if (!rc) rc = on_all([&](uint32_t g) { return gfs_replica_upload(reps[g], pos_inout); });
-    // one epoch at a time over all devices: no device's queue runs far ahead of a peer it will wait for
+    // one SLICE at a time over all devices.  Not an epoch at a time: a device's reconcile waits (on the device) for its
+    // peers' reconcile of the same slice, and the host blocks once a session's ring of 16 timing events is full — with more
+    // than 16 slices per epoch the one host thread would wait for device 0 while device 1 had not been given its work yet
+    // (found with GFASORT_SYNCS=40: the barrier's bounded spin turned it into an error, as designed, not into a hang)
     const uint64_t n_epochs = params->iter_max + 1;
+    const uint32_t n_slices = reps[0] ? reps[0]->syncs : 1;
     for (uint64_t e = 0; e < n_epochs && !rc; ++e)
-        for (uint32_t g = 0; g < G && !rc; ++g) rc = gfs_replica_run(reps[g], e, e + 1);
+        for (uint32_t k = 0; k < n_slices && !rc; ++k)
+            for (uint32_t g = 0; g < G && !rc; ++g) rc = replica_run_slice(reps[g], e, k);
     for (uint32_t g = 0; g < G && !rc; ++g) rc = gfs_replica_sync(reps[g]);
     if (!rc) rc = gfs_replica_download(reps[0], pos_inout);        // the replicas are identical after the last reconcile
     gfs_stats tot{};

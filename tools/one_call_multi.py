@@ -25,11 +25,25 @@ else:
     h = s.step_handles.astype(np.uint32)
 counts = np.diff(s.path_first)
 x0 = s.initial_positions()
-sweep = [tuple(c.split(":")) for c in a.sweep.split(",")] if a.sweep else [(None, None)]
-for sw_gpus, sw_overlap in sweep:
-  if sw_gpus is not None:
-      os.environ["GFASORT_GPUS"] = sw_gpus
-      os.environ["GFASORT_OVERLAP"] = sw_overlap
+# --sweep "GPUS=8,OVERLAP=0;GPUS=8,OVERLAP=2;GPUS=1": configurations run one after the other in this process; every KEY=VAL
+# sets GFASORT_KEY for that configuration (keys of earlier configurations are removed); the old form 8:0,8:2 (GPUS:OVERLAP) still works
+def _parse(item):
+    if "=" in item:
+        return dict(kv.split("=") for kv in item.split(","))
+    g, o = item.split(":")
+    return {"GPUS": g, "OVERLAP": o}
+if a.sweep:
+    sweep = [_parse(c) for c in (a.sweep.split(";") if "=" in a.sweep else a.sweep.split(","))]
+else:
+    sweep = [None]
+swept = set()
+for cfg in sweep:
+  if cfg is not None:
+      for k in swept:
+          os.environ.pop("GFASORT_" + k, None)
+      for k, v in cfg.items():
+          os.environ["GFASORT_" + k] = v
+          swept.add(k)
   rows = []
   for rep in range(a.reps):
       t0 = time.perf_counter()
@@ -62,6 +76,6 @@ for sw_gpus, sw_overlap in sweep:
       rows.append((stress[1], stress[0], t3 - t2, st.syncs_per_epoch))
       ix.close()
   m = np.array([r[:3] for r in rows])
-  print(f"[summary GFASORT_GPUS={os.environ.get('GFASORT_GPUS', '1')} OVERLAP={os.environ.get('GFASORT_OVERLAP', '1')} SYNCS={os.environ.get('GFASORT_SYNCS', 'auto')}"
+  print(f"[summary {cfg if cfg is not None else ''} GFASORT_GPUS={os.environ.get('GFASORT_GPUS', '1')} OVERLAP={os.environ.get('GFASORT_OVERLAP', '0')} SYNCS={os.environ.get('GFASORT_SYNCS', 'auto')}"
         f" -> {rows[-1][3]}/epoch; dims {a.dims}; {a.reps} runs] mean_abs median {np.median(m[:,0]):.4e} [{m[:,0].min():.4e}, {m[:,0].max():.4e}]  "
         f"rms median {np.median(m[:,1]):.4e}  sgd seconds median {np.median(m[:,2]):.3f}", flush=True)
