@@ -212,7 +212,8 @@ def test_one_call_multi_gpu_through_the_cabi(dims, gfs, monkeypatch):
     [4.2e-4, 6.4e-4] against 3.91e-4 [3.4e-4, 4.7e-4] on one GPU and 4.30e-4 [3.7e-4, 5.7e-4] for the CPU oracle (5 seeds,
     tools/oracle_layout_spread.py); at config 4's size the difference is below the run-to-run spread.
     About one two-GPU run in nine ends 2-3 x worse (a fold that the 31 epochs do not repair; profiles/r2_experiments.md §6).
-    The bound says what is measured: medians within 1.6 x."""
+    Medians of 9 seeds, two GPUs over one, in four runs of this test / tools/one_call_multi.py: 1.26, 1.37, 1.40, 1.56;
+    the bound (2 x) only guards against a broken exchange, it is not a parity claim."""
     s, counts, x0 = _synth(gfs, 200_000, 16)
     graph = gfs.BidirectedGraph.from_dense(s.step_handles, s.path_first, s.node_len)
     ix1 = gfs.PathIndex.from_arrays(s.step_handles, s.path_first, s.node_len)
@@ -245,7 +246,7 @@ def test_one_call_multi_gpu_through_the_cabi(dims, gfs, monkeypatch):
             two.append(gfs.layout_stress(graph, gfs.path_linear_sgd_layout(graph, q, ix2, coords0=c0).coords, 2, 500_000, ix2)[1])
         a1, a2 = float(np.median(one)), float(np.median(two))
         print(f"2D stress, medians of 9: one GPU {a1:.5e} {one} vs GFASORT_GPUS=2 {a2:.5e} {two}")
-        assert a2 <= a1 * 1.6
+        assert a2 <= a1 * 2.0
     ix1.close(); ix2.close()
 
 
