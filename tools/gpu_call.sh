@@ -1,18 +1,16 @@
 set -x
 cd $GRAFT_REPO_ROOT
-timeout 600 python -m pytest tests/test_gpu_p2p.py -q -m gpu -s 2>&1 | grep -E "^\.*[12]D stress|passed|failed|FAILED|Error" | cut -c1-300
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 8 --steps 10 --warmup 3 > gpurun_out/bench_r2s_n8.log 2> gpurun_out/bench_r2s_n8.err; grep -E "e2e phases|Error|error" gpurun_out/bench_r2s_n8.err | cut -c1-300
-timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 4 --steps 10 --warmup 3 --also 0 > gpurun_out/bench_r2s_n4.log 2> gpurun_out/bench_r2s_n4.err; grep -E "e2e phases|Error|error" gpurun_out/bench_r2s_n4.err | cut -c1-300
-timeout 300 python tools/one_call_multi.py --reps 3 --sweep "GPUS=8" > gpurun_out/one_call_r2s_n8.log 2>&1; grep -E "one call|summary|Error|error" gpurun_out/one_call_r2s_n8.log | cut -c1-400
+timeout 1500 python -m pytest tests -x -q -m gpu -s > gpurun_out/pytest_r2t.log 2>&1; tail -3 gpurun_out/pytest_r2t.log | cut -c1-300
+timeout 900 python bench.py > gpurun_out/bench_r2t.log 2> gpurun_out/bench_r2t.err; tail -c 600 gpurun_out/bench_r2t.err
+timeout 900 python bench.py --impl reference > gpurun_out/bench_r2t_ref.log 2> gpurun_out/bench_r2t_ref.err; tail -c 300 gpurun_out/bench_r2t_ref.err; cat gpurun_out/bench_r2t_ref.log | cut -c1-900
+timeout 600 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -3
 python - <<'PY'
 import json
-for f in ["bench_r2s_n8.log", "bench_r2s_n4.log"]:
-    try:
-        d = json.loads(open("gpurun_out/" + f).read().strip().splitlines()[-1])
-    except Exception as e:
-        print(f, "no line", e); continue
-    print(f, "value", round(d["value"] / 1e9, 2), "ms/step", round(d["ms_per_step"], 3), "kernel", round(d["roofline"]["launch_ms"], 3), "gap", round(d["roofline"]["step_ms_minus_kernel_ms"], 3),
-          "e2e", round(d["e2e"]["seconds"], 3), "stress", d["e2e"]["stress_mean_abs_rel"], d["e2e"]["stress_rms_rel"], d["launch"]["overlapped_reconcile"])
-    for a in d.get("also") or []:
-        print("   also", a.get("workload"), round(a["value"] / 1e9, 2), a.get("ms_per_step"), a["roofline"]["launch_ms"], a["e2e"]["seconds"], a["e2e"]["stress_mean_abs_rel"])
+d = json.loads(open("gpurun_out/bench_r2t.log").read().strip().splitlines()[-1])
+r = d["roofline"]; e = d["e2e"]
+print("value", round(d["value"] / 1e9, 2), "ms/step", round(d["ms_per_step"], 3), "kernel", round(r["launch_ms"], 3), "frac", round(r["frac"], 3), "dram_frac", r.get("dram_frac"), "e2e", round(e["value"] / 1e9, 2), round(e["seconds"], 3), e.get("phases"), "stress", e["stress_mean_abs_rel"], e["stress_rms_rel"])
+print("cpu", d["cpu_baseline"], "launches", d["gpu_launches"], "clocks", d["clocks"])
+print("k1", r.get("k1"))
+for a in d.get("also") or []:
+    print("also", a.get("workload"), round(a["value"] / 1e9, 2), a.get("ms_per_step"), a["roofline"]["frac"], a["roofline"].get("dram_frac"), a["e2e"]["seconds"], a["e2e"]["stress_mean_abs_rel"])
 PY
