@@ -372,7 +372,11 @@ def measure_workload(a, wl, name, rank, world, local, dev, K, W, with_cpu, e2e_e
     kern_s = torch.tensor([st1["kernel_seconds"] - st0["kernel_seconds"]], dtype=torch.float64, device=dev)
     applied = torch.tensor([st1["applied_updates"] - st0["applied_updates"]], dtype=torch.int64, device=dev)
     attempts = torch.tensor([st1["attempts"] - st0["attempts"]], dtype=torch.int64, device=dev)
+    kern_ranks = None
     if world > 1:
+        gathered = [torch.zeros_like(kern_s) for _ in range(world)]
+        dist.all_gather(gathered, kern_s)                      # per-rank SGD kernel time: the skew the reconcile's start barrier waits for
+        kern_ranks = [float(g.item()) for g in gathered]
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
         dist.all_reduce(kern_s, op=dist.ReduceOp.MAX)
         dist.all_reduce(applied, op=dist.ReduceOp.SUM)
@@ -517,6 +521,7 @@ def measure_workload(a, wl, name, rank, world, local, dev, K, W, with_cpu, e2e_e
                          "traffic": traffic, "traffic_source": traffic_src, "dram_frac": dram_frac, "peak_source": peak_src,
                          "algorithmic_bytes_per_update": ALGO_BYTES_PER_UPDATE,
                          "updates_per_launch": upd_per_launch, "launch_ms": launch_s * 1e3,
+                         "launch_ms_by_rank": [round(k / sgd_launches_per_rank * 1e3, 4) for k in kern_ranks] if kern_ranks else None,
                          "step_ms_minus_kernel_ms": ms / K - launch_s * 1e3 * syncs, "k1": k1},
             "nvlink": nvlink, "cpu_baseline": cpu}
 
