@@ -1,8 +1,8 @@
+# What a gpurun call of this repo runs (edit per call):  gpurun --timeout 2400 -- 'bash tools/gpu_call.sh'
+# This version is the round's final single-GPU validation: GPU tests, the driver's two bench arms, the smoke test.
 set -x
 cd $GRAFT_REPO_ROOT
-timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 8 --steps 10 --warmup 3 --also 0 > gpurun_out/bench_r2w_n8.log 2> gpurun_out/bench_r2w_n8.err; echo rc=$?; grep -E "Error|error|Traceback" gpurun_out/bench_r2w_n8.err | cut -c1-300
-python - <<'PY'
-import json
-d = json.loads(open("gpurun_out/bench_r2w_n8.log").read().strip().splitlines()[-1])
-print("value", round(d["value"] / 1e9, 2), "ms/step", round(d["ms_per_step"], 3), "kernel", round(d["roofline"]["launch_ms"], 3), "by rank", d["roofline"]["launch_ms_by_rank"], "gap", round(d["roofline"]["step_ms_minus_kernel_ms"], 3), "stress", d["e2e"]["stress_mean_abs_rel"])
-PY
+timeout 1500 python -m pytest tests -x -q -m gpu -s > gpurun_out/pytest_final.log 2>&1; tail -3 gpurun_out/pytest_final.log | cut -c1-300
+timeout 900 python bench.py > gpurun_out/bench_final.log 2> gpurun_out/bench_final.err; tail -c 600 gpurun_out/bench_final.err
+timeout 900 python bench.py --impl reference > gpurun_out/bench_final_ref.log 2> gpurun_out/bench_final_ref.err; cut -c1-400 gpurun_out/bench_final_ref.log
+timeout 600 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -3

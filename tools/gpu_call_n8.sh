@@ -1,6 +1,10 @@
+# The scaling run on one 8-GPU box:  gpurun --timeout 1500 --gpus 8 -- 'bash tools/gpu_call_n8.sh'
 set -x
 cd $GRAFT_REPO_ROOT
-nvidia-smi -L | wc -l
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 8 --steps 10 --warmup 3 > gpurun_out/bench_r2g_n8.log 2> gpurun_out/bench_r2g_n8.err; tail -12 gpurun_out/bench_r2g_n8.err; cut -c1-1200 gpurun_out/bench_r2g_n8.log
-timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 4 --steps 10 --warmup 3 --also 0 > gpurun_out/bench_r2g_n4.log 2> gpurun_out/bench_r2g_n4.err; tail -3 gpurun_out/bench_r2g_n4.err; cut -c1-300 gpurun_out/bench_r2g_n4.log
-GFASORT_GPUS=8 timeout 300 python tools/one_call_multi.py > gpurun_out/one_call_r2g_n8.log 2>&1; cat gpurun_out/one_call_r2g_n8.log
+for N in 8 4 2; do
+  ALSO=$([ $N = 8 ] && echo 1 || echo 0)
+  timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 2951$N bench.py --gpus $N --steps 10 --warmup 3 --also $ALSO \
+      > gpurun_out/bench_scale_n$N.log 2> gpurun_out/bench_scale_n$N.err
+  grep -E "e2e phases|Error|error" gpurun_out/bench_scale_n$N.err | cut -c1-300
+  cut -c1-400 gpurun_out/bench_scale_n$N.log
+done
