@@ -243,7 +243,11 @@ def test_one_call_multi_gpu_through_the_cabi(dims, gfs, monkeypatch):
         for k in range(9):              # a 31-epoch 2D layout of this size moves +-30 % from run to run: medians of 9 seeds
             q = replace(p, seed=p.seed + 1000 * k)
             one.append(gfs.layout_stress(graph, gfs.path_linear_sgd_layout(graph, q, ix1, coords0=c0).coords, 2, 500_000, ix1)[1])
-            two.append(gfs.layout_stress(graph, gfs.path_linear_sgd_layout(graph, q, ix2, coords0=c0).coords, 2, 500_000, ix2)[1])
+            c2 = gfs.path_linear_sgd_layout(graph, q, ix2, coords0=c0).coords
+            two.append(gfs.layout_stress(graph, c2, 2, 500_000, ix2)[1])
+            if k == 0:                  # sharded 2D stress == one-GPU stress of the same layout on the same sample
+                s2, s1 = gfs.layout_stress(graph, c2, 2, 500_000, ix2), gfs.layout_stress(graph, c2, 2, 500_000, ix1)
+                assert s2[2] == s1[2] and abs(s2[1] - s1[1]) <= 1e-9 * s1[1] and abs(s2[0] - s1[0]) <= 1e-9 * s1[0]
         a1, a2 = float(np.median(one)), float(np.median(two))
         print(f"2D stress, medians of 9: one GPU {a1:.5e} {one} vs GFASORT_GPUS=2 {a2:.5e} {two}")
         assert a2 <= a1 * 2.0
