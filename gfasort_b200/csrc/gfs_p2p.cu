@@ -43,6 +43,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cmath>
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
@@ -68,6 +69,8 @@ struct P2pArgs {
     unsigned long long* err[P2P_MAX_RANKS];  // every rank's error word
     void* snap[P2P_MAX_RANKS];               // overlapped form: every rank's snapshot x_snap
     void* xs;                                // local x_sync
+    double inv_div[P2P_MAX_RANKS + 1];       // div_pow != 1 (GFASORT_RC_POW): 1 / m^div_pow for m replicas that moved an element
+    uint32_t use_inv_div;                    // 0: divide by the number of replicas that moved it (the moved-replica mean)
     uint64_t nvec;                           // 16-byte vectors per replica (arrays are padded to 256 B)
     uint64_t spin_cap;
     uint32_t rank, world, tag, blocks;
@@ -162,7 +165,8 @@ __device__ __forceinline__ void reduce_scatter_vec(const P2pArgs& a, uint64_t i)
 #pragma unroll
             for (int g = 0; g < W; ++g)
                 if (v[g].v[k] != s.v[k]) { sum += (double)v[g].v[k] - (double)s.v[k]; ++moved; only = v[g].v[k]; }
-            nv.v[k] = moved <= 1 ? only : (T)((double)s.v[k] + sum / (double)moved);    // exact when 0 or 1 replicas moved it
+            nv.v[k] = moved <= 1 ? only                                                 // exact when 0 or 1 replicas moved it
+                      : (T)((double)s.v[k] + (a.use_inv_div ? sum * a.inv_div[moved] : sum / (double)moved));
         }
 #pragma unroll
         for (int g = 0; g < W; ++g) V::st(static_cast<char*>(a.x[g]) + i * 16, nv);
@@ -177,7 +181,9 @@ __device__ __forceinline__ void reduce_scatter_vec(const P2pArgs& a, uint64_t i)
                 if (v.v[k] != s.v[k]) { sum[k] += (double)v.v[k] - (double)s.v[k]; ++moved[k]; only[k] = v.v[k]; }
         }
 #pragma unroll
-        for (int k = 0; k < V::N; ++k) nv.v[k] = moved[k] <= 1 ? only[k] : (T)((double)s.v[k] + sum[k] / (double)moved[k]);
+        for (int k = 0; k < V::N; ++k)
+            nv.v[k] = moved[k] <= 1 ? only[k]
+                      : (T)((double)s.v[k] + (a.use_inv_div ? sum[k] * a.inv_div[moved[k]] : sum[k] / (double)moved[k]));
         for (uint32_t g = 0; g < a.world; ++g) V::st(static_cast<char*>(a.x[g]) + i * 16, nv);
     }
     *reinterpret_cast<V*>(static_cast<char*>(a.xs) + i * 16) = nv;       // the new base of this slice (only its owner ever reads it)
@@ -330,6 +336,7 @@ struct gfs_p2p_region {
     bool ipc_opened[P2P_MAX_RANKS] = {};
     bool connected = false;
     uint64_t spin_cap = 0;
+    double div_pow = 1.0;                               // GFASORT_RC_POW: divisor = (#replicas that moved the element)^div_pow
 };
 
 #define P2P_CUDA(call)                                                                                       \
@@ -362,6 +369,10 @@ extern "C" int gfs_p2p_region_create(int32_t device, uint64_t n, uint32_t elem_b
     r->blocks = std::max(1u, std::min(blocks, P2P_MAX_BLOCKS));
     const char* cap = std::getenv("GFASORT_P2P_SPIN_CAP");
     r->spin_cap = cap && *cap ? std::strtoull(cap, nullptr, 10) : (1ull << 24);   // x >= 64 ns: seconds, not forever
+    // experiment (profiles/r2_experiments.md §6): 1 = the moved-replica mean (default), 0 = the sum of the displacements;
+    // the stop-the-world kernel only
+    const char* dp = std::getenv("GFASORT_RC_POW");
+    if (dp && *dp) r->div_pow = std::min(1.0, std::max(0.0, std::strtod(dp, nullptr)));
     const uint64_t arr = align_up(std::max<uint64_t>(n, 1) * elem_bytes);  // padded: the kernel works on whole 16-byte vectors
     r->off_xs = arr;
     r->off_snap = 2 * arr;
@@ -496,6 +507,8 @@ static P2pArgs make_args(gfs_p2p_region* r, uint32_t blocks) {
     }
     a.xs = r->base + r->off_xs;
     a.nvec = (r->n * r->elem_bytes + 15) / 16;
+    a.use_inv_div = r->div_pow != 1.0;
+    for (uint32_t m = 0; m <= P2P_MAX_RANKS; ++m) a.inv_div[m] = m ? 1.0 / std::pow((double)m, r->div_pow) : 1.0;
     a.spin_cap = r->spin_cap;
     a.rank = r->rank; a.world = r->world;
     a.tag = ++r->tag;
